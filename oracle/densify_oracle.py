@@ -1,0 +1,464 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's post-matching densification path.
+
+This file is the *oracle* for the CUDA path: a numpy / torch-CPU restatement of what the reference
+plugin (shadygm/Lichtfeld-Densification-Plugin v0.8.3) computes between the RoMa matcher and the
+point accumulator.  It is a checker, never a fallback: only ``tests/``, ``__graft_entry__.smoke()``
+and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  The product package
+must not.
+
+Parity status: the reference ships **no** tests, golden vectors or fixtures for this path
+(SURVEY.md section 4), so the restatement is pinned against the *live* reference instead: it was
+checked bit-for-bit against the unmodified ``/root/reference/core`` modules imported in the build
+container (``tests/test_oracle_vs_reference.py``), and against golden vectors generated from that
+live import (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``), which travel to the GPU box.
+
+Every function cites the reference lines it restates (paths relative to the reference root).
+The restatement deliberately keeps the reference's *operation structure* (legacy
+``RandomState.choice``, a Python walk over ``argsort(-weights)``, LAPACK batched SVD, sgemm
+projections) so that timing it is a fair "reference CPU path" baseline, and keeps its dtype flow
+(f32 geometry, f64 Sampson, f64 bilinear weights) so results are bit-identical on the same box.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+__all__ = [
+    "OracleCamera",
+    "OracleConfig",
+    "legacy_choice_no_replace",
+    "sample_weights",
+    "coverage_picks",
+    "select_samples",
+    "best_neighbour",
+    "decode_samples",
+    "bilinear_colour",
+    "fundamental_matrix",
+    "sampson_distance",
+    "dlt_points",
+    "reprojection_error",
+    "in_front",
+    "parallax_ok",
+    "triangulate_ref",
+    "to_uint8_rgb",
+    "ply_bytes",
+    "points3d_bin_bytes",
+]
+
+
+# ----------------------------------------------------------------------------------------------
+# plain-data stand-ins for the reference's types
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class OracleCamera:
+    """Per-view constants, dtype/shape exactly as core/camera_models.py:10-21 holds them
+    (K,R [3,3] f32; t [3,1] f32; P [3,4] f32 = K@[R|t]; C [3] f32 = -R^T t; densify.py:226-230)."""
+
+    uid: int
+    width: int
+    height: int
+    K: np.ndarray
+    R: np.ndarray
+    t: np.ndarray
+    P: np.ndarray
+    C: np.ndarray
+
+
+@dataclass
+class OracleConfig:
+    """The scalars of core/config.py:7-26 that the hot path reads (+ the matcher constants of
+    core/pipeline.py:99-105 / core/matcher.py:92-94)."""
+
+    matches_per_ref: int = 10000
+    reproj_thresh: float = 0.8
+    sampson_thresh: float = 5.0
+    min_parallax_deg: float = 0.5
+    no_filter: bool = False
+    sample_cap: float = 0.9      # matcher.sample_thresh, core/matcher.py:92
+    border: int = 2              # core/pipeline.py:646
+    tiles: int = 24              # core/pipeline.py:647
+    w_match: int = 512
+    h_match: int = 512
+
+
+# ----------------------------------------------------------------------------------------------
+# sampler  (core/sampling.py:8-53)
+# ----------------------------------------------------------------------------------------------
+def legacy_choice_no_replace(p32: np.ndarray, size: int, uniforms: np.ndarray) -> Tuple[np.ndarray, int, int]:
+    """numpy's legacy ``RandomState.choice(n, size, replace=False, p=p)`` restated on an explicit
+    uniform stream (numpy 2.3 ``numpy/random/mtrand.pyx``, pinned by the reference at
+    ``pyproject.toml:12``; called from core/sampling.py:32).
+
+    ``uniforms`` must be the ``random_sample`` stream of the generator ``choice`` would have used
+    (``np.random.RandomState(seed).random_sample(k)``).  Returns ``(found, n_consumed, n_rounds)``;
+    ``found`` is in numpy's draw order.  Raises the same ValueErrors numpy raises.
+    """
+    p = np.array(p32, dtype=np.float64)            # PyArray_FROM_OTF(p, NPY_DOUBLE)
+    n = p.shape[0]
+    if np.isnan(p).any():
+        raise ValueError("probabilities contain NaN")
+    if (p < 0).any():
+        raise ValueError("probabilities are not non-negative")
+    atol = np.sqrt(np.finfo(np.float64).eps)
+    if isinstance(p32, np.ndarray) and np.issubdtype(p32.dtype, np.floating):
+        atol = max(atol, np.sqrt(np.finfo(p32.dtype).eps))
+    if abs(float(np.sum(p)) - 1.0) > atol:         # numpy uses a Kahan sum; same verdict away from atol
+        raise ValueError("probabilities do not sum to 1")
+    if size > n:
+        raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+    if np.count_nonzero(p > 0) < size:
+        raise ValueError("Fewer non-zero entries in p than size")
+
+    found = np.zeros(size, dtype=np.int64)
+    have = 0
+    used = 0
+    rounds = 0
+    while have < size:
+        want = size - have
+        if used + want > uniforms.shape[0]:
+            raise RuntimeError("explicit uniform stream exhausted")
+        x = uniforms[used:used + want]
+        used += want
+        rounds += 1
+        if have > 0:
+            p[found[:have]] = 0.0
+        cdf = np.cumsum(p)                         # sequential f64 running sum
+        cdf /= cdf[-1]
+        hit = cdf.searchsorted(x, side="right")    # first i with cdf[i] > x
+        _, first_pos = np.unique(hit, return_index=True)
+        first_pos.sort()
+        hit = hit.take(first_pos)                  # first occurrence of each value, draw order
+        found[have:have + hit.size] = hit
+        have += hit.size
+    return found, used, rounds
+
+
+def sample_weights(best_cert: torch.Tensor, cap: float, border: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Capped, border-masked f32 weights and their torch-CPU f32 sum (core/sampling.py:12-14,23-26).
+
+    The value of ``s`` depends on torch's CPU reduction order (thread count / SIMD width)
+    -- parity runs hand this exact ``s`` to the CUDA path as ``weight_sum_override``.
+    """
+    cert = torch.clamp(best_cert.clone().to("cpu"), max=cap)
+    H, W = cert.shape
+    rows = torch.arange(H).view(H, 1).expand(H, W)
+    cols = torch.arange(W).view(1, W).expand(H, W)
+    keep = (cols >= border) & (cols <= W - 1 - border) & (rows >= border) & (rows <= H - 1 - border)
+    w = (cert * keep.float()).reshape(-1)
+    return w, w.sum()
+
+
+def coverage_picks(p: np.ndarray, H: int, W: int, tiles: int, budget: int) -> np.ndarray:
+    """Per-tile best pixel, walking pixels in descending weight (core/sampling.py:34-50).
+
+    ``np.argsort(-p)`` is an unstable sort: among equal weights the visiting order -- hence the
+    pick inside a tile whose maximum is tied -- is implementation-defined.
+    """
+    tile = max(1, W // tiles)
+    flat = np.arange(H * W)
+    key = ((flat % W) // tile) * 100000 + ((flat // W) // tile)     # gx*100000 + gy
+    picked: List[int] = []
+    taken = set()
+    for i in np.argsort(-p):
+        if p[i] <= 0:
+            break
+        b = int(key[i])
+        if b in taken:
+            continue
+        taken.add(b)
+        picked.append(i)
+        if len(picked) >= budget:
+            break
+    return np.asarray(picked, dtype=np.int64)
+
+
+def select_samples(best_cert: torch.Tensor, M: int, cap: float = 0.9, border: int = 2, tiles: int = 24,
+                   no_filter: bool = False, rng: Optional[np.random.RandomState] = None,
+                   uniforms: Optional[np.ndarray] = None, taps: Optional[dict] = None,
+                   s_override: Optional[np.float32] = None) -> np.ndarray:
+    """core/sampling.py:8-53.  RNG: ``uniforms`` (explicit stream, restated ``choice``) if given,
+    else ``rng.choice`` if given, else the process-global ``np.random.choice`` like the reference.
+    ``s_override`` replaces the torch-CPU f32 weight sum (box/thread-count dependent)
+    by a recorded one, so golden vectors made on another box replay exactly."""
+    H, W = best_cert.shape
+    if no_filter:                                   # core/sampling.py:15-21
+        flat = torch.clamp(best_cert.clone().to("cpu"), max=cap).reshape(-1).numpy()
+        if flat.size == 0:
+            return np.zeros((0,), dtype=np.int64)
+        return np.argsort(-flat)[:min(M, flat.size)]
+
+    w, s = sample_weights(best_cert, cap, border)
+    if s_override is not None:
+        s = torch.tensor(np.float32(s_override))
+    if taps is not None:
+        taps["weights"] = w.numpy().copy()
+        taps["s"] = np.float32(s.item())
+    if s <= 0:                                      # core/sampling.py:27-28
+        return np.zeros((0,), dtype=np.int64)
+    p = (w / s).numpy()                             # f32 division, core/sampling.py:29
+    m_main = int(M * 0.85)
+    size = min(m_main, p.size)
+    if uniforms is not None:
+        main, used, rounds = legacy_choice_no_replace(p, size, uniforms)
+        if taps is not None:
+            taps["uniforms_used"] = used
+            taps["rounds"] = rounds
+    elif rng is not None:
+        main = rng.choice(p.size, size=size, replace=False, p=p)
+    else:
+        main = np.random.choice(p.size, size=size, replace=False, p=p)
+    cov = coverage_picks(p, H, W, tiles, M - len(main))
+    if taps is not None:
+        taps["p"] = p
+        taps["idx_main"] = np.asarray(main, dtype=np.int64)
+        taps["idx_cov"] = cov
+    return np.unique(np.concatenate([main, cov]))   # ascending, deduped (core/sampling.py:52)
+
+
+# ----------------------------------------------------------------------------------------------
+# two-view geometry  (core/geometry.py:53-141)
+# ----------------------------------------------------------------------------------------------
+def fundamental_matrix(K1, R1, t1, K2, R2, t2) -> np.ndarray:
+    """F = K2^-T [t]x R K1^-1 with R = R2 R1^T, t = t2 - R t1, all f32 (core/geometry.py:53-55,122-130)."""
+    Rrel = R2 @ R1.T
+    trel = (t2 - Rrel @ t1).reshape(3)
+    a, b, c = trel.flatten()
+    tx = np.array([[0, -c, b], [c, 0, -a], [-b, a, 0]], dtype=np.float32)
+    return np.linalg.inv(K2).T @ (tx @ Rrel) @ np.linalg.inv(K1)
+
+
+def sampson_distance(F: np.ndarray, uv1: np.ndarray, uv2: np.ndarray) -> np.ndarray:
+    """First-order geometric error; evaluated in float64 because the homogeneous 1-column is f64
+    (core/geometry.py:133-141)."""
+    n = uv1.shape[0]
+    h1 = np.concatenate([uv1, np.ones((n, 1))], axis=1)
+    h2 = np.concatenate([uv2, np.ones((n, 1))], axis=1)
+    l2 = (F @ h1.T).T
+    l1 = (F.T @ h2.T).T
+    num = np.sum(h2 * l2, axis=1)
+    den = l2[:, 0] ** 2 + l2[:, 1] ** 2 + l1[:, 0] ** 2 + l1[:, 1] ** 2 + 1e-12
+    return (num ** 2) / den
+
+
+def dlt_points(P1: np.ndarray, P2: np.ndarray, uv1: np.ndarray, uv2: np.ndarray) -> np.ndarray:
+    """Homogeneous DLT, null vector by f32 LAPACK SVD, dehomogenised with the +1e-12 guard
+    (core/geometry.py:58-87; N==1 un-batched at :77-82)."""
+    n = uv1.shape[0]
+    if n == 0:
+        return np.zeros((0, 4), dtype=np.float32)
+    A = np.empty((n, 4, 4), dtype=np.float32)
+    A[:, 0, :] = uv1[:, 0:1] * P1[2] - P1[0]
+    A[:, 1, :] = uv1[:, 1:2] * P1[2] - P1[1]
+    A[:, 2, :] = uv2[:, 0:1] * P2[2] - P2[0]
+    A[:, 3, :] = uv2[:, 1:2] * P2[2] - P2[1]
+    if n == 1:
+        v = np.linalg.svd(A[0])[2][-1]
+        w = v[3] if abs(v[3]) > 1e-12 else 1e-12
+        return (v / w)[None, :]
+    v = np.linalg.svd(A)[2][:, -1, :]
+    w = np.where(np.abs(v[:, 3:4]) < 1e-12, 1e-12, v[:, 3:4])
+    return v / w
+
+
+def reprojection_error(P: np.ndarray, X: np.ndarray, uv: np.ndarray) -> np.ndarray:
+    """core/geometry.py:91-104 (sgemm projection, z clamped at 1e-12)."""
+    q = X @ P.T
+    z = np.maximum(q[:, 2], 1e-12)
+    du = q[:, 0] / z - uv[:, 0]
+    dv = q[:, 1] / z - uv[:, 1]
+    return np.sqrt(du * du + dv * dv)
+
+
+def in_front(P: np.ndarray, X: np.ndarray) -> np.ndarray:
+    """core/geometry.py:107-110."""
+    return (P @ X.T)[2, :] > 0.0
+
+
+def parallax_ok(C1: np.ndarray, C2: np.ndarray, X: np.ndarray, min_deg: float) -> np.ndarray:
+    """core/geometry.py:113-119 (f32 throughout)."""
+    r1 = X[:, :3] - C1.reshape(1, 3)
+    r2 = X[:, :3] - C2.reshape(1, 3)
+    r1 /= np.linalg.norm(r1, axis=1, keepdims=True) + 1e-12
+    r2 /= np.linalg.norm(r2, axis=1, keepdims=True) + 1e-12
+    ang = np.degrees(np.arccos(np.clip(np.sum(r1 * r2, axis=1), -1.0, 1.0)))
+    return ang >= float(min_deg)
+
+
+# ----------------------------------------------------------------------------------------------
+# per-reference driver  (core/pipeline.py:602-780)
+# ----------------------------------------------------------------------------------------------
+def best_neighbour(cert_list: Sequence[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-pixel max over neighbours, lowest neighbour index on ties (core/pipeline.py:634-635)."""
+    stack = torch.stack([torch.as_tensor(c) for c in cert_list], dim=0).to("cpu")
+    return torch.max(stack, dim=0)
+
+
+def decode_samples(warp_list, best_k: torch.Tensor, sel_idx: np.ndarray, w_match: int, h_match: int):
+    """Winning-neighbour warp rows at the sampled pixels -> match-res pixel coords
+    (core/pipeline.py:636-640,652-659).  Only the sampled rows are gathered (the reference gathers
+    all H*W rows then indexes; same values)."""
+    H, W = best_k.shape
+    k = best_k.reshape(-1).numpy()[sel_idx]
+    stack = torch.stack([torch.as_tensor(x) for x in warp_list], dim=0).to("cpu")
+    rows = stack.reshape(stack.shape[0], H * W, 4)[torch.from_numpy(k), torch.from_numpy(sel_idx)].numpy()
+    xA = (rows[:, 0] + 1.0) * 0.5 * (w_match - 1)
+    yA = (rows[:, 1] + 1.0) * 0.5 * (h_match - 1)
+    return k, xA, yA, rows[:, 2], rows[:, 3]
+
+
+def bilinear_colour(img_u8: np.ndarray, xA: np.ndarray, yA: np.ndarray, w_match: int, h_match: int) -> np.ndarray:
+    """core/pipeline.py:661-679: clipped-corner bilinear tap of the (resized) reference image; the
+    int32 - float32 subtractions promote the weights to float64."""
+    hh, ww = img_u8.shape[0], img_u8.shape[1]
+    fx = xA * (ww / float(w_match))
+    fy = yA * (hh / float(h_match))
+    x0 = np.clip(np.floor(fx).astype(np.int32), 0, ww - 1)
+    y0 = np.clip(np.floor(fy).astype(np.int32), 0, hh - 1)
+    x1 = np.clip(x0 + 1, 0, ww - 1)
+    y1 = np.clip(y0 + 1, 0, hh - 1)
+    w00 = (x1 - fx) * (y1 - fy)
+    w01 = (fx - x0) * (y1 - fy)
+    w10 = (x1 - fx) * (fy - y0)
+    w11 = (fx - x0) * (fy - y0)
+    t00 = img_u8[y0, x0].astype(np.float32)
+    t01 = img_u8[y0, x1].astype(np.float32)
+    t10 = img_u8[y1, x0].astype(np.float32)
+    t11 = img_u8[y1, x1].astype(np.float32)
+    return (t00 * w00[:, None] + t01 * w01[:, None] + t10 * w10[:, None] + t11 * w11[:, None]) / 255.0
+
+
+@dataclass
+class OracleResult:
+    xyz: np.ndarray
+    rgb: np.ndarray
+    err: np.ndarray
+    sel_idx: np.ndarray
+    debug_matches_by_nbr: Dict[int, np.ndarray] = field(default_factory=dict)
+    debug_cert_by_nbr: Dict[int, np.ndarray] = field(default_factory=dict)
+    taps: dict = field(default_factory=dict)
+
+
+def triangulate_ref(cert_list, warp_list, img_u8: np.ndarray, ref_cam: OracleCamera,
+                    nbr_cams: Sequence[OracleCamera], cfg: OracleConfig,
+                    rng: Optional[np.random.RandomState] = None, uniforms: Optional[np.ndarray] = None,
+                    collect_debug: bool = False, keep_taps: bool = False,
+                    s_override: Optional[np.float32] = None) -> Optional[OracleResult]:
+    """core/pipeline.py:602-780 for one reference view.  ``nbr_cams[k]`` is the camera of
+    ``cert_list[k]`` (the reference's ``nn_ids[k]``).  Returns None where the reference does."""
+    taps: dict = {}
+    best_cert, best_k = best_neighbour(cert_list)
+    H, W = best_cert.shape
+    sel_idx = select_samples(best_cert, cfg.matches_per_ref, cap=cfg.sample_cap, border=cfg.border,
+                             tiles=cfg.tiles, no_filter=cfg.no_filter, rng=rng, uniforms=uniforms,
+                             taps=taps if keep_taps else None, s_override=s_override)
+    if sel_idx.size == 0:
+        return None
+    wm, hm = cfg.w_match, cfg.h_match
+    k_sel, xA, yA, xBn, yBn = decode_samples(warp_list, best_k, sel_idx, wm, hm)
+    cert_sel = best_cert.reshape(-1).numpy()[sel_idx]
+    rgb_all = bilinear_colour(img_u8, xA, yA, wm, hm)
+    uvA_all = np.stack([xA * (ref_cam.width / float(wm)), yA * (ref_cam.height / float(hm))], axis=1)
+
+    members: Dict[int, List[int]] = {}               # first-appearance order (core/pipeline.py:685-688)
+    cam_of: Dict[int, OracleCamera] = {}
+    for pos, kk in enumerate(k_sel):
+        cam = nbr_cams[int(kk)]
+        members.setdefault(cam.uid, []).append(pos)
+        cam_of[cam.uid] = cam
+
+    out_xyz, out_rgb, out_err = [], [], []
+    dbg_m: Dict[int, np.ndarray] = {}
+    dbg_c: Dict[int, np.ndarray] = {}
+    denom = float(cfg.sample_cap) if float(cfg.sample_cap) > 1e-6 else 1.0
+    group_taps = []
+    for uid, pos_list in members.items():
+        pos = np.asarray(pos_list, dtype=np.int64)
+        cam = cam_of[uid]
+        xB = (xBn[pos] + 1.0) * 0.5 * (wm - 1)
+        yB = (yBn[pos] + 1.0) * 0.5 * (hm - 1)
+        uvB = np.stack([xB * (cam.width / float(wm)), yB * (cam.height / float(hm))], axis=1)
+        xAg, yAg, cg = xA[pos], yA[pos], cert_sel[pos]
+        gt = {"uid": uid, "pos_all": pos.copy()}
+        if (not cfg.no_filter) and cfg.sampson_thresh > 0:       # core/pipeline.py:708-727
+            F = fundamental_matrix(ref_cam.K, ref_cam.R, ref_cam.t, cam.K, cam.R, cam.t)
+            se = sampson_distance(F, uvA_all[pos], uvB)
+            ok = se < float(cfg.sampson_thresh)
+            gt["F"], gt["sampson"] = F, se
+            if not np.any(ok):
+                group_taps.append(gt)
+                continue
+            pos, xB, yB, uvB, xAg, yAg, cg = pos[ok], xB[ok], yB[ok], uvB[ok], xAg[ok], yAg[ok], cg[ok]
+        if pos.size == 0:
+            group_taps.append(gt)
+            continue
+        uvA = uvA_all[pos]
+        X = dlt_points(ref_cam.P, cam.P, uvA, uvB)
+        e = np.maximum(reprojection_error(ref_cam.P, X, uvA), reprojection_error(cam.P, X, uvB))
+        if cfg.no_filter:                                        # core/pipeline.py:739-743
+            keep = np.isfinite(X).all(axis=1) & np.isfinite(e)
+        else:                                                    # core/pipeline.py:745-749
+            keep = e <= float(cfg.reproj_thresh)
+            keep &= in_front(ref_cam.P, X)
+            keep &= in_front(cam.P, X)
+            if cfg.min_parallax_deg > 0:
+                keep &= parallax_ok(ref_cam.C, cam.C, X, cfg.min_parallax_deg)
+        gt.update(pos=pos, X=X, err=e, keep=keep, uvA=uvA, uvB=uvB)
+        group_taps.append(gt)
+        if not np.any(keep):
+            continue
+        out_xyz.append(X[keep][:, :3].astype(np.float32))
+        out_rgb.append(rgb_all[pos][keep].astype(np.float32))
+        out_err.append(e[keep].astype(np.float32))
+        if collect_debug:                                        # core/pipeline.py:761-769
+            m = np.stack([np.clip(xAg[keep], 0.0, float(wm - 1)), np.clip(yAg[keep], 0.0, float(hm - 1)),
+                          np.clip(xB[keep], 0.0, float(wm - 1)), np.clip(yB[keep], 0.0, float(hm - 1))], axis=1)
+            dbg_m[uid] = m.astype(np.float32, copy=False)
+            dbg_c[uid] = np.clip(cg[keep] / denom, 0.0, 1.0).astype(np.float32, copy=False)
+    if not out_xyz:
+        return None
+    if keep_taps:
+        taps.update(best_k=best_k.numpy(), best_cert=best_cert.numpy(), k_sel=k_sel, xA=xA, yA=yA,
+                    xBn=xBn, yBn=yBn, uvA_all=uvA_all, rgb_all=rgb_all, groups=group_taps)
+    return OracleResult(xyz=np.concatenate(out_xyz, axis=0), rgb=np.concatenate(out_rgb, axis=0),
+                        err=np.concatenate(out_err, axis=0), sel_idx=sel_idx,
+                        debug_matches_by_nbr=dbg_m, debug_cert_by_nbr=dbg_c, taps=taps)
+
+
+# ----------------------------------------------------------------------------------------------
+# output contract  (core/image_utils.py:24-26, core/writers.py:15-46)
+# ----------------------------------------------------------------------------------------------
+def to_uint8_rgb(rgb01: np.ndarray) -> np.ndarray:
+    """clip(round(x*255)) with numpy's round-half-to-even (core/image_utils.py:24-26)."""
+    return np.clip(np.round(rgb01 * 255.0), 0, 255).astype(np.uint8)
+
+
+def ply_bytes(xyz: np.ndarray, rgb_u8: np.ndarray) -> bytes:
+    """The exact byte stream core/writers.py:29-46 writes (binary little-endian PLY)."""
+    import struct
+    n = xyz.shape[0]
+    head = ("ply\nformat binary_little_endian 1.0\n" f"element vertex {n}\n"
+            "property float x\nproperty float y\nproperty float z\n"
+            "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n")
+    parts = [head.encode("ascii")]
+    for i in range(n):
+        parts.append(struct.pack("<fff", float(xyz[i, 0]), float(xyz[i, 1]), float(xyz[i, 2])))
+        parts.append(struct.pack("BBB", int(rgb_u8[i, 0]), int(rgb_u8[i, 1]), int(rgb_u8[i, 2])))
+    return b"".join(parts)
+
+
+def points3d_bin_bytes(xyz: np.ndarray, rgb_u8: np.ndarray, errors: Optional[np.ndarray] = None) -> bytes:
+    """The exact byte stream core/writers.py:15-26 writes (COLMAP-like points3D.bin without tracks)."""
+    import struct
+    n = xyz.shape[0]
+    if errors is None:
+        errors = np.zeros((n,), dtype=np.float32)
+    parts = [struct.pack("<Q", n)]
+    for i in range(n):
+        parts.append(struct.pack("<Q", i + 1))
+        parts.append(struct.pack("<ddd", float(xyz[i, 0]), float(xyz[i, 1]), float(xyz[i, 2])))
+        parts.append(struct.pack("<BBB", int(rgb_u8[i, 0]), int(rgb_u8[i, 1]), int(rgb_u8[i, 2])))
+        parts.append(struct.pack("<d", float(errors[i])))
+    return b"".join(parts)
