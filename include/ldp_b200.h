@@ -1,0 +1,166 @@
+/*
+ * ldp_b200.h -- C ABI of the B200-native post-matching densification hot path.
+ *
+ * The reference plugin (shadygm/Lichtfeld-Densification-Plugin v0.8.3) has NO FFI / operator ABI for
+ * this path: it is a private Python function,
+ *     core.pipeline._triangulate_ref(matched_ref, tri_ctx, collect_debug_matches)   core/pipeline.py:602-606
+ * called once per reference view from run_dense_pipeline (core/pipeline.py:842-898).  This header is
+ * therefore the boundary a maintainer would bind with ctypes; every entry point
+ * cites the reference code it replaces.  Plain pointers and sizes only; the caller (PyTorch on the
+ * host side) owns every buffer; calls are stream-ordered and never synchronise unless stated.
+ *
+ * All functions return LDP_OK (0) or a negative ldp_error.  Per-reference outcomes that the
+ * reference handles by *skipping the view* (core/pipeline.py:650-651,874-879) are reported in
+ * ldp_outputs.status[r], not as call failures.
+ */
+#ifndef LDP_B200_H
+#define LDP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDP_ABI_VERSION 3
+#define LDP_MAX_NN 16          /* neighbours per reference view (the panel clamps to 10) */
+#define LDP_MAX_BINS 4096      /* coverage tiles per map: ceil(W/tile)*ceil(H/tile), tile = max(1, W/24) */
+
+typedef enum ldp_error {
+    LDP_OK = 0,
+    LDP_ERR_INVALID = -1,      /* bad argument / unsupported shape */
+    LDP_ERR_CUDA = -2,         /* a CUDA runtime call failed; see ldp_last_error_string() */
+    LDP_ERR_WORKSPACE = -3,    /* workspace too small */
+    LDP_ERR_NO_DEVICE = -4     /* no sm_100 device */
+} ldp_error;
+
+/* status[r]: why a reference view produced no samples (the reference returns None / raises and the
+ * caller skips the view).  Bit flags >= 0x100 are informational and accompany LDP_REF_OK. */
+typedef enum ldp_ref_status {
+    LDP_REF_OK = 0,
+    LDP_REF_EMPTY = 1,           /* weight sum s <= 0          -> core/sampling.py:27-28, pipeline.py:650-651 */
+    LDP_REF_FEWER_NONZERO = 2,   /* np.random.choice ValueError "Fewer non-zero entries in p than size" */
+    LDP_REF_BAD_WEIGHTS = 3,     /* NaN / negative probabilities -> ValueError in np.random.choice */
+    LDP_REF_PSUM = 4,            /* "probabilities do not sum to 1" (only with a bad weight_sum_override) */
+    LDP_REF_UNIFORMS_EXHAUSTED = 5, /* explicit uniform stream too short */
+    LDP_REF_ROUNDS_EXCEEDED = 6,
+    LDP_REF_NO_NEIGHBOURS = 7,
+    LDP_REF_INEXACT_SCAN = 0x100 /* flag: f64 prefix sums not provably exact (tiny weights): sampled set is
+                                    numpy's up to draws within ~1e-16 of a cdf step */
+} ldp_ref_status;
+
+typedef enum ldp_rng_mode {
+    LDP_RNG_PHILOX = 0,     /* production: Philox4x32-10, key = seed, stream = rng_stream[r], counter = draw index */
+    LDP_RNG_EXPLICIT = 1    /* parity: uniforms[r*uniforms_per_ref + i] is the i-th double numpy's legacy
+                               RandomState.random_sample would have produced (np.random.choice, core/sampling.py:32) */
+} ldp_rng_mode;
+
+/* Problem shape + the scalars of DensePipelineConfig (core/config.py:7-26) and _TriangulationContext
+ * (core/pipeline.py:99-105) that the path reads. */
+typedef struct ldp_params {
+    int32_t n_refs;            /* reference views in this launch */
+    int32_t H, W;              /* warp / certainty map resolution */
+    int32_t w_match, h_match;  /* matcher resolution W_lr, H_lr (core/matcher.py:93-94) */
+    int32_t matches_per_ref;   /* M */
+    int32_t border;            /* 2   core/pipeline.py:646 */
+    int32_t tiles;             /* 24  core/pipeline.py:647 */
+    float sample_cap;          /* f32(0.9) core/matcher.py:92 */
+    float reproj_thresh;       /* f32(config.reproj_thresh): compared in f32, core/pipeline.py:745 */
+    float min_parallax_deg;    /* f32; <= 0 disables, core/pipeline.py:748 */
+    double sampson_thresh;     /* f64; <= 0 disables, core/pipeline.py:708 */
+    int32_t no_filter;         /* core/sampling.py:15-21 + core/pipeline.py:739-743 */
+    int32_t collect_debug;     /* core/pipeline.py:761-769 */
+    int32_t rng_mode;          /* ldp_rng_mode */
+    int32_t reserved0;
+    uint64_t seed;             /* Philox key */
+    int64_t uniforms_per_ref;  /* explicit mode: doubles available per reference view */
+} ldp_params;
+
+/* Per reference view: where its matcher outputs live and its camera constants.  Array of n_refs in
+ * DEVICE memory.  Camera constants are computed on the host exactly like the reference does
+ * (densify.py:226-230, core/geometry.py:122-130) and uploaded; the kernels stage them in shared memory. */
+typedef struct ldp_ref_desc {
+    const float* cert[LDP_MAX_NN];   /* [H*W] f32 per neighbour       (cert_list_cpu, core/pipeline.py:630) */
+    const float* warp[LDP_MAX_NN];   /* [H*W*4] f32 per neighbour: xA,yA,xB,yB in [-1,1] (warp_list_cpu, :629);
+                                        16-byte aligned; read only at sampled pixels */
+    const uint8_t* image;            /* [img_h*img_w*3] u8 resized reference image (packed.imA_np, :611) */
+    int32_t nn;                      /* neighbours present (len(nn_ids)) */
+    int32_t img_w, img_h;
+    uint32_t rng_stream;             /* Philox stream id (stable across sharding: global reference index) */
+    float weight_sum_override;       /* > 0: use as the f32 normaliser s (core/sampling.py:26); else computed */
+    float sxA, syA;                  /* f32(wA_cam / w_match), f32(hA_cam / h_match)     core/pipeline.py:681-682 */
+    float sx_img, sy_img;            /* f32(img_w / w_match), f32(img_h / h_match)       core/pipeline.py:662-663 */
+    float P1[12];                    /* reference camera P [3,4] row-major */
+    float C1[3];
+    float P2[LDP_MAX_NN][12];        /* neighbour cameras */
+    float C2[LDP_MAX_NN][3];
+    float F[LDP_MAX_NN][9];          /* fundamental_from_world2cam(ref, nbr), f32, row-major */
+    float sxB[LDP_MAX_NN], syB[LDP_MAX_NN];   /* f32(wB_cam / w_match), ...   core/pipeline.py:697-699 */
+    int32_t group[LDP_MAX_NN];       /* output group of neighbour k: smallest k' with nn_ids[k'] == nn_ids[k]
+                                        (the reference groups by neighbour uid, core/pipeline.py:685-688) */
+} ldp_ref_desc;
+
+/* Caller-allocated DEVICE outputs.  Optional pointers may be NULL. */
+typedef struct ldp_outputs {
+    /* packed point cloud, reference emission order (refs in launch order; inside a ref: neighbour groups in
+       first-appearance order over the sample order, samples ascending inside a group; core/pipeline.py:685-780) */
+    float* xyz;                /* [capacity,3] */
+    float* rgb;                /* [capacity,3]  in [0,1] */
+    float* err;                /* [capacity]    max reprojection error, px */
+    int64_t capacity;          /* >= n_refs * ldp_sel_capacity(M) is always enough */
+    int64_t* ref_offset;       /* [n_refs+1] exclusive prefix of kept points per reference view */
+    int32_t* status;           /* [n_refs] ldp_ref_status */
+    int32_t* n_samples;        /* [n_refs] S = |sel_idx| */
+    int32_t* group_count;      /* [n_refs*LDP_MAX_NN] kept points per group id */
+    int32_t* group_order;      /* [n_refs*LDP_MAX_NN] group ids in emission order, -1 padded */
+    /* optional */
+    float* dbg_matches;        /* [capacity,4] clipped match-res px (xA,yA,xB,yB)      core/pipeline.py:762-766 */
+    float* dbg_cert;           /* [capacity]   clip(cert / cap, 0, 1)                  core/pipeline.py:767 */
+    int32_t* sel_idx;          /* [n_refs*sel_capacity] sampled flat pixel indices (ascending; top-M order if no_filter) */
+    uint8_t* sample_flags;     /* [n_refs*sel_capacity] bit0 keep, bit1 sampson-pass, bits 2.. = group id */
+    float* sample_xyzerr;      /* [n_refs*sel_capacity*4] per-sample X,Y,Z,err before filtering (parity taps) */
+    int32_t* uniforms_used;    /* [n_refs] doubles consumed from the stream */
+    int32_t* rounds;           /* [n_refs] rejection rounds of the weighted draw */
+    float* weight_sum;         /* [n_refs] the f32 normaliser s actually used */
+} ldp_outputs;
+
+/* ---- entry points ------------------------------------------------------------------------------- */
+
+int ldp_abi_version(void);
+const char* ldp_last_error_string(void);
+
+/* Rows each reference view can emit at most: S <= max(M, int(0.85*M)+1), rounded up to 4. */
+int64_t ldp_sel_capacity(int32_t matches_per_ref);
+
+/* Bytes of device scratch ldp_densify_refs needs for this shape (n_refs, H, W, matches_per_ref are read). */
+int ldp_workspace_bytes(const ldp_params* params, size_t* bytes_out);
+
+/* The whole path for n_refs reference views: replaces the body of core.pipeline._triangulate_ref
+ * (core/pipeline.py:632-780) and its callees select_samples_with_coverage (core/sampling.py:8-53),
+ * sampson_error / dlt_triangulate_batch / reprojection_errors / cheirality_mask / parallax_mask
+ * (core/geometry.py:58-141).  refs, uniforms (explicit mode; may be NULL otherwise), workspace and
+ * every pointer inside *out are DEVICE pointers.  Enqueues on `stream` (a cudaStream_t) and returns. */
+int ldp_densify_refs(const ldp_params* params, const ldp_ref_desc* refs, const double* uniforms,
+                     const ldp_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stage entry points (same kernels, exposed for stage-level parity tests and for callers that already
+ * hold sample indices).  ldp_sample_refs = core/sampling.py:8-53 on the per-pixel best certainty
+ * (core/pipeline.py:634-635,642-649); ldp_triangulate_samples = core/pipeline.py:652-780 on given indices
+ * (out->sel_idx / out->n_samples are INPUTS here). */
+int ldp_sample_refs(const ldp_params* params, const ldp_ref_desc* refs, const double* uniforms,
+                    const ldp_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
+int ldp_triangulate_samples(const ldp_params* params, const ldp_ref_desc* refs,
+                            const ldp_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Kernel launches enqueued by the last ldp_* call on this thread (for bench.py's gpu_launches). */
+int ldp_last_launch_count(void);
+
+/* sizeof() of the ABI structs as this library was compiled: which = 0 ldp_params, 1 ldp_ref_desc,
+ * 2 ldp_outputs.  Bindings check these against their own struct definitions at load time. */
+int64_t ldp_struct_size(int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDP_B200_H */

@@ -1,0 +1,376 @@
+"""Drop-in host interface of the densification path.
+
+Keeps the reference's names, argument meaning and error behaviour for this path
+(reference core/pipeline.py):
+
+* ``PipelineResult``                          :37-43
+* ``_PackedReferenceBatch`` / ``_CameraLookup`` / ``_MatchedReference`` / ``_TriangulationContext`` /
+  ``_TriangulatedReference``                  :53-114
+* ``_build_camera_lookup``                    :270-281
+* ``_triangulate_ref(matched_ref, tri_ctx, collect_debug_matches)``  :602-780  (one view, host or device tensors)
+* ``run_dense_pipeline(...) -> PipelineResult``                      :783-928  (the matcher is supplied by the caller:
+  the RoMa network is out of scope)
+
+plus the batched form the B200 path is built for: ``triangulate_refs`` processes every reference view
+of a rank in ONE launch sequence.  All compute happens in the CUDA library; without it these functions
+raise (no CPU fallback).
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from ..engine import DensifyEngine, DensifyOutputs, PathConfig, RefBatch
+from .camera_models import CameraRecord
+from .config import RNG_EXPLICIT, RNG_NUMPY_GLOBAL, RNG_PHILOX, DensePipelineConfig
+
+
+@dataclass
+class PipelineResult:
+    xyz: np.ndarray
+    rgb: np.ndarray
+    err: np.ndarray
+    elapsed_seconds: float
+    pairs_processed: int
+
+
+class PipelineCancelled(RuntimeError):
+    """Raised when a running dense pipeline is cancelled."""
+
+
+@dataclass
+class _PackedReferenceBatch:
+    ref_id: int
+    ref_path: str
+    imA_np: np.ndarray
+    maskA_np: Optional[np.ndarray]
+    wA_cam: int
+    hA_cam: int
+    nn_ids: List[int]
+    nn_masks: List[Optional[np.ndarray]]
+    nn_arrays: List[np.ndarray]
+
+
+@dataclass(frozen=True)
+class _CameraLookup:
+    img_ids: List[int]
+    path_by: Dict[int, str]
+    mask_by: Dict[int, Optional[str]]
+    size_by: Dict[int, Tuple[int, int]]
+    K_by: Dict[int, np.ndarray]
+    R_by: Dict[int, np.ndarray]
+    t_by: Dict[int, np.ndarray]
+    P_by: Dict[int, np.ndarray]
+    C_by: Dict[int, np.ndarray]
+    record_by: Dict[int, CameraRecord] = field(default_factory=dict)     # extra: uid -> record
+
+
+@dataclass
+class _MatchedReference:
+    packed: _PackedReferenceBatch
+    warp_list_cpu: List[torch.Tensor]       # host OR device tensors (device tensors skip the H2D copy)
+    cert_list_cpu: List[torch.Tensor]
+    pair_index_by_nbr: Dict[int, int]
+    image_by_nbr: Dict[int, np.ndarray]
+
+
+@dataclass(frozen=True)
+class _TriangulationContext:
+    cameras: _CameraLookup
+    config: DensePipelineConfig
+    matcher_sample_cap: float
+    w_match: int
+    h_match: int
+
+
+@dataclass
+class _TriangulatedReference:
+    xyz: np.ndarray
+    rgb: np.ndarray
+    err: np.ndarray
+    debug_matches_by_nbr: Dict[int, np.ndarray]
+    debug_cert_by_nbr: Dict[int, np.ndarray]
+
+
+def _build_camera_lookup(camera_records: Sequence[CameraRecord]) -> _CameraLookup:
+    recs = list(camera_records)
+    return _CameraLookup(
+        img_ids=[c.uid for c in recs],
+        path_by={c.uid: c.image_path for c in recs},
+        mask_by={c.uid: getattr(c, "mask_path", None) for c in recs},
+        size_by={c.uid: (c.width, c.height) for c in recs},
+        K_by={c.uid: c.K for c in recs},
+        R_by={c.uid: c.R for c in recs},
+        t_by={c.uid: c.t for c in recs},
+        P_by={c.uid: c.P for c in recs},
+        C_by={c.uid: c.C for c in recs},
+        record_by={c.uid: c for c in recs},
+    )
+
+
+def _record_for(cameras: _CameraLookup, uid: int) -> CameraRecord:
+    rec = cameras.record_by.get(uid) if cameras.record_by else None
+    if rec is None:       # a lookup built by the reference's own helper has no record_by
+        w, h = cameras.size_by[uid]
+        rec = CameraRecord(uid=uid, image_path=cameras.path_by.get(uid, ""), width=w, height=h, K=cameras.K_by[uid],
+                           R=cameras.R_by[uid], t=cameras.t_by[uid], P=cameras.P_by[uid], C=cameras.C_by[uid])
+        if cameras.record_by is not None:
+            cameras.record_by[uid] = rec
+    return rec
+
+
+# ------------------------------------------------------------------------------------------------
+_engines: Dict[int, DensifyEngine] = {}
+
+
+def get_engine(device: Optional[torch.device] = None) -> DensifyEngine:
+    if not torch.cuda.is_available():
+        raise N.NativeLibraryError("the densification path needs a CUDA device (there is no CPU fallback)")
+    idx = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    eng = _engines.get(idx)
+    if eng is None:
+        eng = DensifyEngine(torch.device("cuda", idx))
+        _engines[idx] = eng
+    return eng
+
+
+def _to_device(t, device, dtype) -> torch.Tensor:
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(t)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+def _raise_for_status(code: int) -> None:
+    """Same exceptions the reference path raises for a view (np.random.choice ValueErrors)."""
+    code &= N.LDP_REF_CODE_MASK
+    if code in (N.LDP_REF_FEWER_NONZERO, N.LDP_REF_BAD_WEIGHTS, N.LDP_REF_PSUM):
+        raise ValueError(N.REF_STATUS_MESSAGES[code])
+    if code in (N.LDP_REF_UNIFORMS_EXHAUSTED, N.LDP_REF_ROUNDS_EXCEEDED):
+        raise RuntimeError(N.REF_STATUS_MESSAGES[code])
+
+
+def _split_reference(out: DensifyOutputs, host: dict, r: int, nbr_uids: List[int],
+                     collect_debug: bool) -> Optional[_TriangulatedReference]:
+    a, b = int(host["ref_offset"][r]), int(host["ref_offset"][r + 1])
+    if b <= a:
+        return None
+    dbg_m: Dict[int, np.ndarray] = {}
+    dbg_c: Dict[int, np.ndarray] = {}
+    if collect_debug:
+        pos = a
+        for g in host["group_order"][r]:
+            if g < 0:
+                break
+            cnt = int(host["group_count"][r][g])
+            if cnt > 0:
+                dbg_m[nbr_uids[g]] = host["dbg_matches"][pos:pos + cnt].copy()
+                dbg_c[nbr_uids[g]] = host["dbg_cert"][pos:pos + cnt].copy()
+            pos += cnt
+    return _TriangulatedReference(xyz=host["xyz"][a:b].copy(), rgb=host["rgb"][a:b].copy(), err=host["err"][a:b].copy(),
+                                  debug_matches_by_nbr=dbg_m, debug_cert_by_nbr=dbg_c)
+
+
+def _download(out: DensifyOutputs, collect_debug: bool) -> dict:
+    """One synchronising device->host read of everything the host needs."""
+    meta = {"ref_offset": out.ref_offset.cpu().numpy()}
+    total = int(meta["ref_offset"][-1]) if out.n_refs else 0
+    meta["status"] = out.status.cpu().numpy()
+    meta["uniforms_used"] = out.uniforms_used.cpu().numpy()
+    meta["group_order"] = out.group_order.cpu().numpy()
+    meta["group_count"] = out.group_count.cpu().numpy()
+    meta["xyz"] = out.xyz[:total].cpu().numpy()
+    meta["rgb"] = out.rgb[:total].cpu().numpy()
+    meta["err"] = out.err[:total].cpu().numpy()
+    if collect_debug:
+        meta["dbg_matches"] = out.dbg_matches[:total].cpu().numpy()
+        meta["dbg_cert"] = out.dbg_cert[:total].cpu().numpy()
+    return meta
+
+
+def _mt_stream_from_global(n: int) -> np.ndarray:
+    """The next n doubles the process-global MT19937 stream would produce, without consuming them."""
+    rs = np.random.RandomState()
+    rs.set_state(np.random.get_state())
+    return rs.random_sample(n)
+
+
+def triangulate_refs(matched_refs: Sequence[_MatchedReference], tri_ctx: _TriangulationContext,
+                     collect_debug_matches: bool = False, *, rng_streams: Optional[Sequence[int]] = None,
+                     uniforms: Optional[np.ndarray] = None,
+                     weight_sums: Optional[Sequence[float]] = None,
+                     errors: Optional[list] = None) -> List[Optional[_TriangulatedReference]]:
+    """Batched ``_triangulate_ref``: every view of ``matched_refs`` in one launch sequence.
+
+    RNG: ``uniforms`` (f64 [n, U], explicit parity stream per view) or Philox keyed by
+    (config.seed, rng_streams[i]).  Views the reference would skip (None return / exception) come back as
+    None; the exception a per-view call would raise is appended to ``errors`` as (index, exc).
+    """
+    n = len(matched_refs)
+    if n == 0:
+        return []
+    eng = get_engine()
+    dev = eng.device
+    cfg = tri_ctx.config
+    pcfg = PathConfig.from_pipeline_config(cfg, sample_cap=tri_ctx.matcher_sample_cap)
+    first = matched_refs[0].cert_list_cpu[0]
+    H, W = int(first.shape[0]), int(first.shape[1])
+    batch = eng.new_batch(H, W, tri_ctx.w_match, tri_ctx.h_match)
+    for i, mr in enumerate(matched_refs):
+        packed = mr.packed
+        certs = [_to_device(c, dev, torch.float32) for c in mr.cert_list_cpu]
+        warps = [_to_device(w, dev, torch.float32) for w in mr.warp_list_cpu]
+        image = _to_device(packed.imA_np, dev, torch.uint8)
+        ref_cam = _record_for(tri_ctx.cameras, packed.ref_id)
+        if (ref_cam.width, ref_cam.height) != (packed.wA_cam, packed.hA_cam):
+            ref_cam = CameraRecord(uid=ref_cam.uid, image_path=ref_cam.image_path, width=packed.wA_cam, height=packed.hA_cam,
+                                   K=ref_cam.K, R=ref_cam.R, t=ref_cam.t, P=ref_cam.P, C=ref_cam.C)
+        nbrs = [_record_for(tri_ctx.cameras, uid) for uid in packed.nn_ids]
+        batch.add(certs, warps, image, ref_cam, nbrs,
+                  rng_stream=(rng_streams[i] if rng_streams is not None else i),
+                  weight_sum_override=(float(weight_sums[i]) if weight_sums is not None else 0.0))
+    u_dev = None
+    if uniforms is not None:
+        u_dev = torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float64)).to(dev)
+    out = eng.densify(batch, pcfg, uniforms=u_dev, collect_debug=collect_debug_matches)
+    host = _download(out, collect_debug_matches)
+    results: List[Optional[_TriangulatedReference]] = []
+    for r in range(n):
+        try:
+            _raise_for_status(int(host["status"][r]))
+            results.append(_split_reference(out, host, r, batch.nbr_uids[r], collect_debug_matches))
+        except Exception as exc:      # the reference's caller logs and skips (core/pipeline.py:874-879)
+            if errors is not None:
+                errors.append((r, exc))
+            results.append(None)
+    triangulate_refs.last_uniforms_used = host["uniforms_used"]
+    triangulate_refs.last_launches = out.launches
+    return results
+
+
+def _triangulate_ref(matched_ref: _MatchedReference, tri_ctx: _TriangulationContext,
+                     collect_debug_matches: bool = False) -> Optional[_TriangulatedReference]:
+    """Triangulate matches for a single reference view (reference core/pipeline.py:602-780).
+
+    ``config.rng_mode``: "numpy" consumes the process-global MT19937 stream exactly like the reference's
+    ``np.random.choice`` (same draws, same stream position afterwards); "philox" (default) uses the
+    counter-based generator keyed by (config.seed, packed.ref_id).
+    """
+    cfg = tri_ctx.config
+    mode = getattr(cfg, "rng_mode", RNG_PHILOX)
+    errs: list = []
+    if mode == RNG_NUMPY_GLOBAL and not cfg.no_filter:
+        size = int(cfg.matches_per_ref * 0.85)
+        n_uni = 2 * size + 64
+        while True:
+            U = _mt_stream_from_global(n_uni)
+            res = triangulate_refs([matched_ref], tri_ctx, collect_debug_matches, uniforms=U[None, :], errors=errs)
+            if errs and "exhausted" in str(errs[0][1]):
+                errs.clear()
+                n_uni *= 2
+                continue
+            break
+        used = int(triangulate_refs.last_uniforms_used[0])
+        if used > 0:
+            np.random.random_sample(used)          # advance the global stream like np.random.choice did
+    else:
+        res = triangulate_refs([matched_ref], tri_ctx, collect_debug_matches,
+                               rng_streams=[int(matched_ref.packed.ref_id)], errors=errs)
+    if errs:
+        raise errs[0][1]
+    return res[0]
+
+
+# ------------------------------------------------------------------------------------------------
+MatchSource = Callable[[int], Optional[_MatchedReference]]
+
+
+def _is_cancelled(cancel_requested: Optional[Callable[[], bool]]) -> bool:
+    if cancel_requested is None:
+        return False
+    try:
+        return bool(cancel_requested())
+    except Exception:
+        return False
+
+
+def run_dense_pipeline(
+    camera_records: List[CameraRecord],
+    refs_local: List[int],
+    nn_table: np.ndarray,
+    config: DensePipelineConfig,
+    progress_callback: Optional[Callable[[float, str], None]] = None,
+    on_sequential_viz: Optional[Callable[[str], None]] = None,
+    debug_state=None,
+    cancel_requested: Optional[Callable[[], bool]] = None,
+    *,
+    match_source: Optional[MatchSource] = None,
+    w_match: Optional[int] = None,
+    h_match: Optional[int] = None,
+    sample_cap: float = 0.9,
+) -> PipelineResult:
+    """Reference signature (core/pipeline.py:783-792) + ``match_source``: a callable
+    ``ref_local -> _MatchedReference | None`` standing in for pack loader + RoMa matcher (out of scope here;
+    an integrator wraps ``RomaMatcher.match_grids_batch`` and may keep its outputs on the GPU).
+    Views are processed ``config.refs_per_launch`` at a time (0 = all in one launch)."""
+    del on_sequential_viz, debug_state, nn_table
+    if match_source is None:
+        raise RuntimeError("run_dense_pipeline needs a match_source: the RoMa matcher is not part of this package")
+    from .config import ROMA_PRESETS
+    if w_match is None or h_match is None:
+        h_lr, _ = ROMA_PRESETS[config.roma_setting]
+        w_match = h_match = h_lr
+    if getattr(config, "rng_mode", RNG_PHILOX) == RNG_NUMPY_GLOBAL:
+        np.random.seed(config.seed)                                    # core/pipeline.py:793
+    cameras = _build_camera_lookup(camera_records)
+    tri_ctx = _TriangulationContext(cameras=cameras, config=config, matcher_sample_cap=sample_cap,
+                                    w_match=int(w_match), h_match=int(h_match))
+    t0 = time.time()
+    step = int(getattr(config, "refs_per_launch", 0)) or max(1, len(refs_local))
+    parts_xyz, parts_rgb, parts_err = [], [], []
+    pairs = 0
+    total = len(refs_local)
+    for lo in range(0, total, step):
+        if _is_cancelled(cancel_requested):
+            raise PipelineCancelled("Cancelled")
+        chunk = refs_local[lo:lo + step]
+        matched = [(r, match_source(r)) for r in chunk]
+        matched = [(r, m) for r, m in matched if m is not None]
+        if not matched:
+            continue
+        if getattr(config, "rng_mode", RNG_PHILOX) == RNG_NUMPY_GLOBAL:
+            outs = []
+            for _, m in matched:
+                try:
+                    outs.append(_triangulate_ref(m, tri_ctx))
+                except Exception:
+                    outs.append(None)
+        else:
+            outs = triangulate_refs([m for _, m in matched], tri_ctx, rng_streams=[int(r) for r, _ in matched])
+        for tri in outs:
+            if tri is None:
+                continue
+            parts_xyz.append(tri.xyz)
+            parts_rgb.append(tri.rgb)
+            parts_err.append(tri.err)
+            pairs += 1
+        if progress_callback:
+            done = min(total, lo + step)
+            progress_callback(10.0 + 80.0 * done / max(1, total), f"Matching {done}/{total} references")
+    if _is_cancelled(cancel_requested):
+        raise PipelineCancelled("Cancelled")
+    if progress_callback:
+        progress_callback(90.0, "Finalizing triangulation...")
+    if not parts_xyz:
+        raise RuntimeError("No points triangulated. Try adjusting parameters.")
+    return PipelineResult(xyz=np.concatenate(parts_xyz, axis=0), rgb=np.concatenate(parts_rgb, axis=0),
+                          err=np.concatenate(parts_err, axis=0), elapsed_seconds=time.time() - t0,
+                          pairs_processed=pairs)

@@ -1,0 +1,236 @@
+// C ABI of the densification path (include/ldp_b200.h).  Unity build: the kernels live in the two
+// included translation units; this file carves the workspace, picks launch geometry and enqueues.
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "ldp_sample.cu"
+#include "ldp_geometry.cu"
+
+namespace {
+
+thread_local std::string g_last_error;
+thread_local int g_launches = 0;
+
+int fail(int code, const char* what) {
+    g_last_error = what ? what : "";
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    g_last_error = std::string(where) + ": " + cudaGetErrorString(e);
+    return LDP_ERR_CUDA;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr size_t K1_SMEM_BUDGET = 200 * 1024;
+
+struct Plan {
+    ldp::Workspace ws;
+    ldp::SampleGeom geom;
+    size_t bytes;
+    size_t k1_smem;
+};
+
+int64_t sel_capacity(int32_t M) {
+    const int64_t m_main = (int64_t)((double)M * 0.85);      // int(M * 0.85), reference core/sampling.py:31
+    int64_t cap = (M > m_main + 1) ? M : m_main + 1;
+    if (cap < 4) cap = 4;
+    return (cap + 3) / 4 * 4;
+}
+
+int make_plan(const ldp_params* p, void* base, Plan* plan) {
+    if (!p || p->n_refs < 0 || p->H <= 0 || p->W <= 0 || p->matches_per_ref < 0 || p->tiles <= 0 || p->border < 0 ||
+        p->w_match <= 0 || p->h_match <= 0)
+        return fail(LDP_ERR_INVALID, "bad ldp_params");
+    const long long Nll = (long long)p->H * (long long)p->W;
+    if (Nll > 0x3fffffffLL) return fail(LDP_ERR_INVALID, "map too large");
+    const int N = (int)Nll;
+    const size_t R = (size_t)p->n_refs;
+    ldp::SampleGeom& g = plan->geom;
+    g.N = N;
+    g.tile = (p->W / p->tiles > 1) ? p->W / p->tiles : 1;
+    g.nbx = (p->W + g.tile - 1) / g.tile;
+    g.nby = (p->H + g.tile - 1) / g.tile;
+    g.nbins = g.nbx * g.nby;
+    if (g.nbins > LDP_MAX_BINS) return fail(LDP_ERR_INVALID, "too many coverage tiles for this aspect ratio");
+    int nb_pow2 = 1;
+    while (nb_pow2 < g.nbins) nb_pow2 <<= 1;
+    const int m_main = (int)((double)p->matches_per_ref * 0.85);
+    g.size = m_main < N ? m_main : N;
+    g.cov_budget = (p->matches_per_ref - g.size > 1) ? p->matches_per_ref - g.size : 1;
+    g.vec = 0;
+    int cs = 5;
+    for (;; ++cs) {
+        const size_t nchunk = ((size_t)N + ((size_t)1 << cs) - 1) >> cs;
+        if (nchunk * 8 + (size_t)nb_pow2 * 8 <= K1_SMEM_BUDGET) { g.nchunk = (int)nchunk; break; }
+        if (cs > 20) return fail(LDP_ERR_INVALID, "map too large for the chunk table");
+    }
+    g.chunk_shift = cs;
+    plan->k1_smem = (size_t)g.nchunk * 8 + (size_t)nb_pow2 * 8;
+
+    ldp::Workspace& w = plan->ws;
+    w.n_pad = align_up((size_t)N, 128);
+    w.n_words = (w.n_pad + 31) / 32;
+    w.found_cap = align_up((size_t)(g.size > 0 ? g.size : 1), 4);
+    w.sel_cap = (size_t)sel_capacity(p->matches_per_ref);
+    size_t tk = 1;
+    const size_t Mn = (size_t)((p->matches_per_ref < N) ? p->matches_per_ref : N);
+    while (tk < Mn) tk <<= 1;
+    w.topk_cap = p->no_filter ? tk : 0;
+
+    size_t off = 0;
+    char* b = static_cast<char*>(base);
+    auto carve = [&](size_t bytes) { char* q = b ? b + off : nullptr; off = align_up(off + bytes, 256); return q; };
+    w.w = reinterpret_cast<float*>(carve(R * w.n_pad * sizeof(float)));
+    w.bestk = reinterpret_cast<uint8_t*>(carve(R * w.n_pad));
+    w.bitmap = reinterpret_cast<uint32_t*>(carve(R * w.n_words * sizeof(uint32_t)));
+    w.found = reinterpret_cast<int32_t*>(carve(R * w.found_cap * sizeof(int32_t)));
+    w.sel = reinterpret_cast<int32_t*>(carve(R * w.sel_cap * sizeof(int32_t)));
+    w.pt0 = reinterpret_cast<float4*>(carve(R * w.sel_cap * sizeof(float4)));
+    w.pt1 = reinterpret_cast<float4*>(carve(R * w.sel_cap * sizeof(float4)));
+    w.dbgm = reinterpret_cast<float4*>(carve(p->collect_debug ? R * w.sel_cap * sizeof(float4) : 0));
+    w.flags = reinterpret_cast<uint8_t*>(carve(R * w.sel_cap));
+    w.kept = reinterpret_cast<int32_t*>(carve(R * sizeof(int32_t)));
+    w.topk_keys = reinterpret_cast<unsigned long long*>(carve(R * w.topk_cap * sizeof(unsigned long long)));
+    plan->bytes = off;
+    return LDP_OK;
+}
+
+int check_outputs(const ldp_params* p, const ldp_outputs* o) {
+    if (!o) return fail(LDP_ERR_INVALID, "null outputs");
+    if (!o->xyz || !o->rgb || !o->err || !o->ref_offset || !o->status || !o->n_samples || !o->group_count || !o->group_order)
+        return fail(LDP_ERR_INVALID, "a required output pointer is null");
+    if (p->collect_debug && (!o->dbg_matches || !o->dbg_cert))
+        return fail(LDP_ERR_INVALID, "collect_debug needs dbg_matches and dbg_cert");
+    if (o->capacity < 0) return fail(LDP_ERR_INVALID, "negative capacity");
+    return LDP_OK;
+}
+
+int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* uniforms, const ldp_outputs* out,
+                  Plan& plan, int vec_ok, cudaStream_t st) {
+    plan.geom.vec = vec_ok;
+    static size_t configured_smem = 0;
+    if (plan.k1_smem > configured_smem) {
+        cudaError_t e = cudaFuncSetAttribute(ldp::ldp_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(sample)");
+        configured_smem = K1_SMEM_BUDGET;
+    }
+    ldp::ldp_sample_kernel<<<p->n_refs, ldp::K1_THREADS, plan.k1_smem, st>>>(*p, refs, uniforms, plan.ws, *out, plan.geom);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ldp_sample_kernel");
+    if (p->no_filter) {
+        ldp::ldp_topm_kernel<<<p->n_refs, ldp::K1_THREADS, 0, st>>>(*p, refs, plan.ws, *out, plan.geom);
+        ++g_launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "ldp_topm_kernel");
+    }
+    return LDP_OK;
+}
+
+int launch_geometry(const ldp_params* p, const ldp_ref_desc* refs, const ldp_outputs* out, Plan& plan,
+                    int have_bestk, cudaStream_t st) {
+    dim3 grid((unsigned)((plan.ws.sel_cap + ldp::K2_THREADS - 1) / ldp::K2_THREADS), (unsigned)p->n_refs);
+    ldp::ldp_geometry_kernel<<<grid, ldp::K2_THREADS, 0, st>>>(*p, refs, plan.ws, *out, have_bestk);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ldp_geometry_kernel");
+    ldp::ldp_pack_kernel<<<p->n_refs, ldp::K3_THREADS, 0, st>>>(*p, refs, plan.ws, *out);
+    ++g_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ldp_pack_kernel");
+    return LDP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ldp_abi_version(void) { return LDP_ABI_VERSION; }
+
+const char* ldp_last_error_string(void) { return g_last_error.c_str(); }
+
+int64_t ldp_sel_capacity(int32_t matches_per_ref) { return sel_capacity(matches_per_ref); }
+
+int ldp_last_launch_count(void) { return g_launches; }
+
+int64_t ldp_struct_size(int which) {
+    switch (which) {
+        case 0: return (int64_t)sizeof(ldp_params);
+        case 1: return (int64_t)sizeof(ldp_ref_desc);
+        case 2: return (int64_t)sizeof(ldp_outputs);
+        default: return -1;
+    }
+}
+
+int ldp_workspace_bytes(const ldp_params* params, size_t* bytes_out) {
+    if (!bytes_out) return fail(LDP_ERR_INVALID, "null bytes_out");
+    Plan plan;
+    int rc = make_plan(params, nullptr, &plan);
+    if (rc != LDP_OK) return rc;
+    *bytes_out = plan.bytes + 256;
+    return LDP_OK;
+}
+
+// vec_hint: the host wrapper guarantees 16-byte aligned certainty planes when W % 4 == 0; the planes'
+// addresses live in device memory, so alignment cannot be checked here without a copy.  Callers that
+// cannot guarantee it set params->reserved0 = 1 to force the scalar load path.
+static int vec_ok_for(const ldp_params* p) { return (p->W % 4 == 0 && p->reserved0 == 0) ? 1 : 0; }
+
+int ldp_densify_refs(const ldp_params* params, const ldp_ref_desc* refs, const double* uniforms,
+                     const ldp_outputs* out, void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    int rc = check_outputs(params, out);
+    if (rc != LDP_OK) return rc;
+    if (params->n_refs == 0) return LDP_OK;
+    if (!refs || !workspace) return fail(LDP_ERR_INVALID, "null refs/workspace");
+    if (params->rng_mode == LDP_RNG_EXPLICIT && !params->no_filter && !uniforms)
+        return fail(LDP_ERR_INVALID, "explicit rng mode needs a uniform stream");
+    Plan plan;
+    char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+    rc = make_plan(params, base, &plan);
+    if (rc != LDP_OK) return rc;
+    if (plan.bytes + (size_t)(base - static_cast<char*>(workspace)) > workspace_bytes) return fail(LDP_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = launch_sample(params, refs, uniforms, out, plan, vec_ok_for(params), st);
+    if (rc != LDP_OK) return rc;
+    return launch_geometry(params, refs, out, plan, 1, st);
+}
+
+int ldp_sample_refs(const ldp_params* params, const ldp_ref_desc* refs, const double* uniforms,
+                    const ldp_outputs* out, void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    if (!params || !out || !out->status || !out->n_samples || !out->sel_idx) return fail(LDP_ERR_INVALID, "sample stage needs status, n_samples, sel_idx");
+    if (params->n_refs == 0) return LDP_OK;
+    if (!refs || !workspace) return fail(LDP_ERR_INVALID, "null refs/workspace");
+    if (params->rng_mode == LDP_RNG_EXPLICIT && !params->no_filter && !uniforms)
+        return fail(LDP_ERR_INVALID, "explicit rng mode needs a uniform stream");
+    Plan plan;
+    char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+    int rc = make_plan(params, base, &plan);
+    if (rc != LDP_OK) return rc;
+    if (plan.bytes + (size_t)(base - static_cast<char*>(workspace)) > workspace_bytes) return fail(LDP_ERR_WORKSPACE, "workspace too small");
+    return launch_sample(params, refs, uniforms, out, plan, vec_ok_for(params), static_cast<cudaStream_t>(stream));
+}
+
+int ldp_triangulate_samples(const ldp_params* params, const ldp_ref_desc* refs, const ldp_outputs* out,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    int rc = check_outputs(params, out);
+    if (rc != LDP_OK) return rc;
+    if (!out->sel_idx) return fail(LDP_ERR_INVALID, "triangulate stage reads out->sel_idx / out->n_samples");
+    if (params->n_refs == 0) return LDP_OK;
+    if (!refs || !workspace) return fail(LDP_ERR_INVALID, "null refs/workspace");
+    Plan plan;
+    char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+    rc = make_plan(params, base, &plan);
+    if (rc != LDP_OK) return rc;
+    if (plan.bytes + (size_t)(base - static_cast<char*>(workspace)) > workspace_bytes) return fail(LDP_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(plan.ws.kept, 0, (size_t)params->n_refs * sizeof(int32_t), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(kept)");
+    return launch_geometry(params, refs, out, plan, 0, st);
+}
+
+}  // extern "C"

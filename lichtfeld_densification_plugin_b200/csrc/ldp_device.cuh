@@ -1,0 +1,134 @@
+// Internal device-side helpers shared by the densification kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/ldp_b200.h"
+
+namespace ldp {
+
+// ---------------------------------------------------------------------------------------------
+// Workspace carved by the host (ldp_api.cu).  Everything is per reference view r; rows are padded so
+// that float4 / 16-byte accesses stay aligned.
+// ---------------------------------------------------------------------------------------------
+struct Workspace {
+    float* w;            // [R][n_pad]   capped, border-masked weights (zeroed as pixels get drawn)
+    uint8_t* bestk;      // [R][n_pad]   winning neighbour per pixel
+    uint32_t* bitmap;    // [R][n_words] selected-pixel bitmap
+    int32_t* found;      // [R][found_cap] draw list of the weighted sampler (unordered)
+    int32_t* sel;        // [R][sel_cap]  sample indices when the caller does not ask for them
+    float4* pt0;         // [R][sel_cap]  X,Y,Z,err per sample
+    float4* pt1;         // [R][sel_cap]  r,g,b,debug-cert per sample
+    float4* dbgm;        // [R][sel_cap]  clipped match coords per sample (collect_debug)
+    uint8_t* flags;      // [R][sel_cap]  bit0 keep, bit1 sampson-pass, bits2.. group
+    int32_t* kept;       // [R]           kept points (atomic)
+    unsigned long long* topk_keys;  // [R][topk_cap] no_filter candidate keys
+    size_t n_pad, n_words, found_cap, sel_cap, topk_cap;
+};
+
+struct SampleGeom {     // launch-constant shape of the sampler
+    int N;              // H*W
+    int chunk_shift;    // log2(pixels per chunk)
+    int nchunk;
+    int tile;           // max(1, W / tiles)
+    int nbx, nby, nbins;
+    int size;           // min(int(0.85*M), N)
+    int cov_budget;     // max(1, M - size)
+    int vec;            // cert planes are 16-B aligned and W % 4 == 0
+};
+
+// ---------------------------------------------------------------------------------------------
+// warp / block collectives (fixed reduction trees => run-to-run deterministic)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// All threads get the block total.  scratch: >= 32 elements of T in shared memory.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    T r = (lane < nw) ? scratch[lane] : T(0);
+    return warp_sum(r);
+}
+__device__ __forceinline__ int block_min(int v, int* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_min(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    int r = (lane < nw) ? scratch[lane] : 0x7fffffff;
+    return warp_min(r);
+}
+
+// Exclusive scan of one value per thread; *total receives the block sum.  scratch >= 32 elements.
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* scratch, T* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    T inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    __syncthreads();
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    T wv = (lane < nw) ? scratch[lane] : T(0);
+    T winc = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T n = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += n;
+    }
+    T wexc = winc - wv;
+    T base = __shfl_sync(0xffffffffu, wexc, warp);
+    *total = __shfl_sync(0xffffffffu, winc, 31);
+    return base + inc - v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator (Salmon et al. 2011), used for the production uniforms.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// The d-th double of stream `stream`: 53-bit construction identical to numpy's random_sample
+// ((a >> 5) * 2^26 + (b >> 6)) / 2^53, so explicit and Philox streams have the same lattice.
+__device__ __forceinline__ double philox_uniform(uint64_t seed, uint32_t stream, uint32_t d) {
+    uint32_t r[4];
+    philox4x32_10(d >> 1, 0u, stream, 0x4c445031u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const uint32_t a = (d & 1u) ? r[2] : r[0], b = (d & 1u) ? r[3] : r[1];
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ float4 ld_stream4(const float* p) {   // read-once data: evict-first
+    return __ldcs(reinterpret_cast<const float4*>(p));
+}
+
+}  // namespace ldp

@@ -1,0 +1,282 @@
+"""Device-resident batched engine above the C ABI.
+
+``RefBatch`` describes n reference views whose matcher outputs (certainty / warp planes, resized
+reference image) already live on one CUDA device -- by pointer, nothing is stacked or copied -- plus
+their camera constants.  ``DensifyEngine.densify`` runs the whole path for the batch in one call of
+``ldp_densify_refs`` on the current torch stream and returns device tensors.
+
+PyTorch is used for device memory and streams only; all compute is in csrc/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .core.camera_models import CameraRecord
+from .core.geometry import fundamental_from_world2cam
+
+SAMPLE_CAP_DEFAULT = 0.9     # matcher.sample_thresh, reference core/matcher.py:92
+BORDER_DEFAULT = 2           # reference core/pipeline.py:646
+TILES_DEFAULT = 24           # reference core/pipeline.py:647
+
+
+@dataclass
+class PathConfig:
+    """Scalars of the path (subset of DensePipelineConfig + _TriangulationContext)."""
+    matches_per_ref: int = 10000
+    reproj_thresh: float = 0.8
+    sampson_thresh: float = 5.0
+    min_parallax_deg: float = 0.5
+    no_filter: bool = False
+    sample_cap: float = SAMPLE_CAP_DEFAULT
+    border: int = BORDER_DEFAULT
+    tiles: int = TILES_DEFAULT
+    seed: int = 0
+
+    @classmethod
+    def from_pipeline_config(cls, cfg, sample_cap: float = SAMPLE_CAP_DEFAULT) -> "PathConfig":
+        return cls(matches_per_ref=int(cfg.matches_per_ref), reproj_thresh=float(cfg.reproj_thresh),
+                   sampson_thresh=float(cfg.sampson_thresh), min_parallax_deg=float(cfg.min_parallax_deg),
+                   no_filter=bool(cfg.no_filter), sample_cap=float(sample_cap), seed=int(getattr(cfg, "seed", 0)))
+
+
+class PairConstantCache:
+    """Per (reference, neighbour) camera constants, computed once on the host with the reference's
+    float32 numpy arithmetic (reference core/geometry.py:122-130)."""
+
+    def __init__(self) -> None:
+        self._F: Dict[Tuple[int, int], tuple] = {}
+
+    def fundamental(self, a: CameraRecord, b: CameraRecord) -> np.ndarray:
+        key = (id(a), id(b))
+        hit = self._F.get(key)
+        if hit is None:
+            F = np.ascontiguousarray(fundamental_from_world2cam(a.K, a.R, a.t, b.K, b.R, b.t), dtype=np.float32)
+            hit = (F, a, b)            # pin the records so their ids cannot be recycled
+            self._F[key] = hit
+        return hit[0]
+
+
+class RefBatch:
+    """n reference views resident on one CUDA device, described by pointer."""
+
+    def __init__(self, H: int, W: int, w_match: int, h_match: int, device: torch.device,
+                 pair_cache: Optional[PairConstantCache] = None) -> None:
+        self.H, self.W, self.w_match, self.h_match = int(H), int(W), int(w_match), int(h_match)
+        self.device = torch.device(device)
+        self._rows: List[np.void] = []
+        self._keep_alive: List[object] = []
+        self.nbr_uids: List[List[int]] = []
+        self.ref_uids: List[int] = []
+        self.force_scalar_loads = False
+        self.pairs = pair_cache or PairConstantCache()
+
+    def __len__(self) -> int:
+        return len(self._rows)
+
+    def _check_plane(self, t: torch.Tensor, shape, what: str) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor) or t.device != self.device:
+            raise ValueError(f"{what} must be a tensor on {self.device}")
+        if t.dtype != torch.float32 or tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{what} must be float32 {tuple(shape)}, got {t.dtype} {tuple(t.shape)}")
+        if not t.is_contiguous():
+            t = t.contiguous()
+        return t
+
+    def add(self, cert_planes: Sequence[torch.Tensor], warp_planes: Sequence[torch.Tensor], image: torch.Tensor,
+            ref_cam: CameraRecord, nbr_cams: Sequence[CameraRecord], rng_stream: int = 0,
+            weight_sum_override: float = 0.0) -> None:
+        nn = len(cert_planes)
+        if nn != len(warp_planes) or nn != len(nbr_cams):
+            raise ValueError("cert_planes, warp_planes and nbr_cams must have the same length")
+        if nn > N.LDP_MAX_NN:
+            raise ValueError(f"at most {N.LDP_MAX_NN} neighbours per reference view")
+        row = np.zeros((), dtype=N.REF_DESC_DTYPE)
+        for k in range(nn):
+            c = self._check_plane(cert_planes[k], (self.H, self.W), "certainty plane")
+            w = self._check_plane(warp_planes[k], (self.H, self.W, 4), "warp plane")
+            if c.data_ptr() % 16 != 0:
+                self.force_scalar_loads = True
+            if w.data_ptr() % 16 != 0:
+                raise ValueError("warp planes must be 16-byte aligned")
+            row["cert"][k] = c.data_ptr()
+            row["warp"][k] = w.data_ptr()
+            self._keep_alive += [c, w]
+        if image.device != self.device or image.dtype != torch.uint8 or image.dim() != 3 or image.shape[2] != 3:
+            raise ValueError("image must be a uint8 [h, w, 3] tensor on the batch device")
+        image = image.contiguous()
+        self._keep_alive.append(image)
+        ih, iw = int(image.shape[0]), int(image.shape[1])
+        wm, hm = float(self.w_match), float(self.h_match)
+        row["image"] = image.data_ptr()
+        row["nn"] = nn
+        row["img_w"], row["img_h"] = iw, ih
+        row["rng_stream"] = np.uint32(int(rng_stream) & 0xFFFFFFFF)
+        row["weight_sum_override"] = np.float32(weight_sum_override)
+        # python-float scale factors rounded to f32 at the multiply (NEP 50), reference core/pipeline.py:662-663,681-682
+        row["sxA"], row["syA"] = np.float32(ref_cam.width / wm), np.float32(ref_cam.height / hm)
+        row["sx_img"], row["sy_img"] = np.float32(iw / wm), np.float32(ih / hm)
+        row["P1"] = np.asarray(ref_cam.P, dtype=np.float32).reshape(12)
+        row["C1"] = np.asarray(ref_cam.C, dtype=np.float32).reshape(3)
+        uids = [int(c.uid) for c in nbr_cams]
+        for k, cam in enumerate(nbr_cams):
+            row["P2"][k] = np.asarray(cam.P, dtype=np.float32).reshape(12)
+            row["C2"][k] = np.asarray(cam.C, dtype=np.float32).reshape(3)
+            row["F"][k] = self.pairs.fundamental(ref_cam, cam).reshape(9)
+            row["sxB"][k], row["syB"][k] = np.float32(cam.width / wm), np.float32(cam.height / hm)
+            row["group"][k] = uids.index(uids[k])          # the reference groups by neighbour uid
+        self._rows.append(row)
+        self.nbr_uids.append(uids)
+        self.ref_uids.append(int(ref_cam.uid))
+
+    def desc_array(self) -> np.ndarray:
+        if not self._rows:
+            return np.zeros((0,), dtype=N.REF_DESC_DTYPE)
+        return np.stack(self._rows).astype(N.REF_DESC_DTYPE, copy=False)
+
+
+@dataclass
+class DensifyOutputs:
+    """Device tensors written by one launch (see include/ldp_b200.h:ldp_outputs)."""
+    n_refs: int
+    sel_cap: int
+    xyz: torch.Tensor
+    rgb: torch.Tensor
+    err: torch.Tensor
+    ref_offset: torch.Tensor
+    status: torch.Tensor
+    n_samples: torch.Tensor
+    group_count: torch.Tensor
+    group_order: torch.Tensor
+    uniforms_used: torch.Tensor
+    rounds: torch.Tensor
+    weight_sum: torch.Tensor
+    dbg_matches: Optional[torch.Tensor] = None
+    dbg_cert: Optional[torch.Tensor] = None
+    sel_idx: Optional[torch.Tensor] = None
+    sample_flags: Optional[torch.Tensor] = None
+    sample_xyzerr: Optional[torch.Tensor] = None
+    launches: int = 0
+
+    def total_points(self) -> int:
+        """Synchronises."""
+        return int(self.ref_offset[-1].item()) if self.n_refs else 0
+
+
+class DensifyEngine:
+    """Owns the scratch workspace and enqueues launches on the current torch CUDA stream."""
+
+    def __init__(self, device=None) -> None:
+        if not torch.cuda.is_available():
+            raise N.NativeLibraryError("DensifyEngine needs a CUDA device (there is no CPU fallback)")
+        self.lib = N.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._workspace: Optional[torch.Tensor] = None
+        self.pairs = PairConstantCache()
+
+    def new_batch(self, H: int, W: int, w_match: int, h_match: int) -> RefBatch:
+        return RefBatch(H, W, w_match, h_match, self.device, self.pairs)
+
+    def _params(self, batch: RefBatch, cfg: PathConfig, collect_debug: bool, rng_mode: int,
+                uniforms_per_ref: int) -> N.LdpParams:
+        p = N.LdpParams()
+        p.n_refs = len(batch)
+        p.H, p.W, p.w_match, p.h_match = batch.H, batch.W, batch.w_match, batch.h_match
+        p.matches_per_ref = int(cfg.matches_per_ref)
+        p.border, p.tiles = int(cfg.border), int(cfg.tiles)
+        p.sample_cap = float(np.float32(cfg.sample_cap))
+        p.reproj_thresh = float(np.float32(cfg.reproj_thresh))
+        p.min_parallax_deg = float(np.float32(cfg.min_parallax_deg))
+        p.sampson_thresh = float(cfg.sampson_thresh)
+        p.no_filter = 1 if cfg.no_filter else 0
+        p.collect_debug = 1 if collect_debug else 0
+        p.rng_mode = int(rng_mode)
+        p.reserved0 = 1 if batch.force_scalar_loads else 0
+        p.seed = int(cfg.seed) & 0xFFFFFFFFFFFFFFFF
+        p.uniforms_per_ref = int(uniforms_per_ref)
+        return p
+
+    def _ensure_workspace(self, params: N.LdpParams) -> torch.Tensor:
+        need = C.c_size_t(0)
+        N.check(self.lib.ldp_workspace_bytes(C.byref(params), C.byref(need)), "ldp_workspace_bytes")
+        if self._workspace is None or self._workspace.numel() < need.value:
+            self._workspace = None
+            self._workspace = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def sel_capacity(self, matches_per_ref: int) -> int:
+        return int(self.lib.ldp_sel_capacity(int(matches_per_ref)))
+
+    def upload_descs(self, batch: RefBatch) -> torch.Tensor:
+        arr = batch.desc_array()
+        host = torch.from_numpy(arr.view(np.uint8).reshape(-1))
+        return host.to(self.device, non_blocking=False)
+
+    def densify(self, batch: RefBatch, cfg: PathConfig, uniforms: Optional[torch.Tensor] = None,
+                collect_debug: bool = False, taps: bool = False, descs_dev: Optional[torch.Tensor] = None,
+                outputs: Optional[DensifyOutputs] = None) -> DensifyOutputs:
+        """Run the whole path for ``batch``.  ``uniforms``: f64 [n_refs, U] device tensor selects the
+        explicit (parity) RNG mode; otherwise Philox keyed by (cfg.seed, rng_stream)."""
+        R = len(batch)
+        dev = self.device
+        rng_mode = N.LDP_RNG_PHILOX
+        upr = 0
+        if uniforms is not None:
+            if uniforms.dtype != torch.float64 or uniforms.device != dev or uniforms.dim() != 2 or uniforms.shape[0] != R:
+                raise ValueError("uniforms must be a float64 [n_refs, U] tensor on the engine device")
+            uniforms = uniforms.contiguous()
+            rng_mode = N.LDP_RNG_EXPLICIT
+            upr = int(uniforms.shape[1])
+        params = self._params(batch, cfg, collect_debug, rng_mode, upr)
+        ws = self._ensure_workspace(params)
+        sel_cap = self.sel_capacity(cfg.matches_per_ref)
+        out = outputs if outputs is not None else self.alloc_outputs(R, sel_cap, collect_debug, taps)
+        if descs_dev is None:
+            descs_dev = self.upload_descs(batch)
+        o = N.LdpOutputs()
+        o.xyz, o.rgb, o.err = out.xyz.data_ptr(), out.rgb.data_ptr(), out.err.data_ptr()
+        o.capacity = int(out.err.shape[0])
+        o.ref_offset, o.status, o.n_samples = out.ref_offset.data_ptr(), out.status.data_ptr(), out.n_samples.data_ptr()
+        o.group_count, o.group_order = out.group_count.data_ptr(), out.group_order.data_ptr()
+        o.uniforms_used, o.rounds, o.weight_sum = out.uniforms_used.data_ptr(), out.rounds.data_ptr(), out.weight_sum.data_ptr()
+        if out.dbg_matches is not None:
+            o.dbg_matches, o.dbg_cert = out.dbg_matches.data_ptr(), out.dbg_cert.data_ptr()
+        if out.sel_idx is not None:
+            o.sel_idx = out.sel_idx.data_ptr()
+        if out.sample_flags is not None:
+            o.sample_flags, o.sample_xyzerr = out.sample_flags.data_ptr(), out.sample_xyzerr.data_ptr()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = self.lib.ldp_densify_refs(C.byref(params), C.c_void_p(descs_dev.data_ptr()),
+                                       C.c_void_p(uniforms.data_ptr() if uniforms is not None else 0), C.byref(o),
+                                       C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()), C.c_void_p(stream))
+        N.check(rc, "ldp_densify_refs")
+        out.launches = int(self.lib.ldp_last_launch_count())
+        out._keep = (descs_dev, uniforms, batch)      # keep inputs alive until the stream is done with them
+        return out
+
+    def alloc_outputs(self, R: int, sel_cap: int, collect_debug: bool = False, taps: bool = False) -> DensifyOutputs:
+        dev = self.device
+        cap = max(1, R * sel_cap)
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        out = DensifyOutputs(
+            n_refs=R, sel_cap=sel_cap,
+            xyz=torch.empty((cap, 3), **f32), rgb=torch.empty((cap, 3), **f32), err=torch.empty((cap,), **f32),
+            ref_offset=torch.zeros((R + 1,), dtype=torch.int64, device=dev),
+            status=torch.zeros((R,), **i32), n_samples=torch.zeros((R,), **i32),
+            group_count=torch.zeros((R, N.LDP_MAX_NN), **i32), group_order=torch.full((R, N.LDP_MAX_NN), -1, **i32),
+            uniforms_used=torch.zeros((R,), **i32), rounds=torch.zeros((R,), **i32), weight_sum=torch.zeros((R,), **f32),
+        )
+        if collect_debug:
+            out.dbg_matches = torch.empty((cap, 4), **f32)
+            out.dbg_cert = torch.empty((cap,), **f32)
+        if taps:
+            out.sel_idx = torch.zeros((R, sel_cap), **i32)
+            out.sample_flags = torch.zeros((R, sel_cap), dtype=torch.uint8, device=dev)
+            out.sample_xyzerr = torch.zeros((R, sel_cap, 4), **f32)
+        return out

@@ -420,7 +420,7 @@ def triangulate_ref(cert_list, warp_list, img_u8: np.ndarray, ref_cam: OracleCam
     if not out_xyz:
         return None
     if keep_taps:
-        taps.update(best_k=best_k.numpy(), best_cert=best_cert.numpy(), k_sel=k_sel, xA=xA, yA=yA,
+        taps.update(ref_uid=ref_cam.uid, best_k=best_k.numpy(), best_cert=best_cert.numpy(), k_sel=k_sel, xA=xA, yA=yA,
                     xBn=xBn, yBn=yBn, uvA_all=uvA_all, rgb_all=rgb_all, groups=group_taps)
     return OracleResult(xyz=np.concatenate(out_xyz, axis=0), rgb=np.concatenate(out_rgb, axis=0),
                         err=np.concatenate(out_err, axis=0), sel_idx=sel_idx,

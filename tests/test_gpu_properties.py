@@ -1,0 +1,196 @@
+"""GPU: size-independent properties at full BASELINE sizes, edge cases, determinism, the drop-in API."""
+import numpy as np
+import pytest
+import torch
+
+from tests import gpu_harness as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from lichtfeld_densification_plugin_b200.engine import DensifyEngine
+    return DensifyEngine()
+
+
+@pytest.fixture(scope="module")
+def fast_scene():
+    from lichtfeld_densification_plugin_b200 import synth
+    scene = synth.make_scene(40, "fast", ref_fraction=0.2, nn=4)
+    inputs = [synth.synth_ref_inputs(scene, rp, cert_family="R", seed=5) for rp in range(scene.n_refs)]
+    return scene, inputs
+
+
+def test_philox_properties_full_size(engine, fast_scene):
+    scene, inputs = fast_scene
+    c = dict(M=10000, no_filter=False, wm=scene.w_match, hm=scene.h_match)
+    g = G.run_gpu(engine, scene, inputs, G.path_cfg(c, seed=7))
+    H, W = scene.H, scene.W
+    for r, inp in enumerate(inputs):
+        assert g.status[r] & 0xFF == 0
+        sel = g.sel_idx[r]
+        assert np.all(np.diff(sel) > 0), "sel_idx must be strictly ascending (np.unique)"
+        x, y = sel % W, sel // W
+        assert x.min() >= 2 and x.max() <= W - 3 and y.min() >= 2 and y.max() <= H - 3, "border pixels are never sampled"
+        assert 8500 <= sel.size <= 8500 + 625
+        assert g.uniforms_used[r] >= 8500 and g.rounds[r] >= 1
+        # every tile's best pixel is among the samples (coverage)
+        best = inp["cert"].max(dim=0).values.numpy()
+        wts = np.minimum(best, np.float32(0.9))
+        wts[:2] = 0; wts[-2:] = 0; wts[:, :2] = 0; wts[:, -2:] = 0
+        tile = max(1, W // 24)
+        selset = set(sel.tolist())
+        for ty in range(0, H, tile):
+            for tx in range(0, W, tile):
+                blk = wts[ty:ty + tile, tx:tx + tile]
+                if blk.max() > 0:
+                    ys, xs = np.nonzero(blk == blk.max())
+                    assert any(((ty + a) * W + (tx + b)) in selset for a, b in zip(ys, xs))
+        # kept points satisfy the filters when recomputed independently in f64
+        keep = (g.flags[r] & 1).astype(bool)
+        order = G.expected_pack_order(g.flags[r])
+        assert np.array_equal(g.xyz[r], g.xyzerr[r][order, :3])
+        assert g.err[r].size == keep.sum() and np.all(g.err[r] <= np.float32(0.8))
+        cams = scene.cameras
+        P1 = cams[inp["ref_index"]].P.astype(np.float64)
+        Xh = np.concatenate([g.xyz[r].astype(np.float64), np.ones((g.xyz[r].shape[0], 1))], axis=1)
+        assert np.all((Xh @ P1.T)[:, 2] > 0)
+        assert np.all((g.rgb[r] >= 0) & (g.rgb[r] <= 1))
+
+
+def test_deterministic_and_batch_independent(engine, fast_scene):
+    scene, inputs = fast_scene
+    c = dict(M=10000, no_filter=False, wm=scene.w_match, hm=scene.h_match)
+    a = G.run_gpu(engine, scene, inputs, G.path_cfg(c, seed=11))
+    b = G.run_gpu(engine, scene, inputs, G.path_cfg(c, seed=11))
+    solo = G.run_gpu(engine, scene, inputs[2:3], G.path_cfg(c, seed=11))
+    other = G.run_gpu(engine, scene, inputs[2:3], G.path_cfg(c, seed=12))
+    for r in range(len(inputs)):
+        assert np.array_equal(a.sel_idx[r], b.sel_idx[r]) and np.array_equal(a.xyz[r], b.xyz[r])
+        assert np.array_equal(a.rgb[r], b.rgb[r]) and np.array_equal(a.err[r], b.err[r])
+    # a view's result depends on (seed, rng_stream) only, not on what else is in the launch (sharding invariance)
+    assert np.array_equal(a.sel_idx[2], solo.sel_idx[0]) and np.array_equal(a.xyz[2], solo.xyz[0])
+    assert not np.array_equal(a.sel_idx[2], other.sel_idx[0])
+
+
+def test_no_filter_full_size(engine, fast_scene):
+    scene, inputs = fast_scene
+    c = dict(M=10000, no_filter=True, wm=scene.w_match, hm=scene.h_match)
+    g = G.run_gpu(engine, scene, inputs[:3], G.path_cfg(c))
+    for r in range(3):
+        res = G.run_oracle_ref(scene, inputs[r], c)
+        sel = g.sel_idx[r]
+        assert sel.size == 10000 and np.unique(sel).size == 10000
+        capped = np.minimum(inputs[r]["cert"].max(dim=0).values.numpy().reshape(-1), np.float32(0.9))
+        v = capped[sel]
+        assert np.all(np.diff(v) <= 0), "descending certainty"
+        assert np.array_equal(np.sort(v), np.sort(capped[res.sel_idx])), "same multiset of certainties as argsort(-cert)[:M]"
+        assert v.min() >= np.sort(capped)[-10000]
+        keep = (g.flags[r] & 1).astype(bool)
+        assert keep.sum() == np.isfinite(g.xyzerr[r]).all(axis=1).sum()
+
+
+def _mk_single(scene_hw, nn, cert_fn, M):
+    from lichtfeld_densification_plugin_b200 import synth
+    H, W = scene_hw
+    scene = synth.make_scene(8, "turbo", ref_fraction=0.13, nn=nn)
+    scene.H, scene.W, scene.h_match, scene.w_match = H, W, H, W
+    inp = synth.synth_ref_inputs(scene, 0, cert_family="T", seed=9)
+    inp["cert"] = cert_fn(inp["cert"])
+    return scene, inp, dict(M=M, no_filter=False, wm=W, hm=H)
+
+
+def test_edge_all_zero_weights(engine):
+    scene, inp, c = _mk_single((64, 64), 2, lambda x: torch.zeros_like(x), 500)
+    g = G.run_gpu(engine, scene, [inp], G.path_cfg(c))
+    assert g.status[0] & 0xFF == 1 and g.sel_idx[0].size == 0 and g.xyz[0].shape[0] == 0     # LDP_REF_EMPTY
+
+
+def test_edge_fewer_nonzero_than_size(engine):
+    def sparse(x):
+        y = torch.zeros_like(x)
+        y[:, 10:20, 10:20] = x[:, 10:20, 10:20]
+        return y
+    scene, inp, c = _mk_single((64, 64), 2, sparse, 500)
+    g = G.run_gpu(engine, scene, [inp], G.path_cfg(c))
+    assert g.status[0] & 0xFF == 2                                                            # LDP_REF_FEWER_NONZERO
+    with pytest.raises(ValueError, match="Fewer non-zero"):
+        G.run_oracle_ref(scene, inp, c, uniforms=np.zeros(4000))
+
+
+def test_edge_nan_and_ragged_neighbours(engine):
+    def nanify(x):
+        y = x.clone()
+        y[0, 30, 30] = float("nan")
+        return y
+    scene, inp, c = _mk_single((64, 64), 2, nanify, 500)
+    g = G.run_gpu(engine, scene, [inp], G.path_cfg(c))
+    assert g.status[0] & 0xFF == 3                                                            # LDP_REF_BAD_WEIGHTS
+    # ragged: views with 1 and 3 neighbours in the same launch
+    from lichtfeld_densification_plugin_b200 import synth
+    scene = synth.make_scene(10, "turbo", ref_fraction=0.2, nn=3)
+    scene.H = scene.W = scene.h_match = scene.w_match = 96
+    a = synth.synth_ref_inputs(scene, 0, cert_family="T", seed=1)
+    b = synth.synth_ref_inputs(scene, 1, cert_family="T", seed=1)
+    b = dict(b, cert=b["cert"][:1], warp=b["warp"][:1], nbr_indices=b["nbr_indices"][:1])
+    c = dict(M=2000, no_filter=False, wm=96, hm=96)
+    U = np.stack([np.random.RandomState(r).random_sample(6000) for r in range(2)])
+    ress = [G.run_oracle_ref(scene, x, c, uniforms=U[i]) for i, x in enumerate((a, b))]
+    g = G.run_gpu(engine, scene, [a, b], G.path_cfg(c), uniforms=U, weight_sums=[r.taps["s"] for r in ress])
+    for i in range(2):
+        rep = G.compare_ref(g, i, ress[i], c, scene)
+        assert rep.ok(), rep
+
+
+def test_edge_non_multiple_of_four_width_and_tiny_m(engine):
+    from lichtfeld_densification_plugin_b200 import synth
+    scene = synth.make_scene(8, "turbo", ref_fraction=0.13, nn=2)
+    scene.H, scene.W, scene.h_match, scene.w_match = 50, 61, 50, 61
+    inp = synth.synth_ref_inputs(scene, 0, cert_family="T", seed=4)
+    for M in (1, 7, 700):
+        c = dict(M=M, no_filter=False, wm=61, hm=50)
+        U = np.random.RandomState(M).random_sample(3 * M + 16)
+        res = G.run_oracle_ref(scene, inp, c, uniforms=U)
+        g = G.run_gpu(engine, scene, [inp], G.path_cfg(c), uniforms=U[None, :],
+                      weight_sums=[res.taps["s"]] if res is not None else None)
+        if res is None:
+            assert g.xyz[0].shape[0] == 0
+            continue
+        rep = G.compare_ref(g, 0, res, c, scene)
+        assert rep.ok(), (M, rep)
+
+
+def test_drop_in_triangulate_ref_numpy_global_stream(engine):
+    """core.pipeline._triangulate_ref with rng_mode='numpy' consumes np.random's global stream like the reference."""
+    from lichtfeld_densification_plugin_b200 import synth
+    from lichtfeld_densification_plugin_b200.core import pipeline as P
+    from lichtfeld_densification_plugin_b200.core.config import DensePipelineConfig
+    scene = synth.make_scene(10, "turbo", ref_fraction=0.2, nn=3)
+    cams = scene.cameras
+    cfg = DensePipelineConfig(output_path="/tmp/x.ply", rng_mode="numpy")
+    ctx = P._TriangulationContext(cameras=P._build_camera_lookup(cams), config=cfg, matcher_sample_cap=0.9,
+                                  w_match=scene.w_match, h_match=scene.h_match)
+    c = dict(M=10000, no_filter=False, wm=scene.w_match, hm=scene.h_match)
+    np.random.seed(123)
+    outs = []
+    for rp in range(2):
+        inp = synth.synth_ref_inputs(scene, rp, cert_family="T", seed=2)
+        ri, nb = inp["ref_index"], inp["nbr_indices"]
+        packed = P._PackedReferenceBatch(ref_id=cams[ri].uid, ref_path="", imA_np=inp["image"].numpy(), maskA_np=None,
+                                         wA_cam=cams[ri].width, hA_cam=cams[ri].height, nn_ids=[cams[j].uid for j in nb],
+                                         nn_masks=[None] * len(nb), nn_arrays=[None] * len(nb))
+        mr = P._MatchedReference(packed=packed, warp_list_cpu=[inp["warp"][k] for k in range(len(nb))],
+                                 cert_list_cpu=[inp["cert"][k] for k in range(len(nb))], pair_index_by_nbr={}, image_by_nbr={})
+        outs.append((inp, P._triangulate_ref(mr, ctx, collect_debug_matches=True)))
+    after = np.random.random_sample()
+    # oracle: same global stream, sequentially (the reference's production behaviour)
+    rs = np.random.RandomState(123)
+    for inp, tri in outs:
+        res = G.run_oracle_ref(scene, inp, c, rng=rs, collect_debug=True)
+        assert tri is not None and abs(tri.xyz.shape[0] - res.xyz.shape[0]) <= 3
+        if tri.xyz.shape == res.xyz.shape:
+            np.testing.assert_allclose(tri.xyz, res.xyz, rtol=G.XYZ_RTOL, atol=G.XYZ_ATOL)
+            np.testing.assert_allclose(tri.rgb, res.rgb, rtol=G.XYZ_RTOL, atol=G.XYZ_ATOL)
+            assert list(tri.debug_matches_by_nbr.keys()) == list(res.debug_matches_by_nbr.keys())
+    assert after == rs.random_sample(), "global MT19937 stream position must match the reference's"
