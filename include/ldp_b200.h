@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LDP_ABI_VERSION 3
+#define LDP_ABI_VERSION 4
 #define LDP_MAX_NN 16          /* neighbours per reference view (the panel clamps to 10) */
 #define LDP_MAX_BINS 4096      /* coverage tiles per map: ceil(W/tile)*ceil(H/tile), tile = max(1, W/24) */
 
@@ -155,6 +155,13 @@ int ldp_triangulate_samples(const ldp_params* params, const ldp_ref_desc* refs,
 
 /* Kernel launches enqueued by the last ldp_* call on this thread (for bench.py's gpu_launches). */
 int ldp_last_launch_count(void);
+
+/* Per-kernel device timing of subsequent ldp_* calls on this thread (CUDA events recorded on the call's
+ * stream around every kernel; no synchronisation at record time).  ldp_profile_read synchronises on the
+ * last event and returns, for the LAST call, up to max_n kernel durations in ms in launch order
+ * (sample, [topm], geometry, pack); returns the number of kernels, or a negative ldp_error. */
+int ldp_profile_enable(int on);
+int ldp_profile_read(float* ms_out, int max_n);
 
 /* sizeof() of the ABI structs as this library was compiled: which = 0 ldp_params, 1 ldp_ref_desc,
  * 2 ldp_outputs.  Bindings check these against their own struct definitions at load time. */

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import build as _build
 
-LDP_ABI_VERSION = 3
+LDP_ABI_VERSION = 4
 LDP_MAX_NN = 16
 LDP_MAX_BINS = 4096
 
@@ -91,7 +91,7 @@ REF_DESC_DTYPE = np.dtype(LdpRefDesc)
 EXPORTS = [
     "ldp_abi_version", "ldp_last_error_string", "ldp_sel_capacity", "ldp_workspace_bytes",
     "ldp_densify_refs", "ldp_sample_refs", "ldp_triangulate_samples", "ldp_last_launch_count",
-    "ldp_struct_size",
+    "ldp_struct_size", "ldp_profile_enable", "ldp_profile_read",
 ]
 
 _lock = threading.Lock()
@@ -132,6 +132,10 @@ def load(build_if_missing: bool = False):
         lib.ldp_struct_size.restype = C.c_int64
         lib.ldp_struct_size.argtypes = [C.c_int]
         lib.ldp_last_launch_count.restype = C.c_int
+        lib.ldp_profile_enable.restype = C.c_int
+        lib.ldp_profile_enable.argtypes = [C.c_int]
+        lib.ldp_profile_read.restype = C.c_int
+        lib.ldp_profile_read.argtypes = [C.POINTER(C.c_float), C.c_int]
         lib.ldp_workspace_bytes.restype = C.c_int
         lib.ldp_workspace_bytes.argtypes = [C.POINTER(LdpParams), C.POINTER(C.c_size_t)]
         for fn in (lib.ldp_densify_refs, lib.ldp_sample_refs):

@@ -12,6 +12,28 @@ namespace {
 thread_local std::string g_last_error;
 thread_local int g_launches = 0;
 
+// ---- optional per-kernel timing (ldp_profile_enable / ldp_profile_read)
+constexpr int MAX_PROF = 8;
+thread_local bool g_prof_on = false;
+thread_local cudaEvent_t g_prof_ev[2 * MAX_PROF];
+thread_local bool g_prof_ev_ready = false;
+thread_local int g_prof_n = 0;
+
+struct KernelTimer {
+    cudaStream_t st;
+    int slot;
+    explicit KernelTimer(cudaStream_t s) : st(s), slot(-1) {
+        if (!g_prof_on || g_prof_n >= MAX_PROF) return;
+        if (!g_prof_ev_ready) {
+            for (int i = 0; i < 2 * MAX_PROF; ++i) cudaEventCreate(&g_prof_ev[i]);
+            g_prof_ev_ready = true;
+        }
+        slot = g_prof_n++;
+        cudaEventRecord(g_prof_ev[2 * slot], st);
+    }
+    ~KernelTimer() { if (slot >= 0) cudaEventRecord(g_prof_ev[2 * slot + 1], st); }
+};
+
 int fail(int code, const char* what) {
     g_last_error = what ? what : "";
     return code;
@@ -116,12 +138,14 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(sample)");
         configured_smem = K1_SMEM_BUDGET;
     }
-    ldp::ldp_sample_kernel<<<p->n_refs, ldp::K1_THREADS, plan.k1_smem, st>>>(*p, refs, uniforms, plan.ws, *out, plan.geom);
+    { KernelTimer kt(st);
+      ldp::ldp_sample_kernel<<<p->n_refs, ldp::K1_THREADS, plan.k1_smem, st>>>(*p, refs, uniforms, plan.ws, *out, plan.geom); }
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ldp_sample_kernel");
     if (p->no_filter) {
-        ldp::ldp_topm_kernel<<<p->n_refs, ldp::K1_THREADS, 0, st>>>(*p, refs, plan.ws, *out, plan.geom);
+        { KernelTimer kt(st);
+          ldp::ldp_topm_kernel<<<p->n_refs, ldp::K1_THREADS, 0, st>>>(*p, refs, plan.ws, *out, plan.geom); }
         ++g_launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "ldp_topm_kernel");
@@ -132,11 +156,13 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
 int launch_geometry(const ldp_params* p, const ldp_ref_desc* refs, const ldp_outputs* out, Plan& plan,
                     int have_bestk, cudaStream_t st) {
     dim3 grid((unsigned)((plan.ws.sel_cap + ldp::K2_THREADS - 1) / ldp::K2_THREADS), (unsigned)p->n_refs);
-    ldp::ldp_geometry_kernel<<<grid, ldp::K2_THREADS, 0, st>>>(*p, refs, plan.ws, *out, have_bestk);
+    { KernelTimer kt(st);
+      ldp::ldp_geometry_kernel<<<grid, ldp::K2_THREADS, 0, st>>>(*p, refs, plan.ws, *out, have_bestk); }
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ldp_geometry_kernel");
-    ldp::ldp_pack_kernel<<<p->n_refs, ldp::K3_THREADS, 0, st>>>(*p, refs, plan.ws, *out);
+    { KernelTimer kt(st);
+      ldp::ldp_pack_kernel<<<p->n_refs, ldp::K3_THREADS, 0, st>>>(*p, refs, plan.ws, *out); }
     ++g_launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ldp_pack_kernel");
@@ -154,6 +180,20 @@ const char* ldp_last_error_string(void) { return g_last_error.c_str(); }
 int64_t ldp_sel_capacity(int32_t matches_per_ref) { return sel_capacity(matches_per_ref); }
 
 int ldp_last_launch_count(void) { return g_launches; }
+
+int ldp_profile_enable(int on) { g_prof_on = (on != 0); g_prof_n = 0; return LDP_OK; }
+
+int ldp_profile_read(float* ms_out, int max_n) {
+    if (!ms_out || max_n < 0) return fail(LDP_ERR_INVALID, "bad profile buffer");
+    const int n = g_prof_n < max_n ? g_prof_n : max_n;
+    for (int i = 0; i < n; ++i) {
+        cudaError_t e = cudaEventSynchronize(g_prof_ev[2 * i + 1]);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(profile)");
+        e = cudaEventElapsedTime(&ms_out[i], g_prof_ev[2 * i], g_prof_ev[2 * i + 1]);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaEventElapsedTime(profile)");
+    }
+    return g_prof_n;
+}
 
 int64_t ldp_struct_size(int which) {
     switch (which) {
@@ -181,6 +221,7 @@ static int vec_ok_for(const ldp_params* p) { return (p->W % 4 == 0 && p->reserve
 int ldp_densify_refs(const ldp_params* params, const ldp_ref_desc* refs, const double* uniforms,
                      const ldp_outputs* out, void* workspace, size_t workspace_bytes, void* stream) {
     g_launches = 0;
+    g_prof_n = 0;
     int rc = check_outputs(params, out);
     if (rc != LDP_OK) return rc;
     if (params->n_refs == 0) return LDP_OK;
@@ -201,6 +242,7 @@ int ldp_densify_refs(const ldp_params* params, const ldp_ref_desc* refs, const d
 int ldp_sample_refs(const ldp_params* params, const ldp_ref_desc* refs, const double* uniforms,
                     const ldp_outputs* out, void* workspace, size_t workspace_bytes, void* stream) {
     g_launches = 0;
+    g_prof_n = 0;
     if (!params || !out || !out->status || !out->n_samples || !out->sel_idx) return fail(LDP_ERR_INVALID, "sample stage needs status, n_samples, sel_idx");
     if (params->n_refs == 0) return LDP_OK;
     if (!refs || !workspace) return fail(LDP_ERR_INVALID, "null refs/workspace");
@@ -217,6 +259,7 @@ int ldp_sample_refs(const ldp_params* params, const ldp_ref_desc* refs, const do
 int ldp_triangulate_samples(const ldp_params* params, const ldp_ref_desc* refs, const ldp_outputs* out,
                             void* workspace, size_t workspace_bytes, void* stream) {
     g_launches = 0;
+    g_prof_n = 0;
     int rc = check_outputs(params, out);
     if (rc != LDP_OK) return rc;
     if (!out->sel_idx) return fail(LDP_ERR_INVALID, "triangulate stage reads out->sel_idx / out->n_samples");

@@ -37,7 +37,67 @@ struct RefConst {
     const uint8_t* image;
 };
 
-// smallest-eigenvalue eigenvector of M = A^T A (A 4x4 given row-major, f32 values held in f64)
+// Robust fallback: cyclic Jacobi eigen-decomposition of the symmetric 4x4 M (f64); returns the eigenvector
+// of the smallest eigenvalue.  Only reached when inverse iteration has not converged (sigma_4 ~ sigma_3:
+// grossly inconsistent matches), so it is kept out of line to protect the fast path's register budget.
+__device__ __noinline__ void jacobi_smallest_eigvec4(const double* __restrict__ Min, double* __restrict__ vout) {
+    double a[4][4], V[4][4];
+    a[0][0] = Min[0]; a[1][0] = a[0][1] = Min[1]; a[1][1] = Min[2];
+    a[2][0] = a[0][2] = Min[3]; a[2][1] = a[1][2] = Min[4]; a[2][2] = Min[5];
+    a[3][0] = a[0][3] = Min[6]; a[3][1] = a[1][3] = Min[7]; a[3][2] = a[2][3] = Min[8]; a[3][3] = Min[9];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    const double tr = a[0][0] + a[1][1] + a[2][2] + a[3][3];
+    const double tiny = tr * tr * 1e-34;
+    for (int sweep = 0; sweep < 16; ++sweep) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[0][3] * a[0][3] +
+                           a[1][2] * a[1][2] + a[1][3] * a[1][3] + a[2][3] * a[2][3];
+        if (!(off > tiny)) break;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                const double apq = a[p][q];
+                if (fabs(apq) > 1e-300) {
+                    const double tau = (a[q][q] - a[p][p]) / (2.0 * apq);
+                    const double t = ((tau >= 0.0) ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                    const double c = rsqrt(1.0 + t * t), sn = t * c;
+                    a[p][p] -= t * apq;
+                    a[q][q] += t * apq;
+                    a[p][q] = a[q][p] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (k != p && k != q) {
+                            const double akp = a[k][p], akq = a[k][q];
+                            a[k][p] = a[p][k] = c * akp - sn * akq;
+                            a[k][q] = a[q][k] = sn * akp + c * akq;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double vkp = V[k][p], vkq = V[k][q];
+                        V[k][p] = c * vkp - sn * vkq;
+                        V[k][q] = sn * vkp + c * vkq;
+                    }
+                }
+            }
+        }
+    }
+    int j = 0;
+    double best = a[0][0];
+    if (a[1][1] < best) { best = a[1][1]; j = 1; }
+    if (a[2][2] < best) { best = a[2][2]; j = 2; }
+    if (a[3][3] < best) { best = a[3][3]; j = 3; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) vout[k] = (j == 0) ? V[k][0] : (j == 1) ? V[k][1] : (j == 2) ? V[k][2] : V[k][3];
+}
+
+// smallest-eigenvalue eigenvector of M = A^T A (A 4x4 given row-major, f32 values held in f64).
+// Fast path: inverse iteration on the Cholesky factor of M + mu*I (same eigenvectors; converges at
+// (sigma_4/sigma_3)^2 per step: 3-5 steps on consistent matches).  Not converged after INVIT_MAX steps -> Jacobi.
+constexpr int INVIT_MAX = 8;
 __device__ __forceinline__ void null_vector4(const double A[16], double v[4]) {
     double m00 = 0, m10 = 0, m11 = 0, m20 = 0, m21 = 0, m22 = 0, m30 = 0, m31 = 0, m32 = 0, m33 = 0;
 #pragma unroll
@@ -64,7 +124,8 @@ __device__ __forceinline__ void null_vector4(const double A[16], double v[4]) {
     double d3 = m33 + mu - l30 * l30 - l31 * l31 - l32 * l32; d3 = fmax(d3, mu * 1e-3);
     const double i3 = rsqrt(d3);
     double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 1.0;
-    for (int it = 0; it < 24; ++it) {
+    bool converged = false;
+    for (int it = 0; it < INVIT_MAX; ++it) {
         // L y = x
         const double y0 = x0 * i0;
         const double y1 = (x1 - l10 * y0) * i1;
@@ -80,9 +141,14 @@ __device__ __forceinline__ void null_vector4(const double A[16], double v[4]) {
         const double n0 = z0 * sgn, n1 = z1 * sgn, n2 = z2 * sgn, n3 = z3 * sgn;
         const double e0 = n0 - x0, e1 = n1 - x1, e2 = n2 - x2, e3 = n3 - x3;
         x0 = n0; x1 = n1; x2 = n2; x3 = n3;
-        if (e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3 < 1e-26) break;
+        if (e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3 < 1e-26) { converged = true; break; }
     }
-    v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3;
+    if (converged) {
+        v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3;
+    } else {
+        const double Ms[10] = {m00, m10, m11, m20, m21, m22, m30, m31, m32, m33};
+        jacobi_smallest_eigvec4(Ms, v);
+    }
 }
 
 // X @ P^T row: the reference's sgemm accumulates the K=4 products with FMAs in index order
@@ -209,6 +275,8 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
             good = (se < P.sampson_thresh) ? 1 : 0;
         }
 
+        float X0 = 0.f, X1 = 0.f, X2 = 0.f, X3 = 0.f, err = __int_as_float(0x7fc00000);
+        if (good) {        // the reference triangulates only the Sampson survivors (core/pipeline.py:721-733)
         // ---- DLT rows (f32, multiply then subtract): core/geometry.py:72-75
         double A[16];
 #pragma unroll
@@ -221,7 +289,6 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
         double v[4];
         null_vector4(A, v);
         // core/geometry.py:85-87: w = where(|Xh3| < 1e-12, 1e-12, Xh3); X = Xh / w
-        float X0, X1, X2, X3;
         {
             const float w32 = (float)v[3];
             if (fabsf(w32) < 1e-12f) {
@@ -236,7 +303,7 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
         float z1, z2;
         const float e1 = reproj_err(rc.P1, X0, X1, X2, X3, uA, vA, &z1);
         const float e2 = reproj_err(pk.P2, X0, X1, X2, X3, uB, vB, &z2);
-        const float err = (e1 != e1 || e2 != e2) ? __int_as_float(0x7fc00000) : fmaxf(e1, e2);   // np.maximum propagates NaN
+        err = (e1 != e1 || e2 != e2) ? __int_as_float(0x7fc00000) : fmaxf(e1, e2);   // np.maximum propagates NaN
         if (P.no_filter) {                                                        // core/pipeline.py:739-743
             keep = (isfinite(X0) && isfinite(X1) && isfinite(X2) && isfinite(X3) && isfinite(err)) ? 1 : 0;
         } else {                                                                  // core/pipeline.py:745-749
@@ -255,6 +322,7 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
                 keep = (!dnan && ang >= P.min_parallax_deg) ? 1 : 0;
             }
         }
+        }   // good
         const size_t o = (size_t)r * ws.sel_cap + i;
         ws.pt0[o] = make_float4(X0, X1, X2, err);
         float dcert = 0.f;

@@ -79,9 +79,15 @@ class RefBatch:
     def __len__(self) -> int:
         return len(self._rows)
 
-    def _check_plane(self, t: torch.Tensor, shape, what: str) -> torch.Tensor:
-        if not isinstance(t, torch.Tensor) or t.device != self.device:
-            raise ValueError(f"{what} must be a tensor on {self.device}")
+    def _check_plane(self, t: torch.Tensor, shape, what: str, allow_pinned_host: bool = False) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor):
+            raise ValueError(f"{what} must be a tensor")
+        if t.device != self.device:
+            # Warp planes are read only at the ~9k sampled pixels of a view, so they may stay in pinned
+            # (page-locked, UVA-mapped) host memory and be gathered over PCIe instead of being uploaded.
+            if not (allow_pinned_host and t.device.type == "cpu" and t.is_pinned()):
+                raise ValueError(f"{what} must be a tensor on {self.device}"
+                                 + (" or in pinned host memory" if allow_pinned_host else ""))
         if t.dtype != torch.float32 or tuple(t.shape) != tuple(shape):
             raise ValueError(f"{what} must be float32 {tuple(shape)}, got {t.dtype} {tuple(t.shape)}")
         if not t.is_contiguous():
@@ -99,7 +105,7 @@ class RefBatch:
         row = np.zeros((), dtype=N.REF_DESC_DTYPE)
         for k in range(nn):
             c = self._check_plane(cert_planes[k], (self.H, self.W), "certainty plane")
-            w = self._check_plane(warp_planes[k], (self.H, self.W, 4), "warp plane")
+            w = self._check_plane(warp_planes[k], (self.H, self.W, 4), "warp plane", allow_pinned_host=True)
             if c.data_ptr() % 16 != 0:
                 self.force_scalar_loads = True
             if w.data_ptr() % 16 != 0:

@@ -405,7 +405,7 @@ def triangulate_ref(cert_list, warp_list, img_u8: np.ndarray, ref_cam: OracleCam
             keep &= in_front(cam.P, X)
             if cfg.min_parallax_deg > 0:
                 keep &= parallax_ok(ref_cam.C, cam.C, X, cfg.min_parallax_deg)
-        gt.update(pos=pos, X=X, err=e, keep=keep, uvA=uvA, uvB=uvB)
+        gt.update(pos=pos, X=X, err=e, keep=keep, uvA=uvA, uvB=uvB, P1=ref_cam.P, P2=cam.P)
         group_taps.append(gt)
         if not np.any(keep):
             continue
