@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LDP_ABI_VERSION 4
+#define LDP_ABI_VERSION 6
 #define LDP_MAX_NN 16          /* neighbours per reference view (the panel clamps to 10) */
 #define LDP_MAX_BINS 4096      /* coverage tiles per map: ceil(W/tile)*ceil(H/tile), tile = max(1, W/24) */
 
@@ -159,9 +159,18 @@ int ldp_last_launch_count(void);
 /* Per-kernel device timing of subsequent ldp_* calls on this thread (CUDA events recorded on the call's
  * stream around every kernel; no synchronisation at record time).  ldp_profile_read synchronises on the
  * last event and returns, for the LAST call, up to max_n kernel durations in ms in launch order
- * (sample, [topm], geometry, pack); returns the number of kernels, or a negative ldp_error. */
+ * (stream, prep, draw | stream, topm; then geometry, pack); returns the number of kernels, or a negative ldp_error. */
 int ldp_profile_enable(int on);
 int ldp_profile_read(float* ms_out, int max_n);
+const char* ldp_profile_name(int i);      /* name of the i-th kernel of the last profiled call */
+
+/* Test hook: force the thread-block-cluster size of the draw kernel (CTAs per reference view, 1..8);
+ * 0 restores the automatic choice.  Results do not depend on it. */
+int ldp_debug_set_cluster(int csize);
+int ldp_debug_last_cluster(void);
+/* Debug builds (-DLDP_PHASE_CLOCKS) only: copy the draw kernel's per-view phase timestamps [n_refs][32] (SM clocks)
+ * to host memory; synchronises.  Release builds return zeros. */
+int ldp_debug_read_clocks(const ldp_params* params, void* workspace, long long* host_out);          /* cluster size the last draw kernel was launched with */
 
 /* sizeof() of the ABI structs as this library was compiled: which = 0 ldp_params, 1 ldp_ref_desc,
  * 2 ldp_outputs.  Bindings check these against their own struct definitions at load time. */

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import build as _build
 
-LDP_ABI_VERSION = 4
+LDP_ABI_VERSION = 6
 LDP_MAX_NN = 16
 LDP_MAX_BINS = 4096
 
@@ -91,7 +91,7 @@ REF_DESC_DTYPE = np.dtype(LdpRefDesc)
 EXPORTS = [
     "ldp_abi_version", "ldp_last_error_string", "ldp_sel_capacity", "ldp_workspace_bytes",
     "ldp_densify_refs", "ldp_sample_refs", "ldp_triangulate_samples", "ldp_last_launch_count",
-    "ldp_struct_size", "ldp_profile_enable", "ldp_profile_read",
+    "ldp_struct_size", "ldp_profile_enable", "ldp_profile_read", "ldp_profile_name", "ldp_debug_set_cluster", "ldp_debug_last_cluster", "ldp_debug_read_clocks",
 ]
 
 _lock = threading.Lock()
@@ -135,6 +135,11 @@ def load(build_if_missing: bool = False):
         lib.ldp_profile_enable.restype = C.c_int
         lib.ldp_profile_enable.argtypes = [C.c_int]
         lib.ldp_profile_read.restype = C.c_int
+        lib.ldp_debug_last_cluster.restype = C.c_int
+        lib.ldp_debug_set_cluster.restype = C.c_int
+        lib.ldp_debug_set_cluster.argtypes = [C.c_int]
+        lib.ldp_profile_name.restype = C.c_char_p
+        lib.ldp_profile_name.argtypes = [C.c_int]
         lib.ldp_profile_read.argtypes = [C.POINTER(C.c_float), C.c_int]
         lib.ldp_workspace_bytes.restype = C.c_int
         lib.ldp_workspace_bytes.argtypes = [C.POINTER(LdpParams), C.POINTER(C.c_size_t)]

@@ -19,20 +19,45 @@ thread_local cudaEvent_t g_prof_ev[2 * MAX_PROF];
 thread_local bool g_prof_ev_ready = false;
 thread_local int g_prof_n = 0;
 
+thread_local const char* g_prof_name[MAX_PROF];
+
 struct KernelTimer {
     cudaStream_t st;
     int slot;
-    explicit KernelTimer(cudaStream_t s) : st(s), slot(-1) {
+    KernelTimer(cudaStream_t s, const char* name) : st(s), slot(-1) {
         if (!g_prof_on || g_prof_n >= MAX_PROF) return;
         if (!g_prof_ev_ready) {
             for (int i = 0; i < 2 * MAX_PROF; ++i) cudaEventCreate(&g_prof_ev[i]);
             g_prof_ev_ready = true;
         }
         slot = g_prof_n++;
+        g_prof_name[slot] = name;
         cudaEventRecord(g_prof_ev[2 * slot], st);
     }
     ~KernelTimer() { if (slot >= 0) cudaEventRecord(g_prof_ev[2 * slot + 1], st); }
 };
+
+int max_active_clusters(int csize, size_t smem) {
+    static int cache[9] = {0};
+    static size_t cache_smem = 0;
+    if (cache_smem != smem) { for (int i = 0; i < 9; ++i) cache[i] = 0; cache_smem = smem; }
+    if (cache[csize]) return cache[csize];
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(csize * 64));
+    cfg.blockDim = dim3(ldp::KD_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, ldp::ldp_draw_kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    cache[csize] = n > 0 ? n : -1;
+    return cache[csize];
+}
 
 int fail(int code, const char* what) {
     g_last_error = what ? what : "";
@@ -45,6 +70,20 @@ int cuda_fail(cudaError_t e, const char* where) {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+int g_force_cluster = 0;      // test hook (ldp_debug_set_cluster)
+int g_last_cluster = 0;
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+        else cached = 148;
+    }
+    return cached;
+}
+
 constexpr size_t K1_SMEM_BUDGET = 200 * 1024;
 
 struct Plan {
@@ -52,6 +91,7 @@ struct Plan {
     ldp::SampleGeom geom;
     size_t bytes;
     size_t k1_smem;
+    size_t prep_smem;
 };
 
 int64_t sel_capacity(int32_t M) {
@@ -85,14 +125,27 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     int cs = 5;
     for (;; ++cs) {
         const size_t nchunk = ((size_t)N + ((size_t)1 << cs) - 1) >> cs;
-        if (nchunk * 8 + (size_t)nb_pow2 * 8 <= K1_SMEM_BUDGET) { g.nchunk = (int)nchunk; break; }
+        const size_t ept = 8 * ((nchunk + 8 * ldp::KD_THREADS - 1) / (8 * ldp::KD_THREADS));
+        const size_t pre_cap = ept * ldp::KD_THREADS / 8 * 10 + 16;            // padded: 10 doubles per 8 entries
+        size_t ng = 1;
+        while (ng * 2 <= nchunk / 2) ng *= 2;
+        const size_t bytes = pre_cap * 8 + (ng + 2) * 4 + 16;
+        if (bytes <= K1_SMEM_BUDGET && bytes >= (size_t)nb_pow2 * 8) {
+            g.nchunk = (int)nchunk; g.draw_ept = (int)ept; g.draw_pre_cap = (int)pre_cap; g.draw_ng = (int)ng;
+            plan->k1_smem = bytes;
+            break;
+        }
+        if (bytes <= K1_SMEM_BUDGET) {      // tiny map: the coverage sort needs nb_pow2 keys
+            g.nchunk = (int)nchunk; g.draw_ept = (int)ept; g.draw_pre_cap = (int)pre_cap; g.draw_ng = (int)ng;
+            plan->k1_smem = (size_t)nb_pow2 * 8;
+            break;
+        }
         if (cs > 20) return fail(LDP_ERR_INVALID, "map too large for the chunk table");
     }
     g.chunk_shift = cs;
-    plan->k1_smem = (size_t)g.nchunk * 8 + (size_t)nb_pow2 * 8;
 
     ldp::Workspace& w = plan->ws;
-    w.n_pad = align_up((size_t)N, 128);
+    w.n_pad = align_up((size_t)N, 256);
     w.n_words = (w.n_pad + 31) / 32;
     w.found_cap = align_up((size_t)(g.size > 0 ? g.size : 1), 4);
     w.sel_cap = (size_t)sel_capacity(p->matches_per_ref);
@@ -100,6 +153,16 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     const size_t Mn = (size_t)((p->matches_per_ref < N) ? p->matches_per_ref : N);
     while (tk < Mn) tk <<= 1;
     w.topk_cap = p->no_filter ? tk : 0;
+    w.nchunk_pad = align_up((size_t)g.nchunk, 32);
+    w.nblk = ((size_t)N + ldp::KS_SPAN - 1) / ldp::KS_SPAN;
+    w.bins_cap = align_up((size_t)g.nbins, 32);
+    {
+        const int rows = (ldp::KS_SPAN + p->W - 1) / p->W + 1;
+        long long lb = (long long)(rows / g.tile + 2) * g.nbx;
+        if (lb > g.nbins) lb = g.nbins;
+        g.prep_lb_cap = (int)align_up((size_t)lb, 4);
+    }
+    plan->prep_smem = (size_t)g.prep_lb_cap * 8 + align_up((size_t)p->W * 2, 16);
 
     size_t off = 0;
     char* b = static_cast<char*>(base);
@@ -107,7 +170,9 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     w.w = reinterpret_cast<float*>(carve(R * w.n_pad * sizeof(float)));
     w.bestk = reinterpret_cast<uint8_t*>(carve(R * w.n_pad));
     w.bitmap = reinterpret_cast<uint32_t*>(carve(R * w.n_words * sizeof(uint32_t)));
-    w.found = reinterpret_cast<int32_t*>(carve(R * w.found_cap * sizeof(int32_t)));
+    w.draw_cmax = 8;
+    w.found = reinterpret_cast<int32_t*>(carve(R * w.draw_cmax * w.found_cap * sizeof(int32_t)));
+    w.fcnt = reinterpret_cast<int32_t*>(carve(R * w.draw_cmax * sizeof(int32_t)));
     w.sel = reinterpret_cast<int32_t*>(carve(R * w.sel_cap * sizeof(int32_t)));
     w.pt0 = reinterpret_cast<float4*>(carve(R * w.sel_cap * sizeof(float4)));
     w.pt1 = reinterpret_cast<float4*>(carve(R * w.sel_cap * sizeof(float4)));
@@ -115,6 +180,12 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     w.flags = reinterpret_cast<uint8_t*>(carve(R * w.sel_cap));
     w.kept = reinterpret_cast<int32_t*>(carve(R * sizeof(int32_t)));
     w.topk_keys = reinterpret_cast<unsigned long long*>(carve(R * w.topk_cap * sizeof(unsigned long long)));
+    w.csum = reinterpret_cast<double*>(carve(R * w.nchunk_pad * sizeof(double)));
+    w.partial = reinterpret_cast<double*>(carve(R * w.nblk * sizeof(double)));
+    w.bflags = reinterpret_cast<int32_t*>(carve(R * w.nblk * sizeof(int32_t)));
+    w.rstat = reinterpret_cast<ldp::RefStat*>(carve(R * sizeof(ldp::RefStat)));
+    w.gbins = reinterpret_cast<unsigned long long*>(carve(R * w.bins_cap * sizeof(unsigned long long)));
+    w.dbgclk = reinterpret_cast<long long*>(carve(R * 32 * sizeof(long long)));
     plan->bytes = off;
     return LDP_OK;
 }
@@ -132,36 +203,82 @@ int check_outputs(const ldp_params* p, const ldp_outputs* o) {
 int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* uniforms, const ldp_outputs* out,
                   Plan& plan, int vec_ok, cudaStream_t st) {
     plan.geom.vec = vec_ok;
-    static size_t configured_smem = 0;
-    if (plan.k1_smem > configured_smem) {
-        cudaError_t e = cudaFuncSetAttribute(ldp::ldp_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(sample)");
-        configured_smem = K1_SMEM_BUDGET;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ldp::ldp_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(draw)");
+        e = cudaFuncSetAttribute(ldp::ldp_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(prep)");
+        configured = true;
     }
-    { KernelTimer kt(st);
-      ldp::ldp_sample_kernel<<<p->n_refs, ldp::K1_THREADS, plan.k1_smem, st>>>(*p, refs, uniforms, plan.ws, *out, plan.geom); }
+    if (plan.prep_smem > 64 * 1024) return fail(LDP_ERR_INVALID, "map too wide for the prep kernel tables");
+    const dim3 grid((unsigned)plan.ws.nblk, (unsigned)p->n_refs);
+    cudaError_t e;
+    { KernelTimer kt(st, "ldp_stream_kernel");
+      ldp::ldp_stream_kernel<<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); }
     ++g_launches;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "ldp_sample_kernel");
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_stream_kernel");
     if (p->no_filter) {
-        { KernelTimer kt(st);
+        { KernelTimer kt(st, "ldp_topm_kernel");
           ldp::ldp_topm_kernel<<<p->n_refs, ldp::K1_THREADS, 0, st>>>(*p, refs, plan.ws, *out, plan.geom); }
         ++g_launches;
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return cuda_fail(e, "ldp_topm_kernel");
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_topm_kernel");
+        return LDP_OK;
     }
+    if (plan.geom.chunk_shift > 7) {      // chunk sums are accumulated with atomics: start from zero
+        e = cudaMemsetAsync(plan.ws.csum, 0, (size_t)p->n_refs * plan.ws.nchunk_pad * sizeof(double), st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(csum)");
+    }
+    { KernelTimer kt(st, "ldp_prep_kernel");
+      ldp::ldp_prep_kernel<<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom); }
+    ++g_launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_prep_kernel");
+    {
+        // cluster size: as many CTAs per view as keeps every view of the launch resident at once (1 CTA / SM)
+        // largest cluster size for which every view's cluster is resident at once (one wave); GPC boundaries make
+        // this smaller than sm_count / n_refs, so ask the occupancy API
+        int csize = 1;
+        for (int c = 8; c > 1; --c) {
+            if ((long long)p->n_refs * c > sm_count()) continue;
+            if (max_active_clusters(c, plan.k1_smem) >= p->n_refs) { csize = c; break; }
+        }
+        if (g_force_cluster > 0) csize = g_force_cluster;
+        KernelTimer kt(st, "ldp_draw_kernel");
+        for (;;) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(p->n_refs * csize));
+            cfg.blockDim = dim3(ldp::KD_THREADS);
+            cfg.dynamicSmemBytes = plan.k1_smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)csize;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, ldp::ldp_draw_kernel, *p, refs, uniforms, plan.ws, *out, plan.geom);
+            if (e == cudaSuccess) break;
+            (void)cudaGetLastError();
+            if (csize == 1) return cuda_fail(e, "ldp_draw_kernel");
+            csize = (csize > 4) ? 4 : (csize > 2 ? 2 : 1);      // odd sizes may not be schedulable: fall back
+        }
+        g_last_cluster = csize;
+    }
+    ++g_launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_draw_kernel");
     return LDP_OK;
 }
 
 int launch_geometry(const ldp_params* p, const ldp_ref_desc* refs, const ldp_outputs* out, Plan& plan,
                     int have_bestk, cudaStream_t st) {
     dim3 grid((unsigned)((plan.ws.sel_cap + ldp::K2_THREADS - 1) / ldp::K2_THREADS), (unsigned)p->n_refs);
-    { KernelTimer kt(st);
+    { KernelTimer kt(st, "ldp_geometry_kernel");
       ldp::ldp_geometry_kernel<<<grid, ldp::K2_THREADS, 0, st>>>(*p, refs, plan.ws, *out, have_bestk); }
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ldp_geometry_kernel");
-    { KernelTimer kt(st);
+    { KernelTimer kt(st, "ldp_pack_kernel");
       ldp::ldp_pack_kernel<<<p->n_refs, ldp::K3_THREADS, 0, st>>>(*p, refs, plan.ws, *out); }
     ++g_launches;
     e = cudaGetLastError();
@@ -194,6 +311,26 @@ int ldp_profile_read(float* ms_out, int max_n) {
     }
     return g_prof_n;
 }
+
+int ldp_debug_last_cluster(void) { return g_last_cluster; }
+
+int ldp_debug_read_clocks(const ldp_params* params, void* workspace, long long* host_out) {
+    Plan plan;
+    char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+    int rc = make_plan(params, base, &plan);
+    if (rc != LDP_OK) return rc;
+    cudaError_t e = cudaMemcpy(host_out, plan.ws.dbgclk, (size_t)params->n_refs * 32 * sizeof(long long), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(dbgclk)");
+    return LDP_OK;
+}
+
+int ldp_debug_set_cluster(int csize) {
+    if (csize < 0 || csize > 8) return fail(LDP_ERR_INVALID, "cluster size must be 0 (auto) .. 8");
+    g_force_cluster = csize;
+    return LDP_OK;
+}
+
+const char* ldp_profile_name(int i) { return (i >= 0 && i < g_prof_n) ? g_prof_name[i] : ""; }
 
 int64_t ldp_struct_size(int which) {
     switch (which) {

@@ -10,11 +10,20 @@ namespace ldp {
 // Workspace carved by the host (ldp_api.cu).  Everything is per reference view r; rows are padded so
 // that float4 / 16-byte accesses stay aligned.
 // ---------------------------------------------------------------------------------------------
+struct RefStat {        // per-view scalars passed between the sampler kernels
+    float s;            // f32 normaliser (core/sampling.py:26)
+    int npos;           // number of p > 0
+    int emin;           // smallest biased exponent among positive p
+    int bad;            // bit0 NaN weight, bit1 negative weight, bit2 no neighbours
+};
+
 struct Workspace {
-    float* w;            // [R][n_pad]   capped, border-masked weights (zeroed as pixels get drawn)
+    float* w;            // [R][n_pad]   stream: capped, border-masked weights; prep: overwritten by p = w / s
+                         //              (zeroed as pixels get drawn)
     uint8_t* bestk;      // [R][n_pad]   winning neighbour per pixel
     uint32_t* bitmap;    // [R][n_words] selected-pixel bitmap
-    int32_t* found;      // [R][found_cap] draw list of the weighted sampler (unordered)
+    int32_t* found;      // [R][draw_cmax][found_cap] pixel indices: per-CTA find lists of the current round
+    int32_t* fcnt;       // [R][draw_cmax] entries in each list
     int32_t* sel;        // [R][sel_cap]  sample indices when the caller does not ask for them
     float4* pt0;         // [R][sel_cap]  X,Y,Z,err per sample
     float4* pt1;         // [R][sel_cap]  r,g,b,debug-cert per sample
@@ -22,7 +31,13 @@ struct Workspace {
     uint8_t* flags;      // [R][sel_cap]  bit0 keep, bit1 sampson-pass, bits2.. group
     int32_t* kept;       // [R]           kept points (atomic)
     unsigned long long* topk_keys;  // [R][topk_cap] no_filter candidate keys
-    size_t n_pad, n_words, found_cap, sel_cap, topk_cap;
+    double* csum;        // [R][nchunk_pad] f64 sums of p per chunk
+    double* partial;     // [R][nblk]    per-CTA f64 partial weight sums of the stream kernel
+    int32_t* bflags;     // [R][nblk]    per-CTA NaN / negative flags
+    RefStat* rstat;      // [R]
+    unsigned long long* gbins;      // [R][bins_cap] per-tile arg-max keys (p bits << 32 | ~index)
+    long long* dbgclk;   // [R][32] phase timestamps of the draw kernel (written only with -DLDP_PHASE_CLOCKS)
+    size_t n_pad, n_words, found_cap, sel_cap, topk_cap, nchunk_pad, nblk, bins_cap, draw_cmax;
 };
 
 struct SampleGeom {     // launch-constant shape of the sampler
@@ -34,6 +49,10 @@ struct SampleGeom {     // launch-constant shape of the sampler
     int size;           // min(int(0.85*M), N)
     int cov_budget;     // max(1, M - size)
     int vec;            // cert planes are 16-B aligned and W % 4 == 0
+    int prep_lb_cap;    // local tile bins per CTA of the prep kernel
+    int draw_ept;       // draw kernel: chunk-table entries per thread (multiple of 8)
+    int draw_pre_cap;   // draw kernel: doubles in the padded prefix table
+    int draw_ng;        // draw kernel: guide-table buckets
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -125,6 +144,20 @@ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint32_t stream,
     philox4x32_10(d >> 1, 0u, stream, 0x4c445031u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
     const uint32_t a = (d & 1u) ? r[2] : r[0], b = (d & 1u) ? r[3] : r[1];
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+#ifdef LDP_PHASE_CLOCKS
+#define LDP_CLK(ws, r, slot) do { if (threadIdx.x == 0 && (blockIdx.x % cooperative_groups::this_cluster().num_blocks()) == 0) (ws).dbgclk[(size_t)(r) * 32 + (slot)] = clock64(); } while (0)
+#else
+#define LDP_CLK(ws, r, slot) do { } while (0)
+#endif
+
+// Two consecutive draws (d even, d + 1) from ONE Philox call.
+__device__ __forceinline__ void philox_uniform2(uint64_t seed, uint32_t stream, uint32_t d, double u[2]) {
+    uint32_t r[4];
+    philox4x32_10(d >> 1, 0u, stream, 0x4c445031u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    u[0] = ((double)(r[0] >> 5) * 67108864.0 + (double)(r[1] >> 6)) * (1.0 / 9007199254740992.0);
+    u[1] = ((double)(r[2] >> 5) * 67108864.0 + (double)(r[3] >> 6)) * (1.0 / 9007199254740992.0);
 }
 
 __device__ __forceinline__ float4 ld_stream4(const float* p) {   // read-once data: evict-first

@@ -20,26 +20,27 @@
 //            (__ddiv_rn); first-occurrence dedupe by atomicOr on a bitmap; found pixels are zeroed
 //            and their mass subtracted from the chunk table (exact, see DESIGN.md "exact f64 sums").
 //   finish   coverage picks OR-ed into the bitmap; ordered bitmap compaction = sorted unique sel_idx.
+#include <cooperative_groups.h>
 #include "ldp_device.cuh"
 
 namespace ldp {
 
-constexpr int K1_THREADS = 1024;
+constexpr int K1_THREADS = 1024;     // top-M kernel: one CTA per view
+constexpr int KD_THREADS = 1024;     // draw kernel: 1024 threads x 64 registers, DRAW_PASS draws in flight per thread
+constexpr int KS_THREADS = 256;      // stream / prep kernels: full grid
+constexpr int KS_SPAN = 8192;        // pixels per CTA of the full-grid passes (multiple of every chunk size)
 
 struct K1Shared {
     double red_d[32];
     int red_i[32];
     int n_found;
-    int n_new_base;
-    int status;
-    int flags;
 };
 
 __device__ __forceinline__ unsigned long long cov_key(float p, int idx) {
     return ((unsigned long long)__float_as_uint(p) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
 }
 
-// descending bitonic sort of n (power of two) 64-bit keys in shared memory
+// descending bitonic sort of n (power of two) 64-bit keys
 __device__ void bitonic_sort_desc(unsigned long long* a, int n) {
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -56,300 +57,614 @@ __device__ void bitonic_sort_desc(unsigned long long* a, int n) {
     }
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 1)
-ldp_sample_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const double* __restrict__ uniforms,
-                  const Workspace ws, const ldp_outputs out, const SampleGeom G)
+// =============================================================================================
+// K1a  stream: grid (ceil(N / KS_SPAN), n_refs).  Reads every certainty value once (float4, evict-first),
+//      writes w = min(best, cap) * border_mask (f32) and the winning neighbour (u8) to the L2-resident
+//      workspace, and one f64 partial weight sum + NaN/negative flags per CTA.
+//      reference core/pipeline.py:634-635 (torch.max over neighbours), core/sampling.py:12-14,23-25
+// =============================================================================================
+__global__ void __launch_bounds__(KS_THREADS)
+ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const SampleGeom G)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* csum = reinterpret_cast<double*>(smem_raw);                                  // [nchunk]
-    unsigned long long* bins = reinterpret_cast<unsigned long long*>(csum + G.nchunk);   // [nbins_pow2]
-    __shared__ K1Shared sh;
     __shared__ const float* s_cert[LDP_MAX_NN];
-
-    const int r = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int T = blockDim.x;
+    __shared__ double red_d[32];
+    __shared__ int red_i[32];
+    const int r = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
     const int N = G.N;
     const ldp_ref_desc* rd = refs + r;
     const int nn = rd->nn;
-
+    if (tid < LDP_MAX_NN) s_cert[tid] = (tid < nn) ? rd->cert[tid] : nullptr;
+    if (blk == 0) {          // per-view state consumed by the later kernels of this launch
+        if (tid == 0) {
+            ws.rstat[r].s = 0.f; ws.rstat[r].npos = 0; ws.rstat[r].emin = 0x7fffffff; ws.rstat[r].bad = 0;
+            ws.kept[r] = 0;
+        }
+        unsigned long long* gb = ws.gbins + (size_t)r * ws.bins_cap;
+        for (int i = tid; i < (int)ws.bins_cap; i += KS_THREADS) gb[i] = 0ull;
+    }
+    __syncthreads();
     float* __restrict__ w = ws.w + (size_t)r * ws.n_pad;
     uint8_t* __restrict__ bk = ws.bestk + (size_t)r * ws.n_pad;
-    uint32_t* __restrict__ bitmap = ws.bitmap + (size_t)r * ws.n_words;
-    int32_t* __restrict__ found = ws.found + (size_t)r * ws.found_cap;
-    int32_t* __restrict__ sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
+    const float cap = P.sample_cap;
+    const int W = P.W, H = P.H, border = P.border;
+    const int base = blk * KS_SPAN;
+    double lsum = 0.0;
+    int lbad = 0;
+    if (nn > 0) {
+#pragma unroll 2
+        for (int it = 0; it < KS_SPAN / (KS_THREADS * 4); ++it) {
+            const int px = base + (it * KS_THREADS + tid) * 4;
+            if (px >= N) break;
+            float best[4];
+            int bi[4] = {0, 0, 0, 0};
+            if (G.vec) {
+                const float4 v = ld_stream4(s_cert[0] + px);
+                best[0] = v.x; best[1] = v.y; best[2] = v.z; best[3] = v.w;
+#pragma unroll 4
+                for (int k = 1; k < nn; ++k) {
+                    const float4 c = ld_stream4(s_cert[k] + px);
+                    if (c.x > best[0]) { best[0] = c.x; bi[0] = k; }
+                    if (c.y > best[1]) { best[1] = c.y; bi[1] = k; }
+                    if (c.z > best[2]) { best[2] = c.z; bi[2] = k; }
+                    if (c.w > best[3]) { best[3] = c.w; bi[3] = k; }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) best[j] = (px + j < N) ? __ldcs(s_cert[0] + px + j) : 0.f;
+                for (int k = 1; k < nn; ++k) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float c = (px + j < N) ? __ldcs(s_cert[k] + px + j) : 0.f;
+                        if (c > best[j]) { best[j] = c; bi[j] = k; }
+                    }
+                }
+            }
+            int y = px / W, x = px - y * W;
+            float wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float c = (best[j] > cap) ? cap : best[j];          // torch.clamp(max=cap): NaN stays NaN
+                float m = 1.f;
+                if (!P.no_filter)
+                    m = (x >= border && x <= W - 1 - border && y >= border && y <= H - 1 - border) ? 1.f : 0.f;
+                float v = c * m;
+                if (px + j >= N) v = 0.f;
+                wv[j] = v;
+                lbad |= (v != v) ? 1 : 0;
+                lbad |= (v < 0.f) ? 2 : 0;
+                lsum += (double)v;
+                if (++x == W) { x = 0; ++y; }
+            }
+            *reinterpret_cast<float4*>(w + px) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+            *reinterpret_cast<uchar4*>(bk + px) = make_uchar4((unsigned char)bi[0], (unsigned char)bi[1],
+                                                              (unsigned char)bi[2], (unsigned char)bi[3]);
+        }
+    }
+    if (blk == (int)gridDim.x - 1) {       // keep the row padding [N, n_pad) zero: the draw kernel's 32-byte scans read it
+        for (int i = ((N + 3) & ~3) + tid; i < (int)ws.n_pad; i += KS_THREADS) w[i] = 0.f;
+    }
+    const double bsum = block_sum(lsum, red_d);
+    const int bbad = block_sum((lbad & 1) | ((lbad & 2) << 15), red_i);
+    if (tid == 0) {
+        ws.partial[(size_t)r * ws.nblk + blk] = bsum;
+        ws.bflags[(size_t)r * ws.nblk + blk] = ((bbad & 0xffff) ? 1 : 0) | ((bbad >> 16) ? 2 : 0) | ((nn <= 0) ? 4 : 0);
+    }
+}
 
-    if (tid < LDP_MAX_NN) s_cert[tid] = (tid < nn) ? rd->cert[tid] : nullptr;
-    if (tid == 0) { sh.n_found = 0; sh.n_new_base = 0; sh.status = LDP_REF_OK; sh.flags = 0; ws.kept[r] = 0; }
-    for (int i = tid; i < (int)ws.n_words; i += T) bitmap[i] = 0u;
-    for (int i = tid; i < G.nchunk; i += T) csum[i] = 0.0;
-    int nb_pow2 = 1;
-    while (nb_pow2 < G.nbins) nb_pow2 <<= 1;
-    for (int i = tid; i < nb_pow2; i += T) bins[i] = 0ull;
+// =============================================================================================
+// K1b  prep: same grid.  s = f32(sum of the f64 partials) (or the caller's override); p = fl32(w / s) is
+//      written back IN PLACE over w (so the draw kernel never divides); f64 sums of p per chunk go to the
+//      global chunk table; per-tile arg-max of p (the coverage picks) via shared-memory then global 64-bit
+//      atomicMax on (p bits, ~index); number of positive p and their smallest exponent (exactness test).
+//      reference core/sampling.py:26-29 (normalise), :34-50 (coverage walk == per-tile arg-max)
+// =============================================================================================
+__global__ void __launch_bounds__(KS_THREADS)
+ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
+                const SampleGeom G)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red_d[32];
+    __shared__ int red_i[32];
+    __shared__ float s_s;
+    __shared__ int s_bad;
+    const int r = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int N = G.N, W = P.W;
+    const ldp_ref_desc* rd = refs + r;
+    // ---- s: fixed-order reduction of the per-CTA partials (every CTA of the view computes the same value)
+    if (tid < 32) {
+        double a = 0.0;
+        int f = 0;
+        for (int i = lane; i < (int)ws.nblk; i += 32) {
+            a += ws.partial[(size_t)r * ws.nblk + i];
+            f |= ws.bflags[(size_t)r * ws.nblk + i];
+        }
+        a = warp_sum(a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) f |= __shfl_xor_sync(0xffffffffu, f, o);
+        if (lane == 0) {
+            float s = (float)a;
+            if (rd->weight_sum_override > 0.f) s = rd->weight_sum_override;
+            s_s = s;
+            s_bad = f;
+            if (blk == 0) {
+                ws.rstat[r].s = s;
+                ws.rstat[r].bad = f;
+                if (out.weight_sum) out.weight_sum[r] = s;
+            }
+        }
+    }
+    __syncthreads();
+    const float s = s_s;
+    if (s_bad || !(s > 0.f)) return;       // the draw kernel reports the status
+
+    // ---- shared tables: x -> tile column, local tile bins
+    const int base = blk * KS_SPAN;
+    const int end = min(base + KS_SPAN, N);
+    const int y_first = base / W, y_last = (end - 1) / W;
+    const int ty0 = y_first / G.tile, ty1 = y_last / G.tile;
+    const int nlb = (ty1 - ty0 + 1) * G.nbx;
+    unsigned long long* lb = reinterpret_cast<unsigned long long*>(smem_raw);            // [nlb]
+    unsigned short* xt = reinterpret_cast<unsigned short*>(lb + G.prep_lb_cap);          // [W]
+    for (int i = tid; i < nlb; i += KS_THREADS) lb[i] = 0ull;
+    for (int i = tid; i < W; i += KS_THREADS) xt[i] = (unsigned short)(i / G.tile);
     __syncthreads();
 
+    float* __restrict__ w = ws.w + (size_t)r * ws.n_pad;
+    double* __restrict__ csum = ws.csum + (size_t)r * ws.nchunk_pad;
+    const int cs = G.chunk_shift;
+    const int gl = min(32, (1 << cs) >> 2);            // lanes that share one chunk
+    int lpos = 0;
+    int lemin = 0x7fffffff;
+#pragma unroll 2
+    for (int it = 0; it < KS_SPAN / (KS_THREADS * 4); ++it) {
+        const int px = base + (it * KS_THREADS + tid) * 4;     // warp-uniform trip count: whole warps drop out together
+        double a = 0.0;
+        if (px < N) {
+            const float4 v = *reinterpret_cast<const float4*>(w + px);
+            const float wv[4] = {v.x, v.y, v.z, v.w};
+            float pv[4];
+            int y = px / W, x = px - y * W;
+            int lrow = (y / G.tile - ty0) * G.nbx;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float p = __fdiv_rn(wv[j], s);                     // core/sampling.py:29 (f32 division)
+                pv[j] = p;
+                if (p > 0.f) {
+                    a += (double)p;
+                    ++lpos;
+                    lemin = min(lemin, (int)((__float_as_uint(p) >> 23) & 0xffu));
+                    const int b = lrow + xt[x];
+                    const unsigned long long key = cov_key(p, px + j);
+                    if (lb[b] < key) atomicMax(&lb[b], key);
+                }
+                if (++x == W) { x = 0; ++y; lrow = (y / G.tile - ty0) * G.nbx; }
+            }
+            *reinterpret_cast<float4*>(w + px) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+        }
+        for (int o = 1; o < gl; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (px < N && (lane & (gl - 1)) == 0) {
+            if (cs <= 7) csum[px >> cs] = a;
+            else atomicAdd(&csum[px >> cs], a);          // chunks wider than a warp-row (zeroed by the host memset)
+        }
+    }
+    const int npos = block_sum(lpos, red_i);
+    const int emin = block_min(lemin, red_i);
+    if (tid == 0) {
+        if (npos) atomicAdd(&ws.rstat[r].npos, npos);
+        if (emin != 0x7fffffff) atomicMin(&ws.rstat[r].emin, emin);
+    }
+    __syncthreads();
+    unsigned long long* gb = ws.gbins + (size_t)r * ws.bins_cap;
+    for (int i = tid; i < nlb; i += KS_THREADS) {
+        const unsigned long long key = lb[i];
+        if (key) atomicMax(&gb[(ty0 + i / G.nbx) * G.nbx + (i % G.nbx)], key);
+    }
+}
+
+// =============================================================================================
+// K1c  draw: one thread-block CLUSTER of C CTAs per view.  numpy's legacy RandomState.choice(replace=False, p)
+//      restated (oracle/densify_oracle.py:legacy_choice_no_replace): rejection rounds of inverse-CDF draws.
+//
+//      The kernel is bound by the SM's load/store wavefront rate, not by arithmetic (profiles/r01_*), so every
+//      step is organised to touch few 128-byte wavefronts:
+//        * every CTA keeps the view's f64 chunk-prefix table in shared memory, in a padded layout
+//          (2 doubles after every 8) that makes the per-thread 8-entry prefix build conflict-free;
+//        * a guide table (bucket of u -> first candidate chunk) cuts the binary search to 1-3 probes;
+//        * the chunk's p values are scanned with 32-byte (LDG.256) loads and early exit;
+//        * numpy's exact predicate fl64(cum / total) > u (__ddiv_rn) is evaluated once, at the first
+//          approximate crossing (slow exact continuation otherwise);
+//        * first-occurrence dedupe = atomicOr on the global selection bitmap; the found mass leaves the
+//          global chunk sums through fire-and-forget f64 reductions at L2 (exact sums => order-free);
+//          found p are zeroed by their finder after the round's cluster barrier.
+//      Finally CTA 0 ORs the coverage picks in and an ordered bitmap compaction yields np.unique(concat).
+//      reference core/sampling.py:31-32,34-52
+// =============================================================================================
+constexpr int DRAW_PASS = 2;          // draws a thread keeps in flight (they share one Philox call): every phase is
+                                      // batched over them so that its loads overlap -- the kernel is latency- and
+                                      // LSU-wavefront-bound, not ALU-bound (profiles/r01_draw_*.md)
+
+__device__ __forceinline__ int pad8(int i) { return i + ((i >> 3) << 1); }     // padded table index
+
+__device__ __forceinline__ void ldg256(const float* p, float v[8]) {
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void ldg256u(const uint32_t* p, uint32_t v[8]) {
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void red_add_f64(double* addr, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" :: "l"(addr), "d"(v) : "memory");
+}
+
+// (double)f for f >= 0 without the conversion (XU) pipe: rebias the exponent, shift the mantissa.
+// Zero and subnormal inputs take the real conversion (never on the hot path: p >= 2^-126 there).
+__device__ __forceinline__ double widen_pos(float f) {
+    const uint32_t b = __float_as_uint(f);
+    if ((b >> 23) == 0u) return (double)f;
+    return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+}
+
+// numpy's predicate fl64(x / total) > u, decided without dividing whenever x is outside a 2^-50 relative band
+// around t = fl(u * total):  x > t(1+2^-50)  =>  x/total > u(1+2^-51) >= nextafter(u)  => true;
+//                            x < t(1-2^-50)  =>  x/total < u                            => false.
+__device__ __forceinline__ bool cdf_exceeds(double x, double total, double u, double t_hi, double t_lo) {
+    if (x > t_hi) return true;
+    if (x < t_lo) return false;
+    return __ddiv_rn(x, total) > u;
+}
+
+// Exact continuation of a scan (rare: the approximate crossing was not the exact one, or inexact sums).
+__device__ __noinline__ int slow_exact_scan(const float* __restrict__ w, int start, int N, double cum, double total,
+                                            double u, int last, float* pout) {
+    for (int i = start; i < N; ++i) {
+        const float p = __ldcg(w + i);
+        if (p > 0.f) {
+            cum += (double)p;
+            last = i;
+            *pout = p;
+            if (__ddiv_rn(cum, total) > u) return i;
+        }
+    }
+    return last;
+}
+
+__global__ void __launch_bounds__(KD_THREADS, 1)
+ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const double* __restrict__ uniforms,
+                const Workspace ws, const ldp_outputs out, const SampleGeom G)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* pre = reinterpret_cast<double*>(smem_raw);                         // [pad8(nchunk_ept)] padded prefix
+    int* guide = reinterpret_cast<int*>(pre + G.draw_pre_cap);                 // [NG + 2]
+    unsigned long long* bins = reinterpret_cast<unsigned long long*>(smem_raw);   // coverage sort reuses the table
+    __shared__ K1Shared sh;
+
+    const int C = (int)cluster.num_blocks();
+    const int crank = (int)cluster.block_rank();
+    const int r = blockIdx.x / C;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int T = blockDim.x;
+    const int gtid = crank * T + tid, GT = C * T;
+    const int N = G.N;
+    const int nchunk = G.nchunk;
+    const int NG = G.draw_ng;
+    const ldp_ref_desc* rd = refs + r;
+
+    float* __restrict__ w = ws.w + (size_t)r * ws.n_pad;                 // holds p after the prep kernel
+    uint32_t* __restrict__ bitmap = ws.bitmap + (size_t)r * ws.n_words;
+    int32_t* __restrict__ flist = ws.found + ((size_t)r * ws.draw_cmax + crank) * ws.found_cap;
+    int32_t* __restrict__ fcnt = ws.fcnt + (size_t)r * ws.draw_cmax;
+    int32_t* __restrict__ sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
+    double* __restrict__ gcsum = ws.csum + (size_t)r * ws.nchunk_pad;
+    const unsigned long long* __restrict__ gb = ws.gbins + (size_t)r * ws.bins_cap;
+
     auto finish_empty = [&](int status) {
-        if (tid == 0) {
+        if (gtid == 0) {
             out.status[r] = status;
             out.n_samples[r] = 0;
             if (out.uniforms_used) out.uniforms_used[r] = 0;
             if (out.rounds) out.rounds[r] = 0;
         }
     };
-    if (nn <= 0) { finish_empty(LDP_REF_NO_NEIGHBOURS); return; }
+    LDP_CLK(ws, r, 0);
+    // every exit below is taken by all CTAs of the cluster alike (same inputs, same arithmetic)
+    const RefStat st = ws.rstat[r];
+    if (st.bad & 4) { finish_empty(LDP_REF_NO_NEIGHBOURS); return; }
+    if (st.bad & 1) { finish_empty(LDP_REF_BAD_WEIGHTS); return; }          // NaN: `s <= 0` is False, choice raises
+    if (!(st.s > 0.f)) { finish_empty(LDP_REF_EMPTY); return; }             // core/sampling.py:27-28
+    if (st.bad & 2) { finish_empty(LDP_REF_BAD_WEIGHTS); return; }
 
-    // ------------------------------------------------------------------ phase 1: stream certainties
-    const float cap = P.sample_cap;
-    const int W = P.W, H = P.H, border = P.border;
-    const int nquad = (N + 3) >> 2;
-    double lsum = 0.0;
-    int lbad = 0;
-    for (int q = tid; q < nquad; q += T) {
-        const int px = q << 2;
-        float best[4];
-        int bi[4] = {0, 0, 0, 0};
-        if (G.vec) {
-            float4 v = ld_stream4(s_cert[0] + px);
-            best[0] = v.x; best[1] = v.y; best[2] = v.z; best[3] = v.w;
-#pragma unroll 4
-            for (int k = 1; k < nn; ++k) {
-                const float4 c = ld_stream4(s_cert[k] + px);
-                if (c.x > best[0]) { best[0] = c.x; bi[0] = k; }
-                if (c.y > best[1]) { best[1] = c.y; bi[1] = k; }
-                if (c.z > best[2]) { best[2] = c.z; bi[2] = k; }
-                if (c.w > best[3]) { best[3] = c.w; bi[3] = k; }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) best[j] = (px + j < N) ? __ldcs(s_cert[0] + px + j) : 0.f;
-            for (int k = 1; k < nn; ++k) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float c = (px + j < N) ? __ldcs(s_cert[k] + px + j) : 0.f;
-                    if (c > best[j]) { best[j] = c; bi[j] = k; }
-                }
-            }
-        }
-        int y = px / W, x = px - y * W;
-        float wv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float c = (best[j] > cap) ? cap : best[j];          // torch.clamp(max=cap): NaN stays NaN
-            float m = 1.f;
-            if (!P.no_filter)
-                m = (x >= border && x <= W - 1 - border && y >= border && y <= H - 1 - border) ? 1.f : 0.f;
-            float v = c * m;
-            if (px + j >= N) v = 0.f;
-            wv[j] = v;
-            lbad |= (v != v) ? 1 : 0;
-            lbad |= (v < 0.f) ? 2 : 0;
-            lsum += (double)v;
-            if (++x == W) { x = 0; ++y; }
-        }
-        *reinterpret_cast<float4*>(w + px) = make_float4(wv[0], wv[1], wv[2], wv[3]);
-        *reinterpret_cast<uchar4*>(bk + px) = make_uchar4((unsigned char)bi[0], (unsigned char)bi[1],
-                                                          (unsigned char)bi[2], (unsigned char)bi[3]);
-    }
-    const double wsum64 = block_sum(lsum, sh.red_d);
-    const int bad = block_sum(lbad ? ((lbad & 1) | ((lbad & 2) << 15)) : 0, sh.red_i);   // low half: NaN count, high: negatives
-    if (P.no_filter) return;   // top-M selection is done by ldp_topm_kernel
+    for (int i = gtid; i < (int)ws.n_words; i += GT) bitmap[i] = 0u;
 
-    float s = (float)wsum64;
-    if (rd->weight_sum_override > 0.f) s = rd->weight_sum_override;
-    if (tid == 0 && out.weight_sum) out.weight_sum[r] = s;
-    if (bad & 0xffff) { finish_empty(LDP_REF_BAD_WEIGHTS); return; }       // NaN: `s <= 0` is False, choice raises
-    if (!(s > 0.f)) { finish_empty(LDP_REF_EMPTY); return; }               // core/sampling.py:27-28
-    if (bad >> 16) { finish_empty(LDP_REF_BAD_WEIGHTS); return; }
-
-    // ------------------------------------------------------------------ phase 2: chunk sums of p, tile arg-max
-    // (the workspace writes of phase 1 are visible after the barriers inside block_sum)
     const int cs = G.chunk_shift;
-    const int gl = min(32, (1 << cs) >> 2);            // lanes that share one chunk
-    double ltot = 0.0;
-    int lpos = 0;
-    int lemin = 0x7fffffff;
-    const int nunit = (N + 127) >> 7;                  // 128 pixels per warp-iteration
-    for (int u = (tid >> 5); u < nunit; u += (T >> 5)) {
-        const int px = (u << 7) + (lane << 2);
-        double a = 0.0;
-        if (px < N) {
-            const float4 v = *reinterpret_cast<const float4*>(w + px);
-            const float wv[4] = {v.x, v.y, v.z, v.w};
-            int y = px / W, x = px - y * W;
+    const int size = G.size;
+    const int EPT = G.draw_ept;                     // table entries per thread (multiple of 8)
+    int n_have = 0, drawn = 0, rounds = 0, fail = 0, inexact = 0;
+    const double* U = uniforms ? uniforms + (size_t)r * (size_t)P.uniforms_per_ref : nullptr;
+    const uint32_t rng_stream = rd->rng_stream;
+
+    while (true) {
+        // ---- (a) padded inclusive prefix of the global chunk sums: 8-entry rows per thread, one block scan
+        if (tid == 0) sh.n_found = 0;
+        double run = 0.0;
+        const int e0 = tid * EPT;
+        for (int q = 0; q < EPT; q += 8) {
+            const int i0 = e0 + q;
+            double v[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float p = __fdiv_rn(wv[j], s);                     // core/sampling.py:29 (f32 division)
-                if (p > 0.f) {
-                    a += (double)p;
-                    ++lpos;
-                    const int e = (int)((__float_as_uint(p) >> 23) & 0xffu);
-                    lemin = min(lemin, e);
-                    const int b = (x / G.tile) * G.nby + (y / G.tile);
-                    const unsigned long long key = cov_key(p, px + j);
-                    if (bins[b] < key) atomicMax(&bins[b], key);
-                }
-                if (++x == W) { x = 0; ++y; }
+            for (int j = 0; j < 8; j += 2) {
+                double2 d = make_double2(0.0, 0.0);
+                if (i0 + j < nchunk) d = __ldcg(reinterpret_cast<const double2*>(gcsum + i0 + j));   // nchunk_pad is even
+                v[j] = d.x;
+                v[j + 1] = (i0 + j + 1 < nchunk) ? d.y : 0.0;
+            }
+            if (i0 < nchunk) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { run += v[j]; v[j] = run; }
+                double2* dst = reinterpret_cast<double2*>(pre + pad8(i0));
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) dst[j >> 1] = make_double2(v[j], v[j + 1]);
             }
         }
-        ltot += a;
-        for (int o = 1; o < gl; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (px < N && (lane & (gl - 1)) == 0) {
-            if (cs <= 7) csum[px >> cs] = a;
-            else atomicAdd(&csum[px >> cs], a);
+        double total;
+        const double base = block_exclusive_scan(run, sh.red_d, &total);
+        for (int q = 0; q < EPT; q += 8) {
+            const int i0 = e0 + q;
+            if (i0 < nchunk) {
+                double2* dst = reinterpret_cast<double2*>(pre + pad8(i0));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { double2 d = dst[j]; d.x += base; d.y += base; dst[j] = d; }
+            }
         }
-    }
-    const double ptotal = block_sum(ltot, sh.red_d);
-    const int npos = block_sum(lpos, sh.red_i);
-    const int emin = block_min(lemin, sh.red_i);
-    // numpy's checks in RandomState.choice, in numpy's order
-    if (fabs(ptotal - 1.0) > 3.4526698300124393e-4) { finish_empty(LDP_REF_PSUM); return; }
-    if (npos < G.size) { finish_empty(LDP_REF_FEWER_NONZERO); return; }
-    // exactness of every f64 partial sum: all p are multiples of 2^(emin-150) and the total stays below
-    // 2^53 of those units  <=>  ilogb(total) - (emin - 150) < 53
-    int inexact = 0;
-    if (npos > 0) {
-        const int etot = ilogb(ptotal);
-        if (emin == 0 || etot - (emin - 150) >= 53) inexact = 1;
-    }
-
-    // ------------------------------------------------------------------ rejection rounds (numpy legacy choice)
-    const int size = G.size;
-    int n_have = 0;
-    int drawn = 0;
-    int rounds = 0;
-    const double* U = uniforms ? uniforms + (size_t)r * (size_t)P.uniforms_per_ref : nullptr;
-    const int L = (G.nchunk + T - 1) / T;
-    const int seg0 = min(tid * L, G.nchunk), seg1 = min(seg0 + L, G.nchunk);
-    int fail = 0;
-    while (n_have < size) {
+        for (int i = tid; i < NG + 2; i += T) guide[i] = nchunk - 1;
+        __syncthreads();
+        total = pre[pad8(nchunk - 1)];
+        if (rounds == 0) {
+            // numpy's checks in RandomState.choice, in numpy's order
+            if (fabs(total - 1.0) > 3.4526698300124393e-4) { fail = LDP_REF_PSUM; break; }
+            if (st.npos < size) { fail = LDP_REF_FEWER_NONZERO; break; }
+            // exactness of every f64 partial sum: all p are multiples of 2^(emin-150) and the total stays below
+            // 2^53 of those units  <=>  ilogb(total) - (emin - 150) < 53
+            if (st.npos > 0) {
+                const int etot = ilogb(total);
+                if (st.emin == 0 || etot - (st.emin - 150) >= 53) inexact = 1;
+            }
+            if (C > 1) cluster.sync();                 // bitmap is zero everywhere before anybody sets a bit
+        }
+        if (n_have >= size) break;
         const int cnt = size - n_have;
         if (P.rng_mode == LDP_RNG_EXPLICIT && (int64_t)drawn + cnt > P.uniforms_per_ref) { fail = LDP_REF_UNIFORMS_EXHAUSTED; break; }
         if (rounds >= 64) { fail = LDP_REF_ROUNDS_EXCEEDED; break; }
-        // (a) in-place inclusive prefix of the chunk sums
-        double loc = 0.0;
-        for (int i = seg0; i < seg1; ++i) loc += csum[i];
-        double total;
-        double run = block_exclusive_scan(loc, sh.red_d, &total);
-        for (int i = seg0; i < seg1; ++i) { run += csum[i]; csum[i] = run; }
-        __syncthreads();
-        total = csum[G.nchunk - 1];
-        // (b) draws
-        for (int d = tid; d < cnt; d += T) {
-            const double u = (P.rng_mode == LDP_RNG_EXPLICIT) ? U[drawn + d]
-                                                              : philox_uniform(P.seed, rd->rng_stream, (uint32_t)(drawn + d));
-            const double t = u * total;
-            int lo = 0, hi = G.nchunk - 1;               // first chunk with prefix > t (approximate)
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (csum[mid] > t) hi = mid; else lo = mid + 1;
+        // ---- (a') guide table: guide[k] ~ first chunk whose prefix reaches (k / NG) * total.  It only has to be
+        //      approximately right: the exact fix-up after the search walks to numpy's chunk from any start.
+        {
+            const double ngt = (double)NG / total;
+            int kprev = (e0 > 0 && e0 <= nchunk) ? min(NG, (int)(pre[pad8(e0 - 1)] * ngt)) : -1;
+            for (int q = 0; q < EPT; ++q) {
+                const int c = e0 + q;
+                if (c < nchunk) {
+                    int kc = min(NG, (int)(pre[pad8(c)] * ngt));
+                    if (c == nchunk - 1) kc = NG + 1;
+                    for (int k = kprev + 1; k <= kc; ++k) guide[k] = c;
+                    kprev = max(kprev, kc);
+                }
             }
-            int c = lo;
-            // exact predicate of searchsorted(cdf, u, 'right'): fl(prefix / total) > u
-            while (c > 0 && __ddiv_rn(csum[c - 1], total) > u) --c;
-            while (c < G.nchunk - 1 && !(__ddiv_rn(csum[c], total) > u)) ++c;
-            const double tlo = t * (1.0 - 1.0 / 1125899906842624.0);
-            double cum = (c > 0) ? csum[c - 1] : 0.0;
-            int idx = -1, last = -1;
-            for (; c < G.nchunk && idx < 0; ++c) {
-                const int p0 = c << cs, p1 = min(p0 + (1 << cs), N);
-                for (int b = p0; b < p1 && idx < 0; b += 32) {
-                    float4 v[8];
+        }
+        __syncthreads();
+        if (rounds == 0) LDP_CLK(ws, r, 3);
+        // ---- (b) draws: each thread takes DRAW_PASS (=2) consecutive draws per pass (one Philox call)
+        const int pieces = max(1, (1 << cs) >> 3);
+        constexpr double EPS_UP = 1.0 + 1.0 / 1125899906842624.0, EPS_DN = 1.0 - 1.0 / 1125899906842624.0;
+        for (int dw = 2 * (gtid - lane); dw < cnt; dw += 2 * GT) {      // warp-uniform trip count (ballots inside)
+            const int d0 = dw + 2 * lane;
+            double uu[2], tt[2], cum[2];
+            int lo[2], hi[2], ii[2];
+            float hp[2];
+            bool valid[2], hit[2];
+            // 1. uniforms + guide lookups
+            valid[0] = d0 < cnt;
+            valid[1] = d0 + 1 < cnt;
+            if (P.rng_mode == LDP_RNG_EXPLICIT) {
+                uu[0] = valid[0] ? U[drawn + d0] : 0.5;
+                uu[1] = valid[1] ? U[drawn + d0 + 1] : 0.5;
+            } else if (((drawn + d0) & 1) == 0) {
+                philox_uniform2(P.seed, rng_stream, (uint32_t)(drawn + d0), uu);
+            } else {
+                uu[0] = philox_uniform(P.seed, rng_stream, (uint32_t)(drawn + d0));
+                uu[1] = philox_uniform(P.seed, rng_stream, (uint32_t)(drawn + d0 + 1));
+            }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        v[j] = (b + 4 * j < p1) ? *reinterpret_cast<const float4*>(w + b + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < 2; ++k) {
+                tt[k] = uu[k] * total;
+                const int kb = min(NG - 1, (int)(uu[k] * (double)NG));
+                lo[k] = guide[kb];
+                hi[k] = max(lo[k], guide[kb + 1]);
+            }
+            // 2. lock-step binary search inside the guide ranges: first chunk with prefix > u * total (approximate)
+            for (;;) {
+                bool more = false;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float e4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                for (int k = 0; k < 2; ++k) {
+                    if (lo[k] < hi[k]) {
+                        const int mid = (lo[k] + hi[k]) >> 1;
+                        if (pre[pad8(mid)] > tt[k]) hi[k] = mid; else lo[k] = mid + 1;
+                        more |= lo[k] < hi[k];
+                    }
+                }
+                if (!more) break;
+            }
+            // 3. exact predicate of searchsorted(cdf, u, 'right') on the chunk boundaries
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            if (idx < 0 && e4[m] > 0.f) {
-                                const float p = __fdiv_rn(e4[m], s);
-                                if (p > 0.f) {
-                                    cum += (double)p;
-                                    last = b + 4 * j + m;
-                                    if (cum > tlo && __ddiv_rn(cum, total) > u) idx = last;
-                                }
-                            }
+            for (int k = 0; k < 2; ++k) {
+                int c = lo[k];
+                const double thi = tt[k] * EPS_UP, tlo = tt[k] * EPS_DN;
+                double below = (c > 0) ? pre[pad8(c - 1)] : 0.0;
+                const double here = pre[pad8(c)];
+                const bool down = (c > 0) && cdf_exceeds(below, total, uu[k], thi, tlo);
+                const bool up = (c < nchunk - 1) && !cdf_exceeds(here, total, uu[k], thi, tlo);
+                if (down || up) {                             // rare: walk to the exact chunk
+                    while (c > 0 && cdf_exceeds(pre[pad8(c - 1)], total, uu[k], thi, tlo)) --c;
+                    while (c < nchunk - 1 && !cdf_exceeds(pre[pad8(c)], total, uu[k], thi, tlo)) ++c;
+                    below = (c > 0) ? pre[pad8(c - 1)] : 0.0;
+                }
+                lo[k] = c;
+                cum[k] = below;
+                hit[k] = !valid[k];
+                ii[k] = -1;
+                hp[k] = 0.f;
+            }
+            // 4. in-chunk scans: one 32-byte piece per draw per step, both loads in flight together
+            for (int pc = 0; pc < pieces; ++pc) {
+                if (!__any_sync(0xffffffffu, !hit[0] || !hit[1])) break;
+                float e[2][8];
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    if (!hit[k]) ldg256(w + (lo[k] << cs) + (pc << 3), e[k]);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (!hit[k]) {
+                        const double tlo = tt[k] * EPS_DN;
+                        const int b = (lo[k] << cs) + (pc << 3);
+                        double run = cum[k];
+                        int first = -1;
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) {          // padding beyond N is zero (stream kernel), p >= 0
+                            run += widen_pos(e[k][m]);
+                            if (first < 0 && run > tlo && e[k][m] > 0.f) { first = m; cum[k] = run; hp[k] = e[k][m]; }
                         }
+                        if (first >= 0) { hit[k] = true; ii[k] = b + first; }
+                        else cum[k] = run;
                     }
                 }
             }
-            if (idx < 0) idx = last;                     // only reachable when sums are inexact
-            if (idx >= 0) {
-                const uint32_t bit = 1u << (idx & 31);
-                const uint32_t old = atomicOr(&bitmap[idx >> 5], bit);
-                if (!(old & bit)) {
-                    const int pos = atomicAdd(&sh.n_found, 1);
-                    found[pos] = idx;
+            // 5. numpy's exact comparison at the approximate crossing (slow exact continuation otherwise)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (valid[k]) {
+                    const double thi = tt[k] * EPS_UP, tlo = tt[k] * EPS_DN;
+                    if (ii[k] >= 0) {
+                        if (!cdf_exceeds(cum[k], total, uu[k], thi, tlo))
+                            ii[k] = slow_exact_scan(w, ii[k] + 1, N, cum[k], total, uu[k], ii[k], &hp[k]);
+                    } else {
+                        ii[k] = slow_exact_scan(w, min(N, (lo[k] + 1) << cs), N, cum[k], total, uu[k], -1, &hp[k]);
+                    }
+                }
+            }
+            // 6. dedupe (both atomics in flight together), then warp-aggregated append + mass removal
+            uint32_t old[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                old[k] = (ii[k] >= 0) ? atomicOr(&bitmap[ii[k] >> 5], 1u << (ii[k] & 31)) : 0xffffffffu;
+            // two draws of one thread may hit the same pixel: the second is then not fresh
+            const bool fresh0 = ii[0] >= 0 && !(old[0] & (1u << (ii[0] & 31)));
+            const bool fresh1 = ii[1] >= 0 && !(old[1] & (1u << (ii[1] & 31)));
+            const unsigned fm0 = __ballot_sync(0xffffffffu, fresh0), fm1 = __ballot_sync(0xffffffffu, fresh1);
+            if (fm0 | fm1) {
+                const int n0 = __popc(fm0), n1 = __popc(fm1);
+                int basepos = 0;
+                if (lane == 0) basepos = atomicAdd(&sh.n_found, n0 + n1);
+                basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                const unsigned below_mask = (1u << lane) - 1u;
+                if (fresh0) {
+                    flist[basepos + __popc(fm0 & below_mask)] = ii[0];
+                    red_add_f64(gcsum + (ii[0] >> cs), -widen_pos(hp[0]));      // the found mass leaves the chunk sum
+                }
+                if (fresh1) {
+                    flist[basepos + n0 + __popc(fm1 & below_mask)] = ii[1];
+                    red_add_f64(gcsum + (ii[1] >> cs), -widen_pos(hp[1]));
                 }
             }
         }
         __syncthreads();
-        const int n_now = sh.n_found;
+        if (rounds == 0) LDP_CLK(ws, r, 4);
+        const int my_new = sh.n_found;
+        if (tid == 0) fcnt[crank] = my_new;
+        if (C > 1) cluster.sync(); else __syncthreads();          // B1: every draw of the round is done and published
+        if (rounds == 0) LDP_CLK(ws, r, 6);
+        int n_new = 0;
+        for (int c2 = 0; c2 < C; ++c2) n_new += (C > 1) ? __ldcg(fcnt + c2) : my_new;
         drawn += cnt;
         ++rounds;
-        // (c) back to chunk sums (adjacent difference, in place), remove the found mass, zero the weights
-        double prev = (seg0 > 0 && seg0 < G.nchunk) ? csum[seg0 - 1] : 0.0;
-        __syncthreads();
-        for (int i = seg1 - 1; i >= seg0; --i) {
-            const double below = (i > seg0) ? csum[i - 1] : prev;
-            csum[i] = csum[i] - below;
+        n_have += n_new;
+        if (n_have >= size) break;                        // done
+        for (int e0z = 0; e0z < my_new; e0z += 8 * T) {                           // the finder zeroes its p
+            int zi[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const int e = e0z + j * T + tid; zi[j] = (e < my_new) ? flist[e] : -1; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (zi[j] >= 0) w[zi[j]] = 0.f;
         }
-        __syncthreads();
-        for (int e = n_have + tid; e < n_now; e += T) {
-            const int idx = found[e];
-            const float p = __fdiv_rn(w[idx], s);
-            atomicAdd(&csum[idx >> cs], -(double)p);
-            w[idx] = 0.f;
-        }
-        __threadfence_block();
-        __syncthreads();
-        n_have = n_now;
+        if (rounds == 1) LDP_CLK(ws, r, 7);
+        if (C > 1) cluster.sync(); else __syncthreads();          // B2: zeroed p and reduced chunk sums are visible
     }
+    LDP_CLK(ws, r, 8);
     if (fail) { finish_empty(fail); return; }
+    if (crank != 0) return;                               // the rest is cheap: CTA 0 alone (no cluster barrier below)
+    __syncthreads();
 
     // ------------------------------------------------------------------ coverage picks (core/sampling.py:34-50)
     {
         int lp = 0;
-        for (int i = tid; i < G.nbins; i += T) lp += (bins[i] != 0ull) ? 1 : 0;
+        for (int i = tid; i < G.nbins; i += T) lp += (gb[i] != 0ull) ? 1 : 0;
         const int nb_pos = block_sum(lp, sh.red_i);
         if (nb_pos > G.cov_budget) {          // budget binds: keep the cov_budget best tiles (descending weight)
+            int nb_pow2 = 1;
+            while (nb_pow2 < G.nbins) nb_pow2 <<= 1;
+            for (int i = tid; i < nb_pow2; i += T) bins[i] = (i < G.nbins) ? gb[i] : 0ull;
+            __syncthreads();
             bitonic_sort_desc(bins, nb_pow2);
-        }
-        const int take = min(nb_pos, G.cov_budget);
-        const int lim = (nb_pos > G.cov_budget) ? take : G.nbins;
-        for (int i = tid; i < lim; i += T) {
-            const unsigned long long key = bins[i];
-            if (key != 0ull) {
-                const int idx = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
-                atomicOr(&bitmap[idx >> 5], 1u << (idx & 31));
+            for (int i = tid; i < G.cov_budget; i += T) {
+                const unsigned long long key = bins[i];
+                if (key != 0ull) {
+                    const int idx = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+                    atomicOr(&bitmap[idx >> 5], 1u << (idx & 31));
+                }
+            }
+        } else {
+            for (int i = tid; i < G.nbins; i += T) {
+                const unsigned long long key = gb[i];
+                if (key != 0ull) {
+                    const int idx = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+                    atomicOr(&bitmap[idx >> 5], 1u << (idx & 31));
+                }
             }
         }
+        __threadfence_block();
         __syncthreads();
     }
+    LDP_CLK(ws, r, 9);
 
     // ------------------------------------------------------------------ ordered compaction == np.unique(concat)
     {
-        const int nwords = (N + 31) >> 5;
-        const int Lw = (nwords + T - 1) / T;
-        const int w0 = min(tid * Lw, nwords), w1 = min(w0 + Lw, nwords);
-        int cntb = 0;
-        for (int i = w0; i < w1; ++i) cntb += __popc(bitmap[i]);
-        int totalS;
-        int pos = block_exclusive_scan(cntb, sh.red_i, &totalS);
-        for (int i = w0; i < w1; ++i) {
-            uint32_t m = bitmap[i];
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                if (pos < (int)ws.sel_cap) sel[pos] = (i << 5) + b;
-                ++pos;
+        const int nwords = (int)ws.n_words;                    // multiple of 8 (n_pad is a multiple of 256)
+        int carry = 0;
+        for (int t0 = 0; t0 < nwords; t0 += T * 8) {
+            const int w0 = t0 + tid * 8;
+            uint32_t m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (w0 < nwords) ldg256u(bitmap + w0, m);
+            int cntb = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cntb += __popc(m[j]);
+            int tile_total;
+            int pos = carry + block_exclusive_scan(cntb, sh.red_i, &tile_total);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t mm = m[j];
+                while (mm) {
+                    const int b = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    if (pos < (int)ws.sel_cap) sel[pos] = ((w0 + j) << 5) + b;
+                    ++pos;
+                }
             }
+            carry += tile_total;
         }
+        LDP_CLK(ws, r, 10);
         if (tid == 0) {
             out.status[r] = LDP_REF_OK | (inexact ? LDP_REF_INEXACT_SCAN : 0);
-            out.n_samples[r] = min(totalS, (int)ws.sel_cap);
+            out.n_samples[r] = min(carry, (int)ws.sel_cap);
             if (out.uniforms_used) out.uniforms_used[r] = drawn;
             if (out.rounds) out.rounds[r] = rounds;
         }

@@ -194,3 +194,27 @@ def test_drop_in_triangulate_ref_numpy_global_stream(engine):
             np.testing.assert_allclose(tri.rgb, res.rgb, rtol=G.XYZ_RTOL, atol=G.XYZ_ATOL)
             assert list(tri.debug_matches_by_nbr.keys()) == list(res.debug_matches_by_nbr.keys())
     assert after == rs.random_sample(), "global MT19937 stream position must match the reference's"
+
+
+def test_cluster_size_does_not_change_results(engine, fast_scene):
+    """The draw kernel runs as a thread-block cluster per view; any cluster size gives identical samples."""
+    scene, inputs = fast_scene
+    c = dict(M=10000, no_filter=False, wm=scene.w_match, hm=scene.h_match)
+    lib = engine.lib
+    base = None
+    used = []
+    try:
+        for cs in (1, 2, 3, 4, 5, 8):
+            assert lib.ldp_debug_set_cluster(cs) == 0
+            g = G.run_gpu(engine, scene, inputs[:3], G.path_cfg(c, seed=3))
+            used.append(lib.ldp_debug_last_cluster())
+            if base is None:
+                base = g
+                continue
+            for r in range(3):
+                assert np.array_equal(base.sel_idx[r], g.sel_idx[r]), (cs, r)
+                assert np.array_equal(base.xyz[r], g.xyz[r]) and base.uniforms_used[r] == g.uniforms_used[r]
+    finally:
+        lib.ldp_debug_set_cluster(0)
+    print("cluster sizes actually launched:", used)
+    assert used[0] == 1 and max(used) >= 2
