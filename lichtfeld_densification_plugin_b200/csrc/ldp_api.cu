@@ -1,6 +1,8 @@
 // C ABI of the densification path (include/ldp_b200.h).  Unity build: the kernels live in the two
 // included translation units; this file carves the workspace, picks launch geometry and enqueues.
 #include <cstdio>
+#include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <string>
 
@@ -92,6 +94,7 @@ struct Plan {
     size_t bytes;
     size_t k1_smem;
     size_t prep_smem;
+    int nb2;
 };
 
 int64_t sel_capacity(int32_t M) {
@@ -186,6 +189,13 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     w.rstat = reinterpret_cast<ldp::RefStat*>(carve(R * sizeof(ldp::RefStat)));
     w.gbins = reinterpret_cast<unsigned long long*>(carve(R * w.bins_cap * sizeof(unsigned long long)));
     w.dbgclk = reinterpret_cast<long long*>(carve(R * 32 * sizeof(long long)));
+    plan->nb2 = (int)((w.sel_cap + ldp::K2_THREADS - 1) / ldp::K2_THREADS);
+    w.blk_cnt = reinterpret_cast<int32_t*>(carve(R * plan->nb2 * LDP_MAX_NN * sizeof(int32_t)));
+    w.blk_first = reinterpret_cast<int32_t*>(carve(R * plan->nb2 * LDP_MAX_NN * sizeof(int32_t)));
+    w.blk_before = reinterpret_cast<int32_t*>(carve(R * plan->nb2 * LDP_MAX_NN * sizeof(int32_t)));
+    w.grp_base = reinterpret_cast<int32_t*>(carve(R * LDP_MAX_NN * sizeof(int32_t)));
+    w.fix_list = reinterpret_cast<int2*>(carve(R * w.sel_cap * sizeof(int2)));
+    w.fix_count = reinterpret_cast<int32_t*>(carve(sizeof(int32_t)));
     plan->bytes = off;
     return LDP_OK;
 }
@@ -270,19 +280,54 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     return LDP_OK;
 }
 
+// Largest f32 cosine d for which the reference's parallax test passes, i.e. for which
+// f32(arccos(d)) * f32(180/pi) >= min_deg in float32 (core/geometry.py:118-119, arccos correctly rounded).
+// arccos is monotone, so `angle >= min_deg` is `d <= threshold`: the kernel compares cosines and never calls acos.
+float parallax_cos_threshold(float min_deg) {
+    auto pred = [&](float d) {
+        const float a = (float)acos((double)d);
+        const float ang = a * 57.2957763671875f;
+        return ang >= min_deg;
+    };
+    auto ord = [](float f) { uint32_t b; memcpy(&b, &f, 4); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); };
+    auto unord = [](uint32_t k) { uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k; float f; memcpy(&f, &b, 4); return f; };
+    if (!pred(-1.0f)) return -2.0f;
+    if (pred(1.0f)) return 1.0f;
+    uint32_t lo = ord(-1.0f), hi = ord(1.0f);           // pred(lo) true, pred(hi) false
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (pred(unord(mid))) lo = mid; else hi = mid;
+    }
+    return unord(lo);
+}
+
 int launch_geometry(const ldp_params* p, const ldp_ref_desc* refs, const ldp_outputs* out, Plan& plan,
                     int have_bestk, cudaStream_t st) {
-    dim3 grid((unsigned)((plan.ws.sel_cap + ldp::K2_THREADS - 1) / ldp::K2_THREADS), (unsigned)p->n_refs);
+    static float cached_deg = -1.f, cached_cos = 1.f;
+    if (p->min_parallax_deg != cached_deg) { cached_cos = parallax_cos_threshold(p->min_parallax_deg); cached_deg = p->min_parallax_deg; }
+    ldp::GeomArgs ga;
+    ga.par_cos_max = cached_cos;
+    ga.have_bestk = have_bestk;
+    ga.nb2 = plan.nb2;
+    const dim3 grid((unsigned)plan.nb2, (unsigned)p->n_refs);
+    const dim3 ggrid((unsigned)((plan.ws.sel_cap + ldp::KG_THREADS - 1) / ldp::KG_THREADS), (unsigned)p->n_refs);
+    cudaError_t e;
+    { KernelTimer kt(st, "ldp_gather_kernel");
+      ldp::ldp_gather_kernel<<<ggrid, ldp::KG_THREADS, 0, st>>>(*p, refs, plan.ws, *out, ga); }
+    ++g_launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_gather_kernel");
     { KernelTimer kt(st, "ldp_geometry_kernel");
-      ldp::ldp_geometry_kernel<<<grid, ldp::K2_THREADS, 0, st>>>(*p, refs, plan.ws, *out, have_bestk); }
+      ldp::ldp_geometry_kernel<<<grid, ldp::K2_THREADS, 0, st>>>(*p, refs, plan.ws, *out, ga); }
     ++g_launches;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "ldp_geometry_kernel");
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_geometry_kernel");
+    { KernelTimer kt(st, "ldp_fixplan_kernel");
+      ldp::ldp_fixplan_kernel<<<p->n_refs, ldp::K2_THREADS, (size_t)plan.nb2 * LDP_MAX_NN * 2 * sizeof(int), st>>>(*p, refs, plan.ws, *out, ga); }
+    ++g_launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_fixplan_kernel");
     { KernelTimer kt(st, "ldp_pack_kernel");
-      ldp::ldp_pack_kernel<<<p->n_refs, ldp::K3_THREADS, 0, st>>>(*p, refs, plan.ws, *out); }
+      ldp::ldp_pack_kernel<<<grid, ldp::K3_THREADS, 0, st>>>(*p, refs, plan.ws, *out, ga); }
     ++g_launches;
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "ldp_pack_kernel");
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_pack_kernel");
     return LDP_OK;
 }
 
@@ -355,6 +400,49 @@ int ldp_workspace_bytes(const ldp_params* params, size_t* bytes_out) {
 // cannot guarantee it set params->reserved0 = 1 to force the scalar load path.
 static int vec_ok_for(const ldp_params* p) { return (p->W % 4 == 0 && p->reserved0 == 0) ? 1 : 0; }
 
+// L2 residency for the inter-kernel workspace (weights / p, winning neighbour, sample records): the path re-reads
+// them from several kernels of the same call while ~0.2 GB of certainty planes stream through the 126 MB L2.
+// An access-policy window marks the hot prefix of the workspace as persisting for the kernels of this call.
+struct L2Window {
+    cudaStream_t st;
+    bool active;
+    L2Window(cudaStream_t s, void* base, size_t bytes) : st(s), active(false) {
+        static int mode = -1;          // -1 unknown, 0 off, 1 on
+        static size_t max_window = 0, persist_bytes = 0;
+        if (mode < 0) {
+            const char* env = getenv("LDP_L2_PERSIST");
+            mode = (env && env[0] == '1') ? 1 : 0;
+            if (mode) {
+                int dev = 0;
+                cudaDeviceProp prop;
+                if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess ||
+                    prop.persistingL2CacheMaxSize <= 0) { mode = 0; }
+                else {
+                    persist_bytes = (size_t)prop.persistingL2CacheMaxSize;
+                    max_window = (size_t)prop.accessPolicyMaxWindowSize;
+                    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist_bytes) != cudaSuccess) { (void)cudaGetLastError(); mode = 0; }
+                }
+            }
+        }
+        if (mode != 1 || bytes == 0) return;
+        cudaStreamAttrValue v = {};
+        v.accessPolicyWindow.base_ptr = base;
+        v.accessPolicyWindow.num_bytes = bytes < max_window ? bytes : max_window;
+        const double ratio = (double)persist_bytes / (double)v.accessPolicyWindow.num_bytes;
+        v.accessPolicyWindow.hitRatio = ratio >= 1.0 ? 1.0f : (float)ratio;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess) active = true;
+        else (void)cudaGetLastError();
+    }
+    ~L2Window() {
+        if (!active) return;
+        cudaStreamAttrValue v = {};
+        v.accessPolicyWindow.num_bytes = 0;
+        (void)cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+    }
+};
+
 int ldp_densify_refs(const ldp_params* params, const ldp_ref_desc* refs, const double* uniforms,
                      const ldp_outputs* out, void* workspace, size_t workspace_bytes, void* stream) {
     g_launches = 0;
@@ -371,6 +459,8 @@ int ldp_densify_refs(const ldp_params* params, const ldp_ref_desc* refs, const d
     if (rc != LDP_OK) return rc;
     if (plan.bytes + (size_t)(base - static_cast<char*>(workspace)) > workspace_bytes) return fail(LDP_ERR_WORKSPACE, "workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // hot prefix of the workspace: w/p and winning-neighbour planes (carved first)
+    L2Window l2(st, plan.ws.w, (size_t)params->n_refs * plan.ws.n_pad * 5);
     rc = launch_sample(params, refs, uniforms, out, plan, vec_ok_for(params), st);
     if (rc != LDP_OK) return rc;
     return launch_geometry(params, refs, out, plan, 1, st);
@@ -410,6 +500,8 @@ int ldp_triangulate_samples(const ldp_params* params, const ldp_ref_desc* refs, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaMemsetAsync(plan.ws.kept, 0, (size_t)params->n_refs * sizeof(int32_t), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(kept)");
+    e = cudaMemsetAsync(plan.ws.fix_count, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(fix_count)");
     return launch_geometry(params, refs, out, plan, 0, st);
 }
 

@@ -36,6 +36,12 @@ struct Workspace {
     int32_t* bflags;     // [R][nblk]    per-CTA NaN / negative flags
     RefStat* rstat;      // [R]
     unsigned long long* gbins;      // [R][bins_cap] per-tile arg-max keys (p bits << 32 | ~index)
+    int32_t* blk_cnt;    // [R][nb2][LDP_MAX_NN] kept samples per 128-sample tile and group (geometry -> pack)
+    int32_t* blk_first;  // [R][nb2][LDP_MAX_NN] first sample position per tile and group
+    int32_t* blk_before; // [R][nb2][LDP_MAX_NN] kept samples of the group in earlier tiles of the view (pack plan)
+    int32_t* grp_base;   // [R][LDP_MAX_NN] output offset of each group inside the view (pack plan)
+    int2* fix_list;      // [R*sel_cap] (view, sample) pairs whose null-vector iteration did not converge
+    int32_t* fix_count;  // [1]
     long long* dbgclk;   // [R][32] phase timestamps of the draw kernel (written only with -DLDP_PHASE_CLOCKS)
     size_t n_pad, n_words, found_cap, sel_cap, topk_cap, nchunk_pad, nblk, bins_cap, draw_cmax;
 };

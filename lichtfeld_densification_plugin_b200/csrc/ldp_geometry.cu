@@ -1,6 +1,9 @@
-// K2: per-sample decode -> colour -> Sampson gate -> DLT triangulation -> reprojection / cheirality /
-//     parallax filters.  One thread per sampled pixel, grid = (sample tiles, reference views).
-// K3: ordered stream compaction of the kept samples into the packed point cloud.
+// K2 geometry: per-sample decode -> colour -> Sampson gate -> DLT triangulation -> reprojection / cheirality /
+//              parallax filters.  One thread per sampled pixel, grid = (128-sample tiles, reference views).
+// K2b fix-up : the few samples whose null-vector iteration did not converge (grossly inconsistent matches)
+//              are re-evaluated with a Jacobi eigen-solver from a device-side worklist.
+// K3 pack    : ordered stream compaction of the kept samples into the packed point cloud, fully parallel
+//              (grid = tiles x views) from per-tile group counts written by K2.
 //
 // Replaces reference core/pipeline.py:652-780 and core/geometry.py:58-141 (see the per-step citations).
 // Arithmetic mirrors the reference's dtype flow and operation order:
@@ -8,15 +11,21 @@
 //     except where the reference's sgemm uses one (the 4-term projection dot products);
 //   * Sampson distance and the bilinear colour weights in f64;
 //   * the 4x4 null vector: the reference calls LAPACK's f32 SVD; here it is the eigenvector of the
-//     smallest eigenvalue of A^T A by shifted inverse iteration in f64 (both sit ~1e-7 relative from the
-//     exact singular vector of the same f32 matrix; tolerance 1e-4 rel / 1e-5 abs).
+//     smallest eigenvalue of A^T A in f64 (shifted inverse iteration; Jacobi fallback) -- both sit ~1e-7
+//     relative from the exact singular vector of the same f32 matrix; tolerance 1e-4 rel / 1e-5 abs.
+//   * threshold comparisons that the reference makes on a quotient or on arccos are made division-free /
+//     arccos-free where a rigorous bound decides them, and exactly otherwise (same verdicts).
 // Per-pair camera constants (P1,P2,C1,C2,F, pixel scales, group ids) are staged in shared memory.
 #include "ldp_device.cuh"
 
 namespace ldp {
 
 constexpr int K2_THREADS = 128;
-constexpr int K3_THREADS = 1024;
+#ifndef K2_MIN_BLOCKS
+#define K2_MIN_BLOCKS 6
+#endif
+constexpr int K3_THREADS = 128;
+constexpr int KFIX_BLOCKS = 148;
 // np.degrees on float32 multiplies by f32(180) / f32(pi) evaluated in f32 (measured)
 #define RAD2DEG_F32 57.295776367187500f
 
@@ -36,11 +45,31 @@ struct RefConst {
     int img_w, img_h, nn;
     const uint8_t* image;
 };
+struct GeomArgs {           // launch-constant extras computed on the host
+    float par_cos_max;      // parallax: keep iff clip(cos) <= par_cos_max  (== f32 arccos/degrees test, see ldp_api.cu)
+    int have_bestk;
+    int nb2;                // 128-sample tiles per view
+};
 
-// Robust fallback: cyclic Jacobi eigen-decomposition of the symmetric 4x4 M (f64); returns the eigenvector
-// of the smallest eigenvalue.  Only reached when inverse iteration has not converged (sigma_4 ~ sigma_3:
-// grossly inconsistent matches), so it is kept out of line to protect the fast path's register budget.
-__device__ __noinline__ void jacobi_smallest_eigvec4(const double* __restrict__ Min, double* __restrict__ vout) {
+__device__ __forceinline__ void stage_constants(const ldp_ref_desc* rd, RefConst& rc, PairConst* pc, int t, int nt) {
+    if (t < 12) rc.P1[t] = rd->P1[t];
+    if (t < 3) rc.C1[t] = rd->C1[t];
+    if (t == 0) {
+        rc.sxA = rd->sxA; rc.syA = rd->syA; rc.sx_img = rd->sx_img; rc.sy_img = rd->sy_img;
+        rc.img_w = rd->img_w; rc.img_h = rd->img_h; rc.nn = rd->nn; rc.image = rd->image;
+    }
+    const int nn = rd->nn;
+    for (int e = t; e < nn * 12; e += nt) pc[e / 12].P2[e % 12] = rd->P2[e / 12][e % 12];
+    for (int e = t; e < nn * 9; e += nt) pc[e / 9].F[e % 9] = rd->F[e / 9][e % 9];
+    for (int e = t; e < nn * 3; e += nt) pc[e / 3].C2[e % 3] = rd->C2[e / 3][e % 3];
+    for (int e = t; e < nn; e += nt) {
+        pc[e].sxB = rd->sxB[e]; pc[e].syB = rd->syB[e]; pc[e].group = rd->group[e];
+        pc[e].warp = rd->warp[e]; pc[e].cert = rd->cert[e];
+    }
+}
+
+// Cyclic Jacobi eigen-decomposition of the symmetric 4x4 M (f64): eigenvector of the smallest eigenvalue.
+__device__ void jacobi_smallest_eigvec4(const double* __restrict__ Min, double* __restrict__ vout) {
     double a[4][4], V[4][4];
     a[0][0] = Min[0]; a[1][0] = a[0][1] = Min[1]; a[1][1] = Min[2];
     a[2][0] = a[0][2] = Min[3]; a[2][1] = a[1][2] = Min[4]; a[2][2] = Min[5];
@@ -50,7 +79,7 @@ __device__ __noinline__ void jacobi_smallest_eigvec4(const double* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 4; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
     const double tr = a[0][0] + a[1][1] + a[2][2] + a[3][3];
-    const double tiny = tr * tr * 1e-34;
+    const double tiny = tr * tr * 1e-28;      // off-diagonal mass: eigenvector good to ~1e-13 (quadratic convergence)
     for (int sweep = 0; sweep < 16; ++sweep) {
         const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[0][3] * a[0][3] +
                            a[1][2] * a[1][2] + a[1][3] * a[1][3] + a[2][3] * a[2][3];
@@ -94,11 +123,13 @@ __device__ __noinline__ void jacobi_smallest_eigvec4(const double* __restrict__ 
     for (int k = 0; k < 4; ++k) vout[k] = (j == 0) ? V[k][0] : (j == 1) ? V[k][1] : (j == 2) ? V[k][2] : V[k][3];
 }
 
-// smallest-eigenvalue eigenvector of M = A^T A (A 4x4 given row-major, f32 values held in f64).
-// Fast path: inverse iteration on the Cholesky factor of M + mu*I (same eigenvectors; converges at
-// (sigma_4/sigma_3)^2 per step: 3-5 steps on consistent matches).  Not converged after INVIT_MAX steps -> Jacobi.
-constexpr int INVIT_MAX = 8;
-__device__ __forceinline__ void null_vector4(const double A[16], double v[4]) {
+// Smallest-eigenvalue eigenvector of M = A^T A (A 4x4 row-major, f32 values held in f64).
+// ROBUST = false: inverse iteration on the Cholesky factor of M + mu*I (same eigenvectors; converges at
+// (sigma_4/sigma_3)^2 per step: 3-5 steps on consistent matches); returns false if not converged in INVIT_MAX.
+// ROBUST = true : Jacobi.
+constexpr int INVIT_MAX = 24;     // slow convergers are rare; iterating on is far cheaper than the Jacobi fix-up
+template <bool ROBUST>
+__device__ __forceinline__ bool null_vector4(const double A[16], double v[4]) {
     double m00 = 0, m10 = 0, m11 = 0, m20 = 0, m21 = 0, m22 = 0, m30 = 0, m31 = 0, m32 = 0, m33 = 0;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -108,31 +139,30 @@ __device__ __forceinline__ void null_vector4(const double A[16], double v[4]) {
         m30 = fma(d, a, m30); m31 = fma(d, b, m31); m32 = fma(d, c, m32); m33 = fma(d, d, m33);
     }
     const double tr = m00 + m11 + m22 + m33;
-    if (!(tr > 0.0) || !isfinite(tr)) { v[0] = v[1] = v[2] = 0.0; v[3] = 1.0; if (!(tr == tr)) v[0] = tr; return; }
+    if (!(tr > 0.0) || !isfinite(tr)) { v[0] = v[1] = v[2] = 0.0; v[3] = 1.0; if (!(tr == tr)) v[0] = tr; return true; }
+    if (ROBUST) {
+        const double Ms[10] = {m00, m10, m11, m20, m21, m22, m30, m31, m32, m33};
+        jacobi_smallest_eigvec4(Ms, v);
+        return true;
+    }
     // M + mu*I has the same eigenvectors; the shift keeps the Cholesky pivots positive when A is
     // numerically rank-3 (noise-free correspondences).
     const double mu = tr * 1e-13;
-    double d0 = m00 + mu;
-    const double i0 = rsqrt(d0);
+    const double i0 = rsqrt(m00 + mu);
     const double l10 = m10 * i0, l20 = m20 * i0, l30 = m30 * i0;
-    double d1 = m11 + mu - l10 * l10; d1 = fmax(d1, mu * 1e-3);
-    const double i1 = rsqrt(d1);
+    const double i1 = rsqrt(fmax(m11 + mu - l10 * l10, mu * 1e-3));
     const double l21 = (m21 - l20 * l10) * i1, l31 = (m31 - l30 * l10) * i1;
-    double d2 = m22 + mu - l20 * l20 - l21 * l21; d2 = fmax(d2, mu * 1e-3);
-    const double i2 = rsqrt(d2);
+    const double i2 = rsqrt(fmax(m22 + mu - l20 * l20 - l21 * l21, mu * 1e-3));
     const double l32 = (m32 - l30 * l20 - l31 * l21) * i2;
-    double d3 = m33 + mu - l30 * l30 - l31 * l31 - l32 * l32; d3 = fmax(d3, mu * 1e-3);
-    const double i3 = rsqrt(d3);
+    const double i3 = rsqrt(fmax(m33 + mu - l30 * l30 - l31 * l31 - l32 * l32, mu * 1e-3));
     double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 1.0;
     bool converged = false;
     for (int it = 0; it < INVIT_MAX; ++it) {
-        // L y = x
-        const double y0 = x0 * i0;
+        const double y0 = x0 * i0;                                   // L y = x
         const double y1 = (x1 - l10 * y0) * i1;
         const double y2 = (x2 - l20 * y0 - l21 * y1) * i2;
         const double y3 = (x3 - l30 * y0 - l31 * y1 - l32 * y2) * i3;
-        // L^T z = y
-        const double z3 = y3 * i3;
+        const double z3 = y3 * i3;                                   // L^T z = y
         const double z2 = (y2 - l32 * z3) * i2;
         const double z1 = (y1 - l21 * z2 - l31 * z3) * i1;
         const double z0 = (y0 - l10 * z1 - l20 * z2 - l30 * z3) * i0;
@@ -143,12 +173,8 @@ __device__ __forceinline__ void null_vector4(const double A[16], double v[4]) {
         x0 = n0; x1 = n1; x2 = n2; x3 = n3;
         if (e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3 < 1e-26) { converged = true; break; }
     }
-    if (converged) {
-        v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3;
-    } else {
-        const double Ms[10] = {m00, m10, m11, m20, m21, m22, m30, m31, m32, m33};
-        jacobi_smallest_eigvec4(Ms, v);
-    }
+    v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3;
+    return converged;
 }
 
 // X @ P^T row: the reference's sgemm accumulates the K=4 products with FMAs in index order
@@ -171,112 +197,155 @@ __device__ __forceinline__ float reproj_err(const float* P, float X0, float X1, 
     return __fsqrt_rn(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
 }
 
-__global__ void __launch_bounds__(K2_THREADS)
-ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
-                    const int have_bestk)
-{
-    __shared__ RefConst rc;
-    __shared__ PairConst pc[LDP_MAX_NN];
-    const int r = blockIdx.y;
-    const int S = out.n_samples[r];
-    const int i0 = blockIdx.x * blockDim.x;
-    if (i0 >= S) return;
-    const ldp_ref_desc* rd = refs + r;
-    {   // stage the view's camera constants
-        const int t = threadIdx.x;
-        if (t < 12) rc.P1[t] = rd->P1[t];
-        if (t < 3) rc.C1[t] = rd->C1[t];
-        if (t == 0) {
-            rc.sxA = rd->sxA; rc.syA = rd->syA; rc.sx_img = rd->sx_img; rc.sy_img = rd->sy_img;
-            rc.img_w = rd->img_w; rc.img_h = rd->img_h; rc.nn = rd->nn; rc.image = rd->image;
-        }
-        const int nn = rd->nn;
-        for (int e = t; e < nn * 12; e += blockDim.x) pc[e / 12].P2[e % 12] = rd->P2[e / 12][e % 12];
-        for (int e = t; e < nn * 9; e += blockDim.x) pc[e / 9].F[e % 9] = rd->F[e / 9][e % 9];
-        for (int e = t; e < nn * 3; e += blockDim.x) pc[e / 3].C2[e % 3] = rd->C2[e / 3][e % 3];
-        for (int e = t; e < nn; e += blockDim.x) {
-            pc[e].sxB = rd->sxB[e]; pc[e].syB = rd->syB[e]; pc[e].group = rd->group[e];
-            pc[e].warp = rd->warp[e]; pc[e].cert = rd->cert[e];
+// Three channels of the texels (x0,y) and (x0+1,y) of a [h,w,3] u8 image: 6 consecutive bytes starting at `off`,
+// fetched as three aligned 32-bit words (instead of six byte loads) when the window stays inside the image.
+__device__ __forceinline__ void fetch_texel_pair(const uint8_t* __restrict__ im, size_t off, size_t total, bool two,
+                                                 float t0[3], float t1[3]) {
+    const size_t base = off & ~(size_t)3;
+    if ((reinterpret_cast<size_t>(im) & 3) == 0 && base + 12 <= total) {
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(im + base);
+        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+        const unsigned sh = (unsigned)(off & 3) * 8u;
+        const uint32_t a = __funnelshift_r(w0, w1, sh), b = __funnelshift_r(w1, w2, sh);   // bytes off..off+3, off+4..off+7
+        t0[0] = (float)(a & 0xffu); t0[1] = (float)((a >> 8) & 0xffu); t0[2] = (float)((a >> 16) & 0xffu);
+        if (two) { t1[0] = (float)(a >> 24); t1[1] = (float)(b & 0xffu); t1[2] = (float)((b >> 8) & 0xffu); }
+        else { t1[0] = t0[0]; t1[1] = t0[1]; t1[2] = t0[2]; }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            t0[c] = (float)__ldg(im + off + c);
+            t1[c] = two ? (float)__ldg(im + off + 3 + c) : t0[c];
         }
     }
-    __syncthreads();
-    const int i = i0 + threadIdx.x;
-    const bool active = i < S;
-    int keep = 0, good = 0, grp = 0;
-    if (active) {
-        const int32_t* sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
-        const int idx = sel[i];
-        int k = 0;                                                                // core/pipeline.py:634-635,652
-        if (have_bestk) {
-            k = ws.bestk[(size_t)r * ws.n_pad + idx];
-        } else {                           // stage entry point: arg-max over neighbours at the sampled pixel only
-            float best = __ldg(pc[0].cert + idx);
-            for (int q = 1; q < rc.nn; ++q) {
-                const float c = __ldg(pc[q].cert + idx);
-                if (c > best) { best = c; k = q; }
-            }
-        }
-        const PairConst& pk = pc[k];
-        grp = pk.group;
-        const float4 wv = __ldg(reinterpret_cast<const float4*>(pk.warp) + idx);  // core/pipeline.py:636-640,653
-        const float wm1 = (float)(P.w_match - 1), hm1 = (float)(P.h_match - 1);
-        // core/pipeline.py:655-656 and 701-702: ((x + 1.0) * 0.5) * (w_match - 1), f32 op by op
-        const float xA = __fmul_rn(__fmul_rn(__fadd_rn(wv.x, 1.0f), 0.5f), wm1);
-        const float yA = __fmul_rn(__fmul_rn(__fadd_rn(wv.y, 1.0f), 0.5f), hm1);
-        const float xB = __fmul_rn(__fmul_rn(__fadd_rn(wv.z, 1.0f), 0.5f), wm1);
-        const float yB = __fmul_rn(__fmul_rn(__fadd_rn(wv.w, 1.0f), 0.5f), hm1);
+}
 
-        // ---- colour: core/pipeline.py:661-679 (f64 weights, clipped corners)
-        float cr, cg, cb;
-        {
-            const float fx = __fmul_rn(xA, rc.sx_img), fy = __fmul_rn(yA, rc.sy_img);
-            const int iw = rc.img_w, ih = rc.img_h;
-            // floor(...).astype(int32) then clip; clamp in float first so the cast cannot overflow
-            const int x0 = min(max((int)fminf(fmaxf(floorf(fx), -1.f), (float)iw), 0), iw - 1);
-            const int y0 = min(max((int)fminf(fmaxf(floorf(fy), -1.f), (float)ih), 0), ih - 1);
-            const int x1 = min(x0 + 1, iw - 1), y1 = min(y0 + 1, ih - 1);
-            const double dfx = (double)fx, dfy = (double)fy;
-            const double ax = __dsub_rn((double)x1, dfx), bx = __dsub_rn(dfx, (double)x0);
-            const double ay = __dsub_rn((double)y1, dfy), by = __dsub_rn(dfy, (double)y0);
-            const double w00 = __dmul_rn(ax, ay), w01 = __dmul_rn(bx, ay), w10 = __dmul_rn(ax, by), w11 = __dmul_rn(bx, by);
-            const uint8_t* im = rc.image;
-            const uint8_t* t00 = im + ((size_t)y0 * iw + x0) * 3;
-            const uint8_t* t01 = im + ((size_t)y0 * iw + x1) * 3;
-            const uint8_t* t10 = im + ((size_t)y1 * iw + x0) * 3;
-            const uint8_t* t11 = im + ((size_t)y1 * iw + x1) * 3;
-            float col[3];
+struct SampleResult {
+    float X0, X1, X2, err;
+    float cr, cg, cb, dcert;
+    float4 dbg;
+    int keep, good, grp;
+    bool converged;
+};
+
+// Compact per-sample record written by the gather kernel and consumed (coalesced) by the compute kernel.
+struct SampleRec {
+    float4 wv;              // winning neighbour's warp row: xA, yA, xB, yB in [-1, 1]
+    uint32_t tex[3];        // the four bilinear texels, 3 bytes each: t00 t01 t10 t11
+    uint32_t k_cert;        // bits 0..7 neighbour slot k; debug certainty is kept separately
+};
+
+// ---- gather: everything that needs a scattered load (core/pipeline.py:636-640,652-653,661-675)
+__device__ __forceinline__ void gather_sample(const ldp_params& P, const RefConst& rc, const PairConst* pc, const GeomArgs& ga,
+                                              const uint8_t* __restrict__ bestk_row, int idx, SampleRec& rec, float& craw) {
+    int k = 0;                                                                    // core/pipeline.py:634-635,652
+    if (ga.have_bestk) {
+        k = bestk_row[idx];
+    } else {                               // stage entry point: arg-max over neighbours at the sampled pixel only
+        float best = __ldg(pc[0].cert + idx);
+        for (int q = 1; q < rc.nn; ++q) {
+            const float c = __ldg(pc[q].cert + idx);
+            if (c > best) { best = c; k = q; }
+        }
+    }
+    const PairConst& pk = pc[k];
+    const float4 wv = __ldg(reinterpret_cast<const float4*>(pk.warp) + idx);      // core/pipeline.py:636-640,653
+    craw = 0.f;
+    if (P.collect_debug) craw = __ldg(pk.cert + idx);
+    const float wm1 = (float)(P.w_match - 1), hm1 = (float)(P.h_match - 1);
+    const float xA = __fmul_rn(__fmul_rn(__fadd_rn(wv.x, 1.0f), 0.5f), wm1);
+    const float yA = __fmul_rn(__fmul_rn(__fadd_rn(wv.y, 1.0f), 0.5f), hm1);
+    const float fx = __fmul_rn(xA, rc.sx_img), fy = __fmul_rn(yA, rc.sy_img);
+    const int iw = rc.img_w, ih = rc.img_h;
+    const int x0 = min(max((int)fminf(fmaxf(floorf(fx), -1.f), (float)iw), 0), iw - 1);
+    const int y0 = min(max((int)fminf(fmaxf(floorf(fy), -1.f), (float)ih), 0), ih - 1);
+    const int x1 = min(x0 + 1, iw - 1), y1 = min(y0 + 1, ih - 1);
+    float t00[3], t01[3], t10[3], t11[3];
+    const size_t img_bytes = (size_t)iw * ih * 3;
+    fetch_texel_pair(rc.image, ((size_t)y0 * iw + x0) * 3, img_bytes, x1 != x0, t00, t01);
+    fetch_texel_pair(rc.image, ((size_t)y1 * iw + x0) * 3, img_bytes, x1 != x0, t10, t11);
+    rec.wv = wv;
+    rec.tex[0] = (uint32_t)t00[0] | ((uint32_t)t00[1] << 8) | ((uint32_t)t00[2] << 16) | ((uint32_t)t01[0] << 24);
+    rec.tex[1] = (uint32_t)t01[1] | ((uint32_t)t01[2] << 8) | ((uint32_t)t10[0] << 16) | ((uint32_t)t10[1] << 24);
+    rec.tex[2] = (uint32_t)t10[2] | ((uint32_t)t11[0] << 8) | ((uint32_t)t11[1] << 16) | ((uint32_t)t11[2] << 24);
+    rec.k_cert = (uint32_t)k;
+}
+
+// ---- compute: everything else the reference computes for one sampled pixel (core/pipeline.py:653-769)
+template <bool ROBUST>
+__device__ __forceinline__ void eval_sample(const ldp_params& P, const RefConst& rc, const PairConst* pc, const GeomArgs& ga,
+                                            const SampleRec& rec, float craw, SampleResult& o) {
+    const int k = (int)(rec.k_cert & 0xffu);
+    const PairConst& pk = pc[k];
+    o.grp = pk.group;
+    const float4 wv = rec.wv;
+    const float wm1 = (float)(P.w_match - 1), hm1 = (float)(P.h_match - 1);
+    // core/pipeline.py:655-656 and 701-702: ((x + 1.0) * 0.5) * (w_match - 1), f32 op by op
+    const float xA = __fmul_rn(__fmul_rn(__fadd_rn(wv.x, 1.0f), 0.5f), wm1);
+    const float yA = __fmul_rn(__fmul_rn(__fadd_rn(wv.y, 1.0f), 0.5f), hm1);
+    const float xB = __fmul_rn(__fmul_rn(__fadd_rn(wv.z, 1.0f), 0.5f), wm1);
+    const float yB = __fmul_rn(__fmul_rn(__fadd_rn(wv.w, 1.0f), 0.5f), hm1);
+
+    // ---- colour: core/pipeline.py:661-679 (f64 weights, clipped corners)
+    const float fx = __fmul_rn(xA, rc.sx_img), fy = __fmul_rn(yA, rc.sy_img);
+    const int iw = rc.img_w, ih = rc.img_h;
+    // floor(...).astype(int32) then clip; clamp in float first so the cast cannot overflow
+    const int x0 = min(max((int)fminf(fmaxf(floorf(fx), -1.f), (float)iw), 0), iw - 1);
+    const int y0 = min(max((int)fminf(fmaxf(floorf(fy), -1.f), (float)ih), 0), ih - 1);
+    const int x1 = min(x0 + 1, iw - 1), y1 = min(y0 + 1, ih - 1);
+    float t00[3], t01[3], t10[3], t11[3];
+    t00[0] = (float)(rec.tex[0] & 0xffu); t00[1] = (float)((rec.tex[0] >> 8) & 0xffu); t00[2] = (float)((rec.tex[0] >> 16) & 0xffu);
+    t01[0] = (float)(rec.tex[0] >> 24);   t01[1] = (float)(rec.tex[1] & 0xffu);        t01[2] = (float)((rec.tex[1] >> 8) & 0xffu);
+    t10[0] = (float)((rec.tex[1] >> 16) & 0xffu); t10[1] = (float)(rec.tex[1] >> 24);  t10[2] = (float)(rec.tex[2] & 0xffu);
+    t11[0] = (float)((rec.tex[2] >> 8) & 0xffu);  t11[1] = (float)((rec.tex[2] >> 16) & 0xffu); t11[2] = (float)(rec.tex[2] >> 24);
+
+    // ---- full-resolution pixel coordinates: core/pipeline.py:681-683, 697-703
+    const float uA = __fmul_rn(xA, rc.sxA), vA = __fmul_rn(yA, rc.syA);
+    const float uB = __fmul_rn(xB, pk.sxB), vB = __fmul_rn(yB, pk.syB);
+
+    // ---- Sampson gate in f64: core/geometry.py:133-141, core/pipeline.py:708-727.  se < thr is decided on
+    //      num^2 vs thr*den outside a 2^-50 band, by the reference's quotient inside it.
+    o.good = 1;
+    if (!P.no_filter && P.sampson_thresh > 0.0) {
+        const double a0 = uA, a1 = vA, b0 = uB, b1 = vB;
+        const float* F = pk.F;
+        const double l0 = (double)F[0] * a0 + (double)F[1] * a1 + (double)F[2];
+        const double l1 = (double)F[3] * a0 + (double)F[4] * a1 + (double)F[5];
+        const double l2 = (double)F[6] * a0 + (double)F[7] * a1 + (double)F[8];
+        const double m0 = (double)F[0] * b0 + (double)F[3] * b1 + (double)F[6];
+        const double m1 = (double)F[1] * b0 + (double)F[4] * b1 + (double)F[7];
+        const double num = b0 * l0 + b1 * l1 + l2;
+        const double den = l0 * l0 + l1 * l1 + m0 * m0 + m1 * m1 + 1e-12;
+        const double n2 = num * num, td = P.sampson_thresh * den;
+        if (n2 < td * (1.0 - 1.0 / 1125899906842624.0)) o.good = 1;
+        else if (n2 > td * (1.0 + 1.0 / 1125899906842624.0)) o.good = 0;
+        else o.good = (__ddiv_rn(n2, den) < P.sampson_thresh) ? 1 : 0;
+        if (!(n2 == n2) || !(den == den)) o.good = 0;                            // NaN: comparison is False in numpy
+    }
+
+    {   // bilinear blend, f64, left-to-right sum like the reference; /255.0 as an FMA-corrected reciprocal multiply
+        const double dfx = (double)fx, dfy = (double)fy;
+        const double ax = __dsub_rn((double)x1, dfx), bx = __dsub_rn(dfx, (double)x0);
+        const double ay = __dsub_rn((double)y1, dfy), by = __dsub_rn(dfy, (double)y0);
+        const double w00 = __dmul_rn(ax, ay), w01 = __dmul_rn(bx, ay), w10 = __dmul_rn(ax, by), w11 = __dmul_rn(bx, by);
+        float col[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                double acc = __dmul_rn((double)__ldg(t00 + c), w00);
-                acc = __dadd_rn(acc, __dmul_rn((double)__ldg(t01 + c), w01));
-                acc = __dadd_rn(acc, __dmul_rn((double)__ldg(t10 + c), w10));
-                acc = __dadd_rn(acc, __dmul_rn((double)__ldg(t11 + c), w11));
-                col[c] = (float)__ddiv_rn(acc, 255.0);                            // .astype(np.float32) at :754
-            }
-            cr = col[0]; cg = col[1]; cb = col[2];
+        for (int c = 0; c < 3; ++c) {
+            double acc = __dmul_rn((double)t00[c], w00);
+            acc = __dadd_rn(acc, __dmul_rn((double)t01[c], w01));
+            acc = __dadd_rn(acc, __dmul_rn((double)t10[c], w10));
+            acc = __dadd_rn(acc, __dmul_rn((double)t11[c], w11));
+            const double q0 = acc * (1.0 / 255.0);
+            const double rr = fma(-q0, 255.0, acc);
+            col[c] = (float)fma(rr, 1.0 / 255.0, q0);                             // == acc / 255.0 rounded; .astype(f32) at :754
         }
-        // ---- full-resolution pixel coordinates: core/pipeline.py:681-683, 697-703
-        const float uA = __fmul_rn(xA, rc.sxA), vA = __fmul_rn(yA, rc.syA);
-        const float uB = __fmul_rn(xB, pk.sxB), vB = __fmul_rn(yB, pk.syB);
+        o.cr = col[0]; o.cg = col[1]; o.cb = col[2];
+    }
 
-        // ---- Sampson gate in f64: core/geometry.py:133-141, core/pipeline.py:708-727
-        good = 1;
-        if (!P.no_filter && P.sampson_thresh > 0.0) {
-            const double a0 = uA, a1 = vA, b0 = uB, b1 = vB;
-            const float* F = pk.F;
-            const double l0 = (double)F[0] * a0 + (double)F[1] * a1 + (double)F[2];
-            const double l1 = (double)F[3] * a0 + (double)F[4] * a1 + (double)F[5];
-            const double l2 = (double)F[6] * a0 + (double)F[7] * a1 + (double)F[8];
-            const double m0 = (double)F[0] * b0 + (double)F[3] * b1 + (double)F[6];
-            const double m1 = (double)F[1] * b0 + (double)F[4] * b1 + (double)F[7];
-            const double num = b0 * l0 + b1 * l1 + l2;
-            const double den = l0 * l0 + l1 * l1 + m0 * m0 + m1 * m1 + 1e-12;
-            const double se = (num * num) / den;
-            good = (se < P.sampson_thresh) ? 1 : 0;
-        }
-
-        float X0 = 0.f, X1 = 0.f, X2 = 0.f, X3 = 0.f, err = __int_as_float(0x7fc00000);
-        if (good) {        // the reference triangulates only the Sampson survivors (core/pipeline.py:721-733)
+    o.X0 = o.X1 = o.X2 = 0.f;
+    o.err = __int_as_float(0x7fc00000);
+    o.keep = 0;
+    o.converged = true;
+    if (o.good) {          // the reference triangulates only the Sampson survivors (core/pipeline.py:721-733)
         // ---- DLT rows (f32, multiply then subtract): core/geometry.py:72-75
         double A[16];
 #pragma unroll
@@ -287,27 +356,29 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
             A[12 + j] = (double)__fsub_rn(__fmul_rn(vB, pk.P2[8 + j]), pk.P2[4 + j]);
         }
         double v[4];
-        null_vector4(A, v);
+        o.converged = null_vector4<ROBUST>(A, v);
         // core/geometry.py:85-87: w = where(|Xh3| < 1e-12, 1e-12, Xh3); X = Xh / w
+        float X0, X1, X2, X3;
         {
             const float w32 = (float)v[3];
             if (fabsf(w32) < 1e-12f) {
                 X0 = __fdiv_rn((float)v[0], 1e-12f); X1 = __fdiv_rn((float)v[1], 1e-12f);
                 X2 = __fdiv_rn((float)v[2], 1e-12f); X3 = __fdiv_rn(w32, 1e-12f);
             } else {
-                const double iw = 1.0 / v[3];
-                X0 = (float)(v[0] * iw); X1 = (float)(v[1] * iw); X2 = (float)(v[2] * iw); X3 = 1.0f;
+                const double iwv = 1.0 / v[3];
+                X0 = (float)(v[0] * iwv); X1 = (float)(v[1] * iwv); X2 = (float)(v[2] * iwv); X3 = 1.0f;
             }
         }
         // ---- reprojection errors + cheirality: core/geometry.py:91-110, core/pipeline.py:735-737
         float z1, z2;
         const float e1 = reproj_err(rc.P1, X0, X1, X2, X3, uA, vA, &z1);
         const float e2 = reproj_err(pk.P2, X0, X1, X2, X3, uB, vB, &z2);
-        err = (e1 != e1 || e2 != e2) ? __int_as_float(0x7fc00000) : fmaxf(e1, e2);   // np.maximum propagates NaN
+        const float err = (e1 != e1 || e2 != e2) ? __int_as_float(0x7fc00000) : fmaxf(e1, e2);   // np.maximum propagates NaN
+        int keep;
         if (P.no_filter) {                                                        // core/pipeline.py:739-743
             keep = (isfinite(X0) && isfinite(X1) && isfinite(X2) && isfinite(X3) && isfinite(err)) ? 1 : 0;
         } else {                                                                  // core/pipeline.py:745-749
-            keep = (good && err <= P.reproj_thresh && z1 > 0.0f && z2 > 0.0f) ? 1 : 0;
+            keep = (err <= P.reproj_thresh && z1 > 0.0f && z2 > 0.0f) ? 1 : 0;
             if (keep && P.min_parallax_deg > 0.0f) {                              // core/geometry.py:113-119
                 float a0 = __fsub_rn(X0, rc.C1[0]), a1 = __fsub_rn(X1, rc.C1[1]), a2 = __fsub_rn(X2, rc.C1[2]);
                 float b0 = __fsub_rn(X0, pk.C2[0]), b1 = __fsub_rn(X1, pk.C2[1]), b2 = __fsub_rn(X2, pk.C2[2]);
@@ -318,131 +389,268 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
                 float d = __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
                 const bool dnan = (d != d);
                 d = fminf(fmaxf(d, -1.0f), 1.0f);
-                const float ang = __fmul_rn((float)acos((double)d), RAD2DEG_F32);
-                keep = (!dnan && ang >= P.min_parallax_deg) ? 1 : 0;
+                // degrees(arccos(d)) >= min_deg  <=>  d <= par_cos_max (arccos is monotone; threshold found on the host)
+                keep = (!dnan && d <= ga.par_cos_max) ? 1 : 0;
             }
         }
-        }   // good
-        const size_t o = (size_t)r * ws.sel_cap + i;
-        ws.pt0[o] = make_float4(X0, X1, X2, err);
-        float dcert = 0.f;
-        if (P.collect_debug) {                                                    // core/pipeline.py:761-769
-            const float c = __ldg(pk.cert + idx);
-            const float denom = (P.sample_cap > 1e-6f) ? P.sample_cap : 1.0f;
-            dcert = fminf(fmaxf(__fdiv_rn(c, denom), 0.f), 1.f);
-            ws.dbgm[o] = make_float4(fminf(fmaxf(xA, 0.f), wm1), fminf(fmaxf(yA, 0.f), hm1),
-                                     fminf(fmaxf(xB, 0.f), wm1), fminf(fmaxf(yB, 0.f), hm1));
-        }
-        ws.pt1[o] = make_float4(cr, cg, cb, dcert);
-        ws.flags[o] = (uint8_t)(keep | (good << 1) | (grp << 2));
-        if (out.sample_flags) out.sample_flags[o] = (uint8_t)(keep | (good << 1) | (grp << 2));
-        if (out.sample_xyzerr) reinterpret_cast<float4*>(out.sample_xyzerr)[o] = make_float4(X0, X1, X2, err);
+        o.X0 = X0; o.X1 = X1; o.X2 = X2; o.err = err; o.keep = keep;
     }
-    // kept-point count of the view (one atomic per warp)
-    const unsigned km = __ballot_sync(0xffffffffu, keep);
-    if ((threadIdx.x & 31) == 0 && km) atomicAdd(&ws.kept[r], __popc(km));
+    o.dcert = 0.f;
+    o.dbg = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (P.collect_debug) {                                                        // core/pipeline.py:761-769
+        const float denom = (P.sample_cap > 1e-6f) ? P.sample_cap : 1.0f;
+        o.dcert = fminf(fmaxf(__fdiv_rn(craw, denom), 0.f), 1.f);
+        o.dbg = make_float4(fminf(fmaxf(xA, 0.f), wm1), fminf(fmaxf(yA, 0.f), hm1),
+                            fminf(fmaxf(xB, 0.f), wm1), fminf(fmaxf(yB, 0.f), hm1));
+    }
 }
 
-// ---------------------------------------------------------------------------------------------
-// K3: one CTA per reference view.  Output order of the reference (core/pipeline.py:685-695,753-780):
-// neighbour groups in order of first appearance over the sample order, samples in sample order inside
-// a group, only kept samples.  Rank of a kept sample inside its group = ordered ballot scan.
-// The view's base offset is the sum of the kept counts of the views before it (ws.kept from K2).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(K3_THREADS, 1)
-ldp_pack_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out)
-{
-    __shared__ int s_first[LDP_MAX_NN];      // first sample position per group
-    __shared__ int s_count[LDP_MAX_NN];      // kept per group
-    __shared__ int s_base[LDP_MAX_NN];       // output base per group (relative to the view)
-    __shared__ int s_run[LDP_MAX_NN];        // running kept count per group across tiles
-    __shared__ int s_wcnt[32][LDP_MAX_NN];   // per-warp kept count per group in this tile
-    __shared__ int s_order[LDP_MAX_NN];
-    __shared__ long long s_red[32];
-    __shared__ long long s_off;
-    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x;
-    const int nwarp = T >> 5;
-    const int S = out.n_samples[r];
-    const uint8_t* flags = ws.flags + (size_t)r * ws.sel_cap;
+__device__ __forceinline__ void store_sample(const ldp_params& P, const Workspace& ws, const ldp_outputs& out,
+                                             size_t o, const SampleResult& s) {
+    ws.pt0[o] = make_float4(s.X0, s.X1, s.X2, s.err);
+    ws.pt1[o] = make_float4(s.cr, s.cg, s.cb, s.dcert);
+    if (P.collect_debug) ws.dbgm[o] = s.dbg;
+    const uint8_t f = (uint8_t)(s.keep | (s.good << 1) | (s.grp << 2));
+    ws.flags[o] = f;
+    if (out.sample_flags) out.sample_flags[o] = f;
+    if (out.sample_xyzerr) reinterpret_cast<float4*>(out.sample_xyzerr)[o] = make_float4(s.X0, s.X1, s.X2, s.err);
+}
 
-    // base offset of this view
-    long long part = 0;
-    for (int q = tid; q < r; q += T) part += (long long)ws.kept[q];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) s_red[warp] = part;
-    if (tid < LDP_MAX_NN) { s_first[tid] = 0x7fffffff; s_count[tid] = 0; s_run[tid] = 0; }
+// K2a gather: one thread per sample, few registers, full occupancy: the dependent chain of scattered loads
+// (sample index -> winning neighbour -> warp row -> texels) is what bounds this stage, so it runs with as many
+// threads in flight as the SM holds and leaves a 32-byte record per sample for the arithmetic kernel.
+constexpr int KG_THREADS = 256;
+__global__ void __launch_bounds__(KG_THREADS, 8)
+ldp_gather_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
+                  const GeomArgs ga)
+{
+    __shared__ RefConst rc;
+    __shared__ PairConst pc[LDP_MAX_NN];
+    const int r = blockIdx.y;
+    const int S = out.n_samples[r];
+    const int i0 = blockIdx.x * KG_THREADS;
+    if (i0 >= S) return;
+    stage_constants(refs + r, rc, pc, threadIdx.x, KG_THREADS);
     __syncthreads();
-    if (warp == 0) {
-        long long v = (lane < nwarp) ? s_red[lane] : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_off = v;
+    const int i = i0 + threadIdx.x;
+    if (i >= S) return;
+    const int32_t* sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
+    SampleRec rec;
+    float craw;
+    gather_sample(P, rc, pc, ga, ws.bestk + (size_t)r * ws.n_pad, sel[i], rec, craw);
+    const size_t o = (size_t)r * ws.sel_cap + i;
+    ws.pt0[o] = rec.wv;                                                                   // record, part 1
+    ws.pt1[o] = make_float4(__uint_as_float(rec.tex[0]), __uint_as_float(rec.tex[1]), __uint_as_float(rec.tex[2]),
+                            __uint_as_float(rec.k_cert));                                 // record, part 2
+    if (P.collect_debug) ws.dbgm[o].x = craw;
+}
+
+__device__ __forceinline__ void load_record(const Workspace& ws, const ldp_params& P, size_t o, SampleRec& rec, float& craw) {
+    rec.wv = ws.pt0[o];
+    const float4 b = ws.pt1[o];
+    rec.tex[0] = __float_as_uint(b.x); rec.tex[1] = __float_as_uint(b.y); rec.tex[2] = __float_as_uint(b.z);
+    rec.k_cert = __float_as_uint(b.w);
+    craw = P.collect_debug ? ws.dbgm[o].x : 0.f;
+}
+
+// K2b compute: coalesced record in, per-sample result (in place) + per-tile group statistics out.
+__global__ void __launch_bounds__(K2_THREADS, K2_MIN_BLOCKS)
+ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
+                    const GeomArgs ga)
+{
+    __shared__ RefConst rc;
+    __shared__ PairConst pc[LDP_MAX_NN];
+    __shared__ int s_cnt[LDP_MAX_NN], s_first[LDP_MAX_NN];
+    const int r = blockIdx.y;
+    const int S = out.n_samples[r];
+    const int i0 = blockIdx.x * K2_THREADS;
+    if (i0 >= S) return;
+    stage_constants(refs + r, rc, pc, threadIdx.x, K2_THREADS);
+    if (threadIdx.x < LDP_MAX_NN) { s_cnt[threadIdx.x] = 0; s_first[threadIdx.x] = 0x7fffffff; }
+    __syncthreads();
+    const int i = i0 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int keep = 0, grp = -1;
+    if (i < S) {
+        const size_t o = (size_t)r * ws.sel_cap + i;
+        SampleRec rec;
+        float craw;
+        load_record(ws, P, o, rec, craw);
+        SampleResult s;
+        eval_sample<false>(P, rc, pc, ga, rec, craw, s);
+        if (!s.converged) {                 // rare: leave the record in place for the fix-up (flag bit 7), keep = 0 for now
+            const int slot = atomicAdd(ws.fix_count, 1);
+            ws.fix_list[slot] = make_int2(r, i);
+            ws.flags[o] = (uint8_t)(0x80 | (s.grp << 2));
+            s.keep = 0;
+        } else {
+            store_sample(P, ws, out, o, s);
+        }
+        keep = s.keep;
+        grp = s.grp;
     }
-    // pass 1: first appearance + kept count per group
-    for (int i = tid; i < S; i += T) {
-        const int f = flags[i];
-        const int g = f >> 2;
-        atomicMin(&s_first[g], i);
-        if (f & 1) atomicAdd(&s_count[g], 1);
+    // per-tile group statistics for the pack kernels: kept count and first sample position per group
+    const unsigned same = __match_any_sync(0xffffffffu, grp);
+    const unsigned kept_all = __ballot_sync(0xffffffffu, keep);
+    if (grp >= 0 && lane == (__ffs(same) - 1)) {
+        atomicMin(&s_first[grp], i);                                   // lowest lane of the group has the lowest index
+        const unsigned kept_same = same & kept_all;
+        if (kept_same) atomicAdd(&s_cnt[grp], __popc(kept_same));
+    }
+    if (lane == 0 && kept_all) atomicAdd(&ws.kept[r], __popc(kept_all));
+    __syncthreads();
+    if (threadIdx.x < LDP_MAX_NN) {
+        const size_t t = ((size_t)r * ga.nb2 + blockIdx.x) * LDP_MAX_NN + threadIdx.x;
+        ws.blk_cnt[t] = s_cnt[threadIdx.x];
+        ws.blk_first[t] = s_first[threadIdx.x];
+    }
+}
+
+// K2c fix + plan: one CTA per view.  (1) The view's entries of the worklist (null-vector iteration not converged:
+// grossly inconsistent matches) are re-evaluated with the Jacobi solver, one thread each.  (2) The view's pack plan:
+// groups in first-appearance order, and for every 128-sample tile the output offset of each group inside the view.
+__global__ void __launch_bounds__(K2_THREADS)
+ldp_fixplan_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
+                   const GeomArgs ga)
+{
+    __shared__ RefConst rc;
+    __shared__ PairConst pc[LDP_MAX_NN];
+    __shared__ int s_tot[LDP_MAX_NN], s_first[LDP_MAX_NN], s_base[LDP_MAX_NN];
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const int S = out.n_samples[r];
+    const int nb = (S + K2_THREADS - 1) / K2_THREADS;
+    const int n = *ws.fix_count;
+    if (n > 0) {
+        stage_constants(refs + r, rc, pc, tid, K2_THREADS);
+        __syncthreads();
+        for (int e = tid; e < n; e += K2_THREADS) {
+            const int2 it = ws.fix_list[e];
+            if (it.x != r) continue;
+            const int i = it.y;
+            const size_t o = (size_t)r * ws.sel_cap + i;
+            SampleRec rec;
+            float craw;
+            load_record(ws, P, o, rec, craw);
+            SampleResult s;
+            eval_sample<true>(P, rc, pc, ga, rec, craw, s);
+            store_sample(P, ws, out, o, s);
+            if (s.keep) {
+                atomicAdd(&ws.kept[r], 1);
+                atomicAdd(&ws.blk_cnt[((size_t)r * ga.nb2 + i / K2_THREADS) * LDP_MAX_NN + s.grp], 1);
+            }
+        }
+        __threadfence();
+        __syncthreads();
+    }
+    // ---- plan: per-group totals / first appearance / per-tile exclusive prefix.  The tile tables are read once,
+    //      coalesced, by the whole CTA; 16 lanes then walk them in shared memory.
+    {
+        extern __shared__ int s_tab[];                           // [2][nb][LDP_MAX_NN]
+        int* t_cnt = s_tab;
+        int* t_first = s_tab + (size_t)ga.nb2 * LDP_MAX_NN;
+        const int n_ent = nb * LDP_MAX_NN;
+        const int32_t* cnt = ws.blk_cnt + (size_t)r * ga.nb2 * LDP_MAX_NN;
+        const int32_t* fst = ws.blk_first + (size_t)r * ga.nb2 * LDP_MAX_NN;
+        for (int e = tid; e < n_ent; e += K2_THREADS) { t_cnt[e] = __ldcg(cnt + e); t_first[e] = __ldcg(fst + e); }
+        __syncthreads();
+        if (tid < LDP_MAX_NN) {
+            const int g = tid;
+            int tot = 0, first = 0x7fffffff;
+            int32_t* before = ws.blk_before + (size_t)r * ga.nb2 * LDP_MAX_NN + g;
+            for (int bb = 0; bb < nb; ++bb) {
+                before[(size_t)bb * LDP_MAX_NN] = tot;
+                tot += t_cnt[bb * LDP_MAX_NN + g];
+                first = min(first, t_first[bb * LDP_MAX_NN + g]);
+            }
+            s_tot[g] = tot;
+            s_first[g] = first;
+            s_base[g] = 0;
+        }
     }
     __syncthreads();
     if (tid == 0) {
-        // groups in first-appearance order (insertion sort of <= 16 entries)
-        int n = 0;
-        for (int g = 0; g < LDP_MAX_NN; ++g) if (s_first[g] != 0x7fffffff) s_order[n++] = g;
-        for (int a = 1; a < n; ++a) {
-            const int g = s_order[a];
-            int b = a - 1;
-            while (b >= 0 && s_first[s_order[b]] > s_first[g]) { s_order[b + 1] = s_order[b]; --b; }
-            s_order[b + 1] = g;
+        int order[LDP_MAX_NN];
+        int m = 0;
+        for (int g = 0; g < LDP_MAX_NN; ++g) if (s_first[g] != 0x7fffffff) order[m++] = g;
+        for (int a = 1; a < m; ++a) {                       // insertion sort by first appearance
+            const int g = order[a];
+            int q = a - 1;
+            while (q >= 0 && s_first[order[q]] > s_first[g]) { order[q + 1] = order[q]; --q; }
+            order[q + 1] = g;
         }
         int acc = 0;
-        for (int a = 0; a < n; ++a) { s_base[s_order[a]] = acc; acc += s_count[s_order[a]]; }
+        for (int a = 0; a < m; ++a) { s_base[order[a]] = acc; acc += s_tot[order[a]]; }
         for (int a = 0; a < LDP_MAX_NN; ++a) {
-            out.group_order[(size_t)r * LDP_MAX_NN + a] = (a < n) ? s_order[a] : -1;
-            out.group_count[(size_t)r * LDP_MAX_NN + a] = s_count[a];
+            out.group_order[(size_t)r * LDP_MAX_NN + a] = (a < m) ? order[a] : -1;
+            out.group_count[(size_t)r * LDP_MAX_NN + a] = s_tot[a];
+            ws.grp_base[(size_t)r * LDP_MAX_NN + a] = s_base[a];
         }
-        out.ref_offset[r] = s_off;
-        if (r == (int)gridDim.x - 1) out.ref_offset[r + 1] = s_off + acc;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 scatter: grid (tiles, views).  Output order of the reference (core/pipeline.py:685-695,753-780): neighbour
+// groups in order of first appearance over the sample order, sample order inside a group, kept samples only.
+// dst = view base (kept counts of earlier views) + group base + kept samples of the same group in earlier tiles
+//       (both from the plan) + rank inside the tile (ballots).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(K3_THREADS)
+ldp_pack_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
+                const GeomArgs ga)
+{
+    __shared__ int s_start[LDP_MAX_NN];
+    __shared__ int s_wcnt[K3_THREADS / 32][LDP_MAX_NN];
+    __shared__ long long s_red[K3_THREADS / 32];
+    __shared__ long long s_off;
+    const int r = blockIdx.y, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = out.n_samples[r];
+    const int nb = (S + K2_THREADS - 1) / K2_THREADS;
+    if (b >= nb && b != 0) return;
+
+    long long part = 0;
+    for (int q = tid; q < r; q += K3_THREADS) part += (long long)ws.kept[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_red[warp] = part;
+    if (tid < LDP_MAX_NN)
+        s_start[tid] = ws.grp_base[(size_t)r * LDP_MAX_NN + tid] +
+                       ((b < nb) ? ws.blk_before[((size_t)r * ga.nb2 + b) * LDP_MAX_NN + tid] : 0);
     __syncthreads();
-    const long long off = s_off;
-    // pass 2: ordered scatter, tile by tile
-    for (int t0 = 0; t0 < S; t0 += T) {
-        const int i = t0 + tid;
-        const int f = (i < S) ? flags[i] : 0;
-        const int keep = f & 1, g = f >> 2;
-        // per-warp, per-group ballots
-        const unsigned same = __match_any_sync(0xffffffffu, keep ? g : -1);
-        const int rank_in_warp = __popc(same & ((1u << lane) - 1u));
-        for (int e = lane; e < LDP_MAX_NN; e += 32) s_wcnt[warp][e] = 0;
-        __syncwarp();
-        if (keep && rank_in_warp == 0) s_wcnt[warp][g] = __popc(same);
-        __syncthreads();
-        if (keep) {
-            int before = s_run[g];
-            for (int ww = 0; ww < warp; ++ww) before += s_wcnt[ww][g];
-            const long long dst = off + s_base[g] + before + rank_in_warp;
-            if (dst < out.capacity) {
-                const size_t o = (size_t)r * ws.sel_cap + i;
-                const float4 a = ws.pt0[o], b = ws.pt1[o];
-                out.xyz[dst * 3 + 0] = a.x; out.xyz[dst * 3 + 1] = a.y; out.xyz[dst * 3 + 2] = a.z;
-                out.rgb[dst * 3 + 0] = b.x; out.rgb[dst * 3 + 1] = b.y; out.rgb[dst * 3 + 2] = b.z;
-                out.err[dst] = a.w;
-                if (P.collect_debug && out.dbg_matches) {
-                    reinterpret_cast<float4*>(out.dbg_matches)[dst] = ws.dbgm[o];
-                    if (out.dbg_cert) out.dbg_cert[dst] = b.w;
-                }
+    if (tid == 0) {
+        long long v = 0;
+        for (int q = 0; q < K3_THREADS / 32; ++q) v += s_red[q];
+        s_off = v;
+        if (b == 0) {
+            out.ref_offset[r] = v;
+            if (r == (int)gridDim.y - 1) out.ref_offset[r + 1] = v + ws.kept[r];
+        }
+    }
+    if (b >= nb) return;
+    const int i = b * K2_THREADS + tid;
+    const uint8_t* flags = ws.flags + (size_t)r * ws.sel_cap;
+    const int f = (i < S) ? flags[i] : 0;
+    const int keep = f & 1, g = (f >> 2) & 0x1f;
+    const unsigned same = __match_any_sync(0xffffffffu, keep ? g : -1);
+    const int rank_in_warp = __popc(same & ((1u << lane) - 1u));
+    if (lane < LDP_MAX_NN) s_wcnt[warp][lane] = 0;
+    __syncwarp();
+    if (keep && rank_in_warp == 0) s_wcnt[warp][g] = __popc(same);
+    __syncthreads();
+    if (keep) {
+        int before = s_start[g];
+        for (int ww = 0; ww < warp; ++ww) before += s_wcnt[ww][g];
+        const long long dst = s_off + before + rank_in_warp;
+        if (dst < out.capacity) {
+            const size_t o = (size_t)r * ws.sel_cap + i;
+            const float4 a = ws.pt0[o], c = ws.pt1[o];
+            out.xyz[dst * 3 + 0] = a.x; out.xyz[dst * 3 + 1] = a.y; out.xyz[dst * 3 + 2] = a.z;
+            out.rgb[dst * 3 + 0] = c.x; out.rgb[dst * 3 + 1] = c.y; out.rgb[dst * 3 + 2] = c.z;
+            out.err[dst] = a.w;
+            if (P.collect_debug && out.dbg_matches) {
+                reinterpret_cast<float4*>(out.dbg_matches)[dst] = ws.dbgm[o];
+                if (out.dbg_cert) out.dbg_cert[dst] = c.w;
             }
         }
-        __syncthreads();
-        if (tid < LDP_MAX_NN) {
-            int add = 0;
-            for (int ww = 0; ww < nwarp; ++ww) add += s_wcnt[ww][tid];
-            s_run[tid] += add;
-        }
-        __syncthreads();
     }
 }
 

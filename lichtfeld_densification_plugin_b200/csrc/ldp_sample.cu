@@ -78,6 +78,7 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
         if (tid == 0) {
             ws.rstat[r].s = 0.f; ws.rstat[r].npos = 0; ws.rstat[r].emin = 0x7fffffff; ws.rstat[r].bad = 0;
             ws.kept[r] = 0;
+            if (r == 0) *ws.fix_count = 0;
         }
         unsigned long long* gb = ws.gbins + (size_t)r * ws.bins_cap;
         for (int i = tid; i < (int)ws.bins_cap; i += KS_THREADS) gb[i] = 0ull;
