@@ -140,6 +140,26 @@ class RefBatch:
         self.nbr_uids.append(uids)
         self.ref_uids.append(int(ref_cam.uid))
 
+    def add_cert_only(self, cert_planes: Sequence[torch.Tensor], rng_stream: int = 0,
+                      weight_sum_override: float = 0.0) -> None:
+        """A view described by its certainty planes only -- enough for the sampling stage (``ldp_sample_refs``)."""
+        nn = len(cert_planes)
+        if nn > N.LDP_MAX_NN:
+            raise ValueError(f"at most {N.LDP_MAX_NN} neighbours per reference view")
+        row = np.zeros((), dtype=N.REF_DESC_DTYPE)
+        for k in range(nn):
+            c = self._check_plane(cert_planes[k], (self.H, self.W), "certainty plane")
+            if c.data_ptr() % 16 != 0:
+                self.force_scalar_loads = True
+            row["cert"][k] = c.data_ptr()
+            self._keep_alive.append(c)
+        row["nn"] = nn
+        row["rng_stream"] = np.uint32(int(rng_stream) & 0xFFFFFFFF)
+        row["weight_sum_override"] = np.float32(weight_sum_override)
+        self._rows.append(row)
+        self.nbr_uids.append(list(range(nn)))
+        self.ref_uids.append(len(self._rows) - 1)
+
     def desc_array(self) -> np.ndarray:
         if not self._rows:
             return np.zeros((0,), dtype=N.REF_DESC_DTYPE)
@@ -264,6 +284,35 @@ class DensifyEngine:
         out.launches = int(self.lib.ldp_last_launch_count())
         out._keep = (descs_dev, uniforms, batch)      # keep inputs alive until the stream is done with them
         return out
+
+    def sample(self, batch: RefBatch, cfg: PathConfig, uniforms: Optional[torch.Tensor] = None):
+        """Sampling stage only (``ldp_sample_refs``): returns (sel_idx [R, sel_cap] i32, n_samples, status, uniforms_used)."""
+        R = len(batch)
+        dev = self.device
+        rng_mode, upr = N.LDP_RNG_PHILOX, 0
+        if uniforms is not None:
+            uniforms = uniforms.contiguous()
+            rng_mode, upr = N.LDP_RNG_EXPLICIT, int(uniforms.shape[1])
+        params = self._params(batch, cfg, False, rng_mode, upr)
+        ws = self._ensure_workspace(params)
+        sel_cap = self.sel_capacity(cfg.matches_per_ref)
+        sel = torch.zeros((R, sel_cap), dtype=torch.int32, device=dev)
+        n_samples = torch.zeros((R,), dtype=torch.int32, device=dev)
+        status = torch.zeros((R,), dtype=torch.int32, device=dev)
+        used = torch.zeros((R,), dtype=torch.int32, device=dev)
+        rounds = torch.zeros((R,), dtype=torch.int32, device=dev)
+        wsum = torch.zeros((R,), dtype=torch.float32, device=dev)
+        descs = self.upload_descs(batch)
+        o = N.LdpOutputs()
+        o.status, o.n_samples, o.sel_idx = status.data_ptr(), n_samples.data_ptr(), sel.data_ptr()
+        o.uniforms_used, o.rounds, o.weight_sum = used.data_ptr(), rounds.data_ptr(), wsum.data_ptr()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = self.lib.ldp_sample_refs(C.byref(params), C.c_void_p(descs.data_ptr()),
+                                      C.c_void_p(uniforms.data_ptr() if uniforms is not None else 0), C.byref(o),
+                                      C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()), C.c_void_p(stream))
+        N.check(rc, "ldp_sample_refs")
+        torch.cuda.current_stream(dev).synchronize()
+        return sel, n_samples, status, used
 
     def alloc_outputs(self, R: int, sel_cap: int, collect_debug: bool = False, taps: bool = False) -> DensifyOutputs:
         dev = self.device

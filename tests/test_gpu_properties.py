@@ -218,3 +218,28 @@ def test_cluster_size_does_not_change_results(engine, fast_scene):
         lib.ldp_debug_set_cluster(0)
     print("cluster sizes actually launched:", used)
     assert used[0] == 1 and max(used) >= 2
+
+
+def test_select_samples_with_coverage_drop_in(engine):
+    """core.sampling.select_samples_with_coverage: reference signature, reference RNG stream semantics."""
+    from lichtfeld_densification_plugin_b200.core.sampling import select_samples_with_coverage
+    from oracle import densify_oracle as O
+    rs = np.random.RandomState(3)
+    vals = (0.2 + 0.7 * (rs.permutation(120 * 90) + 0.5) / (120 * 90)).astype(np.float32).reshape(90, 120)
+    cert = torch.from_numpy(vals)
+    np.random.seed(77)
+    got = select_samples_with_coverage(cert, 3000)
+    after = np.random.random_sample()
+    ref_rng = np.random.RandomState(77)
+    taps = {}
+    want = O.select_samples(cert, 3000, rng=ref_rng, taps=taps)
+    # the oracle's s comes from torch-CPU; ours from an exact f64 sum: compare through the oracle fed with our s
+    if not np.array_equal(got, want):
+        s_exact = np.float32(taps["weights"].astype(np.float64).sum())
+        want = O.select_samples(cert, 3000, rng=np.random.RandomState(77), s_override=s_exact)
+        ref_rng = np.random.RandomState(77)
+        O.select_samples(cert, 3000, rng=ref_rng, s_override=s_exact)
+    assert np.array_equal(got, want)
+    assert after == ref_rng.random_sample()
+    top = select_samples_with_coverage(cert, 500, no_filter=True)
+    assert np.array_equal(top, O.select_samples(cert, 500, no_filter=True))
