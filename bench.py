@@ -328,18 +328,15 @@ def gpu_arm(args) -> None:
     import ctypes as C
     eng.lib.ldp_profile_enable(1)
     n_prof = 20
-    buf = (C.c_float * 8)()
-    acc, names = None, []
+    buf = (C.c_float * 64)()
+    kdict = {}
     for i in range(n_prof):
         eng.densify(batch, cfg, descs_dev=descs, outputs=outs[0])
-        n = eng.lib.ldp_profile_read(buf, 8)
-        if acc is None:
-            acc = np.zeros(n)
-            names = [eng.lib.ldp_profile_name(k).decode() for k in range(n)]
-        acc += np.array([buf[k] for k in range(n)])
+        n = eng.lib.ldp_profile_read(buf, 64)
+        for k in range(n):                       # kernels of all sub-batches, summed by name
+            name = eng.lib.ldp_profile_name(k).decode()
+            kdict[name] = kdict.get(name, 0.0) + float(buf[k]) / n_prof
     eng.lib.ldp_profile_enable(0)
-    kms = acc / n_prof
-    kdict = {n_: float(v) for n_, v in zip(names, kms)}
     dom = "ldp_stream_kernel"
     peak, peak_src = measured_hbm_peak()
     k1_bytes = R * nn * H * W * 4                     # every certainty value read exactly once

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LDP_ABI_VERSION 6
+#define LDP_ABI_VERSION 7
 #define LDP_MAX_NN 16          /* neighbours per reference view (the panel clamps to 10) */
 #define LDP_MAX_BINS 4096      /* coverage tiles per map: ceil(W/tile)*ceil(H/tile), tile = max(1, W/24) */
 
@@ -72,7 +72,9 @@ typedef struct ldp_params {
     int32_t no_filter;         /* core/sampling.py:15-21 + core/pipeline.py:739-743 */
     int32_t collect_debug;     /* core/pipeline.py:761-769 */
     int32_t rng_mode;          /* ldp_rng_mode */
-    int32_t reserved0;
+    int32_t scalar_loads;      /* 1: certainty planes are not 16-byte aligned -> scalar load path */
+    int32_t nn_max;            /* largest ldp_ref_desc.nn of the launch (0 = unknown): selects the unrolled stream kernel */
+    int32_t reserved1;
     uint64_t seed;             /* Philox key */
     int64_t uniforms_per_ref;  /* explicit mode: doubles available per reference view */
 } ldp_params;

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import build as _build
 
-LDP_ABI_VERSION = 6
+LDP_ABI_VERSION = 7
 LDP_MAX_NN = 16
 LDP_MAX_BINS = 4096
 
@@ -54,7 +54,8 @@ class LdpParams(C.Structure):
         ("matches_per_ref", C.c_int32), ("border", C.c_int32), ("tiles", C.c_int32),
         ("sample_cap", C.c_float), ("reproj_thresh", C.c_float), ("min_parallax_deg", C.c_float),
         ("sampson_thresh", C.c_double),
-        ("no_filter", C.c_int32), ("collect_debug", C.c_int32), ("rng_mode", C.c_int32), ("reserved0", C.c_int32),
+        ("no_filter", C.c_int32), ("collect_debug", C.c_int32), ("rng_mode", C.c_int32), ("scalar_loads", C.c_int32),
+        ("nn_max", C.c_int32), ("reserved1", C.c_int32),
         ("seed", C.c_uint64), ("uniforms_per_ref", C.c_int64),
     ]
 
@@ -91,7 +92,7 @@ REF_DESC_DTYPE = np.dtype(LdpRefDesc)
 EXPORTS = [
     "ldp_abi_version", "ldp_last_error_string", "ldp_sel_capacity", "ldp_workspace_bytes",
     "ldp_densify_refs", "ldp_sample_refs", "ldp_triangulate_samples", "ldp_last_launch_count",
-    "ldp_struct_size", "ldp_profile_enable", "ldp_profile_read", "ldp_profile_name", "ldp_debug_set_cluster", "ldp_debug_last_cluster", "ldp_debug_read_clocks",
+    "ldp_struct_size", "ldp_profile_enable", "ldp_profile_read", "ldp_profile_name", "ldp_debug_set_cluster", "ldp_debug_last_cluster", "ldp_debug_set_subbatches", "ldp_debug_read_clocks",
 ]
 
 _lock = threading.Lock()

@@ -15,7 +15,7 @@ thread_local std::string g_last_error;
 thread_local int g_launches = 0;
 
 // ---- optional per-kernel timing (ldp_profile_enable / ldp_profile_read)
-constexpr int MAX_PROF = 8;
+constexpr int MAX_PROF = 64;
 thread_local bool g_prof_on = false;
 thread_local cudaEvent_t g_prof_ev[2 * MAX_PROF];
 thread_local bool g_prof_ev_ready = false;
@@ -125,6 +125,8 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     g.size = m_main < N ? m_main : N;
     g.cov_budget = (p->matches_per_ref - g.size > 1) ? p->matches_per_ref - g.size : 1;
     g.vec = 0;
+    g.w_magic = ((1ull << 40) + (unsigned long long)p->W - 1) / (unsigned long long)p->W;
+    g.t_magic = ((1ull << 40) + (unsigned long long)g.tile - 1) / (unsigned long long)g.tile;
     int cs = 5;
     for (;; ++cs) {
         const size_t nchunk = ((size_t)N + ((size_t)1 << cs) - 1) >> cs;
@@ -146,6 +148,7 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
         if (cs > 20) return fail(LDP_ERR_INVALID, "map too large for the chunk table");
     }
     g.chunk_shift = cs;
+    g.draw_smem_bytes = (int)plan->k1_smem;
 
     ldp::Workspace& w = plan->ws;
     w.n_pad = align_up((size_t)N, 256);
@@ -165,7 +168,7 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
         if (lb > g.nbins) lb = g.nbins;
         g.prep_lb_cap = (int)align_up((size_t)lb, 4);
     }
-    plan->prep_smem = (size_t)g.prep_lb_cap * 8 + align_up((size_t)p->W * 2, 16);
+    plan->prep_smem = (size_t)g.prep_lb_cap * 8;
 
     size_t off = 0;
     char* b = static_cast<char*>(base);
@@ -195,7 +198,7 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     w.blk_before = reinterpret_cast<int32_t*>(carve(R * plan->nb2 * LDP_MAX_NN * sizeof(int32_t)));
     w.grp_base = reinterpret_cast<int32_t*>(carve(R * LDP_MAX_NN * sizeof(int32_t)));
     w.fix_list = reinterpret_cast<int2*>(carve(R * w.sel_cap * sizeof(int2)));
-    w.fix_count = reinterpret_cast<int32_t*>(carve(sizeof(int32_t)));
+    w.fix_count = reinterpret_cast<int32_t*>(carve(ldp::LDP_MAX_SUB * sizeof(int32_t)));
     plan->bytes = off;
     return LDP_OK;
 }
@@ -211,8 +214,9 @@ int check_outputs(const ldp_params* p, const ldp_outputs* o) {
 }
 
 int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* uniforms, const ldp_outputs* out,
-                  Plan& plan, int vec_ok, cudaStream_t st) {
+                  Plan& plan, int vec_ok, cudaStream_t st, int ref0, int nsubrefs) {
     plan.geom.vec = vec_ok;
+    plan.geom.ref0 = ref0;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(ldp::ldp_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
@@ -222,21 +226,27 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
         configured = true;
     }
     if (plan.prep_smem > 64 * 1024) return fail(LDP_ERR_INVALID, "map too wide for the prep kernel tables");
-    const dim3 grid((unsigned)plan.ws.nblk, (unsigned)p->n_refs);
+    const dim3 grid((unsigned)plan.ws.nblk, (unsigned)nsubrefs);
     cudaError_t e;
     { KernelTimer kt(st, "ldp_stream_kernel");
-      ldp::ldp_stream_kernel<<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); }
+      switch (p->nn_max) {          // max neighbours per view in this launch (0 = unknown)
+          case 1: ldp::ldp_stream_kernel<1><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+          case 2: ldp::ldp_stream_kernel<2><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+          case 3: ldp::ldp_stream_kernel<3><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+          case 4: ldp::ldp_stream_kernel<4><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+          default: ldp::ldp_stream_kernel<0><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+      } }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_stream_kernel");
     if (p->no_filter) {
         { KernelTimer kt(st, "ldp_topm_kernel");
-          ldp::ldp_topm_kernel<<<p->n_refs, ldp::K1_THREADS, 0, st>>>(*p, refs, plan.ws, *out, plan.geom); }
+          ldp::ldp_topm_kernel<<<nsubrefs, ldp::K1_THREADS, 0, st>>>(*p, refs, plan.ws, *out, plan.geom); }
         ++g_launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_topm_kernel");
         return LDP_OK;
     }
     if (plan.geom.chunk_shift > 7) {      // chunk sums are accumulated with atomics: start from zero
-        e = cudaMemsetAsync(plan.ws.csum, 0, (size_t)p->n_refs * plan.ws.nchunk_pad * sizeof(double), st);
+        e = cudaMemsetAsync(plan.ws.csum + (size_t)ref0 * plan.ws.nchunk_pad, 0, (size_t)nsubrefs * plan.ws.nchunk_pad * sizeof(double), st);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(csum)");
     }
     { KernelTimer kt(st, "ldp_prep_kernel");
@@ -249,14 +259,14 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
         // this smaller than sm_count / n_refs, so ask the occupancy API
         int csize = 1;
         for (int c = 8; c > 1; --c) {
-            if ((long long)p->n_refs * c > sm_count()) continue;
-            if (max_active_clusters(c, plan.k1_smem) >= p->n_refs) { csize = c; break; }
+            if ((long long)nsubrefs * c > sm_count()) continue;
+            if (max_active_clusters(c, plan.k1_smem) >= nsubrefs) { csize = c; break; }
         }
         if (g_force_cluster > 0) csize = g_force_cluster;
         KernelTimer kt(st, "ldp_draw_kernel");
         for (;;) {
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(p->n_refs * csize));
+            cfg.gridDim = dim3((unsigned)(nsubrefs * csize));
             cfg.blockDim = dim3(ldp::KD_THREADS);
             cfg.dynamicSmemBytes = plan.k1_smem;
             cfg.stream = st;
@@ -301,16 +311,24 @@ float parallax_cos_threshold(float min_deg) {
     return unord(lo);
 }
 
-int launch_geometry(const ldp_params* p, const ldp_ref_desc* refs, const ldp_outputs* out, Plan& plan,
-                    int have_bestk, cudaStream_t st) {
+ldp::GeomArgs make_geom_args(const ldp_params* p, const Plan& plan, int have_bestk, int ref0, int sub) {
     static float cached_deg = -1.f, cached_cos = 1.f;
     if (p->min_parallax_deg != cached_deg) { cached_cos = parallax_cos_threshold(p->min_parallax_deg); cached_deg = p->min_parallax_deg; }
     ldp::GeomArgs ga;
     ga.par_cos_max = cached_cos;
     ga.have_bestk = have_bestk;
     ga.nb2 = plan.nb2;
-    const dim3 grid((unsigned)plan.nb2, (unsigned)p->n_refs);
-    const dim3 ggrid((unsigned)((plan.ws.sel_cap + ldp::KG_THREADS - 1) / ldp::KG_THREADS), (unsigned)p->n_refs);
+    ga.ref0 = ref0;
+    ga.sub = sub;
+    return ga;
+}
+
+// gather -> compute -> fix+plan for views [ref0, ref0 + nsubrefs)
+int launch_geometry(const ldp_params* p, const ldp_ref_desc* refs, const ldp_outputs* out, Plan& plan,
+                    int have_bestk, cudaStream_t st, int ref0, int nsubrefs, int sub) {
+    const ldp::GeomArgs ga = make_geom_args(p, plan, have_bestk, ref0, sub);
+    const dim3 grid((unsigned)plan.nb2, (unsigned)nsubrefs);
+    const dim3 ggrid((unsigned)((plan.ws.sel_cap + ldp::KG_THREADS - 1) / ldp::KG_THREADS), (unsigned)nsubrefs);
     cudaError_t e;
     { KernelTimer kt(st, "ldp_gather_kernel");
       ldp::ldp_gather_kernel<<<ggrid, ldp::KG_THREADS, 0, st>>>(*p, refs, plan.ws, *out, ga); }
@@ -321,14 +339,57 @@ int launch_geometry(const ldp_params* p, const ldp_ref_desc* refs, const ldp_out
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_geometry_kernel");
     { KernelTimer kt(st, "ldp_fixplan_kernel");
-      ldp::ldp_fixplan_kernel<<<p->n_refs, ldp::K2_THREADS, (size_t)plan.nb2 * LDP_MAX_NN * 2 * sizeof(int), st>>>(*p, refs, plan.ws, *out, ga); }
+      ldp::ldp_fixplan_kernel<<<nsubrefs, ldp::K2_THREADS, (size_t)plan.nb2 * LDP_MAX_NN * 2 * sizeof(int), st>>>(*p, refs, plan.ws, *out, ga); }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_fixplan_kernel");
+    return LDP_OK;
+}
+
+// ordered scatter of all views of the launch (needs every view's kept count)
+int launch_pack(const ldp_params* p, const ldp_ref_desc* refs, const ldp_outputs* out, Plan& plan, cudaStream_t st) {
+    const ldp::GeomArgs ga = make_geom_args(p, plan, 1, 0, 0);
+    const dim3 grid((unsigned)plan.nb2, (unsigned)p->n_refs);
     { KernelTimer kt(st, "ldp_pack_kernel");
       ldp::ldp_pack_kernel<<<grid, ldp::K3_THREADS, 0, st>>>(*p, refs, plan.ws, *out, ga); }
     ++g_launches;
-    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_pack_kernel");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ldp_pack_kernel");
     return LDP_OK;
+}
+
+// Internal streams for pipelining a launch over sub-batches of views: the kernels of the path stress different
+// resources (HBM stream, issue-bound prep, latency-bound draw, DRAM-latency gather, FP64 geometry), so the kernels of
+// one sub-batch overlap those of the next.  Fork/join with events keeps the call stream-ordered for the caller.
+struct SubStreams {
+    cudaStream_t s[ldp::LDP_MAX_SUB];
+    cudaEvent_t start, done[ldp::LDP_MAX_SUB];
+    bool ok = false;
+};
+SubStreams& substreams() {
+    static thread_local SubStreams ss;
+    if (!ss.ok) {
+        bool good = cudaEventCreateWithFlags(&ss.start, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < ldp::LDP_MAX_SUB && good; ++i) {
+            good = cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&ss.done[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        ss.ok = good;
+    }
+    return ss;
+}
+
+int g_force_sub = -1;      // ldp_debug_set_subbatches; -1 = environment / default
+int choose_subbatches(int n_refs) {
+    int n = g_force_sub;
+    if (n < 0) {
+        static int env_n = -2;
+        if (env_n == -2) { const char* e = getenv("LDP_SUBBATCH"); env_n = e ? atoi(e) : 0; }
+        n = env_n;
+    }
+    if (n <= 0) n = 1;
+    if (n > ldp::LDP_MAX_SUB) n = ldp::LDP_MAX_SUB;
+    while (n > 1 && n_refs < 2 * n) --n;
+    return n;
 }
 
 }  // namespace
@@ -358,6 +419,12 @@ int ldp_profile_read(float* ms_out, int max_n) {
 }
 
 int ldp_debug_last_cluster(void) { return g_last_cluster; }
+
+int ldp_debug_set_subbatches(int n) {
+    if (n < -1 || n > ldp::LDP_MAX_SUB) return fail(LDP_ERR_INVALID, "sub-batches must be -1 (default) .. 8");
+    g_force_sub = n;
+    return LDP_OK;
+}
 
 int ldp_debug_read_clocks(const ldp_params* params, void* workspace, long long* host_out) {
     Plan plan;
@@ -397,8 +464,8 @@ int ldp_workspace_bytes(const ldp_params* params, size_t* bytes_out) {
 
 // vec_hint: the host wrapper guarantees 16-byte aligned certainty planes when W % 4 == 0; the planes'
 // addresses live in device memory, so alignment cannot be checked here without a copy.  Callers that
-// cannot guarantee it set params->reserved0 = 1 to force the scalar load path.
-static int vec_ok_for(const ldp_params* p) { return (p->W % 4 == 0 && p->reserved0 == 0) ? 1 : 0; }
+// cannot guarantee it set params->scalar_loads = 1 to force the scalar load path.
+static int vec_ok_for(const ldp_params* p) { return (p->W % 4 == 0 && p->scalar_loads == 0) ? 1 : 0; }
 
 // L2 residency for the inter-kernel workspace (weights / p, winning neighbour, sample records): the path re-reads
 // them from several kernels of the same call while ~0.2 GB of certainty planes stream through the 126 MB L2.
@@ -461,9 +528,31 @@ int ldp_densify_refs(const ldp_params* params, const ldp_ref_desc* refs, const d
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // hot prefix of the workspace: w/p and winning-neighbour planes (carved first)
     L2Window l2(st, plan.ws.w, (size_t)params->n_refs * plan.ws.n_pad * 5);
-    rc = launch_sample(params, refs, uniforms, out, plan, vec_ok_for(params), st);
-    if (rc != LDP_OK) return rc;
-    return launch_geometry(params, refs, out, plan, 1, st);
+    cudaError_t e = cudaMemsetAsync(plan.ws.fix_count, 0, ldp::LDP_MAX_SUB * sizeof(int32_t), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(fix_count)");
+    const int nsub = choose_subbatches(params->n_refs);
+    if (nsub == 1) {
+        rc = launch_sample(params, refs, uniforms, out, plan, vec_ok_for(params), st, 0, params->n_refs);
+        if (rc != LDP_OK) return rc;
+        rc = launch_geometry(params, refs, out, plan, 1, st, 0, params->n_refs, 0);
+        if (rc != LDP_OK) return rc;
+        return launch_pack(params, refs, out, plan, st);
+    }
+    SubStreams& ss = substreams();
+    if (!ss.ok) return fail(LDP_ERR_CUDA, "cannot create internal streams");
+    if ((e = cudaEventRecord(ss.start, st)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord(start)");
+    for (int h = 0; h < nsub; ++h) {
+        const int lo = (int)(((long long)h * params->n_refs) / nsub), hi = (int)(((long long)(h + 1) * params->n_refs) / nsub);
+        cudaStream_t sh = ss.s[h];
+        if ((e = cudaStreamWaitEvent(sh, ss.start, 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent(start)");
+        rc = launch_sample(params, refs, uniforms, out, plan, vec_ok_for(params), sh, lo, hi - lo);
+        if (rc != LDP_OK) return rc;
+        rc = launch_geometry(params, refs, out, plan, 1, sh, lo, hi - lo, h);
+        if (rc != LDP_OK) return rc;
+        if ((e = cudaEventRecord(ss.done[h], sh)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord(done)");
+        if ((e = cudaStreamWaitEvent(st, ss.done[h], 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent(done)");
+    }
+    return launch_pack(params, refs, out, plan, st);
 }
 
 int ldp_sample_refs(const ldp_params* params, const ldp_ref_desc* refs, const double* uniforms,
@@ -480,7 +569,7 @@ int ldp_sample_refs(const ldp_params* params, const ldp_ref_desc* refs, const do
     int rc = make_plan(params, base, &plan);
     if (rc != LDP_OK) return rc;
     if (plan.bytes + (size_t)(base - static_cast<char*>(workspace)) > workspace_bytes) return fail(LDP_ERR_WORKSPACE, "workspace too small");
-    return launch_sample(params, refs, uniforms, out, plan, vec_ok_for(params), static_cast<cudaStream_t>(stream));
+    return launch_sample(params, refs, uniforms, out, plan, vec_ok_for(params), static_cast<cudaStream_t>(stream), 0, params->n_refs);
 }
 
 int ldp_triangulate_samples(const ldp_params* params, const ldp_ref_desc* refs, const ldp_outputs* out,
@@ -500,9 +589,11 @@ int ldp_triangulate_samples(const ldp_params* params, const ldp_ref_desc* refs, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaMemsetAsync(plan.ws.kept, 0, (size_t)params->n_refs * sizeof(int32_t), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(kept)");
-    e = cudaMemsetAsync(plan.ws.fix_count, 0, sizeof(int32_t), st);
+    e = cudaMemsetAsync(plan.ws.fix_count, 0, ldp::LDP_MAX_SUB * sizeof(int32_t), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(fix_count)");
-    return launch_geometry(params, refs, out, plan, 0, st);
+    rc = launch_geometry(params, refs, out, plan, 0, st, 0, params->n_refs, 0);
+    if (rc != LDP_OK) return rc;
+    return launch_pack(params, refs, out, plan, st);
 }
 
 }  // extern "C"

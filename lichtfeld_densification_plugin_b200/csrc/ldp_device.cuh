@@ -6,6 +6,8 @@
 
 namespace ldp {
 
+constexpr int LDP_MAX_SUB = 8;      // sub-batches a launch may be pipelined over
+
 // ---------------------------------------------------------------------------------------------
 // Workspace carved by the host (ldp_api.cu).  Everything is per reference view r; rows are padded so
 // that float4 / 16-byte accesses stay aligned.
@@ -41,7 +43,7 @@ struct Workspace {
     int32_t* blk_before; // [R][nb2][LDP_MAX_NN] kept samples of the group in earlier tiles of the view (pack plan)
     int32_t* grp_base;   // [R][LDP_MAX_NN] output offset of each group inside the view (pack plan)
     int2* fix_list;      // [R*sel_cap] (view, sample) pairs whose null-vector iteration did not converge
-    int32_t* fix_count;  // [1]
+    int32_t* fix_count;  // [LDP_MAX_SUB] one counter per sub-batch (its list starts at ref0 * sel_cap)
     long long* dbgclk;   // [R][32] phase timestamps of the draw kernel (written only with -DLDP_PHASE_CLOCKS)
     size_t n_pad, n_words, found_cap, sel_cap, topk_cap, nchunk_pad, nblk, bins_cap, draw_cmax;
 };
@@ -56,9 +58,13 @@ struct SampleGeom {     // launch-constant shape of the sampler
     int cov_budget;     // max(1, M - size)
     int vec;            // cert planes are 16-B aligned and W % 4 == 0
     int prep_lb_cap;    // local tile bins per CTA of the prep kernel
+    unsigned long long w_magic;   // ceil(2^40 / W): floor(n / W) = (n * w_magic) >> 40 for n < 2^21 * ...
+    unsigned long long t_magic;   // ceil(2^40 / tile)
+    int ref0;           // first view of this sub-launch (views are indexed blockIdx + ref0)
     int draw_ept;       // draw kernel: chunk-table entries per thread (multiple of 8)
     int draw_pre_cap;   // draw kernel: doubles in the padded prefix table
     int draw_ng;        // draw kernel: guide-table buckets
+    int draw_smem_bytes; // draw kernel: dynamic shared memory of the launch
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -90,6 +96,19 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
     __syncthreads();
     T r = (lane < nw) ? scratch[lane] : T(0);
     return warp_sum(r);
+}
+// block-wide maximum of a float (all threads get it)
+__device__ __forceinline__ float block_sum_max(float v, float* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    float r = (lane < nw) ? scratch[lane] : -3.0e38f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+    return r;
 }
 __device__ __forceinline__ int block_min(int v, int* scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;

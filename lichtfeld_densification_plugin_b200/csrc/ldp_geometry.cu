@@ -49,6 +49,8 @@ struct GeomArgs {           // launch-constant extras computed on the host
     float par_cos_max;      // parallax: keep iff clip(cos) <= par_cos_max  (== f32 arccos/degrees test, see ldp_api.cu)
     int have_bestk;
     int nb2;                // 128-sample tiles per view
+    int ref0;               // first view of this sub-launch
+    int sub;                // sub-batch index (selects the fix-up counter)
 };
 
 __device__ __forceinline__ void stage_constants(const ldp_ref_desc* rd, RefConst& rc, PairConst* pc, int t, int nt) {
@@ -426,7 +428,7 @@ ldp_gather_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
 {
     __shared__ RefConst rc;
     __shared__ PairConst pc[LDP_MAX_NN];
-    const int r = blockIdx.y;
+    const int r = blockIdx.y + ga.ref0;
     const int S = out.n_samples[r];
     const int i0 = blockIdx.x * KG_THREADS;
     if (i0 >= S) return;
@@ -461,7 +463,7 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
     __shared__ RefConst rc;
     __shared__ PairConst pc[LDP_MAX_NN];
     __shared__ int s_cnt[LDP_MAX_NN], s_first[LDP_MAX_NN];
-    const int r = blockIdx.y;
+    const int r = blockIdx.y + ga.ref0;
     const int S = out.n_samples[r];
     const int i0 = blockIdx.x * K2_THREADS;
     if (i0 >= S) return;
@@ -479,8 +481,8 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
         SampleResult s;
         eval_sample<false>(P, rc, pc, ga, rec, craw, s);
         if (!s.converged) {                 // rare: leave the record in place for the fix-up (flag bit 7), keep = 0 for now
-            const int slot = atomicAdd(ws.fix_count, 1);
-            ws.fix_list[slot] = make_int2(r, i);
+            const int slot = atomicAdd(ws.fix_count + ga.sub, 1);
+            ws.fix_list[(size_t)ga.ref0 * ws.sel_cap + slot] = make_int2(r, i);
             ws.flags[o] = (uint8_t)(0x80 | (s.grp << 2));
             s.keep = 0;
         } else {
@@ -516,15 +518,16 @@ ldp_fixplan_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, co
     __shared__ RefConst rc;
     __shared__ PairConst pc[LDP_MAX_NN];
     __shared__ int s_tot[LDP_MAX_NN], s_first[LDP_MAX_NN], s_base[LDP_MAX_NN];
-    const int r = blockIdx.x, tid = threadIdx.x;
+    const int r = blockIdx.x + ga.ref0, tid = threadIdx.x;
     const int S = out.n_samples[r];
     const int nb = (S + K2_THREADS - 1) / K2_THREADS;
-    const int n = *ws.fix_count;
+    const int n = ws.fix_count[ga.sub];
+    const int2* fix_list = ws.fix_list + (size_t)ga.ref0 * ws.sel_cap;
     if (n > 0) {
         stage_constants(refs + r, rc, pc, tid, K2_THREADS);
         __syncthreads();
         for (int e = tid; e < n; e += K2_THREADS) {
-            const int2 it = ws.fix_list[e];
+            const int2 it = fix_list[e];
             if (it.x != r) continue;
             const int i = it.y;
             const size_t o = (size_t)r * ws.sel_cap + i;

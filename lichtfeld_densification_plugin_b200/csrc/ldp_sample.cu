@@ -30,6 +30,15 @@ constexpr int KD_THREADS = 1024;     // draw kernel: 1024 threads x 64 registers
 constexpr int KS_THREADS = 256;      // stream / prep kernels: full grid
 constexpr int KS_SPAN = 8192;        // pixels per CTA of the full-grid passes (multiple of every chunk size)
 
+// (double)f without the conversion (XU) pipe for normal f (any sign): rebias the exponent, shift the mantissa.
+// Zero, subnormal, inf and NaN inputs take the real conversion.
+__device__ __forceinline__ double widen_f32(float f) {
+    const uint32_t b = __float_as_uint(f);
+    const uint32_t e = (b >> 23) & 0xffu;
+    if (e == 0u || e == 0xffu) return (double)f;
+    return __hiloint2double((int)((b & 0x80000000u) | (((b & 0x7fffffffu) >> 3) + 0x38000000u)), (int)(b << 29));
+}
+
 struct K1Shared {
     double red_d[32];
     int red_i[32];
@@ -62,14 +71,32 @@ __device__ void bitonic_sort_desc(unsigned long long* a, int n) {
 //      writes w = min(best, cap) * border_mask (f32) and the winning neighbour (u8) to the L2-resident
 //      workspace, and one f64 partial weight sum + NaN/negative flags per CTA.
 //      reference core/pipeline.py:634-635 (torch.max over neighbours), core/sampling.py:12-14,23-25
+//      HBM-bound by design: the instruction budget per 4-pixel quad is kept small (plane pointers in
+//      registers, magic-number row/column, interior fast path for the border mask, NaN found via the sum).
 // =============================================================================================
+__device__ __forceinline__ uint32_t div_magic(uint32_t n, unsigned long long magic) {     // floor(n / d), d's magic = ceil(2^40/d)
+    return (uint32_t)(((unsigned long long)n * magic) >> 40);
+}
+
+__device__ __forceinline__ void quad_border_weights(float wv[4], int px, int x, int y, int W, int H, int border, int N) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float m = (x >= border && x <= W - 1 - border && y >= border && y <= H - 1 - border) ? 1.f : 0.f;
+        float v = wv[j] * m;                                   // cert * inside.float(): inf * 0 = NaN like torch
+        if (px + j >= N) v = 0.f;
+        wv[j] = v;
+        if (++x == W) { x = 0; ++y; }
+    }
+}
+
+template <int NNMAX>      // 1..4: plane pointers held in registers, loop fully unrolled; 0: any nn (pointers in shared memory)
 __global__ void __launch_bounds__(KS_THREADS)
 ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const SampleGeom G)
 {
     __shared__ const float* s_cert[LDP_MAX_NN];
     __shared__ double red_d[32];
-    __shared__ int red_i[32];
-    const int r = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
+    __shared__ float red_f[32];
+    const int r = blockIdx.y + G.ref0, blk = blockIdx.x, tid = threadIdx.x;
     const int N = G.N;
     const ldp_ref_desc* rd = refs + r;
     const int nn = rd->nn;
@@ -78,7 +105,6 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
         if (tid == 0) {
             ws.rstat[r].s = 0.f; ws.rstat[r].npos = 0; ws.rstat[r].emin = 0x7fffffff; ws.rstat[r].bad = 0;
             ws.kept[r] = 0;
-            if (r == 0) *ws.fix_count = 0;
         }
         unsigned long long* gb = ws.gbins + (size_t)r * ws.bins_cap;
         for (int i = tid; i < (int)ws.bins_cap; i += KS_THREADS) gb[i] = 0ull;
@@ -87,68 +113,75 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
     float* __restrict__ w = ws.w + (size_t)r * ws.n_pad;
     uint8_t* __restrict__ bk = ws.bestk + (size_t)r * ws.n_pad;
     const float cap = P.sample_cap;
-    const int W = P.W, H = P.H, border = P.border;
+    const int W = P.W, H = P.H, border = P.no_filter ? 0 : P.border;
     const int base = blk * KS_SPAN;
     double lsum = 0.0;
-    int lbad = 0;
+    float lmin = 0.f;                      // running minimum: negative weights (NaN is caught through the sum)
     if (nn > 0) {
+        const float* c0 = s_cert[0];
+        const float* c1 = (NNMAX >= 2) ? s_cert[min(1, nn - 1)] : nullptr;
+        const float* c2 = (NNMAX >= 3) ? s_cert[min(2, nn - 1)] : nullptr;
+        const float* c3 = (NNMAX >= 4) ? s_cert[min(3, nn - 1)] : nullptr;
 #pragma unroll 2
         for (int it = 0; it < KS_SPAN / (KS_THREADS * 4); ++it) {
             const int px = base + (it * KS_THREADS + tid) * 4;
             if (px >= N) break;
-            float best[4];
+            float wv[4];
             int bi[4] = {0, 0, 0, 0};
             if (G.vec) {
-                const float4 v = ld_stream4(s_cert[0] + px);
-                best[0] = v.x; best[1] = v.y; best[2] = v.z; best[3] = v.w;
+                const float4 v = ld_stream4(c0 + px);
+                wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
+                if (NNMAX > 0) {           // duplicated pointers for k >= nn re-read plane nn-1: never strictly greater
+                    float4 c;
+                    if (NNMAX >= 2) { c = ld_stream4(c1 + px);
+                        if (c.x > wv[0] || c.x != c.x) { wv[0] = c.x; bi[0] = 1; } if (c.y > wv[1] || c.y != c.y) { wv[1] = c.y; bi[1] = 1; }
+                        if (c.z > wv[2] || c.z != c.z) { wv[2] = c.z; bi[2] = 1; } if (c.w > wv[3] || c.w != c.w) { wv[3] = c.w; bi[3] = 1; } }
+                    if (NNMAX >= 3) { c = ld_stream4(c2 + px);
+                        if (c.x > wv[0] || c.x != c.x) { wv[0] = c.x; bi[0] = 2; } if (c.y > wv[1] || c.y != c.y) { wv[1] = c.y; bi[1] = 2; }
+                        if (c.z > wv[2] || c.z != c.z) { wv[2] = c.z; bi[2] = 2; } if (c.w > wv[3] || c.w != c.w) { wv[3] = c.w; bi[3] = 2; } }
+                    if (NNMAX >= 4) { c = ld_stream4(c3 + px);
+                        if (c.x > wv[0] || c.x != c.x) { wv[0] = c.x; bi[0] = 3; } if (c.y > wv[1] || c.y != c.y) { wv[1] = c.y; bi[1] = 3; }
+                        if (c.z > wv[2] || c.z != c.z) { wv[2] = c.z; bi[2] = 3; } if (c.w > wv[3] || c.w != c.w) { wv[3] = c.w; bi[3] = 3; } }
+                } else {
 #pragma unroll 4
-                for (int k = 1; k < nn; ++k) {
-                    const float4 c = ld_stream4(s_cert[k] + px);
-                    if (c.x > best[0]) { best[0] = c.x; bi[0] = k; }
-                    if (c.y > best[1]) { best[1] = c.y; bi[1] = k; }
-                    if (c.z > best[2]) { best[2] = c.z; bi[2] = k; }
-                    if (c.w > best[3]) { best[3] = c.w; bi[3] = k; }
+                    for (int k = 1; k < nn; ++k) {
+                        const float4 c = ld_stream4(s_cert[k] + px);
+                        if (c.x > wv[0] || c.x != c.x) { wv[0] = c.x; bi[0] = k; }
+                        if (c.y > wv[1] || c.y != c.y) { wv[1] = c.y; bi[1] = k; }
+                        if (c.z > wv[2] || c.z != c.z) { wv[2] = c.z; bi[2] = k; }
+                        if (c.w > wv[3] || c.w != c.w) { wv[3] = c.w; bi[3] = k; }
+                    }
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) best[j] = (px + j < N) ? __ldcs(s_cert[0] + px + j) : 0.f;
+                for (int j = 0; j < 4; ++j) wv[j] = (px + j < N) ? __ldcs(c0 + px + j) : 0.f;
                 for (int k = 1; k < nn; ++k) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float c = (px + j < N) ? __ldcs(s_cert[k] + px + j) : 0.f;
-                        if (c > best[j]) { best[j] = c; bi[j] = k; }
+                        if (c > wv[j] || c != c) { wv[j] = c; bi[j] = k; }
                     }
                 }
             }
-            int y = px / W, x = px - y * W;
-            float wv[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float c = (best[j] > cap) ? cap : best[j];          // torch.clamp(max=cap): NaN stays NaN
-                float m = 1.f;
-                if (!P.no_filter)
-                    m = (x >= border && x <= W - 1 - border && y >= border && y <= H - 1 - border) ? 1.f : 0.f;
-                float v = c * m;
-                if (px + j >= N) v = 0.f;
-                wv[j] = v;
-                lbad |= (v != v) ? 1 : 0;
-                lbad |= (v < 0.f) ? 2 : 0;
-                lsum += (double)v;
-                if (++x == W) { x = 0; ++y; }
-            }
+            for (int j = 0; j < 4; ++j) wv[j] = (wv[j] > cap) ? cap : wv[j];          // torch.clamp(max=cap): NaN stays NaN
+            const int y = (int)div_magic((uint32_t)px, G.w_magic), x = px - y * W;
+            const bool interior = y >= border && y <= H - 1 - border && x >= border && x + 3 <= W - 1 - border && px + 3 < N;
+            if (!interior) quad_border_weights(wv, px, x, y, W, H, border, N);
+            lmin = fminf(lmin, fminf(fminf(wv[0], wv[1]), fminf(wv[2], wv[3])));
+            lsum += (widen_f32(wv[0]) + widen_f32(wv[1])) + (widen_f32(wv[2]) + widen_f32(wv[3]));
             *reinterpret_cast<float4*>(w + px) = make_float4(wv[0], wv[1], wv[2], wv[3]);
-            *reinterpret_cast<uchar4*>(bk + px) = make_uchar4((unsigned char)bi[0], (unsigned char)bi[1],
-                                                              (unsigned char)bi[2], (unsigned char)bi[3]);
+            *reinterpret_cast<uint32_t*>(bk + px) = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
         }
     }
     if (blk == (int)gridDim.x - 1) {       // keep the row padding [N, n_pad) zero: the draw kernel's 32-byte scans read it
         for (int i = ((N + 3) & ~3) + tid; i < (int)ws.n_pad; i += KS_THREADS) w[i] = 0.f;
     }
     const double bsum = block_sum(lsum, red_d);
-    const int bbad = block_sum((lbad & 1) | ((lbad & 2) << 15), red_i);
+    const float bmin = -block_sum_max(-lmin, red_f);
     if (tid == 0) {
         ws.partial[(size_t)r * ws.nblk + blk] = bsum;
-        ws.bflags[(size_t)r * ws.nblk + blk] = ((bbad & 0xffff) ? 1 : 0) | ((bbad >> 16) ? 2 : 0) | ((nn <= 0) ? 4 : 0);
+        ws.bflags[(size_t)r * ws.nblk + blk] = ((bsum != bsum) ? 1 : 0) | ((bmin < 0.f) ? 2 : 0) | ((nn <= 0) ? 4 : 0);
     }
 }
 
@@ -158,17 +191,17 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
 //      global chunk table; per-tile arg-max of p (the coverage picks) via shared-memory then global 64-bit
 //      atomicMax on (p bits, ~index); number of positive p and their smallest exponent (exactness test).
 //      reference core/sampling.py:26-29 (normalise), :34-50 (coverage walk == per-tile arg-max)
+//      Issue-bound: per quad one tile lookup (quads that straddle a tile edge take the per-pixel path).
 // =============================================================================================
 __global__ void __launch_bounds__(KS_THREADS)
 ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
                 const SampleGeom G)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red_d[32];
     __shared__ int red_i[32];
     __shared__ float s_s;
     __shared__ int s_bad;
-    const int r = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int r = blockIdx.y + G.ref0, blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int N = G.N, W = P.W;
     const ldp_ref_desc* rd = refs + r;
     // ---- s: fixed-order reduction of the per-CTA partials (every CTA of the view computes the same value)
@@ -198,16 +231,14 @@ ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     const float s = s_s;
     if (s_bad || !(s > 0.f)) return;       // the draw kernel reports the status
 
-    // ---- shared tables: x -> tile column, local tile bins
+    // ---- local tile bins of the rows this CTA covers
     const int base = blk * KS_SPAN;
     const int end = min(base + KS_SPAN, N);
-    const int y_first = base / W, y_last = (end - 1) / W;
-    const int ty0 = y_first / G.tile, ty1 = y_last / G.tile;
+    const int y_first = (int)div_magic((uint32_t)base, G.w_magic), y_last = (int)div_magic((uint32_t)(end - 1), G.w_magic);
+    const int ty0 = (int)div_magic((uint32_t)y_first, G.t_magic), ty1 = (int)div_magic((uint32_t)y_last, G.t_magic);
     const int nlb = (ty1 - ty0 + 1) * G.nbx;
     unsigned long long* lb = reinterpret_cast<unsigned long long*>(smem_raw);            // [nlb]
-    unsigned short* xt = reinterpret_cast<unsigned short*>(lb + G.prep_lb_cap);          // [W]
     for (int i = tid; i < nlb; i += KS_THREADS) lb[i] = 0ull;
-    for (int i = tid; i < W; i += KS_THREADS) xt[i] = (unsigned short)(i / G.tile);
     __syncthreads();
 
     float* __restrict__ w = ws.w + (size_t)r * ws.n_pad;
@@ -215,32 +246,59 @@ ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     const int cs = G.chunk_shift;
     const int gl = min(32, (1 << cs) >> 2);            // lanes that share one chunk
     int lpos = 0;
-    int lemin = 0x7fffffff;
+    uint32_t lminbits = 0x7fffffffu;                   // smallest positive p (bit pattern orders like the value)
 #pragma unroll 2
     for (int it = 0; it < KS_SPAN / (KS_THREADS * 4); ++it) {
         const int px = base + (it * KS_THREADS + tid) * 4;     // warp-uniform trip count: whole warps drop out together
         double a = 0.0;
         if (px < N) {
             const float4 v = *reinterpret_cast<const float4*>(w + px);
-            const float wv[4] = {v.x, v.y, v.z, v.w};
             float pv[4];
-            int y = px / W, x = px - y * W;
-            int lrow = (y / G.tile - ty0) * G.nbx;
+            pv[0] = __fdiv_rn(v.x, s); pv[1] = __fdiv_rn(v.y, s);              // core/sampling.py:29 (f32 division)
+            pv[2] = __fdiv_rn(v.z, s); pv[3] = __fdiv_rn(v.w, s);
+            *reinterpret_cast<float4*>(w + px) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+            a = (widen_f32(pv[0]) + widen_f32(pv[1])) + (widen_f32(pv[2]) + widen_f32(pv[3]));
+            // positives, smallest positive
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float p = __fdiv_rn(wv[j], s);                     // core/sampling.py:29 (f32 division)
-                pv[j] = p;
-                if (p > 0.f) {
-                    a += (double)p;
-                    ++lpos;
-                    lemin = min(lemin, (int)((__float_as_uint(p) >> 23) & 0xffu));
-                    const int b = lrow + xt[x];
-                    const unsigned long long key = cov_key(p, px + j);
-                    if (lb[b] < key) atomicMax(&lb[b], key);
-                }
-                if (++x == W) { x = 0; ++y; lrow = (y / G.tile - ty0) * G.nbx; }
+                const uint32_t b = __float_as_uint(pv[j]);
+                lpos += (pv[j] > 0.f) ? 1 : 0;
+                lminbits = min(lminbits, (pv[j] > 0.f) ? b : 0x7fffffffu);
             }
-            *reinterpret_cast<float4*>(w + px) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+            // per-tile arg-max.  A quad lies in one image row (W % 4 == 0 on this path) and touches at most two tiles:
+            // pixels [0, nsplit) belong to tile tx0, the rest to tx0 + 1.  Both halves are handled without divergence.
+            const int y = (int)div_magic((uint32_t)px, G.w_magic), x = px - y * W;
+            if (G.vec) {
+                const int tx0 = (int)div_magic((uint32_t)x, G.t_magic);
+                const int nsplit = min(4, (tx0 + 1) * G.tile - x);
+                const int brow = ((int)div_magic((uint32_t)y, G.t_magic) - ty0) * G.nbx + tx0;
+                float pm0 = 0.f, pm1 = 0.f;
+                int j0 = 0, j1 = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {                      // strict > keeps the lowest index on ties
+                    if (j < nsplit) { if (pv[j] > pm0) { pm0 = pv[j]; j0 = j; } }
+                    else            { if (pv[j] > pm1) { pm1 = pv[j]; j1 = j; } }
+                }
+                if (pm0 > 0.f) {
+                    const unsigned long long key = cov_key(pm0, px + j0);
+                    if (lb[brow] < key) atomicMax(&lb[brow], key);
+                }
+                if (pm1 > 0.f) {
+                    const unsigned long long key = cov_key(pm1, px + j1);
+                    if (lb[brow + 1] < key) atomicMax(&lb[brow + 1], key);
+                }
+            } else {
+                int yy = y, xx = x;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (pv[j] > 0.f && px + j < N) {
+                        const int b = ((int)div_magic((uint32_t)yy, G.t_magic) - ty0) * G.nbx + (int)div_magic((uint32_t)xx, G.t_magic);
+                        const unsigned long long key = cov_key(pv[j], px + j);
+                        if (lb[b] < key) atomicMax(&lb[b], key);
+                    }
+                    if (++xx == W) { xx = 0; ++yy; }
+                }
+            }
         }
         for (int o = 1; o < gl; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if (px < N && (lane & (gl - 1)) == 0) {
@@ -249,10 +307,10 @@ ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
         }
     }
     const int npos = block_sum(lpos, red_i);
-    const int emin = block_min(lemin, red_i);
+    const int eminbits = block_min((int)lminbits, red_i);
     if (tid == 0) {
         if (npos) atomicAdd(&ws.rstat[r].npos, npos);
-        if (emin != 0x7fffffff) atomicMin(&ws.rstat[r].emin, emin);
+        if (eminbits != 0x7fffffff) atomicMin(&ws.rstat[r].emin, (eminbits >> 23) & 0xff);
     }
     __syncthreads();
     unsigned long long* gb = ws.gbins + (size_t)r * ws.bins_cap;
@@ -302,8 +360,9 @@ __device__ __forceinline__ void red_add_f64(double* addr, double v) {
 // Zero and subnormal inputs take the real conversion (never on the hot path: p >= 2^-126 there).
 __device__ __forceinline__ double widen_pos(float f) {
     const uint32_t b = __float_as_uint(f);
-    if ((b >> 23) == 0u) return (double)f;
-    return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+    if ((b >> 23) == 0u && b != 0u) return (double)f;          // subnormal: never on the hot path
+    const double d = __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+    return (b == 0u) ? 0.0 : d;                                // zeros (border, already drawn) without a branch
 }
 
 // numpy's predicate fl64(x / total) > u, decided without dividing whenever x is outside a 2^-50 relative band
@@ -344,7 +403,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
 
     const int C = (int)cluster.num_blocks();
     const int crank = (int)cluster.block_rank();
-    const int r = blockIdx.x / C;
+    const int r = blockIdx.x / C + G.ref0;
     const int tid = threadIdx.x, lane = tid & 31;
     const int T = blockDim.x;
     const int gtid = crank * T + tid, GT = C * T;
@@ -386,31 +445,35 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     const double* U = uniforms ? uniforms + (size_t)r * (size_t)P.uniforms_per_ref : nullptr;
     const uint32_t rng_stream = rd->rng_stream;
 
+    LDP_CLK(ws, r, 1);
     while (true) {
         // ---- (a) padded inclusive prefix of the global chunk sums: 8-entry rows per thread, one block scan
         if (tid == 0) sh.n_found = 0;
+        // coalesced copy of the global chunk sums into the padded table, then 8-entry rows per thread
+        for (int i = 2 * tid; i < nchunk; i += 2 * T) {
+            const double2 d = __ldcg(reinterpret_cast<const double2*>(gcsum + i));          // nchunk_pad is even
+            *reinterpret_cast<double2*>(pre + pad8(i)) = make_double2(d.x, (i + 1 < nchunk) ? d.y : 0.0);
+        }
+        __syncthreads();
         double run = 0.0;
         const int e0 = tid * EPT;
         for (int q = 0; q < EPT; q += 8) {
             const int i0 = e0 + q;
-            double v[8];
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-                double2 d = make_double2(0.0, 0.0);
-                if (i0 + j < nchunk) d = __ldcg(reinterpret_cast<const double2*>(gcsum + i0 + j));   // nchunk_pad is even
-                v[j] = d.x;
-                v[j + 1] = (i0 + j + 1 < nchunk) ? d.y : 0.0;
-            }
             if (i0 < nchunk) {
+                double2* row = reinterpret_cast<double2*>(pre + pad8(i0));
+                double v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) { const double2 d = row[j >> 1]; v[j] = d.x; v[j + 1] = (i0 + j + 1 < nchunk) ? d.y : 0.0; }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { run += v[j]; v[j] = run; }
-                double2* dst = reinterpret_cast<double2*>(pre + pad8(i0));
 #pragma unroll
-                for (int j = 0; j < 8; j += 2) dst[j >> 1] = make_double2(v[j], v[j + 1]);
+                for (int j = 0; j < 8; j += 2) row[j >> 1] = make_double2(v[j], v[j + 1]);
             }
         }
+        if (rounds == 0) LDP_CLK(ws, r, 14);
         double total;
         const double base = block_exclusive_scan(run, sh.red_d, &total);
+        if (rounds == 0) LDP_CLK(ws, r, 15);
         for (int q = 0; q < EPT; q += 8) {
             const int i0 = e0 + q;
             if (i0 < nchunk) {
@@ -419,8 +482,9 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 for (int j = 0; j < 4; ++j) { double2 d = dst[j]; d.x += base; d.y += base; dst[j] = d; }
             }
         }
-        for (int i = tid; i < NG + 2; i += T) guide[i] = nchunk - 1;
+        if (rounds == 0) for (int i = tid; i < NG + 2; i += T) guide[i] = nchunk - 1;
         __syncthreads();
+        if (rounds == 0) LDP_CLK(ws, r, 16);
         total = pre[pad8(nchunk - 1)];
         if (rounds == 0) {
             // numpy's checks in RandomState.choice, in numpy's order
@@ -433,6 +497,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 if (st.emin == 0 || etot - (st.emin - 150) >= 53) inexact = 1;
             }
             if (C > 1) cluster.sync();                 // bitmap is zero everywhere before anybody sets a bit
+            LDP_CLK(ws, r, 17);
         }
         if (n_have >= size) break;
         const int cnt = size - n_have;
@@ -440,7 +505,9 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
         if (rounds >= 64) { fail = LDP_REF_ROUNDS_EXCEEDED; break; }
         // ---- (a') guide table: guide[k] ~ first chunk whose prefix reaches (k / NG) * total.  It only has to be
         //      approximately right: the exact fix-up after the search walks to numpy's chunk from any start.
-        {
+        //      Built for the first round only (8500 draws); later rounds have a few hundred draws and search the
+        //      whole table.
+        if (rounds == 0) {
             const double ngt = (double)NG / total;
             int kprev = (e0 > 0 && e0 <= nchunk) ? min(NG, (int)(pre[pad8(e0 - 1)] * ngt)) : -1;
             for (int q = 0; q < EPT; ++q) {
@@ -480,8 +547,8 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             for (int k = 0; k < 2; ++k) {
                 tt[k] = uu[k] * total;
                 const int kb = min(NG - 1, (int)(uu[k] * (double)NG));
-                lo[k] = guide[kb];
-                hi[k] = max(lo[k], guide[kb + 1]);
+                lo[k] = (rounds == 0) ? guide[kb] : 0;
+                hi[k] = (rounds == 0) ? max(lo[k], guide[kb + 1]) : nchunk - 1;
             }
             // 2. lock-step binary search inside the guide ranges: first chunk with prefix > u * total (approximate)
             for (;;) {
@@ -640,6 +707,8 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     // ------------------------------------------------------------------ ordered compaction == np.unique(concat)
     {
         const int nwords = (int)ws.n_words;                    // multiple of 8 (n_pad is a multiple of 256)
+        int* stage = reinterpret_cast<int*>(smem_raw);         // the chunk table is dead: stage indices for coalesced stores
+        const int stage_cap = (int)(G.draw_smem_bytes / sizeof(int));
         int carry = 0;
         for (int t0 = 0; t0 < nwords; t0 += T * 8) {
             const int w0 = t0 + tid * 8;
@@ -649,17 +718,25 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
 #pragma unroll
             for (int j = 0; j < 8; ++j) cntb += __popc(m[j]);
             int tile_total;
-            int pos = carry + block_exclusive_scan(cntb, sh.red_i, &tile_total);
+            int pos = block_exclusive_scan(cntb, sh.red_i, &tile_total);
+            const bool staged = tile_total <= stage_cap;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 uint32_t mm = m[j];
                 while (mm) {
                     const int b = __ffs(mm) - 1;
                     mm &= mm - 1;
-                    if (pos < (int)ws.sel_cap) sel[pos] = ((w0 + j) << 5) + b;
+                    const int v = ((w0 + j) << 5) + b;
+                    if (staged) stage[pos] = v;
+                    else if (carry + pos < (int)ws.sel_cap) sel[carry + pos] = v;
                     ++pos;
                 }
             }
+            __syncthreads();
+            if (staged)
+                for (int i = tid; i < tile_total; i += T)
+                    if (carry + i < (int)ws.sel_cap) sel[carry + i] = stage[i];
+            __syncthreads();
             carry += tile_total;
         }
         LDP_CLK(ws, r, 10);
@@ -695,7 +772,7 @@ ldp_topm_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     __shared__ int red_i[32];
     __shared__ uint32_t s_prefix;
     __shared__ int s_remaining;
-    const int r = blockIdx.x, tid = threadIdx.x, T = blockDim.x, N = G.N;
+    const int r = blockIdx.x + G.ref0, tid = threadIdx.x, T = blockDim.x, N = G.N;
     const float* __restrict__ w = ws.w + (size_t)r * ws.n_pad;
     int32_t* __restrict__ sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
     unsigned long long* keys = ws.topk_keys + (size_t)r * ws.topk_cap;

@@ -222,7 +222,8 @@ class DensifyEngine:
         p.no_filter = 1 if cfg.no_filter else 0
         p.collect_debug = 1 if collect_debug else 0
         p.rng_mode = int(rng_mode)
-        p.reserved0 = 1 if batch.force_scalar_loads else 0
+        p.scalar_loads = 1 if batch.force_scalar_loads else 0
+        p.nn_max = max((len(u) for u in batch.nbr_uids), default=0)
         p.seed = int(cfg.seed) & 0xFFFFFFFFFFFFFFFF
         p.uniforms_per_ref = int(uniforms_per_ref)
         return p

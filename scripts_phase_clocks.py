@@ -28,18 +28,18 @@ eng.lib.ldp_debug_read_clocks.argtypes = [C.POINTER(N.LdpParams), C.c_void_p, C.
 rc = eng.lib.ldp_debug_read_clocks(C.byref(params), C.c_void_p(eng._workspace.data_ptr()), host)
 clk = np.array(host[:]).reshape(len(batch), 32)
 print("cluster size used:", eng.lib.ldp_debug_last_cluster())
-names = {0: "start", 3: "prefix+guide 1 done", 4: "draws 1 done", 6: "after B1", 7: "zeroed", 8: "rounds done", 9: "coverage done", 10: "compaction done"}
-order = [0, 3, 4, 6, 7, 8, 9, 10]
+names = {0: "start", 1: "init done", 14: "csum loaded+local", 15: "block scan done", 16: "prefix stored+sync", 17: "after B0", 3: "guide built", 4: "draws 1 done", 6: "after B1", 7: "zeroed", 8: "rounds done", 9: "coverage done", 10: "compaction done"}
+order = [0, 1, 14, 15, 16, 17, 3, 4, 6, 7, 8, 9, 10]
 for a, b in zip(order[:-1], order[1:]):
     dd = clk[:, b] - clk[:, a]
     print(f"{names[a]:>20} -> {names[b]:<20} median {np.median(dd):9.0f}  max {dd.max():9.0f} cycles")
-print("thread0 first pass: searches", np.median(clk[:,11]-clk[:,3]), " scans", np.median(clk[:,12]-clk[:,11]), " atomics issue", np.median(clk[:,13]-clk[:,12]), " rest of round", np.median(clk[:,4]-clk[:,13]))
+#print("thread0 first pass: searches", np.median(clk[:,11]-clk[:,3]), " scans", np.median(clk[:,12]-clk[:,11]), " atomics issue", np.median(clk[:,13]-clk[:,12]), " rest of round", np.median(clk[:,4]-clk[:,13]))
 print("total median", np.median(clk[:, 10] - clk[:, 0]), "max", (clk[:, 10] - clk[:, 0]).max(), "cycles @1.963 GHz")
 sys.exit(0)
 d = clk[:, 1:11] - clk[:, 0:10]
 print("rounds per view:", clk[:, 20][:12], "...")
 for i in range(10):
     print(f"{names[i]:>16} -> {names[i+1]:<16} median {np.median(d[:, i]):9.0f}  max {d[:, i].max():9.0f} cycles")
-print("thread0 first pass: searches", np.median(clk[:,11]-clk[:,3]), " scans", np.median(clk[:,12]-clk[:,11]), " atomics issue", np.median(clk[:,13]-clk[:,12]), " rest of round", np.median(clk[:,4]-clk[:,13]))
+#print("thread0 first pass: searches", np.median(clk[:,11]-clk[:,3]), " scans", np.median(clk[:,12]-clk[:,11]), " atomics issue", np.median(clk[:,13]-clk[:,12]), " rest of round", np.median(clk[:,4]-clk[:,13]))
 print("total median", np.median(clk[:, 10] - clk[:, 0]), "max", (clk[:, 10] - clk[:, 0]).max())
 print("span over all views (first start .. last end):", clk[:, 10].max() - clk[:, 0].min())
