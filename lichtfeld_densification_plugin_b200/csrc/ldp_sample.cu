@@ -90,7 +90,10 @@ __device__ __forceinline__ void quad_border_weights(float wv[4], int px, int x, 
 }
 
 template <int NNMAX>      // 1..4: plane pointers held in registers, loop fully unrolled; 0: any nn (pointers in shared memory)
-__global__ void __launch_bounds__(KS_THREADS)
+#ifndef KS_MIN_BLOCKS
+#define KS_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(KS_THREADS, KS_MIN_BLOCKS)
 ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const SampleGeom G)
 {
     __shared__ const float* s_cert[LDP_MAX_NN];
@@ -122,47 +125,8 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
         const float* c1 = (NNMAX >= 2) ? s_cert[min(1, nn - 1)] : nullptr;
         const float* c2 = (NNMAX >= 3) ? s_cert[min(2, nn - 1)] : nullptr;
         const float* c3 = (NNMAX >= 4) ? s_cert[min(3, nn - 1)] : nullptr;
-#pragma unroll 2
-        for (int it = 0; it < KS_SPAN / (KS_THREADS * 4); ++it) {
-            const int px = base + (it * KS_THREADS + tid) * 4;
-            if (px >= N) break;
-            float wv[4];
-            int bi[4] = {0, 0, 0, 0};
-            if (G.vec) {
-                const float4 v = ld_stream4(c0 + px);
-                wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
-                if (NNMAX > 0) {           // duplicated pointers for k >= nn re-read plane nn-1: never strictly greater
-                    float4 c;
-                    if (NNMAX >= 2) { c = ld_stream4(c1 + px);
-                        if (c.x > wv[0] || c.x != c.x) { wv[0] = c.x; bi[0] = 1; } if (c.y > wv[1] || c.y != c.y) { wv[1] = c.y; bi[1] = 1; }
-                        if (c.z > wv[2] || c.z != c.z) { wv[2] = c.z; bi[2] = 1; } if (c.w > wv[3] || c.w != c.w) { wv[3] = c.w; bi[3] = 1; } }
-                    if (NNMAX >= 3) { c = ld_stream4(c2 + px);
-                        if (c.x > wv[0] || c.x != c.x) { wv[0] = c.x; bi[0] = 2; } if (c.y > wv[1] || c.y != c.y) { wv[1] = c.y; bi[1] = 2; }
-                        if (c.z > wv[2] || c.z != c.z) { wv[2] = c.z; bi[2] = 2; } if (c.w > wv[3] || c.w != c.w) { wv[3] = c.w; bi[3] = 2; } }
-                    if (NNMAX >= 4) { c = ld_stream4(c3 + px);
-                        if (c.x > wv[0] || c.x != c.x) { wv[0] = c.x; bi[0] = 3; } if (c.y > wv[1] || c.y != c.y) { wv[1] = c.y; bi[1] = 3; }
-                        if (c.z > wv[2] || c.z != c.z) { wv[2] = c.z; bi[2] = 3; } if (c.w > wv[3] || c.w != c.w) { wv[3] = c.w; bi[3] = 3; } }
-                } else {
-#pragma unroll 4
-                    for (int k = 1; k < nn; ++k) {
-                        const float4 c = ld_stream4(s_cert[k] + px);
-                        if (c.x > wv[0] || c.x != c.x) { wv[0] = c.x; bi[0] = k; }
-                        if (c.y > wv[1] || c.y != c.y) { wv[1] = c.y; bi[1] = k; }
-                        if (c.z > wv[2] || c.z != c.z) { wv[2] = c.z; bi[2] = k; }
-                        if (c.w > wv[3] || c.w != c.w) { wv[3] = c.w; bi[3] = k; }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) wv[j] = (px + j < N) ? __ldcs(c0 + px + j) : 0.f;
-                for (int k = 1; k < nn; ++k) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float c = (px + j < N) ? __ldcs(s_cert[k] + px + j) : 0.f;
-                        if (c > wv[j] || c != c) { wv[j] = c; bi[j] = k; }
-                    }
-                }
-            }
+        // finishes one quad: cap, border mask, flags, f64 sum, stores
+        auto finish_quad = [&](int px, float wv[4], const int bi[4]) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) wv[j] = (wv[j] > cap) ? cap : wv[j];          // torch.clamp(max=cap): NaN stays NaN
             const int y = (int)div_magic((uint32_t)px, G.w_magic), x = px - y * W;
@@ -172,6 +136,58 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
             lsum += (widen_f32(wv[0]) + widen_f32(wv[1])) + (widen_f32(wv[2]) + widen_f32(wv[3]));
             *reinterpret_cast<float4*>(w + px) = make_float4(wv[0], wv[1], wv[2], wv[3]);
             *reinterpret_cast<uint32_t*>(bk + px) = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+        };
+        auto take = [&](const float4& c, int k, float wv[4], int bi[4]) {              // NaN-propagating max, first index wins
+            if (c.x > wv[0] || c.x != c.x) { wv[0] = c.x; bi[0] = k; }
+            if (c.y > wv[1] || c.y != c.y) { wv[1] = c.y; bi[1] = k; }
+            if (c.z > wv[2] || c.z != c.z) { wv[2] = c.z; bi[2] = k; }
+            if (c.w > wv[3] || c.w != c.w) { wv[3] = c.w; bi[3] = k; }
+        };
+        if (G.vec && NNMAX > 0) {
+            // two quads per step: all 2*NNMAX 128-bit loads are issued before any of them is consumed
+            constexpr int STEP = KS_THREADS * 4;
+            for (int it = 0; it < KS_SPAN / STEP; it += 2) {
+                const int pxa = base + it * STEP + tid * 4, pxb = pxa + STEP;
+                const bool va = pxa < N, vb = pxb < N;
+                if (!va) break;
+                const int qb = vb ? pxb : pxa;                         // clamp: a duplicate load instead of a branch
+                float4 a0, a1, a2, a3, b0, b1, b2, b3;
+                a0 = ld_stream4(c0 + pxa); b0 = ld_stream4(c0 + qb);
+                if (NNMAX >= 2) { a1 = ld_stream4(c1 + pxa); b1 = ld_stream4(c1 + qb); }
+                if (NNMAX >= 3) { a2 = ld_stream4(c2 + pxa); b2 = ld_stream4(c2 + qb); }
+                if (NNMAX >= 4) { a3 = ld_stream4(c3 + pxa); b3 = ld_stream4(c3 + qb); }
+                float wa[4] = {a0.x, a0.y, a0.z, a0.w}, wb[4] = {b0.x, b0.y, b0.z, b0.w};
+                int ia[4] = {0, 0, 0, 0}, ib[4] = {0, 0, 0, 0};
+                if (NNMAX >= 2) { take(a1, 1, wa, ia); take(b1, 1, wb, ib); }
+                if (NNMAX >= 3) { take(a2, 2, wa, ia); take(b2, 2, wb, ib); }
+                if (NNMAX >= 4) { take(a3, 3, wa, ia); take(b3, 3, wb, ib); }
+                finish_quad(pxa, wa, ia);
+                if (vb) finish_quad(pxb, wb, ib);
+            }
+        } else {
+            for (int it = 0; it < KS_SPAN / (KS_THREADS * 4); ++it) {
+                const int px = base + (it * KS_THREADS + tid) * 4;
+                if (px >= N) break;
+                float wv[4];
+                int bi[4] = {0, 0, 0, 0};
+                if (G.vec) {
+                    const float4 v = ld_stream4(c0 + px);
+                    wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
+#pragma unroll 4
+                    for (int k = 1; k < nn; ++k) take(ld_stream4(s_cert[k] + px), k, wv, bi);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) wv[j] = (px + j < N) ? __ldcs(c0 + px + j) : 0.f;
+                    for (int k = 1; k < nn; ++k) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float c = (px + j < N) ? __ldcs(s_cert[k] + px + j) : 0.f;
+                            if (c > wv[j] || c != c) { wv[j] = c; bi[j] = k; }
+                        }
+                    }
+                }
+                finish_quad(px, wv, bi);
+            }
         }
     }
     if (blk == (int)gridDim.x - 1) {       // keep the row padding [N, n_pad) zero: the draw kernel's 32-byte scans read it
