@@ -526,8 +526,8 @@ int ldp_densify_refs(const ldp_params* params, const ldp_ref_desc* refs, const d
     if (rc != LDP_OK) return rc;
     if (plan.bytes + (size_t)(base - static_cast<char*>(workspace)) > workspace_bytes) return fail(LDP_ERR_WORKSPACE, "workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // hot prefix of the workspace: w/p and winning-neighbour planes (carved first)
-    L2Window l2(st, plan.ws.w, (size_t)params->n_refs * plan.ws.n_pad * 5);
+    // the winning-neighbour plane is written by the first kernel and gathered (1 byte per sample, random) by the fifth
+    L2Window l2(st, plan.ws.bestk, (size_t)params->n_refs * plan.ws.n_pad);      // winning-neighbour plane (1 B / px)
     cudaError_t e = cudaMemsetAsync(plan.ws.fix_count, 0, ldp::LDP_MAX_SUB * sizeof(int32_t), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(fix_count)");
     const int nsub = choose_subbatches(params->n_refs);

@@ -91,7 +91,7 @@ __device__ __forceinline__ void quad_border_weights(float wv[4], int px, int x, 
 
 template <int NNMAX>      // 1..4: plane pointers held in registers, loop fully unrolled; 0: any nn (pointers in shared memory)
 #ifndef KS_MIN_BLOCKS
-#define KS_MIN_BLOCKS 4
+#define KS_MIN_BLOCKS 5
 #endif
 __global__ void __launch_bounds__(KS_THREADS, KS_MIN_BLOCKS)
 ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const SampleGeom G)
