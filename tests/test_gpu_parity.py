@@ -107,3 +107,61 @@ def test_computed_weight_sum_is_correctly_rounded(engine):
     rep = G.compare_ref(g, 0, res2, c, scene)
     _report("computed-s", rep)
     assert rep.ok() and (rep.sel_exact or rep.sel_tie_swaps > 0)
+
+
+def test_config3_precise_1280_maps_800_match(engine):
+    """BASELINE config 3 shape: 'precise' preset -> 1280x1280 maps, 800x800 match resolution, 4 neighbours, all filters on.
+    (Distortion parameters of OPENCV cameras are ignored by the reference; bidirectional warps never reach
+    the path, F3.)  Exercises the 128-pixel chunk table."""
+    from lichtfeld_densification_plugin_b200 import synth
+    scene = synth.make_scene(16, "precise", ref_fraction=0.07, nn=4)
+    assert (scene.H, scene.W, scene.h_match, scene.w_match) == (1280, 1280, 800, 800)
+    c = dict(M=10000, no_filter=False, wm=800, hm=800)
+    inp = synth.synth_ref_inputs(scene, 0, cert_family="T", seed=31)
+    U = np.random.RandomState(900).random_sample(3 * c["M"])
+    res = G.run_oracle_ref(scene, inp, c, uniforms=U)
+    g = G.run_gpu(engine, scene, [inp], G.path_cfg(c), uniforms=U[None, :], weight_sums=[res.taps["s"]])
+    rep = G.compare_ref(g, 0, res, c, scene)
+    _report("precise/1280/4nn/T", rep)
+    assert rep.ok(), rep
+    assert rep.sel_exact or rep.sel_tie_swaps > 0
+    assert g.uniforms_used[0] == res.taps["uniforms_used"] and g.rounds[0] == res.taps["rounds"]
+
+
+def test_config4_roi_8_neighbours_no_filter(engine):
+    """BASELINE config 4 shape: 8 neighbours per reference, 'No Filter' raw output path (top-M by certainty, finite-only keep)."""
+    from lichtfeld_densification_plugin_b200 import synth
+    scene = synth.make_scene(40, "fast", ref_fraction=0.05, nn=8)
+    c = dict(M=10000, no_filter=True, wm=scene.w_match, hm=scene.h_match)
+    inputs = [synth.synth_ref_inputs(scene, rp, cert_family="T", seed=33) for rp in range(scene.n_refs)]
+    g = G.run_gpu(engine, scene, inputs, G.path_cfg(c))
+    for r, inp in enumerate(inputs):
+        assert len(inp["nbr_indices"]) == 8
+        res = G.run_oracle_ref(scene, inp, c)
+        rep = G.compare_ref(g, r, res, c, scene)
+        _report(f"roi/8nn/no_filter/ref{r}", rep)
+        assert rep.ok(), rep
+        assert np.array_equal(g.sel_idx[r], res.sel_idx)          # tie-free certainties: even the order is pinned
+        order = G.expected_pack_order(g.flags[r])
+        assert np.array_equal(g.xyz[r], g.xyzerr[r][order, :3])
+
+
+def test_config5_base_640_sharding_invariance(engine):
+    """BASELINE config 5 shape ('base' 640x640, 4 neighbours): a view's result does not depend on which views share
+    its launch, so sharding the reference list over ranks and concatenating in rank order equals the single-GPU run."""
+    from lichtfeld_densification_plugin_b200 import synth
+    from lichtfeld_densification_plugin_b200 import distributed as D
+    scene = synth.make_scene(48, "base", ref_fraction=0.125, nn=4)
+    c = dict(M=10000, no_filter=False, wm=scene.w_match, hm=scene.h_match)
+    inputs = [synth.synth_ref_inputs(scene, rp, cert_family="R", seed=35) for rp in range(scene.n_refs)]
+    streams = list(range(scene.n_refs))
+    whole = G.run_gpu(engine, scene, inputs, G.path_cfg(c, seed=9), rng_streams=streams)
+    for world in (2, 3):
+        xyz = []
+        for rank in range(world):
+            lo, hi = D.shard_bounds(len(inputs), rank, world)
+            part = G.run_gpu(engine, scene, inputs[lo:hi], G.path_cfg(c, seed=9), rng_streams=streams[lo:hi])
+            xyz += part.xyz
+        assert len(xyz) == len(whole.xyz)
+        for a, b in zip(xyz, whole.xyz):
+            assert np.array_equal(a, b)
