@@ -320,6 +320,8 @@ ldp::GeomArgs make_geom_args(const ldp_params* p, const Plan& plan, int have_bes
     ga.nb2 = plan.nb2;
     ga.ref0 = ref0;
     ga.sub = sub;
+    static const int discard_mode = [] { const char* e = getenv("LDP_DISCARD"); return e ? atoi(e) : 1; }();
+    ga.discard = have_bestk ? discard_mode : 0;
     return ga;
 }
 

@@ -83,8 +83,9 @@ class RefBatch:
         if not isinstance(t, torch.Tensor):
             raise ValueError(f"{what} must be a tensor")
         if t.device != self.device:
-            # Warp planes are read only at the ~9k sampled pixels of a view, so they may stay in pinned
-            # (page-locked, UVA-mapped) host memory and be gathered over PCIe instead of being uploaded.
+            # Warp planes are read only at the ~9k sampled pixels of a view, and certainty planes exactly once, front
+            # to back: both may stay in pinned (page-locked, UVA-mapped) host memory and be read over PCIe by the
+            # kernels instead of being uploaded first.
             if not (allow_pinned_host and t.device.type == "cpu" and t.is_pinned()):
                 raise ValueError(f"{what} must be a tensor on {self.device}"
                                  + (" or in pinned host memory" if allow_pinned_host else ""))
@@ -104,7 +105,7 @@ class RefBatch:
             raise ValueError(f"at most {N.LDP_MAX_NN} neighbours per reference view")
         row = np.zeros((), dtype=N.REF_DESC_DTYPE)
         for k in range(nn):
-            c = self._check_plane(cert_planes[k], (self.H, self.W), "certainty plane")
+            c = self._check_plane(cert_planes[k], (self.H, self.W), "certainty plane", allow_pinned_host=True)
             w = self._check_plane(warp_planes[k], (self.H, self.W, 4), "warp plane", allow_pinned_host=True)
             if c.data_ptr() % 16 != 0:
                 self.force_scalar_loads = True
@@ -148,7 +149,7 @@ class RefBatch:
             raise ValueError(f"at most {N.LDP_MAX_NN} neighbours per reference view")
         row = np.zeros((), dtype=N.REF_DESC_DTYPE)
         for k in range(nn):
-            c = self._check_plane(cert_planes[k], (self.H, self.W), "certainty plane")
+            c = self._check_plane(cert_planes[k], (self.H, self.W), "certainty plane", allow_pinned_host=True)
             if c.data_ptr() % 16 != 0:
                 self.force_scalar_loads = True
             row["cert"][k] = c.data_ptr()

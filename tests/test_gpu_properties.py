@@ -264,3 +264,56 @@ def test_subbatch_pipelining_does_not_change_results(engine, fast_scene):
                 assert np.array_equal(base.err[r], g.err[r])
     finally:
         lib.ldp_debug_set_subbatches(-1)
+
+
+def _colliding_weight_map(H=90, W=120, seed=11):
+    """f32 map, distinct values, in which 49 tiles hold an adjacent-float pair (smaller weight at the lower index) whose
+    quotients by s = f32(sum of the border-masked weights) round to the same f32."""
+    tile = max(1, W // 24)
+    rs = np.random.RandomState(seed)
+    vals = (0.2 + 0.6 * (rs.permutation(H * W) + 0.5) / (H * W)).astype(np.float32).reshape(H, W)      # < 0.8, distinct
+    inside = np.zeros((H, W), bool)
+    inside[2:H - 2, 2:W - 2] = True
+    wsum = lambda: np.where(inside, vals, 0).astype(np.float64).sum()
+    s = np.float32(wsum())                                # the normaliser is pinned first ...
+    tiles = [(ty, tx) for ty in range(2, 16, 2) for tx in range(2, 22, 3)]
+    cands = np.arange(0.85, 0.899, 1e-4, dtype=np.float32)
+    ok = [a for a in cands if np.float32(a / s) == np.float32(np.nextafter(a, np.float32(1)) / s)]
+    assert len(ok) >= len(tiles)
+    for (ty, tx), a in zip(tiles, ok):
+        y, x = ty * tile + 1, tx * tile + 1
+        vals[y, x] = a                                    # lower index, smaller weight
+        vals[y + 2, x + 2] = np.nextafter(a, np.float32(1))
+    # ... and the mass the pairs added is taken back from pixels of the last tile row, which stay far from any tile maximum
+    by, bx = np.nonzero(inside & (np.arange(H)[:, None] >= 17 * tile) & (vals > 0.5) & (vals < 0.75))
+    for _ in range(8):
+        d = wsum() - float(s)
+        if np.float32(wsum()) == s and abs(d) < 1e-4:
+            break
+        vals[by, bx] = (vals[by, bx].astype(np.float64) - d / by.size).astype(np.float32)
+    assert np.float32(wsum()) == s and vals[by, bx].min() > 0.2
+    pairs = [((ty * tile + 1) * W + tx * tile + 1, (ty * tile + 3) * W + tx * tile + 3) for ty, tx in tiles]
+    flat = vals.reshape(-1)
+    assert all(np.float32(flat[i] / s) == np.float32(flat[j] / s) and flat[i] < flat[j] for i, j in pairs)
+    return vals, s, pairs
+
+
+def test_coverage_walk_is_on_normalised_p(engine):
+    """core/sampling.py:29 rebinds `weights` to p = weights / s BEFORE the coverage walk (:38): two adjacent f32
+    weights whose quotients round to the same p are a TIE for np.argsort (unstable), not an ordered pair.  The kernel
+    must therefore agree with the reference everywhere except inside such tied pairs, where either pixel is valid."""
+    from lichtfeld_densification_plugin_b200.core.sampling import select_samples_with_coverage
+    from oracle import densify_oracle as O
+    vals, s, pairs = _colliding_weight_map()
+    cert = torch.from_numpy(vals)
+    M = 3000
+    np.random.seed(5)
+    got = set(select_samples_with_coverage(cert, M).tolist())
+    want = set(O.select_samples(cert, M, rng=np.random.RandomState(5), s_override=s).tolist())
+    decided = [(i, j) for i, j in pairs if (i in want) != (j in want)]
+    assert len(decided) >= 10, "test construction: the main draw took too many of the pairs"
+    partner = {i: j for i, j in pairs}
+    partner.update({j: i for i, j in pairs})
+    for only_a, b in ((got - want, want), (want - got, got)):
+        for i in only_a:
+            assert i in partner and partner[i] in b, f"pixel {i} differs outside a tied pair"
