@@ -33,6 +33,10 @@ __all__ = [
     "sample_weights",
     "coverage_picks",
     "select_samples",
+    "resize_mask_nearest",
+    "warp_mask_nearest",
+    "certainty_prologue",
+    "certainty_prologue_torch",
     "best_neighbour",
     "decode_samples",
     "bilinear_colour",
@@ -285,6 +289,78 @@ def parallax_ok(C1: np.ndarray, C2: np.ndarray, X: np.ndarray, min_deg: float) -
     r2 /= np.linalg.norm(r2, axis=1, keepdims=True) + 1e-12
     ang = np.degrees(np.arccos(np.clip(np.sum(r1 * r2, axis=1), -1.0, 1.0)))
     return ang >= float(min_deg)
+
+
+# ----------------------------------------------------------------------------------------------
+# certainty post-processing between the matcher and the path  (core/pipeline.py:405-430)
+# ----------------------------------------------------------------------------------------------
+def resize_mask_nearest(mask_np: np.ndarray, H: int, W: int) -> np.ndarray:
+    """``_mask_tensor_for_hw`` (core/pipeline.py:361-382): mask -> float32 [H, W].  ``F.interpolate(mode="nearest")``
+    picks source index min(floor(dst * f32(in / out)), in - 1) per axis (ATen UpSample.h nearest_idx); equal
+    shapes are passed through."""
+    m = np.asarray(mask_np).astype(np.float32, copy=False)
+    h, w = m.shape
+    if (h, w) == (H, W):
+        return m
+    sy, sx = np.float32(h) / np.float32(H), np.float32(w) / np.float32(W)
+    iy = np.minimum(np.floor(np.arange(H, dtype=np.float32) * sy).astype(np.int64), h - 1)
+    ix = np.minimum(np.floor(np.arange(W, dtype=np.float32) * sx).astype(np.int64), w - 1)
+    return m[iy[:, None], ix[None, :]]
+
+
+def warp_mask_nearest(mask_hw: np.ndarray, grid_xy: np.ndarray) -> np.ndarray:
+    """``F.grid_sample(mask, grid, mode="nearest", padding_mode="zeros", align_corners=False)`` (core/pipeline.py:423-429)
+    for a single-channel [H, W] f32 mask and a [H, W, 2] f32 grid of normalised (x, y): un-normalise
+    (g + 1) * (size / 2) - 0.5 in f32, round half to even, zero outside the image (NaN coordinates fall outside)."""
+    H, W = mask_hw.shape
+    gx = grid_xy[..., 0].astype(np.float32, copy=False)
+    gy = grid_xy[..., 1].astype(np.float32, copy=False)
+    with np.errstate(invalid="ignore", over="ignore"):
+        fx = np.rint(((gx + np.float32(1)) * np.float32(W / 2)).astype(np.float32) - np.float32(0.5))
+        fy = np.rint(((gy + np.float32(1)) * np.float32(H / 2)).astype(np.float32) - np.float32(0.5))
+        ok = (fx > -1) & (fx < W) & (fy > -1) & (fy < H)
+    ix = np.where(ok, fx, 0).astype(np.int64)
+    iy = np.where(ok, fy, 0).astype(np.int64)
+    return np.where(ok, mask_hw[iy, ix], np.float32(0)).astype(np.float32)
+
+
+def certainty_prologue(cert_hw: np.ndarray, warp_hw: np.ndarray, maskA_np: Optional[np.ndarray],
+                       maskB_np: Optional[np.ndarray], certainty_thresh: float) -> np.ndarray:
+    """What ``_collect_reference_matches`` does to one pair's certainty map before the path sees it
+    (core/pipeline.py:405-430), with every index made explicit: floor-clamp (NaN stays NaN), x maskA resized to the
+    map, x maskB resized to the map and sampled at the warp's (xB, yB)."""
+    c = np.asarray(cert_hw, dtype=np.float32)
+    H, W = c.shape
+    with np.errstate(invalid="ignore"):
+        c = np.where(c < np.float32(certainty_thresh), np.float32(certainty_thresh), c).astype(np.float32)   # torch.clamp(min=)
+        if maskA_np is not None:
+            c = c * resize_mask_nearest(maskA_np, H, W)
+        if maskB_np is not None:
+            c = c * warp_mask_nearest(resize_mask_nearest(maskB_np, H, W), np.asarray(warp_hw)[..., 2:4])
+    return c.astype(np.float32)
+
+
+def certainty_prologue_torch(cert_hw: torch.Tensor, warp_hw: torch.Tensor, maskA_np: Optional[np.ndarray],
+                             maskB_np: Optional[np.ndarray], certainty_thresh: float) -> torch.Tensor:
+    """The same step written with the torch calls the reference makes (core/pipeline.py:405-430): pins the explicit
+    index arithmetic of ``certainty_prologue`` to ATen's on this box."""
+    import torch.nn.functional as F
+
+    def to_hw(mask_np, hw):
+        m = torch.from_numpy(np.asarray(mask_np).astype(np.float32, copy=False))
+        if tuple(m.shape) != tuple(hw):
+            m = F.interpolate(m.view(1, 1, m.shape[0], m.shape[1]), size=hw, mode="nearest").squeeze(0).squeeze(0)
+        return m
+
+    c = torch.clamp(torch.as_tensor(cert_hw), min=certainty_thresh)
+    hw = (int(c.shape[0]), int(c.shape[1]))
+    if maskA_np is not None:
+        c = c * to_hw(maskA_np, hw)
+    if maskB_np is not None:
+        mb = to_hw(maskB_np, hw).view(1, 1, hw[0], hw[1])
+        c = c * F.grid_sample(mb, torch.as_tensor(warp_hw)[..., 2:4].unsqueeze(0), mode="nearest",
+                              padding_mode="zeros", align_corners=False).squeeze(0).squeeze(0)
+    return c
 
 
 # ----------------------------------------------------------------------------------------------
