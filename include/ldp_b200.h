@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LDP_ABI_VERSION 7
+#define LDP_ABI_VERSION 8
 #define LDP_MAX_NN 16          /* neighbours per reference view (the panel clamps to 10) */
 #define LDP_MAX_BINS 4096      /* coverage tiles per map: ceil(W/tile)*ceil(H/tile), tile = max(1, W/24) */
 
@@ -74,7 +74,12 @@ typedef struct ldp_params {
     int32_t rng_mode;          /* ldp_rng_mode */
     int32_t scalar_loads;      /* 1: certainty planes are not 16-byte aligned -> scalar load path */
     int32_t nn_max;            /* largest ldp_ref_desc.nn of the launch (0 = unknown): selects the unrolled stream kernel */
-    int32_t reserved1;
+    int32_t prologue;          /* 1: the certainty planes are RAW matcher outputs; the kernels apply the reference's
+                                  post-processing on the fly (core/pipeline.py:405-430): clamp(min = certainty_floor),
+                                  x mask_a (nearest-resized to the map), x mask_b[k] sampled at the warp's (xB, yB)
+                                  (nearest, zeros outside, align_corners = False).  0: planes are already processed */
+    float certainty_floor;     /* f32(config.certainty_thresh), core/pipeline.py:407; read only if prologue */
+    int32_t reserved2;
     uint64_t seed;             /* Philox key */
     int64_t uniforms_per_ref;  /* explicit mode: doubles available per reference view */
 } ldp_params;
@@ -101,6 +106,12 @@ typedef struct ldp_ref_desc {
     float sxB[LDP_MAX_NN], syB[LDP_MAX_NN];   /* f32(wB_cam / w_match), ...   core/pipeline.py:697-699 */
     int32_t group[LDP_MAX_NN];       /* output group of neighbour k: smallest k' with nn_ids[k'] == nn_ids[k]
                                         (the reference groups by neighbour uid, core/pipeline.py:685-688) */
+    /* read only when ldp_params.prologue is set; all masks of a view share one resolution */
+    const uint8_t* mask_a;           /* [mask_h*mask_w] u8 reference-view mask or NULL (packed.maskA_np, core/pipeline.py:415-417) */
+    const uint8_t* mask_b[LDP_MAX_NN]; /* per-neighbour mask or NULL (packed.nn_masks[k], core/pipeline.py:419-430) */
+    int32_t mask_w, mask_h;
+    float mask_sx, mask_sy;          /* f32(mask_w) / f32(W), f32(mask_h) / f32(H): F.interpolate(mode="nearest") source
+                                        index = min(floor(dst * scale), size - 1) (core/pipeline.py:373-378) */
 } ldp_ref_desc;
 
 /* Caller-allocated DEVICE outputs.  Optional pointers may be NULL. */
@@ -155,6 +166,13 @@ int ldp_sample_refs(const ldp_params* params, const ldp_ref_desc* refs, const do
 int ldp_triangulate_samples(const ldp_params* params, const ldp_ref_desc* refs,
                             const ldp_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The certainty post-processing alone (core/pipeline.py:405-430), for callers that want the reference's
+ * cert_list tensors and for stage-level parity tests: for every view r and neighbour k < nn,
+ * out[r*ref_stride + k*plane_stride + i] = processed certainty of pixel i (strides in floats).  params->prologue is
+ * ignored (the step is always applied); certainty_floor, H, W, n_refs are read. */
+int ldp_postprocess_certainty(const ldp_params* params, const ldp_ref_desc* refs, float* out,
+                              size_t ref_stride, size_t plane_stride, void* stream);
+
 /* Kernel launches enqueued by the last ldp_* call on this thread (for bench.py's gpu_launches). */
 int ldp_last_launch_count(void);
 
@@ -169,10 +187,13 @@ const char* ldp_profile_name(int i);      /* name of the i-th kernel of the last
 /* Test hook: force the thread-block-cluster size of the draw kernel (CTAs per reference view, 1..8);
  * 0 restores the automatic choice.  Results do not depend on it. */
 int ldp_debug_set_cluster(int csize);
-int ldp_debug_last_cluster(void);
+int ldp_debug_last_cluster(void);          /* cluster size the last draw kernel was launched with */
 /* Debug builds (-DLDP_PHASE_CLOCKS) only: copy the draw kernel's per-view phase timestamps [n_refs][32] (SM clocks)
  * to host memory; synchronises.  Release builds return zeros. */
-int ldp_debug_read_clocks(const ldp_params* params, void* workspace, long long* host_out);          /* cluster size the last draw kernel was launched with */
+int ldp_debug_read_clocks(const ldp_params* params, void* workspace, long long* host_out);
+/* Test hook: pipeline a launch over n sub-batches of views on internal streams (1..8; 0 restores the default, which is
+ * one batch unless LDP_SUBBATCH is set).  Results do not depend on it. */
+int ldp_debug_set_subbatches(int n);
 
 /* sizeof() of the ABI structs as this library was compiled: which = 0 ldp_params, 1 ldp_ref_desc,
  * 2 ldp_outputs.  Bindings check these against their own struct definitions at load time. */

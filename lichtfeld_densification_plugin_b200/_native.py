@@ -13,7 +13,7 @@ import numpy as np
 
 from . import build as _build
 
-LDP_ABI_VERSION = 7
+LDP_ABI_VERSION = 8
 LDP_MAX_NN = 16
 LDP_MAX_BINS = 4096
 
@@ -55,7 +55,8 @@ class LdpParams(C.Structure):
         ("sample_cap", C.c_float), ("reproj_thresh", C.c_float), ("min_parallax_deg", C.c_float),
         ("sampson_thresh", C.c_double),
         ("no_filter", C.c_int32), ("collect_debug", C.c_int32), ("rng_mode", C.c_int32), ("scalar_loads", C.c_int32),
-        ("nn_max", C.c_int32), ("reserved1", C.c_int32),
+        ("nn_max", C.c_int32), ("prologue", C.c_int32),
+        ("certainty_floor", C.c_float), ("reserved2", C.c_int32),
         ("seed", C.c_uint64), ("uniforms_per_ref", C.c_int64),
     ]
 
@@ -73,6 +74,8 @@ class LdpRefDesc(C.Structure):
         ("F", (C.c_float * 9) * LDP_MAX_NN),
         ("sxB", C.c_float * LDP_MAX_NN), ("syB", C.c_float * LDP_MAX_NN),
         ("group", C.c_int32 * LDP_MAX_NN),
+        ("mask_a", C.c_uint64), ("mask_b", C.c_uint64 * LDP_MAX_NN),
+        ("mask_w", C.c_int32), ("mask_h", C.c_int32), ("mask_sx", C.c_float), ("mask_sy", C.c_float),
     ]
 
 
@@ -91,7 +94,7 @@ REF_DESC_DTYPE = np.dtype(LdpRefDesc)
 
 EXPORTS = [
     "ldp_abi_version", "ldp_last_error_string", "ldp_sel_capacity", "ldp_workspace_bytes",
-    "ldp_densify_refs", "ldp_sample_refs", "ldp_triangulate_samples", "ldp_last_launch_count",
+    "ldp_densify_refs", "ldp_sample_refs", "ldp_triangulate_samples", "ldp_postprocess_certainty", "ldp_last_launch_count",
     "ldp_struct_size", "ldp_profile_enable", "ldp_profile_read", "ldp_profile_name", "ldp_debug_set_cluster", "ldp_debug_last_cluster", "ldp_debug_set_subbatches", "ldp_debug_read_clocks",
 ]
 
@@ -151,6 +154,8 @@ def load(build_if_missing: bool = False):
         lib.ldp_triangulate_samples.restype = C.c_int
         lib.ldp_triangulate_samples.argtypes = [C.POINTER(LdpParams), C.c_void_p, C.POINTER(LdpOutputs), C.c_void_p,
                                                 C.c_size_t, C.c_void_p]
+        lib.ldp_postprocess_certainty.restype = C.c_int
+        lib.ldp_postprocess_certainty.argtypes = [C.POINTER(LdpParams), C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
         if lib.ldp_abi_version() != LDP_ABI_VERSION:
             raise NativeLibraryError(f"ABI version mismatch: library {lib.ldp_abi_version()}, binding {LDP_ABI_VERSION}")
         for which, struct in enumerate((LdpParams, LdpRefDesc, LdpOutputs)):

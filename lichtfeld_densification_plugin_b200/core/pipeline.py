@@ -77,6 +77,9 @@ class _MatchedReference:
     cert_list_cpu: List[torch.Tensor]
     pair_index_by_nbr: Dict[int, int]
     image_by_nbr: Dict[int, np.ndarray]
+    # extra: True when cert_list_cpu holds RAW matcher certainties (made by this package's _collect_reference_matches):
+    # the floor clamp and the masks of ``packed`` are then applied inside the kernels (reference core/pipeline.py:405-430)
+    raw_certainty: bool = False
 
 
 @dataclass(frozen=True)
@@ -221,6 +224,11 @@ def triangulate_refs(matched_refs: Sequence[_MatchedReference], tri_ctx: _Triang
     dev = eng.device
     cfg = tri_ctx.config
     pcfg = PathConfig.from_pipeline_config(cfg, sample_cap=tri_ctx.matcher_sample_cap)
+    raw = [bool(getattr(mr, "raw_certainty", False)) for mr in matched_refs]
+    if any(raw) and not all(raw):
+        raise ValueError("a launch takes either raw or post-processed certainty planes, not a mix")
+    if raw[0]:
+        pcfg.certainty_floor = float(cfg.certainty_thresh)
     first = matched_refs[0].cert_list_cpu[0]
     H, W = int(first.shape[0]), int(first.shape[1])
     batch = eng.new_batch(H, W, tri_ctx.w_match, tri_ctx.h_match)
@@ -234,9 +242,14 @@ def triangulate_refs(matched_refs: Sequence[_MatchedReference], tri_ctx: _Triang
             ref_cam = CameraRecord(uid=ref_cam.uid, image_path=ref_cam.image_path, width=packed.wA_cam, height=packed.hA_cam,
                                    K=ref_cam.K, R=ref_cam.R, t=ref_cam.t, P=ref_cam.P, C=ref_cam.C)
         nbrs = [_record_for(tri_ctx.cameras, uid) for uid in packed.nn_ids]
+        mask_a = masks_b = None
+        if raw[i]:
+            mask_a = None if packed.maskA_np is None else _to_device(packed.maskA_np, dev, torch.uint8)
+            masks_b = [None if m is None else _to_device(m, dev, torch.uint8) for m in packed.nn_masks]
         batch.add(certs, warps, image, ref_cam, nbrs,
                   rng_stream=(rng_streams[i] if rng_streams is not None else i),
-                  weight_sum_override=(float(weight_sums[i]) if weight_sums is not None else 0.0))
+                  weight_sum_override=(float(weight_sums[i]) if weight_sums is not None else 0.0),
+                  mask_a=mask_a, masks_b=masks_b)
     u_dev = None
     if uniforms is not None:
         u_dev = torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float64)).to(dev)
@@ -287,6 +300,41 @@ def _triangulate_ref(matched_ref: _MatchedReference, tri_ctx: _TriangulationCont
     if errs:
         raise errs[0][1]
     return res[0]
+
+
+def _collect_reference_matches(packed: _PackedReferenceBatch, matcher, config: DensePipelineConfig, pair_counter: int,
+                               cancel_requested: Optional[Callable[[], bool]] = None
+                               ) -> Tuple[Optional[_MatchedReference], int]:
+    """Reference signature (core/pipeline.py:385-391).  ``matcher.match_grids_batch(imA, nn_images)`` yields one
+    (warp_hw, cert_hw) pair per neighbour, as ``RomaMatcher`` does (core/matcher.py:141-196).
+
+    Unlike the reference, nothing is post-processed or copied to the host here: the matcher's tensors are handed on
+    as they are (``raw_certainty=True``) and the floor clamp / mask products of core/pipeline.py:405-430 happen inside
+    the kernels that read them.  The ``.to("cpu")`` + ``cuda.synchronize()`` of :432-442 disappears."""
+    imA, nn_images = packed.imA_np, list(packed.nn_arrays)
+    try:                                   # the reference hands PIL images to the matcher (:392-393)
+        from PIL import Image
+        imA = Image.fromarray(np.ascontiguousarray(packed.imA_np))
+        nn_images = [Image.fromarray(np.ascontiguousarray(a)) for a in packed.nn_arrays]
+    except ImportError:
+        pass
+    results = matcher.match_grids_batch(imA, nn_images)
+    if _is_cancelled(cancel_requested):
+        raise PipelineCancelled("Cancelled")
+    warps: List[torch.Tensor] = []
+    certs: List[torch.Tensor] = []
+    pair_index_by_nbr: Dict[int, int] = {}
+    image_by_nbr: Dict[int, np.ndarray] = {}
+    for (warp_hw, cert_hw), nbr_id, imB_np in zip(results, packed.nn_ids, packed.nn_arrays):
+        warps.append(warp_hw.detach())
+        certs.append(cert_hw.detach())
+        pair_counter += 1
+        pair_index_by_nbr[nbr_id] = pair_counter
+        image_by_nbr[nbr_id] = imB_np
+    if not certs:
+        return None, pair_counter
+    return _MatchedReference(packed=packed, warp_list_cpu=warps, cert_list_cpu=certs, pair_index_by_nbr=pair_index_by_nbr,
+                             image_by_nbr=image_by_nbr, raw_certainty=True), pair_counter
 
 
 # ------------------------------------------------------------------------------------------------

@@ -229,12 +229,14 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     const dim3 grid((unsigned)plan.ws.nblk, (unsigned)nsubrefs);
     cudaError_t e;
     { KernelTimer kt(st, "ldp_stream_kernel");
-      switch (p->nn_max) {          // max neighbours per view in this launch (0 = unknown)
-          case 1: ldp::ldp_stream_kernel<1><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
-          case 2: ldp::ldp_stream_kernel<2><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
-          case 3: ldp::ldp_stream_kernel<3><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
-          case 4: ldp::ldp_stream_kernel<4><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
-          default: ldp::ldp_stream_kernel<0><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+      if (p->prologue) {            // raw matcher planes: post-processing fused into the read
+          ldp::ldp_stream_kernel<0, true><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom);
+      } else switch (p->nn_max) {   // max neighbours per view in this launch (0 = unknown)
+          case 1: ldp::ldp_stream_kernel<1, false><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+          case 2: ldp::ldp_stream_kernel<2, false><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+          case 3: ldp::ldp_stream_kernel<3, false><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+          case 4: ldp::ldp_stream_kernel<4, false><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+          default: ldp::ldp_stream_kernel<0, false><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
       } }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_stream_kernel");
@@ -596,6 +598,26 @@ int ldp_triangulate_samples(const ldp_params* params, const ldp_ref_desc* refs, 
     rc = launch_geometry(params, refs, out, plan, 0, st, 0, params->n_refs, 0);
     if (rc != LDP_OK) return rc;
     return launch_pack(params, refs, out, plan, st);
+}
+
+int ldp_postprocess_certainty(const ldp_params* params, const ldp_ref_desc* refs, float* outp,
+                              size_t ref_stride, size_t plane_stride, void* stream) {
+    g_launches = 0;
+    g_prof_n = 0;
+    if (!params || params->n_refs < 0 || params->H <= 0 || params->W <= 0) return fail(LDP_ERR_INVALID, "bad shape");
+    if (params->n_refs == 0) return LDP_OK;
+    if (!refs || !outp) return fail(LDP_ERR_INVALID, "null refs/out");
+    if ((long long)params->H * params->W > (1ll << 24)) return fail(LDP_ERR_INVALID, "map too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int N = params->H * params->W;
+    const int bx = std::min((N + ldp::KP_THREADS - 1) / ldp::KP_THREADS, 4 * sm_count());
+    const dim3 grid((unsigned)bx, LDP_MAX_NN, (unsigned)params->n_refs);
+    { KernelTimer kt(st, "ldp_prologue_kernel");
+      ldp::ldp_prologue_kernel<<<grid, ldp::KP_THREADS, 0, st>>>(*params, refs, outp, ref_stride, plane_stride); }
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ldp_prologue_kernel");
+    return LDP_OK;
 }
 
 }  // extern "C"

@@ -171,6 +171,43 @@ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint32_t stream,
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Certainty post-processing between the matcher and the path (reference core/pipeline.py:405-430), applied on the
+// fly wherever a raw certainty value is read when ldp_params.prologue is set.
+// ---------------------------------------------------------------------------------------------
+struct ProView {            // per-view constants, staged in shared memory
+    const uint8_t* mask_a;
+    const uint8_t* mask_b[LDP_MAX_NN];
+    const float* warp[LDP_MAX_NN];
+    int mask_w, mask_h;
+    float msx, msy;
+};
+__device__ __forceinline__ void stage_proview(const ldp_ref_desc* rd, ProView& pv, int t) {
+    if (t < LDP_MAX_NN) { pv.mask_b[t] = rd->mask_b[t]; pv.warp[t] = rd->warp[t]; }
+    if (t == 0) { pv.mask_a = rd->mask_a; pv.mask_w = rd->mask_w; pv.mask_h = rd->mask_h; pv.msx = rd->mask_sx; pv.msy = rd->mask_sy; }
+}
+// mask value at map pixel (ix, iy): F.interpolate(mode="nearest") to the map size, then .float()
+__device__ __forceinline__ float mask_at(const uint8_t* __restrict__ m, int ix, int iy, const ProView& pv) {
+    const int mx = min((int)floorf(__fmul_rn((float)ix, pv.msx)), pv.mask_w - 1);
+    const int my = min((int)floorf(__fmul_rn((float)iy, pv.msy)), pv.mask_h - 1);
+    return (float)__ldg(m + (size_t)my * pv.mask_w + mx);
+}
+// certainty of neighbour k at pixel px = (x, y) after clamp(min), x maskA, x grid_sample(maskB, warp[..., 2:4])
+__device__ __forceinline__ float prologue_cert(float c, int k, int px, int x, int y, const ldp_params& P, const ProView& pv) {
+    c = (c < P.certainty_floor) ? P.certainty_floor : c;                       // torch.clamp(min=): NaN stays NaN
+    if (pv.mask_a) c = __fmul_rn(c, mask_at(pv.mask_a, x, y, pv));
+    if (pv.mask_b[k]) {
+        const float2 g = __ldg(reinterpret_cast<const float2*>(pv.warp[k] + (size_t)px * 4 + 2));
+        // grid_sampler un-normalise (align_corners=False): (g + 1) * (size / 2) - 0.5, then nearbyint
+        const float fx = rintf(__fsub_rn(__fmul_rn(__fadd_rn(g.x, 1.f), 0.5f * (float)P.W), 0.5f));
+        const float fy = rintf(__fsub_rn(__fmul_rn(__fadd_rn(g.y, 1.f), 0.5f * (float)P.H), 0.5f));
+        float m = 0.f;                                                         // padding_mode="zeros"; NaN coordinates fall outside
+        if (fx > -1.f && fx < (float)P.W && fy > -1.f && fy < (float)P.H) m = mask_at(pv.mask_b[k], (int)fx, (int)fy, pv);
+        c = __fmul_rn(c, m);
+    }
+    return c;
+}
+
 #ifdef LDP_PHASE_CLOCKS
 #define LDP_CLK(ws, r, slot) do { if (threadIdx.x == 0 && (blockIdx.x % cooperative_groups::this_cluster().num_blocks()) == 0) (ws).dbgclk[(size_t)(r) * 32 + (slot)] = clock64(); } while (0)
 #else

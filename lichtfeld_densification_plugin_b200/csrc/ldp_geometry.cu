@@ -245,22 +245,33 @@ struct SampleRec {
 };
 
 // ---- gather: everything that needs a scattered load (core/pipeline.py:636-640,652-653,661-675)
-__device__ __forceinline__ void gather_sample(const ldp_params& P, const RefConst& rc, const PairConst* pc, const GeomArgs& ga,
-                                              const uint8_t* __restrict__ bestk_row, int idx, SampleRec& rec, float& craw) {
+// certainty of neighbour q at pixel idx as the path sees it: raw planes go through the reference's post-processing
+__device__ __forceinline__ float cert_at(const ldp_params& P, const PairConst* pc, const ProView& pv, int q, int idx) {
+    float c = __ldg(pc[q].cert + idx);
+    if (P.prologue) {
+        const int y = idx / P.W;
+        c = prologue_cert(c, q, idx, idx - y * P.W, y, P, pv);
+    }
+    return c;
+}
+
+__device__ __forceinline__ void gather_sample(const ldp_params& P, const RefConst& rc, const PairConst* pc, const ProView& pv,
+                                              const GeomArgs& ga, const uint8_t* __restrict__ bestk_row, int idx,
+                                              SampleRec& rec, float& craw) {
     int k = 0;                                                                    // core/pipeline.py:634-635,652
     if (ga.have_bestk) {
         k = bestk_row[idx];
     } else {                               // stage entry point: arg-max over neighbours at the sampled pixel only
-        float best = __ldg(pc[0].cert + idx);
+        float best = cert_at(P, pc, pv, 0, idx);
         for (int q = 1; q < rc.nn; ++q) {
-            const float c = __ldg(pc[q].cert + idx);
+            const float c = cert_at(P, pc, pv, q, idx);
             if (c > best) { best = c; k = q; }
         }
     }
     const PairConst& pk = pc[k];
     const float4 wv = __ldg(reinterpret_cast<const float4*>(pk.warp) + idx);      // core/pipeline.py:636-640,653
     craw = 0.f;
-    if (P.collect_debug) craw = __ldg(pk.cert + idx);
+    if (P.collect_debug) craw = cert_at(P, pc, pv, k, idx);
     const float wm1 = (float)(P.w_match - 1), hm1 = (float)(P.h_match - 1);
     const float xA = __fmul_rn(__fmul_rn(__fadd_rn(wv.x, 1.0f), 0.5f), wm1);
     const float yA = __fmul_rn(__fmul_rn(__fadd_rn(wv.y, 1.0f), 0.5f), hm1);
@@ -436,6 +447,7 @@ ldp_gather_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
 {
     __shared__ RefConst rc;
     __shared__ PairConst pc[LDP_MAX_NN];
+    __shared__ ProView pv;
     const int r = blockIdx.y + ga.ref0;
     const int S = out.n_samples[r];
     const int i0 = blockIdx.x * KG_THREADS;
@@ -446,13 +458,14 @@ ldp_gather_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
     }
     if (i0 >= S) return;
     stage_constants(refs + r, rc, pc, threadIdx.x, KG_THREADS);
+    if (P.prologue) stage_proview(refs + r, pv, threadIdx.x);
     __syncthreads();
     const int i = i0 + threadIdx.x;
     if (i >= S) return;
     const int32_t* sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
     SampleRec rec;
     float craw;
-    gather_sample(P, rc, pc, ga, ws.bestk + (size_t)r * ws.n_pad, sel[i], rec, craw);
+    gather_sample(P, rc, pc, pv, ga, ws.bestk + (size_t)r * ws.n_pad, sel[i], rec, craw);
     const size_t o = (size_t)r * ws.sel_cap + i;
     ws.pt0[o] = rec.wv;                                                                   // record, part 1
     ws.pt1[o] = make_float4(__uint_as_float(rec.tex[0]), __uint_as_float(rec.tex[1]), __uint_as_float(rec.tex[2]),
@@ -667,6 +680,29 @@ ldp_pack_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 if (out.dbg_cert) out.dbg_cert[dst] = c.w;
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The post-processing alone (core/pipeline.py:405-430): grid (pixel blocks, neighbours, views).
+// ---------------------------------------------------------------------------------------------
+constexpr int KP_THREADS = 256;
+__global__ void __launch_bounds__(KP_THREADS)
+ldp_prologue_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, float* __restrict__ outp,
+                    size_t ref_stride, size_t plane_stride)
+{
+    __shared__ ProView pv;
+    const int r = blockIdx.z, k = blockIdx.y;
+    const ldp_ref_desc* rd = refs + r;
+    if (k >= rd->nn) return;
+    stage_proview(rd, pv, threadIdx.x);
+    __syncthreads();
+    const float* __restrict__ c = rd->cert[k];
+    const int N = P.H * P.W;
+    float* __restrict__ o = outp + (size_t)r * ref_stride + (size_t)k * plane_stride;
+    for (int px = blockIdx.x * KP_THREADS + threadIdx.x; px < N; px += gridDim.x * KP_THREADS) {
+        const int y = px / P.W;
+        o[px] = prologue_cert(__ldcs(c + px), k, px, px - y * P.W, y, P, pv);
     }
 }
 

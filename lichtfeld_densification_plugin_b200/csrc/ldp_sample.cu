@@ -89,21 +89,26 @@ __device__ __forceinline__ void quad_border_weights(float wv[4], int px, int x, 
     }
 }
 
-template <int NNMAX>      // 1..4: plane pointers held in registers, loop fully unrolled; 0: any nn (pointers in shared memory)
 #ifndef KS_MIN_BLOCKS
 #define KS_MIN_BLOCKS 5
 #endif
+// NNMAX 1..4: plane pointers held in registers, loop fully unrolled; 0: any nn (pointers in shared memory).
+// PRO: the planes are raw matcher outputs and the reference's post-processing (core/pipeline.py:405-430) is applied
+//      to every value as it is read (ldp_device.cuh:prologue_cert); always with NNMAX = 0.
+template <int NNMAX, bool PRO>
 __global__ void __launch_bounds__(KS_THREADS, KS_MIN_BLOCKS)
 ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const SampleGeom G)
 {
     __shared__ const float* s_cert[LDP_MAX_NN];
     __shared__ double red_d[32];
     __shared__ float red_f[32];
+    __shared__ ProView s_pv;
     const int r = blockIdx.y + G.ref0, blk = blockIdx.x, tid = threadIdx.x;
     const int N = G.N;
     const ldp_ref_desc* rd = refs + r;
     const int nn = rd->nn;
     if (tid < LDP_MAX_NN) s_cert[tid] = (tid < nn) ? rd->cert[tid] : nullptr;
+    if (PRO) stage_proview(rd, s_pv, tid);
     if (blk == 0) {          // per-view state consumed by the later kernels of this launch
         if (tid == 0) {
             ws.rstat[r].s = 0.f; ws.rstat[r].npos = 0; ws.rstat[r].emin = 0x7fffffff; ws.rstat[r].bad = 0;
@@ -143,7 +148,7 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
             if (c.z > wv[2] || c.z != c.z) { wv[2] = c.z; bi[2] = k; }
             if (c.w > wv[3] || c.w != c.w) { wv[3] = c.w; bi[3] = k; }
         };
-        if (G.vec && NNMAX > 0) {
+        if (!PRO && G.vec && NNMAX > 0) {
             // two quads per step: all 2*NNMAX 128-bit loads are issued before any of them is consumed
             constexpr int STEP = KS_THREADS * 4;
             for (int it = 0; it < KS_SPAN / STEP; it += 2) {
@@ -170,7 +175,24 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
                 if (px >= N) break;
                 float wv[4];
                 int bi[4] = {0, 0, 0, 0};
-                if (G.vec) {
+                if (PRO) {
+                    // raw planes: post-process each value, then the same first-index-wins maximum
+                    int y = (int)div_magic((uint32_t)px, G.w_magic), x = px - y * W;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float best = 0.f;
+                        int bk = 0;
+                        if (px + j < N) {
+                            best = prologue_cert(__ldcs(c0 + px + j), 0, px + j, x, y, P, s_pv);
+                            for (int k = 1; k < nn; ++k) {
+                                const float c = prologue_cert(__ldcs(s_cert[k] + px + j), k, px + j, x, y, P, s_pv);
+                                if (c > best || c != c) { best = c; bk = k; }
+                            }
+                        }
+                        wv[j] = best; bi[j] = bk;
+                        if (++x == W) { x = 0; ++y; }
+                    }
+                } else if (G.vec) {
                     const float4 v = ld_stream4(c0 + px);
                     wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
 #pragma unroll 4

@@ -37,6 +37,10 @@ class PathConfig:
     border: int = BORDER_DEFAULT
     tiles: int = TILES_DEFAULT
     seed: int = 0
+    # None: certainty planes are already post-processed (what the reference's _triangulate_ref receives).
+    # A float: the planes are RAW matcher outputs and the kernels apply clamp(min=certainty_floor) and the masks
+    # registered with RefBatch.add on the fly (reference core/pipeline.py:405-430, config.certainty_thresh).
+    certainty_floor: Optional[float] = None
 
     @classmethod
     def from_pipeline_config(cls, cfg, sample_cap: float = SAMPLE_CAP_DEFAULT) -> "PathConfig":
@@ -97,7 +101,10 @@ class RefBatch:
 
     def add(self, cert_planes: Sequence[torch.Tensor], warp_planes: Sequence[torch.Tensor], image: torch.Tensor,
             ref_cam: CameraRecord, nbr_cams: Sequence[CameraRecord], rng_stream: int = 0,
-            weight_sum_override: float = 0.0) -> None:
+            weight_sum_override: float = 0.0, mask_a: Optional[torch.Tensor] = None,
+            masks_b: Optional[Sequence[Optional[torch.Tensor]]] = None) -> None:
+        """``mask_a`` / ``masks_b[k]``: uint8 [mask_h, mask_w] device tensors (``packed.maskA_np`` / ``packed.nn_masks``),
+        read only when ``PathConfig.certainty_floor`` is set (raw certainty planes)."""
         nn = len(cert_planes)
         if nn != len(warp_planes) or nn != len(nbr_cams):
             raise ValueError("cert_planes, warp_planes and nbr_cams must have the same length")
@@ -137,9 +144,37 @@ class RefBatch:
             row["F"][k] = self.pairs.fundamental(ref_cam, cam).reshape(9)
             row["sxB"][k], row["syB"][k] = np.float32(cam.width / wm), np.float32(cam.height / hm)
             row["group"][k] = uids.index(uids[k])          # the reference groups by neighbour uid
+        self._add_masks(row, nn, mask_a, masks_b)
         self._rows.append(row)
         self.nbr_uids.append(uids)
         self.ref_uids.append(int(ref_cam.uid))
+
+    def _add_masks(self, row, nn: int, mask_a, masks_b) -> None:
+        masks = [mask_a] + list(masks_b if masks_b is not None else [])
+        if len(masks) - 1 not in (0, nn):
+            raise ValueError("masks_b must have one entry (tensor or None) per neighbour")
+        shape = None
+        for j, m in enumerate(masks):
+            if m is None:
+                continue
+            if not isinstance(m, torch.Tensor) or m.device != self.device or m.dtype != torch.uint8 or m.dim() != 2:
+                raise ValueError("masks must be uint8 [h, w] tensors on the batch device")
+            m = m.contiguous()
+            if shape is None:
+                shape = tuple(m.shape)
+            elif tuple(m.shape) != shape:
+                raise ValueError("all masks of a reference view must share one resolution")
+            self._keep_alive.append(m)
+            if j == 0:
+                row["mask_a"] = m.data_ptr()
+            else:
+                row["mask_b"][j - 1] = m.data_ptr()
+        if shape is not None:
+            mh, mw = shape
+            row["mask_w"], row["mask_h"] = mw, mh
+            # F.interpolate(mode="nearest") scale: f32(in) / f32(out) (reference core/pipeline.py:373-378)
+            row["mask_sx"] = np.float32(mw) / np.float32(self.W)
+            row["mask_sy"] = np.float32(mh) / np.float32(self.H)
 
     def add_cert_only(self, cert_planes: Sequence[torch.Tensor], rng_stream: int = 0,
                       weight_sum_override: float = 0.0) -> None:
@@ -225,6 +260,8 @@ class DensifyEngine:
         p.rng_mode = int(rng_mode)
         p.scalar_loads = 1 if batch.force_scalar_loads else 0
         p.nn_max = max((len(u) for u in batch.nbr_uids), default=0)
+        p.prologue = 0 if cfg.certainty_floor is None else 1
+        p.certainty_floor = float(np.float32(cfg.certainty_floor if cfg.certainty_floor is not None else 0.0))
         p.seed = int(cfg.seed) & 0xFFFFFFFFFFFFFFFF
         p.uniforms_per_ref = int(uniforms_per_ref)
         return p
@@ -285,6 +322,23 @@ class DensifyEngine:
         N.check(rc, "ldp_densify_refs")
         out.launches = int(self.lib.ldp_last_launch_count())
         out._keep = (descs_dev, uniforms, batch)      # keep inputs alive until the stream is done with them
+        return out
+
+    def postprocess_certainty(self, batch: RefBatch, certainty_floor: float) -> torch.Tensor:
+        """``ldp_postprocess_certainty``: the reference's certainty post-processing alone (core/pipeline.py:405-430).
+        Returns f32 [n_refs, nn_max, H, W] (planes beyond a view's neighbour count are zero)."""
+        R = len(batch)
+        nn_max = max((len(u) for u in batch.nbr_uids), default=0)
+        out = torch.zeros((R, max(nn_max, 1), batch.H, batch.W), dtype=torch.float32, device=self.device)
+        if R == 0 or nn_max == 0:
+            return out
+        params = self._params(batch, PathConfig(certainty_floor=float(certainty_floor)), False, N.LDP_RNG_PHILOX, 0)
+        descs = self.upload_descs(batch)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.ldp_postprocess_certainty(C.byref(params), C.c_void_p(descs.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                C.c_size_t(out.stride(0)), C.c_size_t(out.stride(1)), C.c_void_p(stream))
+        N.check(rc, "ldp_postprocess_certainty")
+        out._keep = (descs, batch)
         return out
 
     def sample(self, batch: RefBatch, cfg: PathConfig, uniforms: Optional[torch.Tensor] = None):

@@ -56,10 +56,14 @@ def run_gpu(engine: DensifyEngine, scene, inputs: List[dict], cfg: PathConfig, u
         nn = len(inp["nbr_indices"])
         cert = inp["cert"].to(dev)
         warp = inp["warp"].to(dev)
+        # optional raw-certainty mode (PathConfig.certainty_floor set): inp["mask_a"], inp["masks_b"] as uint8 arrays / None
+        to_dev = lambda m: None if m is None else torch.as_tensor(np.ascontiguousarray(m), dtype=torch.uint8).to(dev)
         batch.add([cert[k] for k in range(nn)], [warp[k] for k in range(nn)], inp["image"].to(dev),
                   cams[inp["ref_index"]], [cams[j] for j in inp["nbr_indices"]],
                   rng_stream=(rng_streams[i] if rng_streams is not None else inp["ref_index"]),
-                  weight_sum_override=(float(weight_sums[i]) if weight_sums is not None else 0.0))
+                  weight_sum_override=(float(weight_sums[i]) if weight_sums is not None else 0.0),
+                  mask_a=to_dev(inp.get("mask_a")),
+                  masks_b=[to_dev(m) for m in inp["masks_b"]] if inp.get("masks_b") is not None else None)
     u = torch.from_numpy(np.ascontiguousarray(uniforms)).to(dev) if uniforms is not None else None
     out = engine.densify(batch, cfg, uniforms=u, collect_debug=collect_debug, taps=True)
     torch.cuda.synchronize()
