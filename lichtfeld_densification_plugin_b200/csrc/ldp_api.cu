@@ -229,8 +229,12 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     const dim3 grid((unsigned)plan.ws.nblk, (unsigned)nsubrefs);
     cudaError_t e;
     { KernelTimer kt(st, "ldp_stream_kernel");
-      if (p->prologue) {            // raw matcher planes: post-processing fused into the read
-          ldp::ldp_stream_kernel<0, true><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom);
+      if (p->prologue) switch (p->nn_max) {      // raw matcher planes: post-processing fused into the read
+          case 1: ldp::ldp_stream_kernel<1, true><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+          case 2: ldp::ldp_stream_kernel<2, true><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+          case 3: ldp::ldp_stream_kernel<3, true><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+          case 4: ldp::ldp_stream_kernel<4, true><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+          default: ldp::ldp_stream_kernel<0, true><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
       } else switch (p->nn_max) {   // max neighbours per view in this launch (0 = unknown)
           case 1: ldp::ldp_stream_kernel<1, false><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
           case 2: ldp::ldp_stream_kernel<2, false><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;

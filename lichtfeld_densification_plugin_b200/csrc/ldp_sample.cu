@@ -94,9 +94,9 @@ __device__ __forceinline__ void quad_border_weights(float wv[4], int px, int x, 
 #endif
 // NNMAX 1..4: plane pointers held in registers, loop fully unrolled; 0: any nn (pointers in shared memory).
 // PRO: the planes are raw matcher outputs and the reference's post-processing (core/pipeline.py:405-430) is applied
-//      to every value as it is read (ldp_device.cuh:prologue_cert); always with NNMAX = 0.
+//      to every value as it is read (ldp_device.cuh:prologue_cert).
 template <int NNMAX, bool PRO>
-__global__ void __launch_bounds__(KS_THREADS, KS_MIN_BLOCKS)
+__global__ void __launch_bounds__(KS_THREADS, PRO ? 3 : KS_MIN_BLOCKS)      // PRO holds the warp rows too: more registers
 ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const SampleGeom G)
 {
     __shared__ const float* s_cert[LDP_MAX_NN];
@@ -148,7 +148,41 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
             if (c.z > wv[2] || c.z != c.z) { wv[2] = c.z; bi[2] = k; }
             if (c.w > wv[3] || c.w != c.w) { wv[3] = c.w; bi[3] = k; }
         };
-        if (!PRO && G.vec && NNMAX > 0) {
+        // ---- raw planes (PRO): the reference's post-processing of one quad of neighbour k (core/pipeline.py:405-430);
+        //      a quad lies in one image row on the vector path.  Same arithmetic as ldp_device.cuh:prologue_cert.
+        const bool has_a = PRO && s_pv.mask_a != nullptr;
+        const bool ident_a = has_a && s_pv.mask_w == W && s_pv.mask_h == H && (reinterpret_cast<uintptr_t>(s_pv.mask_a) & 3u) == 0;
+        auto mask_a_quad = [&](int px, float ma[4]) {
+            if (ident_a) {                                             // same resolution: 4 mask bytes in one load
+                const uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(s_pv.mask_a + px));
+                ma[0] = (float)(m & 0xffu); ma[1] = (float)((m >> 8) & 0xffu); ma[2] = (float)((m >> 16) & 0xffu); ma[3] = (float)(m >> 24);
+            } else {
+                const int y = (int)div_magic((uint32_t)px, G.w_magic), x = px - y * W;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ma[j] = mask_at(s_pv.mask_a, x + j, y, s_pv);
+            }
+        };
+        auto warped_mask = [&](const uint8_t* __restrict__ mb, const float2 g) {
+            const float fx = rintf(__fsub_rn(__fmul_rn(__fadd_rn(g.x, 1.f), 0.5f * (float)W), 0.5f));
+            const float fy = rintf(__fsub_rn(__fmul_rn(__fadd_rn(g.y, 1.f), 0.5f * (float)H), 0.5f));
+            float m = 0.f;
+            if (fx > -1.f && fx < (float)W && fy > -1.f && fy < (float)H) m = mask_at(mb, (int)fx, (int)fy, s_pv);
+            return m;
+        };
+        auto pro_quad = [&](float4& c, int k, int px, const float ma[4]) {
+            const float fl = P.certainty_floor;
+            c.x = (c.x < fl) ? fl : c.x; c.y = (c.y < fl) ? fl : c.y;               // torch.clamp(min=): NaN stays NaN
+            c.z = (c.z < fl) ? fl : c.z; c.w = (c.w < fl) ? fl : c.w;
+            if (has_a) { c.x = __fmul_rn(c.x, ma[0]); c.y = __fmul_rn(c.y, ma[1]); c.z = __fmul_rn(c.z, ma[2]); c.w = __fmul_rn(c.w, ma[3]); }
+            const uint8_t* mb = s_pv.mask_b[k];
+            if (mb) {                                                              // (xB, yB) of the 4 rows: read once, evict-first
+                const float2* g = reinterpret_cast<const float2*>(s_pv.warp[k] + (size_t)px * 4 + 2);
+                const float2 g0 = __ldcs(g), g1 = __ldcs(g + 2), g2 = __ldcs(g + 4), g3 = __ldcs(g + 6);
+                c.x = __fmul_rn(c.x, warped_mask(mb, g0)); c.y = __fmul_rn(c.y, warped_mask(mb, g1));
+                c.z = __fmul_rn(c.z, warped_mask(mb, g2)); c.w = __fmul_rn(c.w, warped_mask(mb, g3));
+            }
+        };
+        if (G.vec && NNMAX > 0) {
             // two quads per step: all 2*NNMAX 128-bit loads are issued before any of them is consumed
             constexpr int STEP = KS_THREADS * 4;
             for (int it = 0; it < KS_SPAN / STEP; it += 2) {
@@ -161,6 +195,14 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
                 if (NNMAX >= 2) { a1 = ld_stream4(c1 + pxa); b1 = ld_stream4(c1 + qb); }
                 if (NNMAX >= 3) { a2 = ld_stream4(c2 + pxa); b2 = ld_stream4(c2 + qb); }
                 if (NNMAX >= 4) { a3 = ld_stream4(c3 + pxa); b3 = ld_stream4(c3 + qb); }
+                if (PRO) {
+                    float ma[4] = {1.f, 1.f, 1.f, 1.f}, mb[4] = {1.f, 1.f, 1.f, 1.f};
+                    if (has_a) { mask_a_quad(pxa, ma); mask_a_quad(qb, mb); }
+                    pro_quad(a0, 0, pxa, ma); pro_quad(b0, 0, qb, mb);
+                    if (NNMAX >= 2 && nn >= 2) { pro_quad(a1, 1, pxa, ma); pro_quad(b1, 1, qb, mb); }
+                    if (NNMAX >= 3 && nn >= 3) { pro_quad(a2, 2, pxa, ma); pro_quad(b2, 2, qb, mb); }
+                    if (NNMAX >= 4 && nn >= 4) { pro_quad(a3, 3, pxa, ma); pro_quad(b3, 3, qb, mb); }
+                }
                 float wa[4] = {a0.x, a0.y, a0.z, a0.w}, wb[4] = {b0.x, b0.y, b0.z, b0.w};
                 int ia[4] = {0, 0, 0, 0}, ib[4] = {0, 0, 0, 0};
                 if (NNMAX >= 2) { take(a1, 1, wa, ia); take(b1, 1, wb, ib); }
