@@ -127,6 +127,10 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     g.vec = 0;
     g.w_magic = ((1ull << 40) + (unsigned long long)p->W - 1) / (unsigned long long)p->W;
     g.t_magic = ((1ull << 40) + (unsigned long long)g.tile - 1) / (unsigned long long)g.tile;
+    g.t_magic32 = (g.tile > 1) ? (uint32_t)(((1ull << 32) + (unsigned long long)g.tile - 1) / (unsigned long long)g.tile) : 0u;
+    g.step_dx = (ldp::KS_THREADS * 4) % p->W;
+    g.step_dy = (ldp::KS_THREADS * 4) / p->W;
+    g.prep_lean = (p->W <= 8192 && p->H <= 8192 && g.tile > 1) ? 1 : 0;
     int cs = 5;
     for (;; ++cs) {
         const size_t nchunk = ((size_t)N + ((size_t)1 << cs) - 1) >> cs;
@@ -198,7 +202,8 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     w.blk_before = reinterpret_cast<int32_t*>(carve(R * plan->nb2 * LDP_MAX_NN * sizeof(int32_t)));
     w.grp_base = reinterpret_cast<int32_t*>(carve(R * LDP_MAX_NN * sizeof(int32_t)));
     w.fix_list = reinterpret_cast<int2*>(carve(R * w.sel_cap * sizeof(int2)));
-    w.fix_count = reinterpret_cast<int32_t*>(carve(ldp::LDP_MAX_SUB * sizeof(int32_t)));
+    w.fix_count = reinterpret_cast<int32_t*>(carve((ldp::LDP_MAX_SUB + R) * sizeof(int32_t)));
+    w.arrive = w.fix_count ? w.fix_count + ldp::LDP_MAX_SUB : nullptr;
     plan->bytes = off;
     return LDP_OK;
 }
@@ -221,8 +226,13 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(ldp::ldp_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(draw)");
-        e = cudaFuncSetAttribute(ldp::ldp_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        e = cudaFuncSetAttribute(ldp::ldp_prep_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(prep)");
+        e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(prep lean)");
         configured = true;
     }
     if (plan.prep_smem > 64 * 1024) return fail(LDP_ERR_INVALID, "map too wide for the prep kernel tables");
@@ -256,7 +266,17 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(csum)");
     }
     { KernelTimer kt(st, "ldp_prep_kernel");
-      ldp::ldp_prep_kernel<<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom); }
+      static const bool force_generic = getenv("LDP_PREP_GENERIC") != nullptr;
+      if (vec_ok && plan.geom.prep_lean && !force_generic) {
+          switch (plan.geom.chunk_shift) {
+              case 5: ldp::ldp_prep_kernel<5><<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom); break;
+              case 6: ldp::ldp_prep_kernel<6><<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom); break;
+              case 7: ldp::ldp_prep_kernel<7><<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom); break;
+              default: ldp::ldp_prep_kernel<0><<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom); break;
+          }
+      } else {
+          ldp::ldp_prep_generic_kernel<<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom);
+      } }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_prep_kernel");
     {
@@ -536,7 +556,7 @@ int ldp_densify_refs(const ldp_params* params, const ldp_ref_desc* refs, const d
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // the winning-neighbour plane is written by the first kernel and gathered (1 byte per sample, random) by the fifth
     L2Window l2(st, plan.ws.bestk, (size_t)params->n_refs * plan.ws.n_pad);      // winning-neighbour plane (1 B / px)
-    cudaError_t e = cudaMemsetAsync(plan.ws.fix_count, 0, ldp::LDP_MAX_SUB * sizeof(int32_t), st);
+    cudaError_t e = cudaMemsetAsync(plan.ws.fix_count, 0, (ldp::LDP_MAX_SUB + (size_t)params->n_refs) * sizeof(int32_t), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(fix_count)");
     const int nsub = choose_subbatches(params->n_refs);
     if (nsub == 1) {
@@ -577,6 +597,8 @@ int ldp_sample_refs(const ldp_params* params, const ldp_ref_desc* refs, const do
     int rc = make_plan(params, base, &plan);
     if (rc != LDP_OK) return rc;
     if (plan.bytes + (size_t)(base - static_cast<char*>(workspace)) > workspace_bytes) return fail(LDP_ERR_WORKSPACE, "workspace too small");
+    cudaError_t e = cudaMemsetAsync(plan.ws.fix_count, 0, (ldp::LDP_MAX_SUB + (size_t)params->n_refs) * sizeof(int32_t), static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(counters)");
     return launch_sample(params, refs, uniforms, out, plan, vec_ok_for(params), static_cast<cudaStream_t>(stream), 0, params->n_refs);
 }
 
@@ -597,7 +619,7 @@ int ldp_triangulate_samples(const ldp_params* params, const ldp_ref_desc* refs, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaMemsetAsync(plan.ws.kept, 0, (size_t)params->n_refs * sizeof(int32_t), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(kept)");
-    e = cudaMemsetAsync(plan.ws.fix_count, 0, ldp::LDP_MAX_SUB * sizeof(int32_t), st);
+    e = cudaMemsetAsync(plan.ws.fix_count, 0, (ldp::LDP_MAX_SUB + (size_t)params->n_refs) * sizeof(int32_t), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(fix_count)");
     rc = launch_geometry(params, refs, out, plan, 0, st, 0, params->n_refs, 0);
     if (rc != LDP_OK) return rc;

@@ -44,6 +44,7 @@ struct Workspace {
     int32_t* grp_base;   // [R][LDP_MAX_NN] output offset of each group inside the view (pack plan)
     int2* fix_list;      // [R*sel_cap] (view, sample) pairs whose null-vector iteration did not converge
     int32_t* fix_count;  // [LDP_MAX_SUB] one counter per sub-batch (its list starts at ref0 * sel_cap)
+    int32_t* arrive;     // [R] stream-kernel CTAs of the view that have finished (directly after fix_count: one memset)
     long long* dbgclk;   // [R][32] phase timestamps of the draw kernel (written only with -DLDP_PHASE_CLOCKS)
     size_t n_pad, n_words, found_cap, sel_cap, topk_cap, nchunk_pad, nblk, bins_cap, draw_cmax;
 };
@@ -60,6 +61,9 @@ struct SampleGeom {     // launch-constant shape of the sampler
     int prep_lb_cap;    // local tile bins per CTA of the prep kernel
     unsigned long long w_magic;   // ceil(2^40 / W): floor(n / W) = (n * w_magic) >> 40 for n < 2^21 * ...
     unsigned long long t_magic;   // ceil(2^40 / tile)
+    uint32_t t_magic32;           // ceil(2^32 / tile): floor(n / tile) = umulhi(n, t_magic32) for n * tile < 2^32
+    int step_dx, step_dy;         // (KS_THREADS * 4) % W, (KS_THREADS * 4) / W: pixel step of the full-grid passes
+    int prep_lean;                // the lean prep kernel applies (vector path, W <= 8192)
     int ref0;           // first view of this sub-launch (views are indexed blockIdx + ref0)
     int draw_ept;       // draw kernel: chunk-table entries per thread (multiple of 8)
     int draw_pre_cap;   // draw kernel: doubles in the padded prefix table

@@ -274,8 +274,8 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
 //      Issue-bound: per quad one tile lookup (quads that straddle a tile edge take the per-pixel path).
 // =============================================================================================
 __global__ void __launch_bounds__(KS_THREADS)
-ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
-                const SampleGeom G)
+ldp_prep_generic_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
+                        const SampleGeom G)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int red_i[32];
@@ -398,6 +398,204 @@ ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
         const unsigned long long key = lb[i];
         if (key) atomicMax(&gb[(ty0 + i / G.nbx) * G.nbx + (i % G.nbx)], key);
     }
+}
+
+// =============================================================================================
+// K1b' prep, lean variant for the vector path (W % 4 == 0, 16-byte aligned rows, W <= 8192): same outputs as
+//      ldp_prep_generic_kernel with ~4x fewer instructions per pixel (the generic kernel is issue-bound):
+//        * p = fl32(w / s) with the correctly rounded reciprocal of s hoisted out of the loop and two FMA residual
+//          corrections per value (div_by); zeros and tiny quotients take the IEEE division.
+//        * positives / smallest positive exponent from the quad minimum; zeros (border, masked) take a side path;
+//        * per-tile arg-max of p in two phases with native 32-bit shared atomics: (A) tile maximum of the value,
+//          (B) after a CTA barrier, lowest pixel index among the pixels that reach it -- only quads whose maximum
+//          equals their tile's maximum look at single pixels.  One 64-bit key per tile and CTA goes to the global
+//          table, as before.
+//      CS = chunk_shift (5..7: chunk sums by shuffles inside a warp row of 128 pixels; 0: wider chunks, atomics).
+// =============================================================================================
+// fl32(a / b) for b > 0 with y = RN(1/b) hoisted: two residual corrections on the FMA pipe.  q1 is a faithful quotient
+// (error <= 1/2 ulp + 2^-23 ulp), so by Markstein's theorem (y correctly rounded, residual exact) the second correction
+// rounds to RN(a / b).  Requires exact residuals: a >= 2^-100 or a == 0, results in the normal range (callers guard).
+// Checked against __fdiv_rn on 2^32 operand pairs by scratch/divcheck.cu.
+__device__ __forceinline__ float div_by(float a, float b, float y) {
+    const float q0 = __fmul_rn(a, y);
+    const float r0 = __fmaf_rn(-b, q0, a);
+    const float q1 = __fmaf_rn(r0, y, q0);
+    const float r1 = __fmaf_rn(-b, q1, a);
+    return __fmaf_rn(r1, y, q1);
+}
+
+#ifdef LDP_PHASE_CLOCKS
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define LDP_PCLK(slot) do { if (threadIdx.x == 0 && (blockIdx.x == 3 || blockIdx.x == 31)) ws.dbgclk[(size_t)r * 32 + (blockIdx.x == 3 ? 18 : 24) + (slot)] = gtimer(); } while (0)
+#else
+#define LDP_PCLK(slot) do { } while (0)
+#endif
+#ifndef KP_MIN_BLOCKS
+#define KP_MIN_BLOCKS 5
+#endif
+template <int CS>
+__global__ void __launch_bounds__(KS_THREADS, KP_MIN_BLOCKS)
+ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
+                const SampleGeom G)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int red_i[32];
+    __shared__ float s_s;
+    __shared__ int s_bad;
+    constexpr int NIT = KS_SPAN / (KS_THREADS * 4);
+    constexpr int STEP = KS_THREADS * 4;
+    const int r = blockIdx.y + G.ref0, blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int N = G.N, W = P.W;
+    const ldp_ref_desc* rd = refs + r;
+    LDP_PCLK(0);
+    float* __restrict__ w = ws.w + (size_t)r * ws.n_pad;
+    const int base = blk * KS_SPAN;
+    int px = base + tid * 4;
+    // the first quad's load is in flight while the normaliser is reduced
+    float4 vnext = (px < N) ? __ldcg(reinterpret_cast<const float4*>(w + px)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- s: fixed-order reduction of the per-CTA partials (every CTA of the view computes the same value)
+    if (tid < 32) {
+        double a = 0.0;
+        int f = 0;
+        for (int i = lane; i < (int)ws.nblk; i += 32) {
+            a += ws.partial[(size_t)r * ws.nblk + i];
+            f |= ws.bflags[(size_t)r * ws.nblk + i];
+        }
+        a = warp_sum(a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) f |= __shfl_xor_sync(0xffffffffu, f, o);
+        if (lane == 0) {
+            float s = (float)a;
+            if (rd->weight_sum_override > 0.f) s = rd->weight_sum_override;
+            s_s = s;
+            s_bad = f;
+            if (blk == 0) {
+                ws.rstat[r].s = s;
+                ws.rstat[r].bad = f;
+                if (out.weight_sum) out.weight_sum[r] = s;
+            }
+        }
+    }
+
+    const int end = min(base + KS_SPAN, N);
+    const int y_first = (int)div_magic((uint32_t)base, G.w_magic), y_last = (int)div_magic((uint32_t)(end - 1), G.w_magic);
+    const int ty0 = (int)__umulhi((uint32_t)y_first, G.t_magic32), ty1 = (int)__umulhi((uint32_t)y_last, G.t_magic32);
+    const int nlb = (ty1 - ty0 + 1) * G.nbx;
+    uint32_t* tmax = reinterpret_cast<uint32_t*>(smem_raw);              // [nlb] tile maximum of p (bit pattern)
+    uint32_t* lidx = tmax + G.prep_lb_cap;                               // [nlb] lowest pixel index reaching it
+    for (int i = tid; i < nlb; i += KS_THREADS) { tmax[i] = 0u; lidx[i] = 0xFFFFFFFFu; }
+    __syncthreads();
+    const float s = s_s;
+    if (s_bad || !(s > 0.f)) return;       // the draw kernel reports the status
+    const float yr = __frcp_rn(s);                     // correctly rounded reciprocal, once per thread
+    const bool fast_div = (s >= 1.0f) && (s < 3.0e8f);  // then p >= 2^-90 implies w >= 2^-90: every residual below is exact
+    LDP_PCLK(1);
+
+    double* __restrict__ csum = ws.csum + (size_t)r * ws.nchunk_pad;
+    int lpos = 0;
+    uint32_t lminbits = 0x7fffffffu;                   // smallest positive p (bit pattern orders like the value)
+    uint32_t qm0[NIT], qm1[NIT];                       // per quad: maximum of its pixels in the first / second tile it touches
+    uint32_t jpack = 0u;                               // per quad, 2 + 2 bits: first pixel reaching qm0 / qm1
+    int y = (int)div_magic((uint32_t)px, G.w_magic), x = px - y * W;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        double a = 0.0;
+        qm0[it] = 0u;
+        qm1[it] = 0u;
+        const float4 v = vnext;
+        if (it + 1 < NIT) {
+            const int qn = px + STEP;
+            vnext = (qn < N) ? __ldcg(reinterpret_cast<const float4*>(w + qn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (px < N) {
+            float p0 = div_by(v.x, s, yr), p1 = div_by(v.y, s, yr), p2 = div_by(v.z, s, yr), p3 = div_by(v.w, s, yr);   // core/sampling.py:29
+            const float pmin = fminf(fminf(p0, p1), fminf(p2, p3));
+            if (!(pmin >= 8.0e-28f) || !fast_div) {    // zeros (border, masked) or quotients near the subnormal range: side path
+                if (v.x != 0.f) p0 = __fdiv_rn(v.x, s);
+                if (v.y != 0.f) p1 = __fdiv_rn(v.y, s);
+                if (v.z != 0.f) p2 = __fdiv_rn(v.z, s);
+                if (v.w != 0.f) p3 = __fdiv_rn(v.w, s);
+                const float pv[4] = {p0, p1, p2, p3};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    lpos += (pv[j] > 0.f) ? 1 : 0;
+                    lminbits = min(lminbits, (pv[j] > 0.f) ? __float_as_uint(pv[j]) : 0x7fffffffu);
+                }
+            } else {
+                lpos += 4;
+                lminbits = min(lminbits, __float_as_uint(pmin));
+            }
+            *reinterpret_cast<float4*>(w + px) = make_float4(p0, p1, p2, p3);
+            a = ((double)p0 + (double)p1) + ((double)p2 + (double)p3);
+            // ---- phase A of the per-tile arg-max: tile maximum.  The quad lies in one row; pixels [0, nsplit) are in
+            //      tile tx0, the rest in tx0 + 1.
+            const int tx0 = (int)__umulhi((uint32_t)x, G.t_magic32);
+            const int nsplit = (tx0 + 1) * G.tile - x;                                  // >= 4: no straddle
+            const int b0 = ((int)__umulhi((uint32_t)y, G.t_magic32) - ty0) * G.nbx + tx0;
+            const bool s1 = nsplit > 1, s2 = nsplit > 2, s3 = nsplit > 3;               // pixel j belongs to the first tile
+            const float m0 = fmaxf(fmaxf(p0, s1 ? p1 : 0.f), fmaxf(s2 ? p2 : 0.f, s3 ? p3 : 0.f));
+            const float m1 = fmaxf(fmaxf(s1 ? 0.f : p1, s2 ? 0.f : p2), s3 ? 0.f : p3);
+            const uint32_t u0 = __float_as_uint(m0), u1 = __float_as_uint(m1);
+            const uint32_t j0 = (p0 == m0) ? 0u : (s1 && p1 == m0) ? 1u : (s2 && p2 == m0) ? 2u : 3u;
+            const uint32_t j1 = (!s1 && p1 == m1) ? 1u : (!s2 && p2 == m1) ? 2u : 3u;
+            jpack |= (j0 | (j1 << 2)) << (4 * it);
+            if (u0 > tmax[b0]) atomicMax(&tmax[b0], u0);
+            if (u1 != 0u) { if (u1 > tmax[b0 + 1]) atomicMax(&tmax[b0 + 1], u1); }
+            qm0[it] = u0;
+            qm1[it] = u1;
+        }
+        // ---- chunk sums
+        if (CS >= 5 && CS <= 7) {
+            constexpr int GL = (CS >= 5 && CS <= 7) ? ((1 << CS) >> 2) : 1;
+#pragma unroll
+            for (int o = 1; o < GL; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (px < N && (lane & (GL - 1)) == 0) csum[px >> CS] = a;
+        } else {
+            const int cs = G.chunk_shift;          // chunks wider than a warp row (zeroed by the host memset)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (px < N && lane == 0) atomicAdd(&csum[px >> cs], a);
+        }
+        px += STEP;
+        x += G.step_dx; y += G.step_dy;
+        if (x >= W) { x -= W; ++y; }
+    }
+    LDP_PCLK(2);
+    const int npos = block_sum(lpos, red_i);
+    const int eminbits = block_min((int)lminbits, red_i);
+    if (tid == 0) {
+        if (npos) atomicAdd(&ws.rstat[r].npos, npos);
+        if (eminbits != 0x7fffffff) atomicMin(&ws.rstat[r].emin, (eminbits >> 23) & 0xff);
+    }
+    __syncthreads();                                   // tile maxima complete
+    LDP_PCLK(3);
+    // ---- phase B: lowest index among the pixels that reach their tile's maximum (registers and shared memory only)
+    px = base + tid * 4;
+    y = (int)div_magic((uint32_t)px, G.w_magic); x = px - y * W;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        if (qm0[it] | qm1[it]) {
+            const int tx0 = (int)__umulhi((uint32_t)x, G.t_magic32);
+            const int b0 = ((int)__umulhi((uint32_t)y, G.t_magic32) - ty0) * G.nbx + tx0;
+            const uint32_t i0 = (uint32_t)px + ((jpack >> (4 * it)) & 3u), i1 = (uint32_t)px + ((jpack >> (4 * it + 2)) & 3u);
+            // many pixels tie at the certainty cap: only an index below the best one so far is worth an atomic
+            if (qm0[it] != 0u && qm0[it] == tmax[b0] && i0 < lidx[b0]) atomicMin(&lidx[b0], i0);
+            if (qm1[it] != 0u && qm1[it] == tmax[b0 + 1] && i1 < lidx[b0 + 1]) atomicMin(&lidx[b0 + 1], i1);
+        }
+        px += STEP;
+        x += G.step_dx; y += G.step_dy;
+        if (x >= W) { x -= W; ++y; }
+    }
+    __syncthreads();
+    LDP_PCLK(4);
+    unsigned long long* gb = ws.gbins + (size_t)r * ws.bins_cap;
+    for (int i = tid; i < nlb; i += KS_THREADS) {
+        if (tmax[i]) {
+            const unsigned long long key = ((unsigned long long)tmax[i] << 32) | (unsigned long long)(0xFFFFFFFFu - lidx[i]);
+            atomicMax(&gb[(ty0 + i / G.nbx) * G.nbx + (i % G.nbx)], key);
+        }
+    }
+    LDP_PCLK(5);
 }
 
 // =============================================================================================
