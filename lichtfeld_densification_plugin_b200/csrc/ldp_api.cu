@@ -228,10 +228,14 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(draw)");
         e = cudaFuncSetAttribute(ldp::ldp_prep_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(prep)");
-        e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_prep_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(prep lean)");
         configured = true;
     }
@@ -268,12 +272,17 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     { KernelTimer kt(st, "ldp_prep_kernel");
       static const bool force_generic = getenv("LDP_PREP_GENERIC") != nullptr;
       if (vec_ok && plan.geom.prep_lean && !force_generic) {
+          const bool xc = plan.geom.step_dx == 0;       // W divides the pass stride: a thread stays in one pixel column
+#define LDP_PREP_LAUNCH(CSV) \
+          do { if (xc) ldp::ldp_prep_kernel<CSV, true><<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom); \
+               else ldp::ldp_prep_kernel<CSV, false><<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom); } while (0)
           switch (plan.geom.chunk_shift) {
-              case 5: ldp::ldp_prep_kernel<5><<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom); break;
-              case 6: ldp::ldp_prep_kernel<6><<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom); break;
-              case 7: ldp::ldp_prep_kernel<7><<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom); break;
-              default: ldp::ldp_prep_kernel<0><<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom); break;
+              case 5: LDP_PREP_LAUNCH(5); break;
+              case 6: LDP_PREP_LAUNCH(6); break;
+              case 7: LDP_PREP_LAUNCH(7); break;
+              default: LDP_PREP_LAUNCH(0); break;
           }
+#undef LDP_PREP_LAUNCH
       } else {
           ldp::ldp_prep_generic_kernel<<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom);
       } }

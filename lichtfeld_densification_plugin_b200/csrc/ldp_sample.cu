@@ -433,7 +433,7 @@ __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u
 #ifndef KP_MIN_BLOCKS
 #define KP_MIN_BLOCKS 5
 #endif
-template <int CS>
+template <int CS, bool XCONST>
 __global__ void __launch_bounds__(KS_THREADS, KP_MIN_BLOCKS)
 ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
                 const SampleGeom G)
@@ -481,68 +481,66 @@ ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     const int y_first = (int)div_magic((uint32_t)base, G.w_magic), y_last = (int)div_magic((uint32_t)(end - 1), G.w_magic);
     const int ty0 = (int)__umulhi((uint32_t)y_first, G.t_magic32), ty1 = (int)__umulhi((uint32_t)y_last, G.t_magic32);
     const int nlb = (ty1 - ty0 + 1) * G.nbx;
-    uint32_t* tmax = reinterpret_cast<uint32_t*>(smem_raw);              // [nlb] tile maximum of p (bit pattern)
-    uint32_t* lidx = tmax + G.prep_lb_cap;                               // [nlb] lowest pixel index reaching it
-    for (int i = tid; i < nlb; i += KS_THREADS) { tmax[i] = 0u; lidx[i] = 0xFFFFFFFFu; }
+    unsigned long long* lb = reinterpret_cast<unsigned long long*>(smem_raw);            // [nlb] (p bits << 32) | ~index
+    for (int i = tid; i < nlb; i += KS_THREADS) lb[i] = 0ull;
     __syncthreads();
     const float s = s_s;
     if (s_bad || !(s > 0.f)) return;       // the draw kernel reports the status
     const float yr = __frcp_rn(s);                     // correctly rounded reciprocal, once per thread
-    const bool fast_div = (s >= 1.0f) && (s < 3.0e8f);  // then p >= 2^-90 implies w >= 2^-90: every residual below is exact
+    const bool fast_div = (s >= 1.0f) && (s < 3.0e8f);  // then p >= 2^-90 implies w >= 2^-90: every residual of div_by is exact
     LDP_PCLK(1);
 
     double* __restrict__ csum = ws.csum + (size_t)r * ws.nchunk_pad;
     int lpos = 0;
-    uint32_t lminbits = 0x7fffffffu;                   // smallest positive p (bit pattern orders like the value)
-    uint32_t qm0[NIT], qm1[NIT];                       // per quad: maximum of its pixels in the first / second tile it touches
-    uint32_t jpack = 0u;                               // per quad, 2 + 2 bits: first pixel reaching qm0 / qm1
+    uint32_t lmin1 = 0xFFFFFFFFu;                      // (bit pattern - 1) of the smallest positive p; zeros wrap to the top
     int y = (int)div_magic((uint32_t)px, G.w_magic), x = px - y * W;
+    // tile geometry of the quad: pixels [0, nsplit) lie in tile column tx0, the rest in tx0 + 1 (a quad lies in one row)
+    int tx0 = (int)__umulhi((uint32_t)x, G.t_magic32);
+    int nsplit = (tx0 + 1) * G.tile - x;               // >= 4: no straddle
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
         double a = 0.0;
-        qm0[it] = 0u;
-        qm1[it] = 0u;
         const float4 v = vnext;
         if (it + 1 < NIT) {
             const int qn = px + STEP;
             vnext = (qn < N) ? __ldcg(reinterpret_cast<const float4*>(w + qn)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (px < N) {
-            float p0 = div_by(v.x, s, yr), p1 = div_by(v.y, s, yr), p2 = div_by(v.z, s, yr), p3 = div_by(v.w, s, yr);   // core/sampling.py:29
-            const float pmin = fminf(fminf(p0, p1), fminf(p2, p3));
-            if (!(pmin >= 8.0e-28f) || !fast_div) {    // zeros (border, masked) or quotients near the subnormal range: side path
-                if (v.x != 0.f) p0 = __fdiv_rn(v.x, s);
-                if (v.y != 0.f) p1 = __fdiv_rn(v.y, s);
-                if (v.z != 0.f) p2 = __fdiv_rn(v.z, s);
-                if (v.w != 0.f) p3 = __fdiv_rn(v.w, s);
-                const float pv[4] = {p0, p1, p2, p3};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    lpos += (pv[j] > 0.f) ? 1 : 0;
-                    lminbits = min(lminbits, (pv[j] > 0.f) ? __float_as_uint(pv[j]) : 0x7fffffffu);
-                }
-            } else {
-                lpos += 4;
-                lminbits = min(lminbits, __float_as_uint(pmin));
+            // core/sampling.py:29 -- zeros (border, masked) divide to exact zeros on the fast path too
+            float p0 = div_by(v.x, s, yr), p1 = div_by(v.y, s, yr), p2 = div_by(v.z, s, yr), p3 = div_by(v.w, s, yr);
+            const uint32_t c0 = __float_as_uint(p0) - 1u, c1 = __float_as_uint(p1) - 1u, c2 = __float_as_uint(p2) - 1u, c3 = __float_as_uint(p3) - 1u;
+            uint32_t cmin = min(min(c0, c1), min(c2, c3));
+            if (cmin < 0x12000000u || !fast_div) {     // a non-zero quotient below 2^-91 (or an unusual s): IEEE division
+                p0 = __fdiv_rn(v.x, s); p1 = __fdiv_rn(v.y, s); p2 = __fdiv_rn(v.z, s); p3 = __fdiv_rn(v.w, s);
+                cmin = min(min(__float_as_uint(p0) - 1u, __float_as_uint(p1) - 1u), min(__float_as_uint(p2) - 1u, __float_as_uint(p3) - 1u));
             }
+            lmin1 = min(lmin1, cmin);
+            const float pmin = fminf(fminf(p0, p1), fminf(p2, p3));
+            if (pmin > 0.f) lpos += 4;
+            else lpos += ((p0 > 0.f) ? 1 : 0) + ((p1 > 0.f) ? 1 : 0) + ((p2 > 0.f) ? 1 : 0) + ((p3 > 0.f) ? 1 : 0);
             *reinterpret_cast<float4*>(w + px) = make_float4(p0, p1, p2, p3);
             a = ((double)p0 + (double)p1) + ((double)p2 + (double)p3);
-            // ---- phase A of the per-tile arg-max: tile maximum.  The quad lies in one row; pixels [0, nsplit) are in
-            //      tile tx0, the rest in tx0 + 1.
-            const int tx0 = (int)__umulhi((uint32_t)x, G.t_magic32);
-            const int nsplit = (tx0 + 1) * G.tile - x;                                  // >= 4: no straddle
+            // ---- per-tile arg-max of p, lowest index on ties: 64-bit key, exact pre-filter, rare CAS
+            if (!XCONST) {
+                tx0 = (int)__umulhi((uint32_t)x, G.t_magic32);
+                nsplit = (tx0 + 1) * G.tile - x;
+            }
             const int b0 = ((int)__umulhi((uint32_t)y, G.t_magic32) - ty0) * G.nbx + tx0;
             const bool s1 = nsplit > 1, s2 = nsplit > 2, s3 = nsplit > 3;               // pixel j belongs to the first tile
             const float m0 = fmaxf(fmaxf(p0, s1 ? p1 : 0.f), fmaxf(s2 ? p2 : 0.f, s3 ? p3 : 0.f));
-            const float m1 = fmaxf(fmaxf(s1 ? 0.f : p1, s2 ? 0.f : p2), s3 ? 0.f : p3);
-            const uint32_t u0 = __float_as_uint(m0), u1 = __float_as_uint(m1);
-            const uint32_t j0 = (p0 == m0) ? 0u : (s1 && p1 == m0) ? 1u : (s2 && p2 == m0) ? 2u : 3u;
-            const uint32_t j1 = (!s1 && p1 == m1) ? 1u : (!s2 && p2 == m1) ? 2u : 3u;
-            jpack |= (j0 | (j1 << 2)) << (4 * it);
-            if (u0 > tmax[b0]) atomicMax(&tmax[b0], u0);
-            if (u1 != 0u) { if (u1 > tmax[b0 + 1]) atomicMax(&tmax[b0 + 1], u1); }
-            qm0[it] = u0;
-            qm1[it] = u1;
+            const unsigned long long k0 = ((unsigned long long)__float_as_uint(m0) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)px);
+            if (k0 > lb[b0]) {                         // could improve the tile (k0 bounds the exact key from above)
+                const int j0 = (p0 == m0) ? 0 : (s1 && p1 == m0) ? 1 : (s2 && p2 == m0) ? 2 : 3;
+                if (m0 > 0.f) atomicMax(&lb[b0], k0 - (unsigned long long)j0);
+            }
+            if (!s3) {                                 // the quad straddles a tile edge
+                const float m1 = fmaxf(fmaxf(s1 ? 0.f : p1, s2 ? 0.f : p2), p3);
+                const unsigned long long k1 = ((unsigned long long)__float_as_uint(m1) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)px);
+                if (k1 > lb[b0 + 1]) {
+                    const int j1 = (!s1 && p1 == m1) ? 1 : (!s2 && p2 == m1) ? 2 : 3;
+                    if (m1 > 0.f) atomicMax(&lb[b0 + 1], k1 - (unsigned long long)j1);
+                }
+            }
         }
         // ---- chunk sums
         if (CS >= 5 && CS <= 7) {
@@ -557,45 +555,28 @@ ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             if (px < N && lane == 0) atomicAdd(&csum[px >> cs], a);
         }
         px += STEP;
-        x += G.step_dx; y += G.step_dy;
-        if (x >= W) { x -= W; ++y; }
+        if (XCONST) {
+            y += G.step_dy;
+        } else {
+            x += G.step_dx; y += G.step_dy;
+            if (x >= W) { x -= W; ++y; }
+        }
     }
     LDP_PCLK(2);
     const int npos = block_sum(lpos, red_i);
-    const int eminbits = block_min((int)lminbits, red_i);
+    const uint32_t min1 = (uint32_t)block_min((int)(lmin1 ^ 0x80000000u), red_i) ^ 0x80000000u;   // unsigned order through the signed reduction
     if (tid == 0) {
         if (npos) atomicAdd(&ws.rstat[r].npos, npos);
-        if (eminbits != 0x7fffffff) atomicMin(&ws.rstat[r].emin, (eminbits >> 23) & 0xff);
-    }
-    __syncthreads();                                   // tile maxima complete
-    LDP_PCLK(3);
-    // ---- phase B: lowest index among the pixels that reach their tile's maximum (registers and shared memory only)
-    px = base + tid * 4;
-    y = (int)div_magic((uint32_t)px, G.w_magic); x = px - y * W;
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-        if (qm0[it] | qm1[it]) {
-            const int tx0 = (int)__umulhi((uint32_t)x, G.t_magic32);
-            const int b0 = ((int)__umulhi((uint32_t)y, G.t_magic32) - ty0) * G.nbx + tx0;
-            const uint32_t i0 = (uint32_t)px + ((jpack >> (4 * it)) & 3u), i1 = (uint32_t)px + ((jpack >> (4 * it + 2)) & 3u);
-            // many pixels tie at the certainty cap: only an index below the best one so far is worth an atomic
-            if (qm0[it] != 0u && qm0[it] == tmax[b0] && i0 < lidx[b0]) atomicMin(&lidx[b0], i0);
-            if (qm1[it] != 0u && qm1[it] == tmax[b0 + 1] && i1 < lidx[b0 + 1]) atomicMin(&lidx[b0 + 1], i1);
-        }
-        px += STEP;
-        x += G.step_dx; y += G.step_dy;
-        if (x >= W) { x -= W; ++y; }
+        if (min1 != 0xFFFFFFFFu) atomicMin(&ws.rstat[r].emin, (int)(((min1 + 1u) >> 23) & 0xffu));
     }
     __syncthreads();
-    LDP_PCLK(4);
+    LDP_PCLK(3);
     unsigned long long* gb = ws.gbins + (size_t)r * ws.bins_cap;
     for (int i = tid; i < nlb; i += KS_THREADS) {
-        if (tmax[i]) {
-            const unsigned long long key = ((unsigned long long)tmax[i] << 32) | (unsigned long long)(0xFFFFFFFFu - lidx[i]);
-            atomicMax(&gb[(ty0 + i / G.nbx) * G.nbx + (i % G.nbx)], key);
-        }
+        const unsigned long long key = lb[i];
+        if (key) atomicMax(&gb[(ty0 + i / G.nbx) * G.nbx + (i % G.nbx)], key);
     }
-    LDP_PCLK(5);
+    LDP_PCLK(4);
 }
 
 // =============================================================================================
