@@ -365,7 +365,7 @@ int launch_geometry(const ldp_params* p, const ldp_ref_desc* refs, const ldp_out
                     int have_bestk, cudaStream_t st, int ref0, int nsubrefs, int sub) {
     const ldp::GeomArgs ga = make_geom_args(p, plan, have_bestk, ref0, sub);
     const dim3 grid((unsigned)plan.nb2, (unsigned)nsubrefs);
-    const dim3 ggrid((unsigned)((plan.ws.sel_cap + ldp::KG_THREADS - 1) / ldp::KG_THREADS), (unsigned)nsubrefs);
+    const dim3 ggrid((unsigned)((plan.ws.sel_cap + ldp::KG_THREADS * KG_SPT - 1) / (ldp::KG_THREADS * KG_SPT)), (unsigned)nsubrefs);
     cudaError_t e;
     { KernelTimer kt(st, "ldp_gather_kernel");
       ldp::ldp_gather_kernel<<<ggrid, ldp::KG_THREADS, 0, st>>>(*p, refs, plan.ws, *out, ga); }

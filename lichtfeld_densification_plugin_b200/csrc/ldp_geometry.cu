@@ -441,7 +441,13 @@ __device__ __forceinline__ void store_sample(const ldp_params& P, const Workspac
 // (sample index -> winning neighbour -> warp row -> texels) is what bounds this stage, so it runs with as many
 // threads in flight as the SM holds and leaves a 32-byte record per sample for the arithmetic kernel.
 constexpr int KG_THREADS = 256;
-__global__ void __launch_bounds__(KG_THREADS, 8)
+#ifndef KG_SPT
+#define KG_SPT 2                    // samples per thread: their dependent load chains overlap, and the grid is one wave
+#endif
+#ifndef KG_MIN_BLOCKS
+#define KG_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(KG_THREADS, KG_MIN_BLOCKS)
 ldp_gather_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
                   const GeomArgs ga)
 {
@@ -449,28 +455,43 @@ ldp_gather_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
     __shared__ PairConst pc[LDP_MAX_NN];
     __shared__ ProView pv;
     const int r = blockIdx.y + ga.ref0;
+    const int i0 = blockIdx.x * (KG_THREADS * KG_SPT);
+    const int32_t* sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
+    // the sample indices do not depend on anything staged below: fetch them first (rows are sel_cap long, always readable)
+    int idx[KG_SPT];
+#pragma unroll
+    for (int q = 0; q < KG_SPT; ++q) {
+        const int i = i0 + q * KG_THREADS + threadIdx.x;
+        idx[q] = (i < (int)ws.sel_cap) ? __ldg(sel + i) : 0;
+    }
     const int S = out.n_samples[r];
-    const int i0 = blockIdx.x * KG_THREADS;
     if (ga.discard & 1) {          // the draw kernel was the last reader of this view's p row
         const char* row = reinterpret_cast<const char*>(ws.w + (size_t)r * ws.n_pad);
         const int nlines = (int)(ws.n_pad * sizeof(float) / 128);
-        for (int l = i0 + threadIdx.x; l < nlines; l += gridDim.x * KG_THREADS) l2_discard_line(row + (size_t)l * 128);
+        for (int l = blockIdx.x * KG_THREADS + threadIdx.x; l < nlines; l += gridDim.x * KG_THREADS) l2_discard_line(row + (size_t)l * 128);
     }
     if (i0 >= S) return;
     stage_constants(refs + r, rc, pc, threadIdx.x, KG_THREADS);
     if (P.prologue) stage_proview(refs + r, pv, threadIdx.x);
     __syncthreads();
-    const int i = i0 + threadIdx.x;
-    if (i >= S) return;
-    const int32_t* sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
-    SampleRec rec;
-    float craw;
-    gather_sample(P, rc, pc, pv, ga, ws.bestk + (size_t)r * ws.n_pad, sel[i], rec, craw);
-    const size_t o = (size_t)r * ws.sel_cap + i;
-    ws.pt0[o] = rec.wv;                                                                   // record, part 1
-    ws.pt1[o] = make_float4(__uint_as_float(rec.tex[0]), __uint_as_float(rec.tex[1]), __uint_as_float(rec.tex[2]),
-                            __uint_as_float(rec.k_cert));                                 // record, part 2
-    if (P.collect_debug) ws.dbgm[o].x = craw;
+    SampleRec rec[KG_SPT];
+    float craw[KG_SPT];
+#pragma unroll
+    for (int q = 0; q < KG_SPT; ++q) {
+        const int i = i0 + q * KG_THREADS + threadIdx.x;
+        if (i < S) gather_sample(P, rc, pc, pv, ga, ws.bestk + (size_t)r * ws.n_pad, idx[q], rec[q], craw[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < KG_SPT; ++q) {
+        const int i = i0 + q * KG_THREADS + threadIdx.x;
+        if (i < S) {
+            const size_t o = (size_t)r * ws.sel_cap + i;
+            ws.pt0[o] = rec[q].wv;                                                                   // record, part 1
+            ws.pt1[o] = make_float4(__uint_as_float(rec[q].tex[0]), __uint_as_float(rec[q].tex[1]), __uint_as_float(rec[q].tex[2]),
+                                    __uint_as_float(rec[q].k_cert));                                 // record, part 2
+            if (P.collect_debug) ws.dbgm[o].x = craw[q];
+        }
+    }
 }
 
 __device__ __forceinline__ void load_record(const Workspace& ws, const ldp_params& P, size_t o, SampleRec& rec, float& craw) {
