@@ -709,11 +709,22 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
         // ---- (a) padded inclusive prefix of the global chunk sums: 8-entry rows per thread, one block scan
         if (tid == 0) sh.n_found = 0;
         // coalesced copy of the global chunk sums into the padded table, then 8-entry rows per thread
-        for (int i = 2 * tid; i < nchunk; i += 2 * T) {
-            const double2 d = __ldcg(reinterpret_cast<const double2*>(gcsum + i));          // nchunk_pad is even
-            *reinterpret_cast<double2*>(pre + pad8(i)) = make_double2(d.x, (i + 1 < nchunk) ? d.y : 0.0);
+        for (int i0 = 2 * tid; i0 < nchunk; i0 += 8 * T) {          // 4 loads in flight per thread (L2 latency, not bandwidth)
+            double2 d[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + 2 * j * T;
+                d[j] = (i < nchunk) ? __ldcg(reinterpret_cast<const double2*>(gcsum + i)) : make_double2(0.0, 0.0);   // nchunk_pad is even
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + 2 * j * T;
+                if (i < nchunk) *reinterpret_cast<double2*>(pre + pad8(i)) = make_double2(d[j].x, (i + 1 < nchunk) ? d[j].y : 0.0);
+            }
         }
+        if (rounds == 0) LDP_CLK(ws, r, 11);
         __syncthreads();
+        if (rounds == 0) LDP_CLK(ws, r, 12);
         double run = 0.0;
         const int e0 = tid * EPT;
         for (int q = 0; q < EPT; q += 8) {
@@ -779,7 +790,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 }
             }
         }
-        __syncthreads();
+        if (rounds > 0 && C > 1) cluster.sync(); else __syncthreads();    // B2: the p zeroed after the last round are visible
         if (rounds == 0) LDP_CLK(ws, r, 3);
         // ---- (b) draws: each thread takes DRAW_PASS (=2) consecutive draws per pass (one Philox call)
         const int pieces = max(1, (1 << cs) >> 3);
@@ -924,7 +935,8 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             for (int j = 0; j < 8; ++j) if (zi[j] >= 0) w[zi[j]] = 0.f;
         }
         if (rounds == 1) LDP_CLK(ws, r, 7);
-        if (C > 1) cluster.sync(); else __syncthreads();          // B2: zeroed p and reduced chunk sums are visible
+        // no barrier here: the chunk sums were complete at B1; the zeroing stores drain while the table is rebuilt and
+        // are ordered before the next round's scans by the cluster barrier B2 above
     }
     LDP_CLK(ws, r, 8);
     if (fail) { finish_empty(fail); return; }

@@ -28,8 +28,8 @@ eng.lib.ldp_debug_read_clocks.argtypes = [C.POINTER(N.LdpParams), C.c_void_p, C.
 rc = eng.lib.ldp_debug_read_clocks(C.byref(params), C.c_void_p(eng._workspace.data_ptr()), host)
 clk = np.array(host[:]).reshape(len(batch), 32)
 print("cluster size used:", eng.lib.ldp_debug_last_cluster())
-names = {0: "start", 1: "init done", 14: "csum loaded+local", 15: "block scan done", 16: "prefix stored+sync", 17: "after B0", 3: "guide built", 4: "draws 1 done", 6: "after B1", 7: "zeroed", 8: "rounds done", 9: "coverage done", 10: "compaction done"}
-order = [0, 1, 14, 15, 16, 17, 3, 4, 6, 7, 8, 9, 10]
+names = {0: "start", 1: "init done", 11: "csum copied", 12: "copy synced", 14: "csum loaded+local", 15: "block scan done", 16: "prefix stored+sync", 17: "after B0", 3: "guide built", 4: "draws 1 done", 6: "after B1", 7: "zeroed", 8: "rounds done", 9: "coverage done", 10: "compaction done"}
+order = [0, 1, 11, 12, 14, 15, 16, 17, 3, 4, 6, 7, 8, 9, 10]
 for a, b in zip(order[:-1], order[1:]):
     dd = clk[:, b] - clk[:, a]
     print(f"{names[a]:>20} -> {names[b]:<20} median {np.median(dd):9.0f}  max {dd.max():9.0f} cycles")
