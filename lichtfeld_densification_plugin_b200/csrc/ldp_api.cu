@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <utility>
 
 #include "ldp_sample.cu"
 #include "ldp_geometry.cu"
@@ -87,6 +88,25 @@ int sm_count() {
 }
 
 constexpr size_t K1_SMEM_BUDGET = 200 * 1024;
+
+// Every kernel is launched with programmatic dependent launch allowed: its CTAs may be scheduled while the previous
+// kernel of the stream drains, and block in griddepcontrol.wait (ldp_device.cuh:grid_dependency_sync) until that kernel's
+// memory is visible.  Hides the launch latency at each of the 6 kernel boundaries of a step.  LDP_PDL=0 turns it off.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    static const int pdl = [] { const char* e = getenv("LDP_PDL"); return e ? atoi(e) : 1; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 struct Plan {
     ldp::Workspace ws;
@@ -244,23 +264,23 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     cudaError_t e;
     { KernelTimer kt(st, "ldp_stream_kernel");
       if (p->prologue) switch (p->nn_max) {      // raw matcher planes: post-processing fused into the read
-          case 1: ldp::ldp_stream_kernel<1, true><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
-          case 2: ldp::ldp_stream_kernel<2, true><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
-          case 3: ldp::ldp_stream_kernel<3, true><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
-          case 4: ldp::ldp_stream_kernel<4, true><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
-          default: ldp::ldp_stream_kernel<0, true><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+          case 1: (void)launch_k(ldp::ldp_stream_kernel<1, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 2: (void)launch_k(ldp::ldp_stream_kernel<2, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 3: (void)launch_k(ldp::ldp_stream_kernel<3, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 4: (void)launch_k(ldp::ldp_stream_kernel<4, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          default: (void)launch_k(ldp::ldp_stream_kernel<0, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
       } else switch (p->nn_max) {   // max neighbours per view in this launch (0 = unknown)
-          case 1: ldp::ldp_stream_kernel<1, false><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
-          case 2: ldp::ldp_stream_kernel<2, false><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
-          case 3: ldp::ldp_stream_kernel<3, false><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
-          case 4: ldp::ldp_stream_kernel<4, false><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
-          default: ldp::ldp_stream_kernel<0, false><<<grid, ldp::KS_THREADS, 0, st>>>(*p, refs, plan.ws, plan.geom); break;
+          case 1: (void)launch_k(ldp::ldp_stream_kernel<1, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 2: (void)launch_k(ldp::ldp_stream_kernel<2, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 3: (void)launch_k(ldp::ldp_stream_kernel<3, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 4: (void)launch_k(ldp::ldp_stream_kernel<4, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          default: (void)launch_k(ldp::ldp_stream_kernel<0, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
       } }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_stream_kernel");
     if (p->no_filter) {
         { KernelTimer kt(st, "ldp_topm_kernel");
-          ldp::ldp_topm_kernel<<<nsubrefs, ldp::K1_THREADS, 0, st>>>(*p, refs, plan.ws, *out, plan.geom); }
+          (void)launch_k(ldp::ldp_topm_kernel, dim3(nsubrefs), dim3(ldp::K1_THREADS), 0, st, *p, refs, plan.ws, *out, plan.geom); }
         ++g_launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_topm_kernel");
         return LDP_OK;
@@ -274,8 +294,8 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
       if (vec_ok && plan.geom.prep_lean && !force_generic) {
           const bool xc = plan.geom.step_dx == 0;       // W divides the pass stride: a thread stays in one pixel column
 #define LDP_PREP_LAUNCH(CSV) \
-          do { if (xc) ldp::ldp_prep_kernel<CSV, true><<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom); \
-               else ldp::ldp_prep_kernel<CSV, false><<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom); } while (0)
+          do { if (xc) (void)launch_k(ldp::ldp_prep_kernel<CSV, true>, dim3(grid), dim3(ldp::KS_THREADS), plan.prep_smem, st, *p, refs, plan.ws, *out, plan.geom); \
+               else (void)launch_k(ldp::ldp_prep_kernel<CSV, false>, dim3(grid), dim3(ldp::KS_THREADS), plan.prep_smem, st, *p, refs, plan.ws, *out, plan.geom); } while (0)
           switch (plan.geom.chunk_shift) {
               case 5: LDP_PREP_LAUNCH(5); break;
               case 6: LDP_PREP_LAUNCH(6); break;
@@ -284,7 +304,7 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
           }
 #undef LDP_PREP_LAUNCH
       } else {
-          ldp::ldp_prep_generic_kernel<<<grid, ldp::KS_THREADS, plan.prep_smem, st>>>(*p, refs, plan.ws, *out, plan.geom);
+          (void)launch_k(ldp::ldp_prep_generic_kernel, dim3(grid), dim3(ldp::KS_THREADS), plan.prep_smem, st, *p, refs, plan.ws, *out, plan.geom);
       } }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_prep_kernel");
@@ -305,13 +325,16 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
             cfg.blockDim = dim3(ldp::KD_THREADS);
             cfg.dynamicSmemBytes = plan.k1_smem;
             cfg.stream = st;
-            cudaLaunchAttribute attr[1];
+            static const int pdl = [] { const char* e = getenv("LDP_PDL"); return e ? atoi(e) : 1; }();
+            cudaLaunchAttribute attr[2];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = (unsigned)csize;
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = pdl;
             cfg.attrs = attr;
-            cfg.numAttrs = 1;
+            cfg.numAttrs = 2;
             e = cudaLaunchKernelEx(&cfg, ldp::ldp_draw_kernel, *p, refs, uniforms, plan.ws, *out, plan.geom);
             if (e == cudaSuccess) break;
             (void)cudaGetLastError();
@@ -368,15 +391,15 @@ int launch_geometry(const ldp_params* p, const ldp_ref_desc* refs, const ldp_out
     const dim3 ggrid((unsigned)((plan.ws.sel_cap + ldp::KG_THREADS * KG_SPT - 1) / (ldp::KG_THREADS * KG_SPT)), (unsigned)nsubrefs);
     cudaError_t e;
     { KernelTimer kt(st, "ldp_gather_kernel");
-      ldp::ldp_gather_kernel<<<ggrid, ldp::KG_THREADS, 0, st>>>(*p, refs, plan.ws, *out, ga); }
+      (void)launch_k(ldp::ldp_gather_kernel, dim3(ggrid), dim3(ldp::KG_THREADS), 0, st, *p, refs, plan.ws, *out, ga); }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_gather_kernel");
     { KernelTimer kt(st, "ldp_geometry_kernel");
-      ldp::ldp_geometry_kernel<<<grid, ldp::K2_THREADS, 0, st>>>(*p, refs, plan.ws, *out, ga); }
+      (void)launch_k(ldp::ldp_geometry_kernel, dim3(grid), dim3(ldp::K2_THREADS), 0, st, *p, refs, plan.ws, *out, ga); }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_geometry_kernel");
     { KernelTimer kt(st, "ldp_fixplan_kernel");
-      ldp::ldp_fixplan_kernel<<<nsubrefs, ldp::K2_THREADS, (size_t)plan.nb2 * LDP_MAX_NN * 2 * sizeof(int), st>>>(*p, refs, plan.ws, *out, ga); }
+      (void)launch_k(ldp::ldp_fixplan_kernel, dim3(nsubrefs), dim3(ldp::K2_THREADS), (size_t)plan.nb2 * LDP_MAX_NN * 2 * sizeof(int), st, *p, refs, plan.ws, *out, ga); }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_fixplan_kernel");
     return LDP_OK;
@@ -387,7 +410,7 @@ int launch_pack(const ldp_params* p, const ldp_ref_desc* refs, const ldp_outputs
     const ldp::GeomArgs ga = make_geom_args(p, plan, 1, 0, 0);
     const dim3 grid((unsigned)plan.nb2, (unsigned)p->n_refs);
     { KernelTimer kt(st, "ldp_pack_kernel");
-      ldp::ldp_pack_kernel<<<grid, ldp::K3_THREADS, 0, st>>>(*p, refs, plan.ws, *out, ga); }
+      (void)launch_k(ldp::ldp_pack_kernel, dim3(grid), dim3(ldp::K3_THREADS), 0, st, *p, refs, plan.ws, *out, ga); }
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ldp_pack_kernel");
@@ -648,7 +671,7 @@ int ldp_postprocess_certainty(const ldp_params* params, const ldp_ref_desc* refs
     const int bx = std::min((N + ldp::KP_THREADS - 1) / ldp::KP_THREADS, 4 * sm_count());
     const dim3 grid((unsigned)bx, LDP_MAX_NN, (unsigned)params->n_refs);
     { KernelTimer kt(st, "ldp_prologue_kernel");
-      ldp::ldp_prologue_kernel<<<grid, ldp::KP_THREADS, 0, st>>>(*params, refs, outp, ref_stride, plane_stride); }
+      (void)launch_k(ldp::ldp_prologue_kernel, dim3(grid), dim3(ldp::KP_THREADS), 0, st, *params, refs, outp, ref_stride, plane_stride); }
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ldp_prologue_kernel");

@@ -72,6 +72,16 @@ struct SampleGeom {     // launch-constant shape of the sampler
 };
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (ldp_api.cu:launch_k): wait until the previous kernel of the stream has completed and
+// its memory is visible, then allow the NEXT kernel's CTAs to be scheduled as soon as all CTAs of this grid are resident.
+// Must precede the first access to anything another kernel of the stream writes or reads.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_dependency_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // warp / block collectives (fixed reduction trees => run-to-run deterministic)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

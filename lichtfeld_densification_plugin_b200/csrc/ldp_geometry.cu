@@ -456,6 +456,9 @@ ldp_gather_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
     __shared__ ProView pv;
     const int r = blockIdx.y + ga.ref0;
     const int i0 = blockIdx.x * (KG_THREADS * KG_SPT);
+    stage_constants(refs + r, rc, pc, threadIdx.x, KG_THREADS);          // host-written descriptors: no kernel produces them
+    if (P.prologue) stage_proview(refs + r, pv, threadIdx.x);
+    grid_dependency_sync();
     const int32_t* sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
     // the sample indices do not depend on anything staged below: fetch them first (rows are sel_cap long, always readable)
     int idx[KG_SPT];
@@ -471,8 +474,6 @@ ldp_gather_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
         for (int l = blockIdx.x * KG_THREADS + threadIdx.x; l < nlines; l += gridDim.x * KG_THREADS) l2_discard_line(row + (size_t)l * 128);
     }
     if (i0 >= S) return;
-    stage_constants(refs + r, rc, pc, threadIdx.x, KG_THREADS);
-    if (P.prologue) stage_proview(refs + r, pv, threadIdx.x);
     __syncthreads();
     SampleRec rec[KG_SPT];
     float craw[KG_SPT];
@@ -511,10 +512,11 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
     __shared__ PairConst pc[LDP_MAX_NN];
     __shared__ int s_cnt[LDP_MAX_NN], s_first[LDP_MAX_NN];
     const int r = blockIdx.y + ga.ref0;
+    stage_constants(refs + r, rc, pc, threadIdx.x, K2_THREADS);          // host-written descriptors: no kernel produces them
+    grid_dependency_sync();
     const int S = out.n_samples[r];
     const int i0 = blockIdx.x * K2_THREADS;
     if (i0 >= S) return;
-    stage_constants(refs + r, rc, pc, threadIdx.x, K2_THREADS);
     if (threadIdx.x < LDP_MAX_NN) { s_cnt[threadIdx.x] = 0; s_first[threadIdx.x] = 0x7fffffff; }
     __syncthreads();
     const int i = i0 + threadIdx.x;
@@ -562,6 +564,7 @@ __global__ void __launch_bounds__(K2_THREADS)
 ldp_fixplan_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
                    const GeomArgs ga)
 {
+    grid_dependency_sync();
     __shared__ RefConst rc;
     __shared__ PairConst pc[LDP_MAX_NN];
     __shared__ int s_tot[LDP_MAX_NN], s_first[LDP_MAX_NN], s_base[LDP_MAX_NN];
@@ -648,6 +651,7 @@ __global__ void __launch_bounds__(K3_THREADS)
 ldp_pack_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
                 const GeomArgs ga)
 {
+    grid_dependency_sync();
     __shared__ int s_start[LDP_MAX_NN];
     __shared__ int s_wcnt[K3_THREADS / 32][LDP_MAX_NN];
     __shared__ long long s_red[K3_THREADS / 32];
@@ -712,6 +716,7 @@ __global__ void __launch_bounds__(KP_THREADS)
 ldp_prologue_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, float* __restrict__ outp,
                     size_t ref_stride, size_t plane_stride)
 {
+    grid_dependency_sync();
     __shared__ ProView pv;
     const int r = blockIdx.z, k = blockIdx.y;
     const ldp_ref_desc* rd = refs + r;

@@ -99,6 +99,7 @@ template <int NNMAX, bool PRO>
 __global__ void __launch_bounds__(KS_THREADS, PRO ? 3 : KS_MIN_BLOCKS)      // PRO holds the warp rows too: more registers
 ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const SampleGeom G)
 {
+    grid_dependency_sync();
     __shared__ const float* s_cert[LDP_MAX_NN];
     __shared__ double red_d[32];
     __shared__ float red_f[32];
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(KS_THREADS)
 ldp_prep_generic_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
                         const SampleGeom G)
 {
+    grid_dependency_sync();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int red_i[32];
     __shared__ float s_s;
@@ -438,6 +440,7 @@ __global__ void __launch_bounds__(KS_THREADS, KP_MIN_BLOCKS)
 ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
                 const SampleGeom G)
 {
+    grid_dependency_sync();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int red_i[32];
     __shared__ float s_s;
@@ -687,6 +690,9 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             if (out.rounds) out.rounds[r] = 0;
         }
     };
+    // The selection bitmap is touched by no other kernel: clear it while the prep kernel may still be draining.
+    for (int i = gtid; i < (int)ws.n_words; i += GT) bitmap[i] = 0u;
+    grid_dependency_sync();
     LDP_CLK(ws, r, 0);
     // every exit below is taken by all CTAs of the cluster alike (same inputs, same arithmetic)
     const RefStat st = ws.rstat[r];
@@ -694,8 +700,6 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     if (st.bad & 1) { finish_empty(LDP_REF_BAD_WEIGHTS); return; }          // NaN: `s <= 0` is False, choice raises
     if (!(st.s > 0.f)) { finish_empty(LDP_REF_EMPTY); return; }             // core/sampling.py:27-28
     if (st.bad & 2) { finish_empty(LDP_REF_BAD_WEIGHTS); return; }
-
-    for (int i = gtid; i < (int)ws.n_words; i += GT) bitmap[i] = 0u;
 
     const int cs = G.chunk_shift;
     const int size = G.size;
@@ -1039,6 +1043,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
 ldp_topm_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws,
                 const ldp_outputs out, const SampleGeom G)
 {
+    grid_dependency_sync();
     __shared__ int hist[256];
     __shared__ int red_i[32];
     __shared__ uint32_t s_prefix;
