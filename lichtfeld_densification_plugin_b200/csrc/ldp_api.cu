@@ -219,8 +219,6 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     plan->nb2 = (int)((w.sel_cap + ldp::K2_THREADS - 1) / ldp::K2_THREADS);
     w.blk_cnt = reinterpret_cast<int32_t*>(carve(R * plan->nb2 * LDP_MAX_NN * sizeof(int32_t)));
     w.blk_first = reinterpret_cast<int32_t*>(carve(R * plan->nb2 * LDP_MAX_NN * sizeof(int32_t)));
-    w.blk_before = reinterpret_cast<int32_t*>(carve(R * plan->nb2 * LDP_MAX_NN * sizeof(int32_t)));
-    w.grp_base = reinterpret_cast<int32_t*>(carve(R * LDP_MAX_NN * sizeof(int32_t)));
     w.fix_list = reinterpret_cast<int2*>(carve(R * w.sel_cap * sizeof(int2)));
     w.fix_count = reinterpret_cast<int32_t*>(carve((ldp::LDP_MAX_SUB + R) * sizeof(int32_t)));
     w.arrive = w.fix_count ? w.fix_count + ldp::LDP_MAX_SUB : nullptr;
@@ -398,10 +396,10 @@ int launch_geometry(const ldp_params* p, const ldp_ref_desc* refs, const ldp_out
       (void)launch_k(ldp::ldp_geometry_kernel, dim3(grid), dim3(ldp::K2_THREADS), 0, st, *p, refs, plan.ws, *out, ga); }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_geometry_kernel");
-    { KernelTimer kt(st, "ldp_fixplan_kernel");
-      (void)launch_k(ldp::ldp_fixplan_kernel, dim3(nsubrefs), dim3(ldp::K2_THREADS), (size_t)plan.nb2 * LDP_MAX_NN * 2 * sizeof(int), st, *p, refs, plan.ws, *out, ga); }
+    { KernelTimer kt(st, "ldp_fix_kernel");
+      (void)launch_k(ldp::ldp_fix_kernel, dim3(nsubrefs), dim3(ldp::K2_THREADS), 0, st, *p, refs, plan.ws, *out, ga); }
     ++g_launches;
-    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_fixplan_kernel");
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_fix_kernel");
     return LDP_OK;
 }
 

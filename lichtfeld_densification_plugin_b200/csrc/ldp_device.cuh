@@ -40,8 +40,6 @@ struct Workspace {
     unsigned long long* gbins;      // [R][bins_cap] per-tile arg-max keys (p bits << 32 | ~index)
     int32_t* blk_cnt;    // [R][nb2][LDP_MAX_NN] kept samples per 128-sample tile and group (geometry -> pack)
     int32_t* blk_first;  // [R][nb2][LDP_MAX_NN] first sample position per tile and group
-    int32_t* blk_before; // [R][nb2][LDP_MAX_NN] kept samples of the group in earlier tiles of the view (pack plan)
-    int32_t* grp_base;   // [R][LDP_MAX_NN] output offset of each group inside the view (pack plan)
     int2* fix_list;      // [R*sel_cap] (view, sample) pairs whose null-vector iteration did not converge
     int32_t* fix_count;  // [LDP_MAX_SUB] one counter per sub-batch (its list starts at ref0 * sel_cap)
     int32_t* arrive;     // [R] stream-kernel CTAs of the view that have finished (directly after fix_count: one memset)

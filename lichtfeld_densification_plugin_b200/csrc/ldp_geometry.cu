@@ -557,71 +557,98 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
     }
 }
 
-// K2c fix + plan: one CTA per view.  (1) The view's entries of the worklist (null-vector iteration not converged:
-// grossly inconsistent matches) are re-evaluated with the Jacobi solver, one thread each.  (2) The view's pack plan:
-// groups in first-appearance order, and for every 128-sample tile the output offset of each group inside the view.
+// K2c fix-up: one CTA per view.  The view's entries of the worklist (null-vector iteration not converged: grossly
+// inconsistent matches) are re-evaluated with the Jacobi solver, one thread each.  Usually the list is empty and the
+// kernel ends at once.
 __global__ void __launch_bounds__(K2_THREADS)
-ldp_fixplan_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
-                   const GeomArgs ga)
+ldp_fix_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
+               const GeomArgs ga)
 {
-    grid_dependency_sync();
     __shared__ RefConst rc;
     __shared__ PairConst pc[LDP_MAX_NN];
-    __shared__ int s_tot[LDP_MAX_NN], s_first[LDP_MAX_NN], s_base[LDP_MAX_NN];
+    grid_dependency_sync();
     const int r = blockIdx.x + ga.ref0, tid = threadIdx.x;
+    const int n = ws.fix_count[ga.sub];
+    if (n <= 0) return;
+    const int2* fix_list = ws.fix_list + (size_t)ga.ref0 * ws.sel_cap;
+    stage_constants(refs + r, rc, pc, tid, K2_THREADS);
+    __syncthreads();
+    for (int e = tid; e < n; e += K2_THREADS) {
+        const int2 it = fix_list[e];
+        if (it.x != r) continue;
+        const int i = it.y;
+        const size_t o = (size_t)r * ws.sel_cap + i;
+        SampleRec rec;
+        float craw;
+        load_record(ws, P, o, rec, craw);
+        SampleResult s;
+        eval_sample<true>(P, rc, pc, ga, rec, craw, s);
+        store_sample(P, ws, out, o, s);
+        if (s.keep) {
+            atomicAdd(&ws.kept[r], 1);
+            atomicAdd(&ws.blk_cnt[((size_t)r * ga.nb2 + i / K2_THREADS) * LDP_MAX_NN + s.grp], 1);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 plan + scatter: grid (tiles, views).  Output order of the reference (core/pipeline.py:685-695,753-780): neighbour
+// groups in order of first appearance over the sample order, sample order inside a group, kept samples only.
+// Every CTA derives the view's plan from the per-tile group statistics of the geometry kernel (a few KB, L2): group
+// totals, first appearances, kept samples of each group in earlier tiles; then
+// dst = view base (kept counts of earlier views) + group base + earlier tiles of the group + rank inside the tile.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(K3_THREADS)
+ldp_pack_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
+                const GeomArgs ga)
+{
+    static_assert(K3_THREADS == K2_THREADS && K3_THREADS % LDP_MAX_NN == 0, "one pack CTA per geometry tile");
+    constexpr int NPART = K3_THREADS / LDP_MAX_NN;
+    __shared__ int s_part[3][NPART][LDP_MAX_NN];
+    __shared__ int s_tot[LDP_MAX_NN], s_first[LDP_MAX_NN], s_start[LDP_MAX_NN];
+    __shared__ int s_wcnt[K3_THREADS / 32][LDP_MAX_NN];
+    __shared__ long long s_red[K3_THREADS / 32];
+    __shared__ long long s_off;
+    grid_dependency_sync();
+    const int r = blockIdx.y, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = out.n_samples[r];
     const int nb = (S + K2_THREADS - 1) / K2_THREADS;
-    const int n = ws.fix_count[ga.sub];
-    const int2* fix_list = ws.fix_list + (size_t)ga.ref0 * ws.sel_cap;
-    if (n > 0) {
-        stage_constants(refs + r, rc, pc, tid, K2_THREADS);
-        __syncthreads();
-        for (int e = tid; e < n; e += K2_THREADS) {
-            const int2 it = fix_list[e];
-            if (it.x != r) continue;
-            const int i = it.y;
-            const size_t o = (size_t)r * ws.sel_cap + i;
-            SampleRec rec;
-            float craw;
-            load_record(ws, P, o, rec, craw);
-            SampleResult s;
-            eval_sample<true>(P, rc, pc, ga, rec, craw, s);
-            store_sample(P, ws, out, o, s);
-            if (s.keep) {
-                atomicAdd(&ws.kept[r], 1);
-                atomicAdd(&ws.blk_cnt[((size_t)r * ga.nb2 + i / K2_THREADS) * LDP_MAX_NN + s.grp], 1);
-            }
-        }
-        __threadfence();
-        __syncthreads();
-    }
-    // ---- plan: per-group totals / first appearance / per-tile exclusive prefix.  The tile tables are read once,
-    //      coalesced, by the whole CTA; 16 lanes then walk them in shared memory.
+    if (b >= nb && b != 0) return;
+
+    // ---- the tile's sample flags and the plan inputs are fetched together
+    const int i = b * K2_THREADS + tid;
+    const uint8_t* flags = ws.flags + (size_t)r * ws.sel_cap;
+    const int f = (i < S) ? flags[i] : 0;
     {
-        extern __shared__ int s_tab[];                           // [2][nb][LDP_MAX_NN]
-        int* t_cnt = s_tab;
-        int* t_first = s_tab + (size_t)ga.nb2 * LDP_MAX_NN;
-        const int n_ent = nb * LDP_MAX_NN;
+        const int g = tid % LDP_MAX_NN, part = tid / LDP_MAX_NN;
         const int32_t* cnt = ws.blk_cnt + (size_t)r * ga.nb2 * LDP_MAX_NN;
         const int32_t* fst = ws.blk_first + (size_t)r * ga.nb2 * LDP_MAX_NN;
-        for (int e = tid; e < n_ent; e += K2_THREADS) { t_cnt[e] = __ldcg(cnt + e); t_first[e] = __ldcg(fst + e); }
-        __syncthreads();
-        if (tid < LDP_MAX_NN) {
-            const int g = tid;
-            int tot = 0, first = 0x7fffffff;
-            int32_t* before = ws.blk_before + (size_t)r * ga.nb2 * LDP_MAX_NN + g;
-            for (int bb = 0; bb < nb; ++bb) {
-                before[(size_t)bb * LDP_MAX_NN] = tot;
-                tot += t_cnt[bb * LDP_MAX_NN + g];
-                first = min(first, t_first[bb * LDP_MAX_NN + g]);
-            }
-            s_tot[g] = tot;
-            s_first[g] = first;
-            s_base[g] = 0;
+        int tot = 0, bef = 0, first = 0x7fffffff;
+        for (int t = part; t < nb; t += NPART) {
+            const int c = __ldcg(cnt + t * LDP_MAX_NN + g);
+            tot += c;
+            bef += (t < b) ? c : 0;
+            first = min(first, __ldcg(fst + t * LDP_MAX_NN + g));
         }
+        s_part[0][part][g] = tot; s_part[1][part][g] = bef; s_part[2][part][g] = first;
+    }
+    long long partk = 0;
+    for (int q = tid; q < r; q += K3_THREADS) partk += (long long)ws.kept[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) partk += __shfl_xor_sync(0xffffffffu, partk, o);
+    if (lane == 0) s_red[warp] = partk;
+    __syncthreads();
+    if (tid < LDP_MAX_NN) {
+        int tot = 0, bef = 0, first = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < NPART; ++q) { tot += s_part[0][q][tid]; bef += s_part[1][q][tid]; first = min(first, s_part[2][q][tid]); }
+        s_tot[tid] = tot; s_start[tid] = bef; s_first[tid] = first;
     }
     __syncthreads();
     if (tid == 0) {
+        long long v = 0;
+        for (int q = 0; q < K3_THREADS / 32; ++q) v += s_red[q];
+        s_off = v;
         int order[LDP_MAX_NN];
         int m = 0;
         for (int g = 0; g < LDP_MAX_NN; ++g) if (s_first[g] != 0x7fffffff) order[m++] = g;
@@ -632,57 +659,17 @@ ldp_fixplan_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, co
             order[q + 1] = g;
         }
         int acc = 0;
-        for (int a = 0; a < m; ++a) { s_base[order[a]] = acc; acc += s_tot[order[a]]; }
-        for (int a = 0; a < LDP_MAX_NN; ++a) {
-            out.group_order[(size_t)r * LDP_MAX_NN + a] = (a < m) ? order[a] : -1;
-            out.group_count[(size_t)r * LDP_MAX_NN + a] = s_tot[a];
-            ws.grp_base[(size_t)r * LDP_MAX_NN + a] = s_base[a];
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K3 scatter: grid (tiles, views).  Output order of the reference (core/pipeline.py:685-695,753-780): neighbour
-// groups in order of first appearance over the sample order, sample order inside a group, kept samples only.
-// dst = view base (kept counts of earlier views) + group base + kept samples of the same group in earlier tiles
-//       (both from the plan) + rank inside the tile (ballots).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(K3_THREADS)
-ldp_pack_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
-                const GeomArgs ga)
-{
-    grid_dependency_sync();
-    __shared__ int s_start[LDP_MAX_NN];
-    __shared__ int s_wcnt[K3_THREADS / 32][LDP_MAX_NN];
-    __shared__ long long s_red[K3_THREADS / 32];
-    __shared__ long long s_off;
-    const int r = blockIdx.y, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = out.n_samples[r];
-    const int nb = (S + K2_THREADS - 1) / K2_THREADS;
-    if (b >= nb && b != 0) return;
-
-    long long part = 0;
-    for (int q = tid; q < r; q += K3_THREADS) part += (long long)ws.kept[q];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) s_red[warp] = part;
-    if (tid < LDP_MAX_NN)
-        s_start[tid] = ws.grp_base[(size_t)r * LDP_MAX_NN + tid] +
-                       ((b < nb) ? ws.blk_before[((size_t)r * ga.nb2 + b) * LDP_MAX_NN + tid] : 0);
-    __syncthreads();
-    if (tid == 0) {
-        long long v = 0;
-        for (int q = 0; q < K3_THREADS / 32; ++q) v += s_red[q];
-        s_off = v;
+        for (int a = 0; a < m; ++a) { const int g = order[a]; s_start[g] += acc; acc += s_tot[g]; }
         if (b == 0) {
             out.ref_offset[r] = v;
             if (r == (int)gridDim.y - 1) out.ref_offset[r + 1] = v + ws.kept[r];
+            for (int a = 0; a < LDP_MAX_NN; ++a) {
+                out.group_order[(size_t)r * LDP_MAX_NN + a] = (a < m) ? order[a] : -1;
+                out.group_count[(size_t)r * LDP_MAX_NN + a] = s_tot[a];
+            }
         }
     }
     if (b >= nb) return;
-    const int i = b * K2_THREADS + tid;
-    const uint8_t* flags = ws.flags + (size_t)r * ws.sel_cap;
-    const int f = (i < S) ? flags[i] : 0;
     const int keep = f & 1, g = (f >> 2) & 0x1f;
     const unsigned same = __match_any_sync(0xffffffffu, keep ? g : -1);
     const int rank_in_warp = __popc(same & ((1u << lane) - 1u));
