@@ -195,6 +195,12 @@ int ldp_debug_read_clocks(const ldp_params* params, void* workspace, long long* 
  * one batch unless LDP_SUBBATCH is set).  Results do not depend on it. */
 int ldp_debug_set_subbatches(int n);
 
+/* Measurement hook: enqueue `reps` back-to-back launches of the path's first (dominant, HBM-bound) kernel alone on
+ * `stream`, so that bench.py can time its average launch duration with two CUDA events instead of bracketing every
+ * launch.  Writes only the scratch workspace. */
+int ldp_debug_launch_stream(const ldp_params* params, const ldp_ref_desc* refs, void* workspace, size_t workspace_bytes,
+                            void* stream, int reps);
+
 /* sizeof() of the ABI structs as this library was compiled: which = 0 ldp_params, 1 ldp_ref_desc,
  * 2 ldp_outputs.  Bindings check these against their own struct definitions at load time. */
 int64_t ldp_struct_size(int which);

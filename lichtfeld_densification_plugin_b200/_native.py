@@ -95,7 +95,7 @@ REF_DESC_DTYPE = np.dtype(LdpRefDesc)
 EXPORTS = [
     "ldp_abi_version", "ldp_last_error_string", "ldp_sel_capacity", "ldp_workspace_bytes",
     "ldp_densify_refs", "ldp_sample_refs", "ldp_triangulate_samples", "ldp_postprocess_certainty", "ldp_last_launch_count",
-    "ldp_struct_size", "ldp_profile_enable", "ldp_profile_read", "ldp_profile_name", "ldp_debug_set_cluster", "ldp_debug_last_cluster", "ldp_debug_set_subbatches", "ldp_debug_read_clocks",
+    "ldp_struct_size", "ldp_profile_enable", "ldp_profile_read", "ldp_profile_name", "ldp_debug_set_cluster", "ldp_debug_last_cluster", "ldp_debug_set_subbatches", "ldp_debug_read_clocks", "ldp_debug_launch_stream",
 ]
 
 _lock = threading.Lock()
@@ -154,6 +154,8 @@ def load(build_if_missing: bool = False):
         lib.ldp_triangulate_samples.restype = C.c_int
         lib.ldp_triangulate_samples.argtypes = [C.POINTER(LdpParams), C.c_void_p, C.POINTER(LdpOutputs), C.c_void_p,
                                                 C.c_size_t, C.c_void_p]
+        lib.ldp_debug_launch_stream.restype = C.c_int
+        lib.ldp_debug_launch_stream.argtypes = [C.POINTER(LdpParams), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
         lib.ldp_postprocess_certainty.restype = C.c_int
         lib.ldp_postprocess_certainty.argtypes = [C.POINTER(LdpParams), C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
         if lib.ldp_abi_version() != LDP_ABI_VERSION:

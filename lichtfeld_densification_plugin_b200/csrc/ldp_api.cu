@@ -236,6 +236,26 @@ int check_outputs(const ldp_params* p, const ldp_outputs* o) {
     return LDP_OK;
 }
 
+static int vec_ok_for(const ldp_params* p) { return (p->W % 4 == 0 && p->scalar_loads == 0) ? 1 : 0; }
+
+// the first kernel of the path (also launched alone by ldp_debug_launch_stream for the roofline measurement)
+void launch_stream(const ldp_params* p, const ldp_ref_desc* refs, Plan& plan, cudaStream_t st, int nsubrefs) {
+    const dim3 grid((unsigned)plan.ws.nblk, (unsigned)nsubrefs);
+    if (p->prologue) switch (p->nn_max) {      // raw matcher planes: post-processing fused into the read
+          case 1: (void)launch_k(ldp::ldp_stream_kernel<1, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 2: (void)launch_k(ldp::ldp_stream_kernel<2, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 3: (void)launch_k(ldp::ldp_stream_kernel<3, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 4: (void)launch_k(ldp::ldp_stream_kernel<4, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          default: (void)launch_k(ldp::ldp_stream_kernel<0, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+      } else switch (p->nn_max) {   // max neighbours per view in this launch (0 = unknown)
+          case 1: (void)launch_k(ldp::ldp_stream_kernel<1, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 2: (void)launch_k(ldp::ldp_stream_kernel<2, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 3: (void)launch_k(ldp::ldp_stream_kernel<3, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 4: (void)launch_k(ldp::ldp_stream_kernel<4, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          default: (void)launch_k(ldp::ldp_stream_kernel<0, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+      }
+}
+
 int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* uniforms, const ldp_outputs* out,
                   Plan& plan, int vec_ok, cudaStream_t st, int ref0, int nsubrefs) {
     plan.geom.vec = vec_ok;
@@ -261,19 +281,7 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     const dim3 grid((unsigned)plan.ws.nblk, (unsigned)nsubrefs);
     cudaError_t e;
     { KernelTimer kt(st, "ldp_stream_kernel");
-      if (p->prologue) switch (p->nn_max) {      // raw matcher planes: post-processing fused into the read
-          case 1: (void)launch_k(ldp::ldp_stream_kernel<1, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 2: (void)launch_k(ldp::ldp_stream_kernel<2, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 3: (void)launch_k(ldp::ldp_stream_kernel<3, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 4: (void)launch_k(ldp::ldp_stream_kernel<4, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          default: (void)launch_k(ldp::ldp_stream_kernel<0, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-      } else switch (p->nn_max) {   // max neighbours per view in this launch (0 = unknown)
-          case 1: (void)launch_k(ldp::ldp_stream_kernel<1, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 2: (void)launch_k(ldp::ldp_stream_kernel<2, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 3: (void)launch_k(ldp::ldp_stream_kernel<3, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 4: (void)launch_k(ldp::ldp_stream_kernel<4, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          default: (void)launch_k(ldp::ldp_stream_kernel<0, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-      } }
+      launch_stream(p, refs, plan, st, nsubrefs); }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_stream_kernel");
     if (p->no_filter) {
@@ -484,6 +492,23 @@ int ldp_debug_set_subbatches(int n) {
     return LDP_OK;
 }
 
+int ldp_debug_launch_stream(const ldp_params* params, const ldp_ref_desc* refs, void* workspace, size_t workspace_bytes,
+                            void* stream, int reps) {
+    if (!params || !refs || !workspace || reps < 1) return fail(LDP_ERR_INVALID, "bad arguments");
+    Plan plan;
+    char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+    int rc = make_plan(params, base, &plan);
+    if (rc != LDP_OK) return rc;
+    if (plan.bytes + (size_t)(base - static_cast<char*>(workspace)) > workspace_bytes) return fail(LDP_ERR_WORKSPACE, "workspace too small");
+    plan.geom.vec = vec_ok_for(params);
+    plan.geom.ref0 = 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int i = 0; i < reps; ++i) launch_stream(params, refs, plan, st, params->n_refs);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ldp_stream_kernel");
+    return LDP_OK;
+}
+
 int ldp_debug_read_clocks(const ldp_params* params, void* workspace, long long* host_out) {
     Plan plan;
     char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
@@ -523,7 +548,6 @@ int ldp_workspace_bytes(const ldp_params* params, size_t* bytes_out) {
 // vec_hint: the host wrapper guarantees 16-byte aligned certainty planes when W % 4 == 0; the planes'
 // addresses live in device memory, so alignment cannot be checked here without a copy.  Callers that
 // cannot guarantee it set params->scalar_loads = 1 to force the scalar load path.
-static int vec_ok_for(const ldp_params* p) { return (p->W % 4 == 0 && p->scalar_loads == 0) ? 1 : 0; }
 
 // L2 residency for the inter-kernel workspace (weights / p, winning neighbour, sample records): the path re-reads
 // them from several kernels of the same call while ~0.2 GB of certainty planes stream through the 126 MB L2.
