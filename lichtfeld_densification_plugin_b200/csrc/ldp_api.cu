@@ -57,7 +57,7 @@ int max_active_clusters(int csize, size_t smem) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, ldp::ldp_draw_kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, ldp::ldp_draw_kernel<2>, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
     cache[csize] = n > 0 ? n : -1;
     return cache[csize];
 }
@@ -222,6 +222,7 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     w.fix_list = reinterpret_cast<int2*>(carve(R * w.sel_cap * sizeof(int2)));
     w.fix_count = reinterpret_cast<int32_t*>(carve((ldp::LDP_MAX_SUB + R) * sizeof(int32_t)));
     w.arrive = w.fix_count ? w.fix_count + ldp::LDP_MAX_SUB : nullptr;
+    w.dstat = reinterpret_cast<int32_t*>(carve(R * sizeof(int32_t)));
     plan->bytes = off;
     return LDP_OK;
 }
@@ -262,7 +263,8 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     plan.geom.ref0 = ref0;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ldp::ldp_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
+        cudaError_t e = cudaFuncSetAttribute(ldp::ldp_draw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_draw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(draw)");
         e = cudaFuncSetAttribute(ldp::ldp_prep_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(prep)");
@@ -314,17 +316,26 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
       } }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_prep_kernel");
+    // ---- round 1: independent CTAs, as many per view as the device has SMs for (one CTA per SM: the table fills it)
+    int c_first = sm_count() / nsubrefs;
+    if (c_first < 1) c_first = 1;
+    if (c_first > (int)plan.ws.draw_cmax) c_first = (int)plan.ws.draw_cmax;
+    if (g_force_cluster > 0) c_first = g_force_cluster;
+    { KernelTimer kt(st, "ldp_draw_kernel");
+      (void)launch_k(ldp::ldp_draw_kernel<1>, dim3((unsigned)(nsubrefs * c_first)), dim3(ldp::KD_THREADS), plan.k1_smem, st,
+                     *p, refs, uniforms, plan.ws, *out, plan.geom, c_first); }
+    ++g_launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_draw_kernel<1>");
     {
-        // cluster size: as many CTAs per view as keeps every view of the launch resident at once (1 CTA / SM)
-        // largest cluster size for which every view's cluster is resident at once (one wave); GPC boundaries make
-        // this smaller than sm_count / n_refs, so ask the occupancy API
+        // ---- rounds 2.., coverage, compaction: one cluster per view; the largest size for which every view's cluster
+        // is resident at once (GPC boundaries make this smaller than sm_count / n_refs, so ask the occupancy API)
         int csize = 1;
         for (int c = 8; c > 1; --c) {
             if ((long long)nsubrefs * c > sm_count()) continue;
             if (max_active_clusters(c, plan.k1_smem) >= nsubrefs) { csize = c; break; }
         }
         if (g_force_cluster > 0) csize = g_force_cluster;
-        KernelTimer kt(st, "ldp_draw_kernel");
+        KernelTimer kt(st, "ldp_resume_kernel");
         for (;;) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)(nsubrefs * csize));
@@ -341,10 +352,10 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
             attr[1].val.programmaticStreamSerializationAllowed = pdl;
             cfg.attrs = attr;
             cfg.numAttrs = 2;
-            e = cudaLaunchKernelEx(&cfg, ldp::ldp_draw_kernel, *p, refs, uniforms, plan.ws, *out, plan.geom);
+            e = cudaLaunchKernelEx(&cfg, ldp::ldp_draw_kernel<2>, *p, refs, uniforms, plan.ws, *out, plan.geom, c_first);
             if (e == cudaSuccess) break;
             (void)cudaGetLastError();
-            if (csize == 1) return cuda_fail(e, "ldp_draw_kernel");
+            if (csize == 1) return cuda_fail(e, "ldp_draw_kernel<2>");
             csize = (csize > 4) ? 4 : (csize > 2 ? 2 : 1);      // odd sizes may not be schedulable: fall back
         }
         g_last_cluster = csize;

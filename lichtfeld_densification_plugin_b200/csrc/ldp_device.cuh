@@ -42,7 +42,8 @@ struct Workspace {
     int32_t* blk_first;  // [R][nb2][LDP_MAX_NN] first sample position per tile and group
     int2* fix_list;      // [R*sel_cap] (view, sample) pairs whose null-vector iteration did not converge
     int32_t* fix_count;  // [LDP_MAX_SUB] one counter per sub-batch (its list starts at ref0 * sel_cap)
-    int32_t* arrive;     // [R] stream-kernel CTAs of the view that have finished (directly after fix_count: one memset)
+    int32_t* arrive;     // [R] (spare counters, zeroed with fix_count)
+    int32_t* dstat;      // [R] verdict of the first draw round for the rounds that follow: fail code | inexact << 8
     long long* dbgclk;   // [R][32] phase timestamps of the draw kernel (written only with -DLDP_PHASE_CLOCKS)
     size_t n_pad, n_words, found_cap, sel_cap, topk_cap, nchunk_pad, nblk, bins_cap, draw_cmax;
 };

@@ -279,6 +279,10 @@ ldp_prep_generic_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ ref
                         const SampleGeom G)
 {
     grid_dependency_sync();
+    {   // the draw kernels' selection bitmap: cleared here, one kernel ahead of its first use
+        uint32_t* bm = ws.bitmap + (size_t)(blockIdx.y + G.ref0) * ws.n_words;
+        for (int i = blockIdx.x * KS_THREADS + threadIdx.x; i < (int)ws.n_words; i += gridDim.x * KS_THREADS) bm[i] = 0u;
+    }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int red_i[32];
     __shared__ float s_s;
@@ -441,6 +445,10 @@ ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 const SampleGeom G)
 {
     grid_dependency_sync();
+    {   // the draw kernels' selection bitmap: cleared here, one kernel ahead of its first use
+        uint32_t* bm = ws.bitmap + (size_t)(blockIdx.y + G.ref0) * ws.n_words;
+        for (int i = blockIdx.x * KS_THREADS + threadIdx.x; i < (int)ws.n_words; i += gridDim.x * KS_THREADS) bm[i] = 0u;
+    }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int red_i[32];
     __shared__ float s_s;
@@ -651,9 +659,15 @@ __device__ __noinline__ int slow_exact_scan(const float* __restrict__ w, int sta
     return last;
 }
 
+// MODE 1: the first rejection round only (all `size` draws), c_first INDEPENDENT CTAs per view -- they meet only in
+//         the selection bitmap (atomicOr), the global chunk sums (red.add) and their own find lists, so no cluster is
+//         needed and every SM of the device can take part;
+// MODE 2: everything after it, one thread-block cluster per view: zero the found p, rounds 2.., coverage picks,
+//         ordered compaction.  The kernel boundary is the barrier between round 1 and round 2.
+template <int MODE>
 __global__ void __launch_bounds__(KD_THREADS, 1)
 ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const double* __restrict__ uniforms,
-                const Workspace ws, const ldp_outputs out, const SampleGeom G)
+                const Workspace ws, const ldp_outputs out, const SampleGeom G, const int c_first)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -663,8 +677,8 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     unsigned long long* bins = reinterpret_cast<unsigned long long*>(smem_raw);   // coverage sort reuses the table
     __shared__ K1Shared sh;
 
-    const int C = (int)cluster.num_blocks();
-    const int crank = (int)cluster.block_rank();
+    const int C = (MODE == 1) ? c_first : (int)cluster.num_blocks();
+    const int crank = (MODE == 1) ? (int)(blockIdx.x % (unsigned)C) : (int)cluster.block_rank();
     const int r = blockIdx.x / C + G.ref0;
     const int tid = threadIdx.x, lane = tid & 31;
     const int T = blockDim.x;
@@ -690,16 +704,14 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             if (out.rounds) out.rounds[r] = 0;
         }
     };
-    // The selection bitmap is touched by no other kernel: clear it while the prep kernel may still be draining.
-    for (int i = gtid; i < (int)ws.n_words; i += GT) bitmap[i] = 0u;
     grid_dependency_sync();
     LDP_CLK(ws, r, 0);
-    // every exit below is taken by all CTAs of the cluster alike (same inputs, same arithmetic)
+    // every exit below is taken by all CTAs of the view alike (same inputs, same arithmetic); MODE 2 reports
     const RefStat st = ws.rstat[r];
-    if (st.bad & 4) { finish_empty(LDP_REF_NO_NEIGHBOURS); return; }
-    if (st.bad & 1) { finish_empty(LDP_REF_BAD_WEIGHTS); return; }          // NaN: `s <= 0` is False, choice raises
-    if (!(st.s > 0.f)) { finish_empty(LDP_REF_EMPTY); return; }             // core/sampling.py:27-28
-    if (st.bad & 2) { finish_empty(LDP_REF_BAD_WEIGHTS); return; }
+    if (st.bad & 4) { if (MODE == 2) finish_empty(LDP_REF_NO_NEIGHBOURS); return; }
+    if (st.bad & 1) { if (MODE == 2) finish_empty(LDP_REF_BAD_WEIGHTS); return; }          // NaN: `s <= 0` is False, choice raises
+    if (!(st.s > 0.f)) { if (MODE == 2) finish_empty(LDP_REF_EMPTY); return; }             // core/sampling.py:27-28
+    if (st.bad & 2) { if (MODE == 2) finish_empty(LDP_REF_BAD_WEIGHTS); return; }
 
     const int cs = G.chunk_shift;
     const int size = G.size;
@@ -708,8 +720,32 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     const double* U = uniforms ? uniforms + (size_t)r * (size_t)P.uniforms_per_ref : nullptr;
     const uint32_t rng_stream = rd->rng_stream;
 
+    if (MODE == 2) {
+        // ---- pick up after round 1: its verdict, its finds; the finders' p are zeroed here (the barrier before the
+        //      next draws orders these stores)
+        const int ds = __ldcg(ws.dstat + r);
+        fail = ds & 0xff;
+        inexact = (ds >> 8) & 1;
+        if (fail) { finish_empty(fail); return; }
+        drawn = size;
+        rounds = 1;
+        for (int c2 = 0; c2 < c_first; ++c2) {
+            const int nfc = __ldcg(fcnt + c2);
+            n_have += nfc;
+            if (nfc > 0) {
+                const int32_t* __restrict__ fl = ws.found + ((size_t)r * ws.draw_cmax + c2) * ws.found_cap;
+                for (int e0z = gtid; e0z < nfc; e0z += 4 * GT) {
+                    int zi[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const int e = e0z + j * GT; zi[j] = (e < nfc) ? __ldcg(fl + e) : -1; }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (zi[j] >= 0) w[zi[j]] = 0.f;
+                }
+            }
+        }
+    }
     LDP_CLK(ws, r, 1);
-    while (true) {
+    while (MODE == 1 || n_have < size) {
         // ---- (a) padded inclusive prefix of the global chunk sums: 8-entry rows per thread, one block scan
         if (tid == 0) sh.n_found = 0;
         // coalesced copy of the global chunk sums into the padded table, then 8-entry rows per thread
@@ -770,8 +806,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 const int etot = ilogb(total);
                 if (st.emin == 0 || etot - (st.emin - 150) >= 53) inexact = 1;
             }
-            if (C > 1) cluster.sync();                 // bitmap is zero everywhere before anybody sets a bit
-            LDP_CLK(ws, r, 17);
+            LDP_CLK(ws, r, 17);                        // (the selection bitmap was cleared by the prep kernel)
         }
         if (n_have >= size) break;
         const int cnt = size - n_have;
@@ -857,10 +892,14 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 ii[k] = -1;
                 hp[k] = 0.f;
             }
-            // 4. in-chunk scans: one 32-byte piece per draw per step, both loads in flight together
+            // 4. in-chunk scans: one 32-byte piece per draw per step, both loads in flight together.  The kernel is bound
+            //    by instruction issue here, so a piece costs 8 conversions + 8 DADD + 8 compares: p >= 0 makes the running
+            //    sums monotone, hence the first pixel whose sum exceeds the target is found by COUNTING the sums that do
+            //    not (its own weight is then necessarily positive).  A draw that hits keeps its piece in registers.
+            float e[2][8];
+            int fm[2] = {-1, -1};
             for (int pc = 0; pc < pieces; ++pc) {
                 if (!__any_sync(0xffffffffu, !hit[0] || !hit[1])) break;
-                float e[2][8];
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
                     if (!hit[k]) ldg256(w + (lo[k] << cs) + (pc << 3), e[k]);
@@ -869,16 +908,32 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                     if (!hit[k]) {
                         const double tlo = tt[k] * EPS_DN;
                         const int b = (lo[k] << cs) + (pc << 3);
-                        double run = cum[k];
-                        int first = -1;
+                        if (cum[k] > tlo) {            // rare: the sum entered the piece inside the tolerance band already:
+                            int f = -1;                // the first positive weight is the candidate
 #pragma unroll
-                        for (int m = 0; m < 8; ++m) {          // padding beyond N is zero (stream kernel), p >= 0
-                            run += widen_pos(e[k][m]);
-                            if (first < 0 && run > tlo && e[k][m] > 0.f) { first = m; cum[k] = run; hp[k] = e[k][m]; }
+                            for (int m = 7; m >= 0; --m) if (e[k][m] > 0.f) f = m;
+                            if (f >= 0) { hit[k] = true; fm[k] = f; ii[k] = b + f; }
+                        } else {
+                            double c = cum[k];         // padding beyond N is zero (stream kernel)
+                            int nle = 0;
+#pragma unroll
+                            for (int m = 0; m < 8; ++m) { c += (double)e[k][m]; nle += (c <= tlo) ? 1 : 0; }
+                            if (nle < 8) { hit[k] = true; fm[k] = nle; ii[k] = b + nle; }      // cum stays the sum before the piece
+                            else cum[k] = c;
                         }
-                        if (first >= 0) { hit[k] = true; ii[k] = b + first; }
-                        else cum[k] = run;
                     }
+                }
+            }
+            // 4b. running sum and weight at the candidate (once per draw)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (fm[k] >= 0) {
+                    double c = cum[k];
+                    float h = 0.f;
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) if (m <= fm[k]) { c += (double)e[k][m]; h = e[k][m]; }
+                    cum[k] = c;
+                    hp[k] = h;
                 }
             }
             // 5. numpy's exact comparison at the approximate crossing (slow exact continuation otherwise)
@@ -898,7 +953,11 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             uint32_t old[2];
 #pragma unroll
             for (int k = 0; k < 2; ++k)
+#ifdef LDP_EXP_NOOR
+                old[k] = (ii[k] >= 0) ? 0u : 0xffffffffu;
+#else
                 old[k] = (ii[k] >= 0) ? atomicOr(&bitmap[ii[k] >> 5], 1u << (ii[k] & 31)) : 0xffffffffu;
+#endif
             // two draws of one thread may hit the same pixel: the second is then not fresh
             const bool fresh0 = ii[0] >= 0 && !(old[0] & (1u << (ii[0] & 31)));
             const bool fresh1 = ii[1] >= 0 && !(old[1] & (1u << (ii[1] & 31)));
@@ -911,11 +970,15 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 const unsigned below_mask = (1u << lane) - 1u;
                 if (fresh0) {
                     flist[basepos + __popc(fm0 & below_mask)] = ii[0];
+#ifndef LDP_EXP_NORED
                     red_add_f64(gcsum + (ii[0] >> cs), -widen_pos(hp[0]));      // the found mass leaves the chunk sum
+#endif
                 }
                 if (fresh1) {
                     flist[basepos + n0 + __popc(fm1 & below_mask)] = ii[1];
+#ifndef LDP_EXP_NORED
                     red_add_f64(gcsum + (ii[1] >> cs), -widen_pos(hp[1]));
+#endif
                 }
             }
         }
@@ -923,6 +986,10 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
         if (rounds == 0) LDP_CLK(ws, r, 4);
         const int my_new = sh.n_found;
         if (tid == 0) fcnt[crank] = my_new;
+        if (MODE == 1) {                   // round 1 ends with the kernel; MODE 2 continues
+            if (gtid == 0) ws.dstat[r] = inexact << 8;
+            return;
+        }
         if (C > 1) cluster.sync(); else __syncthreads();          // B1: every draw of the round is done and published
         if (rounds == 0) LDP_CLK(ws, r, 6);
         int n_new = 0;
@@ -943,6 +1010,11 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
         // are ordered before the next round's scans by the cluster barrier B2 above
     }
     LDP_CLK(ws, r, 8);
+    if (MODE == 1) {                       // reached only through a failed check or size == 0: no draws were made
+        if (tid == 0) fcnt[crank] = 0;
+        if (gtid == 0) ws.dstat[r] = fail | (inexact << 8);
+        return;
+    }
     if (fail) { finish_empty(fail); return; }
     if (crank != 0) return;                               // the rest is cheap: CTA 0 alone (no cluster barrier below)
     __syncthreads();
