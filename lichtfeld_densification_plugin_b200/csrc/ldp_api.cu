@@ -335,6 +335,8 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
             if (max_active_clusters(c, plan.k1_smem) >= nsubrefs) { csize = c; break; }
         }
         if (g_force_cluster > 0) csize = g_force_cluster;
+        static const int env_c = [] { const char* e = getenv("LDP_RESUME_CLUSTER"); return e ? atoi(e) : 0; }();
+        if (env_c > 0) csize = env_c;
         KernelTimer kt(st, "ldp_resume_kernel");
         for (;;) {
             cudaLaunchConfig_t cfg = {};

@@ -706,6 +706,13 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     };
     grid_dependency_sync();
     LDP_CLK(ws, r, 0);
+    // MODE 2: everything the prologue needs is fetched in one batch (each L2 round trip costs ~0.75 us here)
+    int ds = 0, nfc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (MODE == 2) {
+        ds = __ldcg(ws.dstat + r);
+#pragma unroll
+        for (int c2 = 0; c2 < 8; ++c2) nfc[c2] = (c2 < c_first) ? __ldcg(fcnt + c2) : 0;
+    }
     // every exit below is taken by all CTAs of the view alike (same inputs, same arithmetic); MODE 2 reports
     const RefStat st = ws.rstat[r];
     if (st.bad & 4) { if (MODE == 2) finish_empty(LDP_REF_NO_NEIGHBOURS); return; }
@@ -723,29 +730,36 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     if (MODE == 2) {
         // ---- pick up after round 1: its verdict, its finds; the finders' p are zeroed here (the barrier before the
         //      next draws orders these stores)
-        const int ds = __ldcg(ws.dstat + r);
         fail = ds & 0xff;
         inexact = (ds >> 8) & 1;
         if (fail) { finish_empty(fail); return; }
         drawn = size;
         rounds = 1;
-        for (int c2 = 0; c2 < c_first; ++c2) {
-            const int nfc = __ldcg(fcnt + c2);
-            n_have += nfc;
-            if (nfc > 0) {
-                const int32_t* __restrict__ fl = ws.found + ((size_t)r * ws.draw_cmax + c2) * ws.found_cap;
-                for (int e0z = gtid; e0z < nfc; e0z += 4 * GT) {
-                    int zi[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { const int e = e0z + j * GT; zi[j] = (e < nfc) ? __ldcg(fl + e) : -1; }
+        for (int c2 = 0; c2 < 8; ++c2) n_have += nfc[c2];
+        if (n_have < size) {
+            // the lists are walked as one concatenated sequence, 4 entries per thread in flight
+            const int total_f = n_have;
+            for (int e0z = gtid; e0z < total_f; e0z += 4 * GT) {
+                int zi[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) if (zi[j] >= 0) w[zi[j]] = 0.f;
+                for (int j = 0; j < 4; ++j) {
+                    int e = e0z + j * GT, c2 = 0;
+                    zi[j] = -1;
+                    if (e < total_f) {
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) if (c2 == q && e >= nfc[q]) { e -= nfc[q]; c2 = q + 1; }
+                        zi[j] = __ldcg(ws.found + ((size_t)r * ws.draw_cmax + c2) * ws.found_cap + e);
+                    }
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (zi[j] >= 0) w[zi[j]] = 0.f;
             }
         }
     }
     LDP_CLK(ws, r, 1);
     while (MODE == 1 || n_have < size) {
+        if (MODE == 2 && rounds <= 4) LDP_CLK(ws, r, 18 + 2 * rounds);
         // ---- (a) padded inclusive prefix of the global chunk sums: 8-entry rows per thread, one block scan
         if (tid == 0) sh.n_found = 0;
         // coalesced copy of the global chunk sums into the padded table, then 8-entry rows per thread
@@ -830,9 +844,9 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             }
         }
         if (rounds > 0 && C > 1) cluster.sync(); else __syncthreads();    // B2: the p zeroed after the last round are visible
+        if (MODE == 2 && rounds == 1) LDP_CLK(ws, r, 2);
         if (rounds == 0) LDP_CLK(ws, r, 3);
         // ---- (b) draws: each thread takes DRAW_PASS (=2) consecutive draws per pass (one Philox call)
-        const int pieces = max(1, (1 << cs) >> 3);
         constexpr double EPS_UP = 1.0 + 1.0 / 1125899906842624.0, EPS_DN = 1.0 - 1.0 / 1125899906842624.0;
         for (int dw = 2 * (gtid - lane); dw < cnt; dw += 2 * GT) {      // warp-uniform trip count (ballots inside)
             const int d0 = dw + 2 * lane;
@@ -896,29 +910,35 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             //    by instruction issue here, so a piece costs 8 conversions + 8 DADD + 8 compares: p >= 0 makes the running
             //    sums monotone, hence the first pixel whose sum exceeds the target is found by COUNTING the sums that do
             //    not (its own weight is then necessarily positive).  A draw that hits keeps its piece in registers.
-            float e[2][8];
+            constexpr int PW = 8;                             // weights examined per step (two pieces per step measured no gain
+                                                              // in the later rounds)
+            const int steps = (1 << cs) / PW;                 // chunks hold at least 32 weights
+            float e[2][PW];
             int fm[2] = {-1, -1};
-            for (int pc = 0; pc < pieces; ++pc) {
+            for (int pc = 0; pc < steps; ++pc) {
                 if (!__any_sync(0xffffffffu, !hit[0] || !hit[1])) break;
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
-                    if (!hit[k]) ldg256(w + (lo[k] << cs) + (pc << 3), e[k]);
+                    if (!hit[k]) {
+#pragma unroll
+                        for (int q = 0; q < PW; q += 8) ldg256(w + (lo[k] << cs) + pc * PW + q, e[k] + q);
+                    }
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     if (!hit[k]) {
                         const double tlo = tt[k] * EPS_DN;
-                        const int b = (lo[k] << cs) + (pc << 3);
+                        const int b = (lo[k] << cs) + pc * PW;
                         if (cum[k] > tlo) {            // rare: the sum entered the piece inside the tolerance band already:
                             int f = -1;                // the first positive weight is the candidate
 #pragma unroll
-                            for (int m = 7; m >= 0; --m) if (e[k][m] > 0.f) f = m;
+                            for (int m = PW - 1; m >= 0; --m) if (e[k][m] > 0.f) f = m;
                             if (f >= 0) { hit[k] = true; fm[k] = f; ii[k] = b + f; }
                         } else {
                             double c = cum[k];         // padding beyond N is zero (stream kernel)
                             int nle = 0;
 #pragma unroll
-                            for (int m = 0; m < 8; ++m) { c += (double)e[k][m]; nle += (c <= tlo) ? 1 : 0; }
-                            if (nle < 8) { hit[k] = true; fm[k] = nle; ii[k] = b + nle; }      // cum stays the sum before the piece
+                            for (int m = 0; m < PW; ++m) { c += (double)e[k][m]; nle += (c <= tlo) ? 1 : 0; }
+                            if (nle < PW) { hit[k] = true; fm[k] = nle; ii[k] = b + nle; }     // cum stays the sum before the piece
                             else cum[k] = c;
                         }
                     }
@@ -931,7 +951,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                     double c = cum[k];
                     float h = 0.f;
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) if (m <= fm[k]) { c += (double)e[k][m]; h = e[k][m]; }
+                    for (int m = 0; m < PW; ++m) if (m <= fm[k]) { c += (double)e[k][m]; h = e[k][m]; }
                     cum[k] = c;
                     hp[k] = h;
                 }
@@ -984,6 +1004,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
         }
         __syncthreads();
         if (rounds == 0) LDP_CLK(ws, r, 4);
+        if (MODE == 2 && rounds <= 4) LDP_CLK(ws, r, 19 + 2 * rounds);
         const int my_new = sh.n_found;
         if (tid == 0) fcnt[crank] = my_new;
         if (MODE == 1) {                   // round 1 ends with the kernel; MODE 2 continues
@@ -1064,8 +1085,10 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             int cntb = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) cntb += __popc(m[j]);
+            LDP_CLK(ws, r, 28);
             int tile_total;
             int pos = block_exclusive_scan(cntb, sh.red_i, &tile_total);
+            LDP_CLK(ws, r, 29);
             const bool staged = tile_total <= stage_cap;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -1080,6 +1103,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 }
             }
             __syncthreads();
+            LDP_CLK(ws, r, 30);
             if (staged)
                 for (int i = tid; i < tile_total; i += T)
                     if (carry + i < (int)ws.sel_cap) sel[carry + i] = stage[i];

@@ -35,6 +35,12 @@ for a, b in zip(order[:-1], order[1:]):
     print(f"{names[a]:>20} -> {names[b]:<20} median {np.median(dd):9.0f}  max {dd.max():9.0f} cycles")
 #print("thread0 first pass: searches", np.median(clk[:,11]-clk[:,3]), " scans", np.median(clk[:,12]-clk[:,11]), " atomics issue", np.median(clk[:,13]-clk[:,12]), " rest of round", np.median(clk[:,4]-clk[:,13]))
 print("total median", np.median(clk[:, 10] - clk[:, 0]), "max", (clk[:, 10] - clk[:, 0]).max(), "cycles @1.963 GHz")
+print("---- resume kernel (rounds 2..): cycles")
+seq = [(0, "start"), (1, "round-1 finds zeroed"), (20, "round 2 top"), (2, "table rebuilt + B2"), (21, "round 2 draws done"), (22, "round 3 top"), (23, "round 3 draws done"), (24, "round 4 top"), (25, "round 4 draws done"), (8, "rounds done"), (9, "coverage done"), (28, "bitmap loaded+popc"), (29, "block scan"), (30, "bits extracted+sync"), (10, "compaction done")]
+for (a, na), (b, nb_) in zip(seq[:-1], seq[1:]):
+    dd = clk[:, b] - clk[:, a]
+    ok = (clk[:, b] > 0) & (clk[:, a] > 0) & (dd > 0) & (dd < 10**7)
+    if ok.sum(): print(f"{na:>24} -> {nb_:<24} median {np.median(dd[ok]):9.0f}  max {dd[ok].max():9.0f}  (n={ok.sum()})")
 sys.exit(0)
 d = clk[:, 1:11] - clk[:, 0:10]
 print("rounds per view:", clk[:, 20][:12], "...")
