@@ -1073,10 +1073,16 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     LDP_CLK(ws, r, 9);
 
     // ------------------------------------------------------------------ ordered compaction == np.unique(concat)
+    // Two passes per tile of T*8 bitmap words.  (1) each thread counts the bits of 8 CONSECUTIVE words, one block scan
+    // gives every word its output offset (shared memory).  (2) the words are walked again INTERLEAVED over the threads
+    // (word t, t + T, ...): the selected pixels cluster in the confident regions of the map, and the bit extraction of
+    // a thread that owns 256 consecutive pixels of such a region would serialise its whole warp.
     {
         const int nwords = (int)ws.n_words;                    // multiple of 8 (n_pad is a multiple of 256)
-        int* stage = reinterpret_cast<int*>(smem_raw);         // the chunk table is dead: stage indices for coalesced stores
-        const int stage_cap = (int)(G.draw_smem_bytes / sizeof(int));
+        int* woff = reinterpret_cast<int*>(smem_raw);          // the chunk table is dead: [T*8] per-word output offsets,
+        const int wcap = min(nwords, T * 8);
+        int* stage = woff + wcap;                              // then staged indices for coalesced stores
+        const int stage_cap = (int)(G.draw_smem_bytes / sizeof(int)) - wcap;
         int carry = 0;
         for (int t0 = 0; t0 < nwords; t0 += T * 8) {
             const int w0 = t0 + tid * 8;
@@ -1089,17 +1095,32 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             int tile_total;
             int pos = block_exclusive_scan(cntb, sh.red_i, &tile_total);
             LDP_CLK(ws, r, 29);
+            if (w0 < nwords) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { woff[tid * 8 + j] = pos; pos += __popc(m[j]); }
+            }
             const bool staged = tile_total <= stage_cap;
+            __syncthreads();
+            uint32_t mw[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                uint32_t mm = m[j];
-                while (mm) {
-                    const int b = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    const int v = ((w0 + j) << 5) + b;
-                    if (staged) stage[pos] = v;
-                    else if (carry + pos < (int)ws.sel_cap) sel[carry + pos] = v;
-                    ++pos;
+                const int wq = t0 + j * T + tid;
+                mw[j] = (wq < nwords) ? __ldcg(bitmap + wq) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t mm = mw[j];
+                if (mm) {
+                    const int wq = t0 + j * T + tid;
+                    int o = woff[wq - t0];
+                    while (mm) {
+                        const int b = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const int v = (wq << 5) + b;
+                        if (staged) stage[o] = v;
+                        else if (carry + o < (int)ws.sel_cap) sel[carry + o] = v;
+                        ++o;
+                    }
                 }
             }
             __syncthreads();
