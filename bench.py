@@ -9,7 +9,7 @@ per reference, all filters on; synthetic matcher outputs (the RoMa network is ou
 of sample -> triangulate -> filter -> colour over all 46 reference views (one launch sequence of the C-ABI call).
 
 value      filtered 3D points / s, inputs resident in HBM, CUDA-event timed, max over ranks (weak scaling: every
-           rank processes its own 46-view scene; for N > 1 the per-step NCCL all-gather of the packed points is
+           rank processes its own 46-view scene; for N > 1 the per-step NCCL all-gather of the kept-point counts is
            enqueued on a side stream and is inside the timed region).
 e2e        same metric through the public batched API from HOST buffers: certainty planes + reference images are
            copied host->device from pinned memory every step, the warp planes stay in pinned host memory and are
@@ -194,6 +194,11 @@ def recorded_traffic():
         return None
 
 
+def _dbg(msg: str) -> None:
+    if os.environ.get("BENCH_DEBUG"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def gpu_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -217,6 +222,9 @@ def gpu_arm(args) -> None:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # the collective of the previous step runs beside the kernels: keep a few SMs free for it, or the one-CTA-per-SM
+        # draw kernel splits into two waves (the counts exchange is one small CTA; gathering all points needs channels)
+        os.environ.setdefault("LDP_SM_RESERVE", "16" if int(os.environ.get("BENCH_GATHER_POINTS", "0")) else "4")
 
     scene = synth.make_scene(WORKLOAD["n_views"], WORKLOAD["setting"], WORKLOAD["ref_fraction"], WORKLOAD["nn"])
     R, nn, H, W = scene.n_refs, scene.nn, scene.H, scene.W
@@ -249,13 +257,16 @@ def gpu_arm(args) -> None:
     outs = [eng.alloc_outputs(R, sel_cap) for _ in range(2)]
     cap = R * sel_cap
 
-    # multi-GPU: per-step all-gather of the packed points (padded to capacity) on a side stream
+    # multi-GPU: the views are sharded, the points stay on the rank that made them (as they stay in HBM at N = 1); what
+    # the ranks exchange every step is their kept-point COUNT (distributed.exchange_counts semantics: one int64 per rank,
+    # NCCL all-gather on a side stream), which gives each rank the global row offset of its slice of the output
+    # (distributed.write_ply_sharded).  BENCH_GATHER_POINTS=1 ships every point to every rank instead (28 B/point).
     comm = torch.cuda.Stream(dev) if world > 1 else None
+    gather_points = bool(int(os.environ.get("BENCH_GATHER_POINTS", "0")))
     if world > 1:
-        gathered = [dict(xyz=torch.empty((world, cap, 3), dtype=torch.float32, device=dev),
-                         rgb=torch.empty((world, cap, 3), dtype=torch.float32, device=dev),
-                         err=torch.empty((world, cap), dtype=torch.float32, device=dev),
-                         off=torch.empty((world, R + 1), dtype=torch.int64, device=dev)) for _ in range(2)]
+        if gather_points:
+            gathered = [torch.empty((world, outs[0].packed.numel()), dtype=torch.uint8, device=dev) for _ in range(2)]
+        counts_all = [torch.zeros((world,), dtype=torch.int64, device=dev) for _ in range(2)]
         gather_done = [torch.cuda.Event() for _ in range(2)]
         step_done = [torch.cuda.Event() for _ in range(2)]
 
@@ -269,11 +280,9 @@ def gpu_arm(args) -> None:
             step_done[i % 2].record(main)
             with torch.cuda.stream(comm):
                 comm.wait_event(step_done[i % 2])
-                gbuf = gathered[i % 2]
-                dist.all_gather_into_tensor(gbuf["xyz"], o.xyz)
-                dist.all_gather_into_tensor(gbuf["rgb"], o.rgb)
-                dist.all_gather_into_tensor(gbuf["err"], o.err)
-                dist.all_gather_into_tensor(gbuf["off"], o.ref_offset)
+                dist.all_gather_into_tensor(counts_all[i % 2], o.ref_offset[-1:])
+                if gather_points:      # offsets | xyz | rgb | err of a rank are one allocation: a single collective
+                    dist.all_gather_into_tensor(gathered[i % 2], o.packed)
                 gather_done[i % 2].record(comm)
         return o
 
@@ -282,9 +291,11 @@ def gpu_arm(args) -> None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    _dbg("setup done")
     for i in range(max(3, args.warmup)):
         step(i)
     barrier()
+    _dbg("warmup done")
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -297,17 +308,20 @@ def gpu_arm(args) -> None:
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
+    _dbg("timed loop done")
     # keep the GPU under the same load a little longer so the clock sampler sees the loaded state
     t_end = time.time() + (0.0 if args.quick else max(0.0, 0.6 - ms_total / 1e3))
     j = 0
     while time.time() < t_end:
-        step(j)
+        # wall-clock bounded, so the ranks run different numbers of iterations: no collectives in here
+        eng.densify(batch, cfg, descs_dev=descs, outputs=outs[j % 2])
         j += 1
         if j % 64 == 0:
             torch.cuda.synchronize(dev)
     torch.cuda.synchronize(dev)
     clocks = sampler.stop()
 
+    _dbg("clock load loop done")
     launches_per_step = o.launches
     total_pts = o.total_points()
     S_total = int(o.n_samples.sum().item())
@@ -337,6 +351,7 @@ def gpu_arm(args) -> None:
             name = eng.lib.ldp_profile_name(k).decode()
             kdict[name] = kdict.get(name, 0.0) + float(buf[k]) / n_prof
     eng.lib.ldp_profile_enable(0)
+    _dbg("per-kernel profile done")
     dom = "ldp_stream_kernel"
     peak, peak_src = measured_hbm_peak()
     k1_bytes = R * nn * H * W * 4                     # every certainty value read exactly once
@@ -370,6 +385,7 @@ def gpu_arm(args) -> None:
             print(json.dumps({"quick": True, "ms_per_step": ms_step, "kernels_ms": kdict, "stream_kernel_alone_ms": dom_ms,
                               "k1_frac": achieved / peak, "path_frac": (path_gbs / peak) if path_gbs else None}))
         return
+    _dbg("stream-only timing done")
     # ---- e2e through the public API from host buffers.  The views are handed over in E2E_CHUNKS groups: the pinned
     #      host->device copy of group g+1 (copy stream) overlaps the kernels of group g, whose warp rows are gathered
     #      straight from pinned host memory over PCIe (the 0.77 GB of warp planes are never uploaded).
@@ -422,6 +438,7 @@ def gpu_arm(args) -> None:
         main.synchronize()
         return base
 
+    _dbg("e2e setup done")
     e2e_steps = max(3, min(args.steps, 20))
     for _ in range(3):
         n_e2e = e2e_step()
@@ -450,7 +467,9 @@ def gpu_arm(args) -> None:
             "dtype": "f32 geometry / f64 cdf, sampson, colour", "data": "synthetic",
             "config": {"workload": WORKLOAD["name"], "refs_per_gpu": R, "pairs_per_gpu": scene.n_pairs,
                        "l2_policy": "inputs larger than L2 (0.97 GB per step vs 126 MB)",
-                       "rng": "philox4x32-10", "multi_gpu": "per-step NCCL all-gather of packed points on a side stream" if world > 1 else "none"},
+                       "rng": "philox4x32-10", "multi_gpu": (("per-step NCCL all-gather of every rank's packed points (28 B/point) on a side stream" if gather_points else
+                                      "views sharded, points stay on their rank; per-step NCCL all-gather of the per-rank kept-point "
+                                      "counts (global row offsets) on a side stream") if world > 1 else "none")},
             "pairs_per_sec": pairs_per_s, "points_per_step": total_pts_all, "samples_per_step": S_all,
             "gpu_launches": launches_per_step * args.steps,
             "kernels_ms": kdict,

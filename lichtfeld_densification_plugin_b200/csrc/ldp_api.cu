@@ -322,7 +322,8 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_prep_kernel");
     // ---- round 1: independent CTAs, as many per view as the device has SMs for (one CTA per SM: the table fills it)
-    int c_first = sm_count() / nsubrefs;
+    static const int sm_reserve = [] { const char* e = getenv("LDP_SM_RESERVE"); return e ? atoi(e) : 0; }();   // SMs left to concurrent
+    int c_first = (sm_count() - sm_reserve) / nsubrefs;                                                            // (communication) kernels
     if (c_first < 1) c_first = 1;
     if (c_first > (int)plan.ws.draw_cmax) c_first = (int)plan.ws.draw_cmax;
     if (g_force_cluster > 0) c_first = g_force_cluster;

@@ -1,9 +1,13 @@
-"""Multi-GPU plumbing: reference views shard across ranks, one final point all-gather.
+"""Multi-GPU plumbing: reference views shard across ranks; the ranks exchange point COUNTS, not points.
 
 The path partitions naturally -- reference views are independent units once the sampler's RNG is keyed per
-view (Philox stream = global reference index) -- so each rank processes a contiguous slice of ``refs_local``
-and the only exchange is the final gather of the packed points.  Concatenating the ranks' outputs
-in rank order reproduces the single-GPU output order exactly.
+view (Philox stream = global reference index) -- so each rank processes a contiguous slice of ``refs_local``.
+Concatenating the ranks' outputs in rank order reproduces the single-GPU output order exactly, so the only thing a rank
+needs from the others is how many points they kept: ``exchange_counts`` (8 bytes per rank) gives every rank its global
+row offset, and ``write_ply_sharded`` lets each rank write its own slice of the output file (the reference's single
+process concatenates and writes everything itself, core/pipeline.py:914-928, core/writers.py:29-46).  Shipping every
+point to every rank (``all_gather_points``, 28 B/point) is available for callers that want the whole cloud on each GPU,
+but it grows with the number of ranks and is not needed to produce the file.
 
 Works with any ``torch.distributed`` backend (NCCL over NVLink on the GPU box, gloo in the CPU tests).
 """
@@ -29,6 +33,48 @@ def shard_refs(refs: Sequence[int], rank: Optional[int] = None, world: Optional[
         world = dist.get_world_size() if dist.is_initialized() else 1
     lo, hi = shard_bounds(len(refs), rank, world)
     return list(refs[lo:hi])
+
+
+def exchange_counts(n_points: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-gather of one int64 per rank (the rank's kept-point count, a 1-element tensor on the compute device; no host
+    synchronisation).  Returns (counts [world], exclusive prefix = global row offset of each rank's first point)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        counts = n_points.reshape(1).to(torch.int64)
+        return counts, torch.zeros_like(counts)
+    world = dist.get_world_size(group)
+    counts = torch.empty(world, dtype=torch.int64, device=n_points.device)
+    dist.all_gather_into_tensor(counts, n_points.reshape(1).to(torch.int64), group=group)
+    return counts, torch.cumsum(counts, 0) - counts
+
+
+def write_ply_sharded(path_out: str, xyz, rgb_uint8, row_offset: int, total_rows: int, rank: int, group=None) -> None:
+    """Every rank writes its own rows of ONE binary PLY file, byte-identical to ``core.writers.write_ply`` of the
+    rank-order concatenation: rank 0 writes the header for ``total_rows`` vertices, each rank writes 15-byte records at
+    header + 15 * row_offset.  ``xyz`` / ``rgb_uint8``: this rank's numpy arrays.  Needs a file system all ranks share."""
+    import os
+
+    import numpy as np
+
+    from .core.writers import _PLY_VERTEX, ply_header
+
+    header = ply_header(int(total_rows))
+    n = int(xyz.shape[0])
+    rec = np.empty(n, dtype=_PLY_VERTEX)
+    rec["x"], rec["y"], rec["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    rec["r"], rec["g"], rec["b"] = rgb_uint8[:, 0], rgb_uint8[:, 1], rgb_uint8[:, 2]
+    if rank == 0:
+        with open(path_out, "wb") as f:
+            f.write(header)
+            f.truncate(len(header) + 15 * int(total_rows))
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.barrier(group=group)                    # the file exists with its final size before anybody seeks into it
+    fd = os.open(path_out, os.O_WRONLY)
+    try:
+        os.pwrite(fd, rec.tobytes(), len(header) + 15 * int(row_offset))
+    finally:
+        os.close(fd)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.barrier(group=group)
 
 
 def all_gather_points(xyz: torch.Tensor, rgb: torch.Tensor, err: torch.Tensor, n_valid: Optional[int] = None,

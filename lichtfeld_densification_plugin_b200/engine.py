@@ -224,6 +224,7 @@ class DensifyOutputs:
     sample_flags: Optional[torch.Tensor] = None
     sample_xyzerr: Optional[torch.Tensor] = None
     launches: int = 0
+    packed: Optional[torch.Tensor] = None      # the u8 allocation behind ref_offset | xyz | rgb | err
 
     def total_points(self) -> int:
         """Synchronises."""
@@ -375,14 +376,21 @@ class DensifyEngine:
         cap = max(1, R * sel_cap)
         i32 = dict(dtype=torch.int32, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
+        # ref_offset | xyz | rgb | err live in ONE allocation (`packed`), so that a rank can hand its whole packed result
+        # to a single collective (distributed.all_gather_packed / bench.py) instead of one per array
+        off_bytes = (8 * (R + 1) + 15) // 16 * 16
+        packed = torch.zeros((off_bytes + 28 * cap,), dtype=torch.uint8, device=dev)
+        xyz_b, rgb_b, err_b = off_bytes, off_bytes + 12 * cap, off_bytes + 24 * cap
         out = DensifyOutputs(
             n_refs=R, sel_cap=sel_cap,
-            xyz=torch.empty((cap, 3), **f32), rgb=torch.empty((cap, 3), **f32), err=torch.empty((cap,), **f32),
-            ref_offset=torch.zeros((R + 1,), dtype=torch.int64, device=dev),
+            xyz=packed[xyz_b:rgb_b].view(torch.float32).view(cap, 3), rgb=packed[rgb_b:err_b].view(torch.float32).view(cap, 3),
+            err=packed[err_b:err_b + 4 * cap].view(torch.float32),
+            ref_offset=packed[:8 * (R + 1)].view(torch.int64),
             status=torch.zeros((R,), **i32), n_samples=torch.zeros((R,), **i32),
             group_count=torch.zeros((R, N.LDP_MAX_NN), **i32), group_order=torch.full((R, N.LDP_MAX_NN), -1, **i32),
             uniforms_used=torch.zeros((R,), **i32), rounds=torch.zeros((R,), **i32), weight_sum=torch.zeros((R,), **f32),
         )
+        out.packed = packed
         if collect_debug:
             out.dbg_matches = torch.empty((cap, 4), **f32)
             out.dbg_cert = torch.empty((cap,), **f32)

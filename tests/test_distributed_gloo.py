@@ -67,3 +67,44 @@ def test_all_gather_points_world2(tmp_path):
         assert np.array_equal(z["xyz"][:, 0], want) and np.array_equal(z["rgb"][:, 2], want)
         assert z["counts"].sum() == want.size
     assert shards[0] + shards[1] == list(range(11))
+
+
+def _worker_sharded_write(rank, world, port, tmp, q):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lichtfeld_densification_plugin_b200 import distributed as D
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        rs = np.random.RandomState(5)
+        xyz_all = rs.standard_normal((1000, 3)).astype(np.float32)
+        rgb_all = rs.randint(0, 256, size=(1000, 3)).astype(np.uint8)
+        bounds = [0, 377, 1000]                                   # uneven shards, as kept-point counts are
+        lo, hi = bounds[rank], bounds[rank + 1]
+        counts, offs = D.exchange_counts(torch.tensor([hi - lo]))
+        assert counts.tolist() == [377, 623] and offs.tolist() == [0, 377]
+        path = os.path.join(tmp, "sharded.ply")
+        D.write_ply_sharded(path, xyz_all[lo:hi], rgb_all[lo:hi], int(offs[rank]), int(counts.sum()), rank)
+        if rank == 0:
+            from lichtfeld_densification_plugin_b200.core.writers import write_ply
+            ref = os.path.join(tmp, "whole.ply")
+            write_ply(ref, xyz_all, rgb_all)
+            q.put(open(path, "rb").read() == open(ref, "rb").read())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_counts_exchange_and_sharded_ply_world2(tmp_path):
+    """World size 2, gloo: the ranks exchange only their kept-point counts and each writes its slice of one PLY file,
+    which is byte-identical to the single-process writer's file for the rank-order concatenation."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sharded_write, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    for p_ in procs:
+        p_.join(120)
+        assert p_.exitcode == 0
+    assert q.get(timeout=10) is True
