@@ -205,6 +205,7 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     w.w = reinterpret_cast<float*>(carve(R * w.n_pad * sizeof(float)));
     w.bestk = reinterpret_cast<uint8_t*>(carve(R * w.n_pad));
     w.bitmap = reinterpret_cast<uint32_t*>(carve(R * w.n_words * sizeof(uint32_t)));
+    w.gone = reinterpret_cast<uint32_t*>(carve(R * w.n_words * sizeof(uint32_t)));
     w.draw_cmax = 8;
     w.found = reinterpret_cast<int32_t*>(carve(R * w.draw_cmax * w.found_cap * sizeof(int32_t)));
     w.fcnt = reinterpret_cast<int32_t*>(carve(R * w.draw_cmax * sizeof(int32_t)));

@@ -24,6 +24,7 @@ struct Workspace {
                          //              (zeroed as pixels get drawn)
     uint8_t* bestk;      // [R][n_pad]   winning neighbour per pixel
     uint32_t* bitmap;    // [R][n_words] selected-pixel bitmap
+    uint32_t* gone;      // [R][n_words] the bitmap as the first draw round left it: those pixels weigh nothing afterwards
     int32_t* found;      // [R][draw_cmax][found_cap] pixel indices: per-CTA find lists of the current round
     int32_t* fcnt;       // [R][draw_cmax] entries in each list
     int32_t* sel;        // [R][sel_cap]  sample indices when the caller does not ask for them

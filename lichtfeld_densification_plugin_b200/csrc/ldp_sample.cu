@@ -645,10 +645,11 @@ __device__ __forceinline__ bool cdf_exceeds(double x, double total, double u, do
 }
 
 // Exact continuation of a scan (rare: the approximate crossing was not the exact one, or inexact sums).
-__device__ __noinline__ int slow_exact_scan(const float* __restrict__ w, int start, int N, double cum, double total,
-                                            double u, int last, float* pout) {
+__device__ __noinline__ int slow_exact_scan(const float* __restrict__ w, const uint32_t* __restrict__ gone, int start, int N,
+                                            double cum, double total, double u, int last, float* pout) {
     for (int i = start; i < N; ++i) {
-        const float p = __ldcg(w + i);
+        float p = __ldcg(w + i);
+        if (gone && ((__ldcg(gone + (i >> 5)) >> (i & 31)) & 1u)) p = 0.f;         // drawn in round 1
         if (p > 0.f) {
             cum += (double)p;
             last = i;
@@ -695,6 +696,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     int32_t* __restrict__ sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
     double* __restrict__ gcsum = ws.csum + (size_t)r * ws.nchunk_pad;
     const unsigned long long* __restrict__ gb = ws.gbins + (size_t)r * ws.bins_cap;
+    const uint32_t* __restrict__ gone = (MODE == 2) ? ws.gone + (size_t)r * ws.n_words : nullptr;   // drawn in round 1
 
     auto finish_empty = [&](int status) {
         if (gtid == 0) {
@@ -738,23 +740,13 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
 #pragma unroll
         for (int c2 = 0; c2 < 8; ++c2) n_have += nfc[c2];
         if (n_have < size) {
-            // the lists are walked as one concatenated sequence, 4 entries per thread in flight
-            const int total_f = n_have;
-            for (int e0z = gtid; e0z < total_f; e0z += 4 * GT) {
-                int zi[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    int e = e0z + j * GT, c2 = 0;
-                    zi[j] = -1;
-                    if (e < total_f) {
-#pragma unroll
-                        for (int q = 0; q < 7; ++q) if (c2 == q && e >= nfc[q]) { e -= nfc[q]; c2 = q + 1; }
-                        zi[j] = __ldcg(ws.found + ((size_t)r * ws.draw_cmax + c2) * ws.found_cap + e);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) if (zi[j] >= 0) w[zi[j]] = 0.f;
-            }
+            // The pixels drawn in round 1 must weigh nothing from now on.  Zeroing their p would be ~8500 scattered
+            // 4-byte stores per view (one load/store wavefront each); instead the selection bitmap as round 1 left it
+            // is copied (coalesced, 32 KB) and the scans of the later rounds mask by it.  The few pixels drawn in the
+            // later rounds are zeroed in place as before.
+            const uint4* src = reinterpret_cast<const uint4*>(bitmap);
+            uint4* dst = reinterpret_cast<uint4*>(ws.gone + (size_t)r * ws.n_words);
+            for (int i = gtid; i < (int)(ws.n_words / 4); i += GT) dst[i] = __ldcg(src + i);
         }
     }
     LDP_CLK(ws, r, 1);
@@ -918,11 +910,22 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             for (int pc = 0; pc < steps; ++pc) {
                 if (!__any_sync(0xffffffffu, !hit[0] || !hit[1])) break;
 #pragma unroll
+                uint32_t gm[2] = {0u, 0u};
+#pragma unroll
                 for (int k = 0; k < 2; ++k)
                     if (!hit[k]) {
 #pragma unroll
                         for (int q = 0; q < PW; q += 8) ldg256(w + (lo[k] << cs) + pc * PW + q, e[k] + q);
+                        if (MODE == 2) { const int b = (lo[k] << cs) + pc * PW; gm[k] = __ldcg(gone + (b >> 5)) >> (b & 31); }
                     }
+                if (MODE == 2) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        if (!hit[k]) {
+#pragma unroll
+                            for (int m = 0; m < PW; ++m) if ((gm[k] >> m) & 1u) e[k][m] = 0.f;
+                        }
+                }
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     if (!hit[k]) {
@@ -963,9 +966,9 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                     const double thi = tt[k] * EPS_UP, tlo = tt[k] * EPS_DN;
                     if (ii[k] >= 0) {
                         if (!cdf_exceeds(cum[k], total, uu[k], thi, tlo))
-                            ii[k] = slow_exact_scan(w, ii[k] + 1, N, cum[k], total, uu[k], ii[k], &hp[k]);
+                            ii[k] = slow_exact_scan(w, gone, ii[k] + 1, N, cum[k], total, uu[k], ii[k], &hp[k]);
                     } else {
-                        ii[k] = slow_exact_scan(w, min(N, (lo[k] + 1) << cs), N, cum[k], total, uu[k], -1, &hp[k]);
+                        ii[k] = slow_exact_scan(w, gone, min(N, (lo[k] + 1) << cs), N, cum[k], total, uu[k], -1, &hp[k]);
                     }
                 }
             }
