@@ -174,7 +174,7 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     g.chunk_shift = cs;
     {   // the ordered compaction keeps one output offset per bitmap word of a tile in shared memory, plus staging
         const size_t nw = (align_up((size_t)N, 256) + 31) / 32;
-        const size_t need = std::min(nw, (size_t)ldp::KD_THREADS * 8) * 4 + 4096;
+        const size_t need = (std::min(nw, (size_t)ldp::KD_THREADS * 8) + 1) * 4 + 4096;
         if (plan->k1_smem < need) plan->k1_smem = need;
     }
     g.draw_smem_bytes = (int)plan->k1_smem;

@@ -1040,11 +1040,14 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
         return;
     }
     if (fail) { finish_empty(fail); return; }
-    if (crank != 0) return;                               // the rest is cheap: CTA 0 alone (no cluster barrier below)
+    // The coverage picks are CTA 0's; the ordered compaction is shared by the CTAs of the cluster when its size divides
+    // the 8 bitmap words a thread owns (every CTA scans the whole bitmap, each extracts a contiguous range of words).
+    const bool share = (C == 2 || C == 4 || C == 8);
+    if (crank != 0 && !share) return;
     __syncthreads();
 
     // ------------------------------------------------------------------ coverage picks (core/sampling.py:34-50)
-    {
+    if (crank == 0) {
         int lp = 0;
         for (int i = tid; i < G.nbins; i += T) lp += (gb[i] != 0ull) ? 1 : 0;
         const int nb_pos = block_sum(lp, sh.red_i);
@@ -1070,22 +1073,25 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 }
             }
         }
-        __threadfence_block();
+        __threadfence();
         __syncthreads();
     }
+    if (share) cluster.sync();                            // the picks are in the bitmap before anybody counts it
     LDP_CLK(ws, r, 9);
 
     // ------------------------------------------------------------------ ordered compaction == np.unique(concat)
     // Two passes per tile of T*8 bitmap words.  (1) each thread counts the bits of 8 CONSECUTIVE words, one block scan
-    // gives every word its output offset (shared memory).  (2) the words are walked again INTERLEAVED over the threads
-    // (word t, t + T, ...): the selected pixels cluster in the confident regions of the map, and the bit extraction of
-    // a thread that owns 256 consecutive pixels of such a region would serialise its whole warp.
+    // gives every word its output offset (shared memory).  (2) the CTA's range of words is walked again INTERLEAVED over
+    // the threads (word t, t + T, ...): the selected pixels cluster in the confident regions of the map, and the bit
+    // extraction of a thread that owns 256 consecutive pixels of such a region would serialise its whole warp.
     {
         const int nwords = (int)ws.n_words;                    // multiple of 8 (n_pad is a multiple of 256)
-        int* woff = reinterpret_cast<int*>(smem_raw);          // the chunk table is dead: [T*8] per-word output offsets,
-        const int wcap = min(nwords, T * 8);
+        int* woff = reinterpret_cast<int*>(smem_raw);          // the chunk table is dead: [T*8 + 1] per-word output offsets,
+        const int wcap = min(nwords, T * 8) + 1;
         int* stage = woff + wcap;                              // then staged indices for coalesced stores
         const int stage_cap = (int)(G.draw_smem_bytes / sizeof(int)) - wcap;
+        const int nshare = share ? C : 1;
+        const int wpc = (T * 8) / nshare;                      // words of a tile this CTA extracts
         int carry = 0;
         for (int t0 = 0; t0 < nwords; t0 += T * 8) {
             const int w0 = t0 + tid * 8;
@@ -1098,29 +1104,26 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             int tile_total;
             int pos = block_exclusive_scan(cntb, sh.red_i, &tile_total);
             LDP_CLK(ws, r, 29);
+            const int tw = min(T * 8, nwords - t0);                              // words in this tile
             if (w0 < nwords) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { woff[tid * 8 + j] = pos; pos += __popc(m[j]); }
             }
-            const bool staged = tile_total <= stage_cap;
+            if (tid == 0) woff[tw] = tile_total;                                 // sentinel
             __syncthreads();
-            uint32_t mw[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int wq = t0 + j * T + tid;
-                mw[j] = (wq < nwords) ? __ldcg(bitmap + wq) : 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                uint32_t mm = mw[j];
-                if (mm) {
-                    const int wq = t0 + j * T + tid;
-                    int o = woff[wq - t0];
+            const int lo_w = min(crank * wpc, tw), hi_w = min(lo_w + wpc, tw);   // this CTA's words of the tile (tile-relative)
+            const int out_lo = woff[lo_w], out_hi = woff[hi_w];
+            const bool staged = (out_hi - out_lo) <= stage_cap;
+            for (int jj = 0; jj < wpc; jj += T) {
+                const int wr = lo_w + jj + tid;                                  // tile-relative word
+                if (wr < hi_w) {
+                    uint32_t mm = __ldcg(bitmap + t0 + wr);
+                    int o = woff[wr];
                     while (mm) {
                         const int b = __ffs(mm) - 1;
                         mm &= mm - 1;
-                        const int v = (wq << 5) + b;
-                        if (staged) stage[o] = v;
+                        const int v = ((t0 + wr) << 5) + b;
+                        if (staged) stage[o - out_lo] = v;
                         else if (carry + o < (int)ws.sel_cap) sel[carry + o] = v;
                         ++o;
                     }
@@ -1129,11 +1132,12 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             __syncthreads();
             LDP_CLK(ws, r, 30);
             if (staged)
-                for (int i = tid; i < tile_total; i += T)
-                    if (carry + i < (int)ws.sel_cap) sel[carry + i] = stage[i];
+                for (int i = tid; i < out_hi - out_lo; i += T)
+                    if (carry + out_lo + i < (int)ws.sel_cap) sel[carry + out_lo + i] = stage[i];
             __syncthreads();
             carry += tile_total;
         }
+        if (crank != 0) return;
         LDP_CLK(ws, r, 10);
         if (tid == 0) {
             out.status[r] = LDP_REF_OK | (inexact ? LDP_REF_INEXACT_SCAN : 0);
