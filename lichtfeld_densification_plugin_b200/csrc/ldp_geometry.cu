@@ -611,26 +611,45 @@ ldp_pack_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     __shared__ long long s_off;
     grid_dependency_sync();
     const int r = blockIdx.y, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = out.n_samples[r];
+    // ---- everything the CTA needs is requested in ONE batch, before the sample count that decides what is used:
+    //      the kernel is a chain of dependent L2 round trips otherwise.  Rows are sel_cap long and the tile tables nb2
+    //      long, so every address is valid; what lies beyond the view's samples is ignored below.
+    const int i = b * K2_THREADS + tid;
+    const bool in_row = i < (int)ws.sel_cap;
+    const size_t o = (size_t)r * ws.sel_cap + i;
+    const int S = __ldcg(out.n_samples + r);
+    const int f_raw = in_row ? __ldcg(ws.flags + o) : 0;
+    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pc4 = pa, pd = pa;
+    if (in_row) { pa = __ldcg(ws.pt0 + o); pc4 = __ldcg(ws.pt1 + o); }
+    if (in_row && P.collect_debug && out.dbg_matches) pd = __ldcg(ws.dbgm + o);
+    constexpr int TMAX = 10;                              // table rows a thread owns in registers (80 tiles = 10240 samples); more: loop below
+    const int g_own = tid % LDP_MAX_NN, part = tid / LDP_MAX_NN;
+    const int32_t* cnt = ws.blk_cnt + (size_t)r * ga.nb2 * LDP_MAX_NN;
+    const int32_t* fst = ws.blk_first + (size_t)r * ga.nb2 * LDP_MAX_NN;
+    int cv[TMAX], fv[TMAX];
+#pragma unroll
+    for (int q = 0; q < TMAX; ++q) {
+        const int t = part + q * NPART;
+        cv[q] = (t < ga.nb2) ? __ldcg(cnt + t * LDP_MAX_NN + g_own) : 0;
+        fv[q] = (t < ga.nb2) ? __ldcg(fst + t * LDP_MAX_NN + g_own) : 0x7fffffff;
+    }
     const int nb = (S + K2_THREADS - 1) / K2_THREADS;
     if (b >= nb && b != 0) return;
-
-    // ---- the tile's sample flags and the plan inputs are fetched together
-    const int i = b * K2_THREADS + tid;
-    const uint8_t* flags = ws.flags + (size_t)r * ws.sel_cap;
-    const int f = (i < S) ? flags[i] : 0;
+    const int f = (i < S) ? f_raw : 0;
     {
-        const int g = tid % LDP_MAX_NN, part = tid / LDP_MAX_NN;
-        const int32_t* cnt = ws.blk_cnt + (size_t)r * ga.nb2 * LDP_MAX_NN;
-        const int32_t* fst = ws.blk_first + (size_t)r * ga.nb2 * LDP_MAX_NN;
         int tot = 0, bef = 0, first = 0x7fffffff;
-        for (int t = part; t < nb; t += NPART) {
-            const int c = __ldcg(cnt + t * LDP_MAX_NN + g);
+#pragma unroll
+        for (int q = 0; q < TMAX; ++q) {
+            const int t = part + q * NPART;
+            if (t < nb) { tot += cv[q]; bef += (t < b) ? cv[q] : 0; first = min(first, fv[q]); }
+        }
+        for (int t = part + TMAX * NPART; t < nb; t += NPART) {          // very large M only
+            const int c = __ldcg(cnt + t * LDP_MAX_NN + g_own);
             tot += c;
             bef += (t < b) ? c : 0;
-            first = min(first, __ldcg(fst + t * LDP_MAX_NN + g));
+            first = min(first, __ldcg(fst + t * LDP_MAX_NN + g_own));
         }
-        s_part[0][part][g] = tot; s_part[1][part][g] = bef; s_part[2][part][g] = first;
+        s_part[0][part][g_own] = tot; s_part[1][part][g_own] = bef; s_part[2][part][g_own] = first;
     }
     long long partk = 0;
     for (int q = tid; q < r; q += K3_THREADS) partk += (long long)ws.kept[q];
@@ -682,14 +701,12 @@ ldp_pack_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
         for (int ww = 0; ww < warp; ++ww) before += s_wcnt[ww][g];
         const long long dst = s_off + before + rank_in_warp;
         if (dst < out.capacity) {
-            const size_t o = (size_t)r * ws.sel_cap + i;
-            const float4 a = ws.pt0[o], c = ws.pt1[o];
-            out.xyz[dst * 3 + 0] = a.x; out.xyz[dst * 3 + 1] = a.y; out.xyz[dst * 3 + 2] = a.z;
-            out.rgb[dst * 3 + 0] = c.x; out.rgb[dst * 3 + 1] = c.y; out.rgb[dst * 3 + 2] = c.z;
-            out.err[dst] = a.w;
+            out.xyz[dst * 3 + 0] = pa.x; out.xyz[dst * 3 + 1] = pa.y; out.xyz[dst * 3 + 2] = pa.z;
+            out.rgb[dst * 3 + 0] = pc4.x; out.rgb[dst * 3 + 1] = pc4.y; out.rgb[dst * 3 + 2] = pc4.z;
+            out.err[dst] = pa.w;
             if (P.collect_debug && out.dbg_matches) {
-                reinterpret_cast<float4*>(out.dbg_matches)[dst] = ws.dbgm[o];
-                if (out.dbg_cert) out.dbg_cert[dst] = c.w;
+                reinterpret_cast<float4*>(out.dbg_matches)[dst] = pd;
+                if (out.dbg_cert) out.dbg_cert[dst] = pc4.w;
             }
         }
     }
