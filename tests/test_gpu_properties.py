@@ -317,3 +317,28 @@ def test_coverage_walk_is_on_normalised_p(engine):
     for only_a, b in ((got - want, want), (want - got, got)):
         for i in only_a:
             assert i in partner and partner[i] in b, f"pixel {i} differs outside a tied pair"
+
+
+def test_more_views_than_sms(engine):
+    """A launch with more reference views than the device has SMs (the draw kernels then run one CTA per view in
+    several waves): every view's result equals its result in a launch of its own."""
+    from lichtfeld_densification_plugin_b200 import synth
+    scene = synth.make_scene(340, "turbo", ref_fraction=0.5, nn=2)
+    scene.H = scene.W = scene.h_match = scene.w_match = 64
+    R = scene.n_refs
+    assert R > 160
+    c = dict(M=600, no_filter=False, wm=64, hm=64)
+    inputs = [synth.synth_ref_inputs(scene, rp, cert_family="T", seed=3) for rp in range(R)]
+    streams = list(range(R))
+    whole = G.run_gpu(engine, scene, inputs, G.path_cfg(c, seed=5), rng_streams=streams)
+    assert (whole.status & 0xFF == 0).all()
+    for rp in (0, 1, 77, 159, R - 1):
+        single = G.run_gpu(engine, scene, [inputs[rp]], G.path_cfg(c, seed=5), rng_streams=[streams[rp]])
+        assert np.array_equal(single.sel_idx[0], whole.sel_idx[rp]), rp
+        assert np.array_equal(single.xyz[0], whole.xyz[rp]) and np.array_equal(single.rgb[0], whole.rgb[rp])
+        assert single.uniforms_used[0] == whole.uniforms_used[rp]
+    res = G.run_oracle_ref(scene, inputs[77], c, uniforms=np.random.RandomState(1).random_sample(3000))
+    g1 = G.run_gpu(engine, scene, [inputs[77]], G.path_cfg(c), uniforms=np.random.RandomState(1).random_sample(3000)[None, :],
+                   weight_sums=[res.taps["s"]])
+    rep = G.compare_ref(g1, 0, res, c, scene)
+    assert rep.ok(), rep
