@@ -22,7 +22,7 @@ namespace ldp {
 
 constexpr int K2_THREADS = 128;
 #ifndef K2_MIN_BLOCKS
-#define K2_MIN_BLOCKS 6
+#define K2_MIN_BLOCKS 8
 #endif
 constexpr int K3_THREADS = 128;
 constexpr int KFIX_BLOCKS = 148;
