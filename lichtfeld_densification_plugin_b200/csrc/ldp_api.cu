@@ -406,6 +406,8 @@ ldp::GeomArgs make_geom_args(const ldp_params* p, const Plan& plan, int have_bes
     ga.sub = sub;
     static const int discard_mode = [] { const char* e = getenv("LDP_DISCARD"); return e ? atoi(e) : 1; }();
     ga.discard = have_bestk ? discard_mode : 0;
+    static const int fuse_mode = [] { const char* e = getenv("LDP_FUSE_GATHER"); return e ? atoi(e) : 1; }();
+    ga.fused = fuse_mode;
     return ga;
 }
 
@@ -416,6 +418,7 @@ int launch_geometry(const ldp_params* p, const ldp_ref_desc* refs, const ldp_out
     const dim3 grid((unsigned)plan.nb2, (unsigned)nsubrefs);
     const dim3 ggrid((unsigned)((plan.ws.sel_cap + ldp::KG_THREADS * KG_SPT - 1) / (ldp::KG_THREADS * KG_SPT)), (unsigned)nsubrefs);
     cudaError_t e;
+    if (!ga.fused)
     { KernelTimer kt(st, "ldp_gather_kernel");
       (void)launch_k(ldp::ldp_gather_kernel, dim3(ggrid), dim3(ldp::KG_THREADS), 0, st, *p, refs, plan.ws, *out, ga); }
     ++g_launches;

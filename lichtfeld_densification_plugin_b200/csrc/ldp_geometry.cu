@@ -52,6 +52,7 @@ struct GeomArgs {           // launch-constant extras computed on the host
     int ref0;               // first view of this sub-launch
     int sub;                // sub-batch index (selects the fix-up counter)
     int discard;            // 1: drop the dead weight rows from L2 (LDP_DISCARD=0 turns it off)
+    int fused;              // 1: the geometry kernel gathers its own inputs (no gather kernel, no record round trip)
 };
 
 // The workspace rows are dead once their last consumer ran; telling L2 so spares the write-back of lines
@@ -511,11 +512,24 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
     __shared__ RefConst rc;
     __shared__ PairConst pc[LDP_MAX_NN];
     __shared__ int s_cnt[LDP_MAX_NN], s_first[LDP_MAX_NN];
+    __shared__ ProView pv;
     const int r = blockIdx.y + ga.ref0;
     stage_constants(refs + r, rc, pc, threadIdx.x, K2_THREADS);          // host-written descriptors: no kernel produces them
+    if (ga.fused && P.prologue) stage_proview(refs + r, pv, threadIdx.x);
     grid_dependency_sync();
-    const int S = out.n_samples[r];
     const int i0 = blockIdx.x * K2_THREADS;
+    int idx_f = 0;
+    if (ga.fused) {
+        const int32_t* sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
+        const int i_ = i0 + threadIdx.x;
+        idx_f = (i_ < (int)ws.sel_cap) ? __ldg(sel + i_) : 0;
+        if (ga.discard & 1) {
+            const char* row = reinterpret_cast<const char*>(ws.w + (size_t)r * ws.n_pad);
+            const int nlines = (int)(ws.n_pad * sizeof(float) / 128);
+            for (int l = i0 + threadIdx.x; l < nlines; l += gridDim.x * K2_THREADS) l2_discard_line(row + (size_t)l * 128);
+        }
+    }
+    const int S = out.n_samples[r];
     if (i0 >= S) return;
     if (threadIdx.x < LDP_MAX_NN) { s_cnt[threadIdx.x] = 0; s_first[threadIdx.x] = 0x7fffffff; }
     __syncthreads();
@@ -526,9 +540,16 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
         const size_t o = (size_t)r * ws.sel_cap + i;
         SampleRec rec;
         float craw;
-        load_record(ws, P, o, rec, craw);
+        if (ga.fused) gather_sample(P, rc, pc, pv, ga, ws.bestk + (size_t)r * ws.n_pad, idx_f, rec, craw);
+        else load_record(ws, P, o, rec, craw);
         SampleResult s;
         eval_sample<false>(P, rc, pc, ga, rec, craw, s);
+        if (!s.converged && ga.fused) {     // the fix-up reads the record
+            ws.pt0[o] = rec.wv;
+            ws.pt1[o] = make_float4(__uint_as_float(rec.tex[0]), __uint_as_float(rec.tex[1]), __uint_as_float(rec.tex[2]),
+                                    __uint_as_float(rec.k_cert));
+            if (P.collect_debug) ws.dbgm[o].x = craw;
+        }
         if (!s.converged) {                 // rare: leave the record in place for the fix-up (flag bit 7), keep = 0 for now
             const int slot = atomicAdd(ws.fix_count + ga.sub, 1);
             ws.fix_list[(size_t)ga.ref0 * ws.sel_cap + slot] = make_int2(r, i);
