@@ -840,18 +840,26 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
         if (rounds == 0) LDP_CLK(ws, r, 3);
         // ---- (b) draws: each thread takes DRAW_PASS (=2) consecutive draws per pass (one Philox call)
         constexpr double EPS_UP = 1.0 + 1.0 / 1125899906842624.0, EPS_DN = 1.0 - 1.0 / 1125899906842624.0;
-        for (int dw = 2 * (gtid - lane); dw < cnt; dw += 2 * GT) {      // warp-uniform trip count (ballots inside)
-            const int d0 = dw + 2 * lane;
+        // MODE 1 (8500 draws, issue bound): two draws per thread and pass, sharing one Philox call, 8 weights per scan step.
+        // MODE 2 (a few hundred draws, latency bound): one draw per thread, a branch-free search over the whole table and
+        // the whole 32-weight line of the chunk requested at once -- every dependent L2 round trip costs ~0.7 us here.
+        constexpr int ND = (MODE == 2) ? 1 : 2;
+        for (int dw = ND * (gtid - lane); dw < cnt; dw += ND * GT) {      // warp-uniform trip count (ballots inside)
+            const int d0 = dw + ND * lane;
             double uu[2], tt[2], cum[2];
             int lo[2], hi[2], ii[2];
             float hp[2];
             bool valid[2], hit[2];
+            cum[1] = 0.0; lo[1] = hi[1] = 0; ii[1] = -1; hp[1] = 0.f; hit[1] = true; tt[1] = 0.0;      // (absent when ND == 1)
             // 1. uniforms + guide lookups
             valid[0] = d0 < cnt;
-            valid[1] = d0 + 1 < cnt;
+            valid[1] = (ND == 2) && d0 + 1 < cnt;
             if (P.rng_mode == LDP_RNG_EXPLICIT) {
                 uu[0] = valid[0] ? U[drawn + d0] : 0.5;
                 uu[1] = valid[1] ? U[drawn + d0 + 1] : 0.5;
+            } else if (ND == 1) {
+                uu[0] = philox_uniform(P.seed, rng_stream, (uint32_t)(drawn + d0));
+                uu[1] = 0.5;
             } else if (((drawn + d0) & 1) == 0) {
                 philox_uniform2(P.seed, rng_stream, (uint32_t)(drawn + d0), uu);
             } else {
@@ -859,17 +867,26 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 uu[1] = philox_uniform(P.seed, rng_stream, (uint32_t)(drawn + d0 + 1));
             }
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
+            for (int k = 0; k < ND; ++k) {
                 tt[k] = uu[k] * total;
                 const int kb = min(NG - 1, (int)(uu[k] * (double)NG));
                 lo[k] = (rounds == 0) ? guide[kb] : 0;
                 hi[k] = (rounds == 0) ? max(lo[k], guide[kb + 1]) : nchunk - 1;
             }
             // 2. lock-step binary search inside the guide ranges: first chunk with prefix > u * total (approximate)
+            if (MODE == 2 && rounds == 1 && dw == ND * (gtid - lane)) LDP_CLK(ws, r, 11);
+            if (MODE == 2) {            // branch-free upper bound over the whole table: #entries <= target, one probe per bit
+                int pos = 0;
+                for (int step = 1 << (31 - __clz(max(nchunk, 1))); step > 0; step >>= 1) {
+                    const int q = pos + step;
+                    if (q <= nchunk && !(pre[pad8(q - 1)] > tt[0])) pos = q;
+                }
+                lo[0] = min(pos, nchunk - 1);
+            } else
             for (;;) {
                 bool more = false;
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
+                for (int k = 0; k < ND; ++k) {
                     if (lo[k] < hi[k]) {
                         const int mid = (lo[k] + hi[k]) >> 1;
                         if (pre[pad8(mid)] > tt[k]) hi[k] = mid; else lo[k] = mid + 1;
@@ -879,8 +896,9 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 if (!more) break;
             }
             // 3. exact predicate of searchsorted(cdf, u, 'right') on the chunk boundaries
+            if (MODE == 2 && rounds == 1 && dw == ND * (gtid - lane)) LDP_CLK(ws, r, 12);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
+            for (int k = 0; k < ND; ++k) {
                 int c = lo[k];
                 const double thi = tt[k] * EPS_UP, tlo = tt[k] * EPS_DN;
                 double below = (c > 0) ? pre[pad8(c - 1)] : 0.0;
@@ -899,11 +917,11 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 hp[k] = 0.f;
             }
             // 4. in-chunk scans: one 32-byte piece per draw per step, both loads in flight together.  The kernel is bound
+            if (MODE == 2 && rounds == 1 && dw == ND * (gtid - lane)) LDP_CLK(ws, r, 14);
             //    by instruction issue here, so a piece costs 8 conversions + 8 DADD + 8 compares: p >= 0 makes the running
             //    sums monotone, hence the first pixel whose sum exceeds the target is found by COUNTING the sums that do
             //    not (its own weight is then necessarily positive).  A draw that hits keeps its piece in registers.
-            constexpr int PW = 8;                             // weights examined per step (two pieces per step measured no gain
-                                                              // in the later rounds)
+            constexpr int PW = (MODE == 2) ? 32 : 8;          // weights examined per step
             const int steps = (1 << cs) / PW;                 // chunks hold at least 32 weights
             float e[2][PW];
             int fm[2] = {-1, -1};
@@ -912,7 +930,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
 #pragma unroll
                 uint32_t gm[2] = {0u, 0u};
 #pragma unroll
-                for (int k = 0; k < 2; ++k)
+                for (int k = 0; k < ND; ++k)
                     if (!hit[k]) {
 #pragma unroll
                         for (int q = 0; q < PW; q += 8) ldg256(w + (lo[k] << cs) + pc * PW + q, e[k] + q);
@@ -920,14 +938,14 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                     }
                 if (MODE == 2) {
 #pragma unroll
-                    for (int k = 0; k < 2; ++k)
+                    for (int k = 0; k < ND; ++k)
                         if (!hit[k]) {
 #pragma unroll
                             for (int m = 0; m < PW; ++m) if ((gm[k] >> m) & 1u) e[k][m] = 0.f;
                         }
                 }
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
+                for (int k = 0; k < ND; ++k) {
                     if (!hit[k]) {
                         const double tlo = tt[k] * EPS_DN;
                         const int b = (lo[k] << cs) + pc * PW;
@@ -948,8 +966,9 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 }
             }
             // 4b. running sum and weight at the candidate (once per draw)
+            if (MODE == 2 && rounds == 1 && dw == ND * (gtid - lane)) LDP_CLK(ws, r, 15);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
+            for (int k = 0; k < ND; ++k) {
                 if (fm[k] >= 0) {
                     double c = cum[k];
                     float h = 0.f;
@@ -961,7 +980,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             }
             // 5. numpy's exact comparison at the approximate crossing (slow exact continuation otherwise)
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
+            for (int k = 0; k < ND; ++k) {
                 if (valid[k]) {
                     const double thi = tt[k] * EPS_UP, tlo = tt[k] * EPS_DN;
                     if (ii[k] >= 0) {
@@ -973,9 +992,10 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 }
             }
             // 6. dedupe (both atomics in flight together), then warp-aggregated append + mass removal
-            uint32_t old[2];
+            if (MODE == 2 && rounds == 1 && dw == ND * (gtid - lane)) LDP_CLK(ws, r, 16);
+            uint32_t old[2] = {0xffffffffu, 0xffffffffu};
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
+            for (int k = 0; k < ND; ++k)
 #ifdef LDP_EXP_NOOR
                 old[k] = (ii[k] >= 0) ? 0u : 0xffffffffu;
 #else

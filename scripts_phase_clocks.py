@@ -36,7 +36,7 @@ for a, b in zip(order[:-1], order[1:]):
 #print("thread0 first pass: searches", np.median(clk[:,11]-clk[:,3]), " scans", np.median(clk[:,12]-clk[:,11]), " atomics issue", np.median(clk[:,13]-clk[:,12]), " rest of round", np.median(clk[:,4]-clk[:,13]))
 print("total median", np.median(clk[:, 10] - clk[:, 0]), "max", (clk[:, 10] - clk[:, 0]).max(), "cycles @1.963 GHz")
 print("---- resume kernel (rounds 2..): cycles")
-seq = [(0, "start"), (1, "round-1 finds zeroed"), (20, "round 2 top"), (2, "table rebuilt + B2"), (21, "round 2 draws done"), (22, "round 3 top"), (23, "round 3 draws done"), (24, "round 4 top"), (25, "round 4 draws done"), (8, "rounds done"), (9, "coverage done"), (28, "bitmap loaded+popc"), (29, "block scan"), (30, "bits extracted+sync"), (10, "compaction done")]
+seq = [(0, "start"), (1, "round-1 finds zeroed"), (20, "round 2 top"), (2, "table rebuilt + B2"), (11, "r2 uniforms+guide"), (12, "r2 binary search"), (14, "r2 exact chunk"), (15, "r2 scans"), (16, "r2 exact crossing"), (21, "round 2 draws done"), (22, "round 3 top"), (23, "round 3 draws done"), (24, "round 4 top"), (25, "round 4 draws done"), (8, "rounds done"), (9, "coverage done"), (28, "bitmap loaded+popc"), (29, "block scan"), (30, "bits extracted+sync"), (10, "compaction done")]
 for (a, na), (b, nb_) in zip(seq[:-1], seq[1:]):
     dd = clk[:, b] - clk[:, a]
     ok = (clk[:, b] > 0) & (clk[:, a] > 0) & (dd > 0) & (dd < 10**7)
