@@ -28,11 +28,11 @@ eng.lib.ldp_debug_read_clocks.argtypes = [C.POINTER(N.LdpParams), C.c_void_p, C.
 eng.lib.ldp_debug_read_clocks(C.byref(params), C.c_void_p(eng._workspace.data_ptr()), host)
 clk = np.array(host[:]).reshape(len(batch), 32)
 t0 = clk[:, 16].min()
-names = ["start", "s read+bins zeroed", "main loop done", "reductions done", "phase B done", "flushed"]
+names = ["start", "s reduced+bins zeroed", "main loop done", "reductions done", "flushed", "-"]
 for base, label in ((16, "CTA 3"), (24, "CTA 31")):
     c = clk[:, base:base + 6] - t0
     print(label, "start times (ns) by view:", np.sort(c[:, 0])[::5])
-    for k in range(5):
+    for k in range(4):
         d = c[:, k + 1] - c[:, k]
         print(f"  {names[k]:>20} -> {names[k+1]:<20} median {np.median(d):7.0f} ns  max {d.max():7.0f}")
-    print("  CTA lifetime median", np.median(c[:, 5] - c[:, 0]), "ns; last end", c[:, 5].max(), "ns")
+    print("  CTA lifetime median", np.median(c[:, 4] - c[:, 0]), "ns; last end", c[:, 4].max(), "ns")
