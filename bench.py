@@ -409,11 +409,13 @@ def gpu_arm(args) -> None:
     e2e_descs = [eng.upload_descs(b) for b in e2e_batches]
     e2e_outs = [eng.alloc_outputs(hi - lo, sel_cap) for lo, hi in bounds]
     copy_stream = torch.cuda.Stream(dev)
+    back_stream = torch.cuda.Stream(dev)
     copied = [torch.cuda.Event() for _ in bounds]
-    h_xyz = torch.empty((cap, 3), dtype=torch.float32).pin_memory()
-    h_rgb = torch.empty((cap, 3), dtype=torch.float32).pin_memory()
-    h_err = torch.empty((cap,), dtype=torch.float32).pin_memory()
-    h_offs = [torch.empty((hi - lo + 1,), dtype=torch.int64).pin_memory() for lo, hi in bounds]
+    computed = [torch.cuda.Event() for _ in bounds]
+    # a group's whole packed result (offsets | xyz | rgb | err, padded to capacity) goes back in ONE device->host copy on
+    # a third stream as soon as the group is done: no intermediate synchronisation to learn the counts first, and the
+    # copy runs in the other PCIe direction while the next groups are still being uploaded
+    h_packed = [torch.empty_like(o.packed, device="cpu").pin_memory() for o in e2e_outs]
 
     def e2e_step():
         main = torch.cuda.current_stream(dev)
@@ -426,17 +428,15 @@ def gpu_arm(args) -> None:
         for g in range(E2E_CHUNKS):
             main.wait_event(copied[g])
             eng.densify(e2e_batches[g], cfg, descs_dev=e2e_descs[g], outputs=e2e_outs[g])
-            h_offs[g].copy_(e2e_outs[g].ref_offset, non_blocking=True)
-        main.synchronize()
-        base = 0
-        for g in range(E2E_CHUNKS):
-            n = int(h_offs[g][-1])
-            h_xyz[base:base + n].copy_(e2e_outs[g].xyz[:n], non_blocking=True)
-            h_rgb[base:base + n].copy_(e2e_outs[g].rgb[:n], non_blocking=True)
-            h_err[base:base + n].copy_(e2e_outs[g].err[:n], non_blocking=True)
-            base += n
-        main.synchronize()
-        return base
+            computed[g].record(main)
+            with torch.cuda.stream(back_stream):
+                back_stream.wait_event(computed[g])
+                h_packed[g].copy_(e2e_outs[g].packed, non_blocking=True)
+        back_stream.synchronize()
+        n = 0
+        for g, (lo, hi) in enumerate(bounds):          # the result the caller reads: per-group offsets from the host copy
+            n += int(h_packed[g][:8 * (hi - lo + 1)].view(torch.int64)[-1])
+        return n
 
     _dbg("e2e setup done")
     e2e_steps = max(3, min(args.steps, 20))
@@ -455,10 +455,11 @@ def gpu_arm(args) -> None:
     S_e2e = int(sum(int(o.n_samples.sum().item()) for o in e2e_outs))
     e2e = {"value": world * n_e2e / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": int(h_cert.numel() * 4 + h_img.numel() + S_e2e * 16),
-           "d2h_bytes_per_step": int(n_e2e * 28 + (R + E2E_CHUNKS) * 8), "ms_per_step": 1e3 * e2e_s,
+           "d2h_bytes_per_step": int(sum(h.numel() for h in h_packed)), "ms_per_step": 1e3 * e2e_s,
            "note": f"cert planes + ref images copied H2D from pinned memory in {E2E_CHUNKS} groups of views, the copy of a "
                    "group overlapping the kernels of the previous one; warp planes stay pinned on the host and only the "
-                   "sampled rows (16 B each) are gathered over PCIe; xyz/rgb/err + offsets copied D2H"}
+                   "sampled rows (16 B each) are gathered over PCIe; each group's packed result (offsets, xyz, rgb, err, padded to "
+                   "capacity) is copied D2H on a third stream as soon as the group is done"}
 
     if rank == 0:
         line = {
