@@ -418,11 +418,12 @@ int launch_geometry(const ldp_params* p, const ldp_ref_desc* refs, const ldp_out
     const dim3 grid((unsigned)plan.nb2, (unsigned)nsubrefs);
     const dim3 ggrid((unsigned)((plan.ws.sel_cap + ldp::KG_THREADS * KG_SPT - 1) / (ldp::KG_THREADS * KG_SPT)), (unsigned)nsubrefs);
     cudaError_t e;
-    if (!ga.fused)
-    { KernelTimer kt(st, "ldp_gather_kernel");
-      (void)launch_k(ldp::ldp_gather_kernel, dim3(ggrid), dim3(ldp::KG_THREADS), 0, st, *p, refs, plan.ws, *out, ga); }
-    ++g_launches;
-    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_gather_kernel");
+    if (!ga.fused) {
+        { KernelTimer kt(st, "ldp_gather_kernel");
+          (void)launch_k(ldp::ldp_gather_kernel, dim3(ggrid), dim3(ldp::KG_THREADS), 0, st, *p, refs, plan.ws, *out, ga); }
+        ++g_launches;
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_gather_kernel");
+    }
     { KernelTimer kt(st, "ldp_geometry_kernel");
       (void)launch_k(ldp::ldp_geometry_kernel, dim3(grid), dim3(ldp::K2_THREADS), 0, st, *p, refs, plan.ws, *out, ga); }
     ++g_launches;
