@@ -608,6 +608,9 @@ ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
 //      Finally CTA 0 ORs the coverage picks in and an ordered bitmap compaction yields np.unique(concat).
 //      reference core/sampling.py:31-32,34-52
 // =============================================================================================
+#ifndef LDP_NO_GUIDE
+#define LDP_USE_GUIDE 1              // round 1 searches inside guide-table ranges (measured: 32.8 vs 41.0 us without the table)
+#endif
 constexpr int DRAW_PASS = 2;          // draws a thread keeps in flight (they share one Philox call): every phase is
                                       // batched over them so that its loads overlap -- the kernel is latency- and
                                       // LSU-wavefront-bound, not ALU-bound (profiles/r01_draw_*.md)
@@ -798,7 +801,9 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 for (int j = 0; j < 4; ++j) { double2 d = dst[j]; d.x += base; d.y += base; dst[j] = d; }
             }
         }
+#ifdef LDP_USE_GUIDE
         if (rounds == 0) for (int i = tid; i < NG + 2; i += T) guide[i] = nchunk - 1;
+#endif
         __syncthreads();
         if (rounds == 0) LDP_CLK(ws, r, 16);
         total = pre[pad8(nchunk - 1)];
@@ -822,6 +827,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
         //      approximately right: the exact fix-up after the search walks to numpy's chunk from any start.
         //      Built for the first round only (8500 draws); later rounds have a few hundred draws and search the
         //      whole table.
+#ifdef LDP_USE_GUIDE
         if (rounds == 0) {
             const double ngt = (double)NG / total;
             int kprev = (e0 > 0 && e0 <= nchunk) ? min(NG, (int)(pre[pad8(e0 - 1)] * ngt)) : -1;
@@ -835,6 +841,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 }
             }
         }
+#endif
         if (rounds > 0 && C > 1) cluster.sync(); else __syncthreads();    // B2: the p zeroed after the last round are visible
         if (MODE == 2 && rounds == 1) LDP_CLK(ws, r, 2);
         if (rounds == 0) LDP_CLK(ws, r, 3);
@@ -869,20 +876,33 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
 #pragma unroll
             for (int k = 0; k < ND; ++k) {
                 tt[k] = uu[k] * total;
+#ifdef LDP_USE_GUIDE
                 const int kb = min(NG - 1, (int)(uu[k] * (double)NG));
                 lo[k] = (rounds == 0) ? guide[kb] : 0;
                 hi[k] = (rounds == 0) ? max(lo[k], guide[kb + 1]) : nchunk - 1;
+#else
+                lo[k] = 0; hi[k] = nchunk - 1;
+#endif
             }
             // 2. lock-step binary search inside the guide ranges: first chunk with prefix > u * total (approximate)
             if (MODE == 2 && rounds == 1 && dw == ND * (gtid - lane)) LDP_CLK(ws, r, 11);
-            if (MODE == 2) {            // branch-free upper bound over the whole table: #entries <= target, one probe per bit
-                int pos = 0;
+#ifdef LDP_USE_GUIDE
+            if (MODE == 2)
+#endif
+            {                           // branch-free upper bound over the whole table: #entries <= target, one probe per bit
+                int pos[2] = {0, 0};    // (the probes of the two draws are independent and pipeline)
                 for (int step = 1 << (31 - __clz(max(nchunk, 1))); step > 0; step >>= 1) {
-                    const int q = pos + step;
-                    if (q <= nchunk && !(pre[pad8(q - 1)] > tt[0])) pos = q;
+#pragma unroll
+                    for (int k = 0; k < ND; ++k) {
+                        const int q = pos[k] + step;
+                        if (q <= nchunk && !(pre[pad8(q - 1)] > tt[k])) pos[k] = q;
+                    }
                 }
-                lo[0] = min(pos, nchunk - 1);
-            } else
+#pragma unroll
+                for (int k = 0; k < ND; ++k) lo[k] = min(pos[k], nchunk - 1);
+            }
+#ifdef LDP_USE_GUIDE
+            else
             for (;;) {
                 bool more = false;
 #pragma unroll
@@ -895,6 +915,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 }
                 if (!more) break;
             }
+#endif
             // 3. exact predicate of searchsorted(cdf, u, 'right') on the chunk boundaries
             if (MODE == 2 && rounds == 1 && dw == ND * (gtid - lane)) LDP_CLK(ws, r, 12);
 #pragma unroll
