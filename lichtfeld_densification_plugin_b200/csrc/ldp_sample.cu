@@ -782,7 +782,11 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 double2* row = reinterpret_cast<double2*>(pre + pad8(i0));
                 double v[8];
 #pragma unroll
-                for (int j = 0; j < 8; j += 2) { const double2 d = row[j >> 1]; v[j] = d.x; v[j + 1] = (i0 + j + 1 < nchunk) ? d.y : 0.0; }
+                for (int j = 0; j < 8; j += 2) {          // entries beyond the table are whatever shared memory held: mask both halves
+                    const double2 d = row[j >> 1];
+                    v[j] = (i0 + j < nchunk) ? d.x : 0.0;
+                    v[j + 1] = (i0 + j + 1 < nchunk) ? d.y : 0.0;
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { run += v[j]; v[j] = run; }
 #pragma unroll
@@ -836,7 +840,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 if (c < nchunk) {
                     int kc = min(NG, (int)(pre[pad8(c)] * ngt));
                     if (c == nchunk - 1) kc = NG + 1;
-                    for (int k = kprev + 1; k <= kc; ++k) guide[k] = c;
+                    for (int k = max(kprev, -1) + 1; k <= kc; ++k) guide[k] = c;       // (max: never below the table, whatever the sums)
                     kprev = max(kprev, kc);
                 }
             }

@@ -165,3 +165,36 @@ def test_config5_base_640_sharding_invariance(engine):
         assert len(xyz) == len(whole.xyz)
         for a, b in zip(xyz, whole.xyz):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("case", range(10))
+def test_randomised_shapes(engine, case):
+    """Seeded random shapes through every kernel variant (vector / scalar rows, column-constant or not, generic prep,
+    ragged neighbour counts, map != match resolution, small and binding coverage budgets) against the oracle."""
+    from lichtfeld_densification_plugin_b200 import synth
+    rs = np.random.RandomState(1000 + case)
+    H = int(rs.choice([40, 57, 64, 96, 128, 150]))
+    W = int(rs.choice([48, 61, 64, 100, 128, 256]))
+    hm = int(rs.choice([H, max(16, H // 2), H + 7]))
+    wm = int(rs.choice([W, max(16, W // 2), W + 5]))
+    nn = int(rs.randint(1, 6))
+    M = int(rs.choice([50, 400, 1500, min(4000, H * W // 3)]))
+    fam = "T" if case % 3 else "R"
+    no_filter = bool(case == 7)
+    scene = synth.make_scene(10, "turbo", ref_fraction=0.2, nn=nn)
+    scene.H, scene.W, scene.h_match, scene.w_match = H, W, hm, wm
+    c = dict(M=M, no_filter=no_filter, wm=wm, hm=hm, sampson=float(rs.choice([5.0, 0.0])), parallax=float(rs.choice([0.5, 0.0])))
+    inputs = [synth.synth_ref_inputs(scene, rp, cert_family=fam, seed=200 + case) for rp in range(scene.n_refs)]
+    U = np.stack([np.random.RandomState(case * 10 + r).random_sample(3 * M + 64) for r in range(len(inputs))])
+    ress = [G.run_oracle_ref(scene, inp, c, uniforms=U[r]) for r, inp in enumerate(inputs)]
+    g = G.run_gpu(engine, scene, inputs, G.path_cfg(c), uniforms=None if no_filter else U,
+                  weight_sums=None if no_filter else [res.taps["s"] if res is not None else 0.0 for res in ress])
+    for r, res in enumerate(ress):
+        if res is None:
+            assert g.xyz[r].shape[0] == 0
+            continue
+        rep = G.compare_ref(g, r, res, c, scene)
+        _report(f"random{case}/{H}x{W}/m{hm}x{wm}/nn{nn}/M{M}/{fam}/ref{r}", rep)
+        assert rep.ok(), (case, H, W, hm, wm, nn, M, fam, rep)
+        if not no_filter:
+            assert g.uniforms_used[r] == res.taps["uniforms_used"] and g.rounds[r] == res.taps["rounds"]
