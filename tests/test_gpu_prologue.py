@@ -161,3 +161,51 @@ def test_collect_reference_matches_drop_in(engine):
         np.testing.assert_allclose(tri.xyz, z["xyz"], rtol=G.XYZ_RTOL, atol=G.XYZ_ATOL)
         np.testing.assert_allclose(tri.rgb, z["rgb"], rtol=G.XYZ_RTOL, atol=G.XYZ_ATOL)
         assert list(tri.debug_matches_by_nbr.keys()) == [int(u) for u in z["dbg_uids"]]
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_randomised_raw_planes(engine, case):
+    """Seeded random shapes with raw certainties, a random floor and random masks (also at a resolution different from
+    the maps): the fused path against the oracle run on planes post-processed by the oracle's explicit restatement."""
+    from lichtfeld_densification_plugin_b200 import synth
+    from oracle import densify_oracle as O
+    rs = np.random.RandomState(4000 + case)
+    H = int(rs.choice([48, 64, 96, 120]))
+    W = int(rs.choice([48, 60, 64, 128]))
+    hm = int(rs.choice([H, max(16, (H * 5) // 8)]))
+    wm = int(rs.choice([W, max(16, (W * 5) // 8)]))
+    nn = int(rs.randint(1, 5))
+    M = int(rs.choice([300, 1200, 2500]))
+    floor = float(rs.choice([0.2, 0.35, 0.0]))
+    scene = synth.make_scene(10, "turbo", ref_fraction=0.2, nn=nn)
+    scene.H, scene.W, scene.h_match, scene.w_match = H, W, hm, wm
+    c = dict(M=M, no_filter=False, wm=wm, hm=hm)
+    inputs, ress = [], []
+    U = np.stack([np.random.RandomState(case * 7 + r).random_sample(3 * M + 64) for r in range(scene.n_refs)])
+    for rp in range(scene.n_refs):
+        inp = synth.synth_ref_inputs(scene, rp, cert_family="T", seed=300 + case)
+        inp["cert"] = inp["cert"] - 0.15 * torch.rand(inp["cert"].shape, generator=torch.Generator().manual_seed(case * 10 + rp))
+        k = len(inp["nbr_indices"])
+        inp["mask_a"] = (rs.rand(hm, wm) > 0.25).astype(np.uint8) if rs.rand() < 0.7 else None
+        inp["masks_b"] = [(rs.rand(hm, wm) > 0.2).astype(np.uint8) if rs.rand() < 0.6 else None for _ in range(k)]
+        post = torch.from_numpy(np.stack([O.certainty_prologue(inp["cert"][q].numpy(), inp["warp"][q].numpy(), inp["mask_a"],
+                                                               inp["masks_b"][q], floor) for q in range(k)]))
+        try:
+            res = G.run_oracle_ref(scene, dict(inp, cert=post), c, uniforms=U[rp])
+        except ValueError as exc:                      # masks left fewer positive weights than the draw size
+            assert "Fewer non-zero" in str(exc)
+            res = "fewer"
+        inputs.append(inp)
+        ress.append(res)
+    g = G.run_gpu(engine, scene, inputs, dataclasses.replace(G.path_cfg(c), certainty_floor=floor), uniforms=U,
+                  weight_sums=[res.taps["s"] if res not in (None, "fewer") else 0.0 for res in ress], collect_debug=True)
+    for r, res in enumerate(ress):
+        if res == "fewer":
+            assert g.status[r] & 0xFF == 2 and g.xyz[r].shape[0] == 0            # LDP_REF_FEWER_NONZERO, view skipped
+            continue
+        if res is None:
+            assert g.xyz[r].shape[0] == 0
+            continue
+        rep = G.compare_ref(g, r, res, c, scene)
+        assert rep.ok(), (case, H, W, hm, wm, nn, M, floor, rep)
+        assert g.uniforms_used[r] == res.taps["uniforms_used"] and g.rounds[r] == res.taps["rounds"]
