@@ -294,7 +294,18 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_stream_kernel");
     if (p->no_filter) {
         { KernelTimer kt(st, "ldp_topm_kernel");
-          (void)launch_k(ldp::ldp_topm_kernel, dim3(nsubrefs), dim3(ldp::K1_THREADS), 0, st, *p, refs, plan.ws, *out, plan.geom); }
+          size_t n2 = 1;
+          const size_t Mn = (size_t)std::min((long long)p->matches_per_ref, (long long)plan.geom.N);
+          while (n2 < Mn) n2 <<= 1;
+          static bool topm_configured = false;
+          if (!topm_configured) {
+              (void)cudaFuncSetAttribute(ldp::ldp_topm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
+              topm_configured = true;
+          }
+          if (n2 * 8 <= K1_SMEM_BUDGET - 16 * 1024 && !getenv("LDP_TOPM_GENERIC"))     // keys sorted in shared memory
+              (void)launch_k(ldp::ldp_topm_kernel, dim3(nsubrefs), dim3(ldp::K1_THREADS), n2 * 8, st, *p, refs, plan.ws, *out, plan.geom);
+          else
+              (void)launch_k(ldp::ldp_topm_generic_kernel, dim3(nsubrefs), dim3(ldp::K1_THREADS), 0, st, *p, refs, plan.ws, *out, plan.geom); }
         ++g_launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_topm_kernel");
         return LDP_OK;

@@ -1209,7 +1209,7 @@ __device__ __forceinline__ uint32_t f32_order_key(float f) {
 }
 
 __global__ void __launch_bounds__(K1_THREADS, 1)
-ldp_topm_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws,
+ldp_topm_generic_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws,
                 const ldp_outputs out, const SampleGeom G)
 {
     grid_dependency_sync();
@@ -1281,6 +1281,198 @@ ldp_topm_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     __syncthreads();
     // 3. sort descending (global memory, L2-resident)
     bitonic_sort_desc(keys, n2);
+    for (int i = tid; i < M; i += T) sel[i] = (int)(0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull));
+    if (tid == 0) {
+        out.status[r] = LDP_REF_OK;
+        out.n_samples[r] = M;
+        if (out.uniforms_used) out.uniforms_used[r] = 0;
+        if (out.rounds) out.rounds[r] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// no_filter, fast variant (M <= 16384): same result as ldp_topm_generic_kernel, one CTA per view, everything after
+// the selection in shared memory.
+//   1. 3-pass radix select (11 + 11 + 10 bits) of the M-th largest key: coalesced reads, one shared atomic per
+//      distinct bin and warp (__match_any_sync: certainties saturated at the cap would otherwise serialise on one bin),
+//      the crossing bin found by a block-wide suffix scan;
+//   2. if more pixels tie at that key than are needed, the ones with the lowest indices win (np.argsort is unstable in
+//      the reference; ours is "ascending index"): the index of the last one taken is found by the same radix select
+//      over the pixel index of the tied pixels;
+//   3. unordered gather of the M keys into shared memory (warp-aggregated counter), bitonic sort there, write out.
+// ---------------------------------------------------------------------------------------------
+constexpr int KT_BINS = 2048;
+constexpr int KT_UNROLL = 4;
+__device__ __forceinline__ void topm_hist_add(int* hist, bool take, int bin) {
+    // one atomic for the whole warp when every lane hits the same bin (certainties saturated at the cap: the common
+    // heavy-contention case); plain shared atomics otherwise (__match_any_sync costs a loop over the distinct values)
+    const int v = take ? bin : -1;
+    const int v0 = __shfl_sync(0xffffffffu, v, 0);
+    if (__all_sync(0xffffffffu, v == v0)) {
+        if (take && (threadIdx.x & 31) == 0) atomicAdd(&hist[bin], 32);
+    } else if (take) {
+        atomicAdd(&hist[bin], 1);
+    }
+}
+// Finds, scanning the bins from the top (DESC) or from the bottom, the bin in which the running count reaches `rem`;
+// returns the bin and leaves in *rem_out how many are still needed inside it.  All threads get the result.
+template <bool DESC>
+__device__ __forceinline__ int topm_crossing_bin(const int* hist, int nbins, int rem, int* red_i, int* s_bin, int* s_rem, int* rem_out) {
+    const int tid = threadIdx.x;                         // nbins <= 2 * blockDim.x
+    const int b0 = 2 * tid, b1 = 2 * tid + 1;
+    const int i0 = DESC ? nbins - 1 - b0 : b0, i1 = DESC ? nbins - 1 - b1 : b1;
+    const int h0 = (b0 < nbins) ? hist[i0] : 0, h1 = (b1 < nbins) ? hist[i1] : 0;
+    int total;
+    const int before = block_exclusive_scan(h0 + h1, red_i, &total);
+    if (before < rem && rem <= before + h0) { *s_bin = i0; *s_rem = rem - before; }
+    else if (before + h0 < rem && rem <= before + h0 + h1) { *s_bin = i1; *s_rem = rem - before - h0; }
+    __syncthreads();
+    *rem_out = *s_rem;
+    const int b = *s_bin;
+    __syncthreads();
+    return b;
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 1)
+ldp_topm_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws,
+                const ldp_outputs out, const SampleGeom G)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);       // [n2]
+    __shared__ int hist[KT_BINS];
+    __shared__ int red_i[32];
+    __shared__ int s_bin, s_rem, s_cnt;
+    grid_dependency_sync();
+    const int r = blockIdx.x + G.ref0, tid = threadIdx.x, T = blockDim.x, N = G.N;
+    const float* __restrict__ w = ws.w + (size_t)r * ws.n_pad;
+    int32_t* __restrict__ sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
+    const int M = min(P.matches_per_ref, N);
+    if (refs[r].nn <= 0 || M <= 0) {
+        if (tid == 0) { out.status[r] = (refs[r].nn <= 0) ? LDP_REF_NO_NEIGHBOURS : LDP_REF_EMPTY; out.n_samples[r] = 0; }
+        return;
+    }
+    const int N4 = (int)(ws.n_pad / 4);                 // rows are padded to a multiple of 256 floats (padding is zero)
+#ifdef LDP_PHASE_CLOCKS
+    if (tid == 0) ws.dbgclk[(size_t)r * 32 + 0] = clock64();
+#endif
+    // ---- 1. the M-th largest key
+    uint32_t prefix = 0u, pmask = 0u;
+    int rem = M;
+    const int shifts[3] = {21, 10, 0}, widths[3] = {11, 11, 10};
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = shifts[pass], nb = 1 << widths[pass];
+        for (int i = tid; i < KT_BINS; i += T) hist[i] = 0;
+        __syncthreads();
+        for (int q0 = tid; q0 < N4; q0 += KT_UNROLL * T) {           // KT_UNROLL loads in flight per thread: one CTA streams the view
+            float4 v[KT_UNROLL];
+#pragma unroll
+            for (int u = 0; u < KT_UNROLL; ++u) {
+                const int q = q0 + u * T;
+                v[u] = (q < N4) ? __ldcg(reinterpret_cast<const float4*>(w) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < KT_UNROLL; ++u) {
+                const int q = q0 + u * T;
+                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t k = f32_order_key(e[j]);
+                    topm_hist_add(hist, (4 * q + j < N) && (k & pmask) == prefix, (int)((k >> shift) & (uint32_t)(nb - 1)));
+                }
+            }
+        }
+        __syncthreads();
+        const int b = topm_crossing_bin<true>(hist, nb, rem, red_i, &s_bin, &s_rem, &rem);
+        prefix |= (uint32_t)b << shift;
+        pmask |= (uint32_t)(nb - 1) << shift;
+    }
+    const uint32_t kth = prefix;
+    const int need_eq = rem;                             // pixels with key == kth that are taken (lowest indices first)
+#ifdef LDP_PHASE_CLOCKS
+    if (tid == 0) ws.dbgclk[(size_t)r * 32 + 1] = clock64();
+#endif
+    // ---- 2. index of the last tied pixel taken
+    uint32_t ilast = 0xFFFFFFFFu;
+    {
+        int idx_bits = 0;
+        while ((1u << idx_bits) < (uint32_t)N) ++idx_bits;
+        uint32_t ipre = 0u, imask = 0u;
+        int irem = need_eq;
+        for (int top = idx_bits; top > 0; top -= 11) {
+            const int width = min(11, top), shift = top - width, nb = 1 << width;
+            for (int i = tid; i < KT_BINS; i += T) hist[i] = 0;
+            __syncthreads();
+            for (int q0 = tid; q0 < N4; q0 += KT_UNROLL * T) {
+                float4 v[KT_UNROLL];
+#pragma unroll
+                for (int u = 0; u < KT_UNROLL; ++u) {
+                    const int q = q0 + u * T;
+                    v[u] = (q < N4) ? __ldcg(reinterpret_cast<const float4*>(w) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < KT_UNROLL; ++u) {
+                    const int q = q0 + u * T;
+                    const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t i = (uint32_t)(4 * q + j);
+                        topm_hist_add(hist, q < N4 && i < (uint32_t)N && f32_order_key(e[j]) == kth && (i & imask) == ipre, (int)((i >> shift) & (uint32_t)(nb - 1)));
+                    }
+                }
+            }
+            __syncthreads();
+            const int b = topm_crossing_bin<false>(hist, nb, irem, red_i, &s_bin, &s_rem, &irem);
+            ipre |= (uint32_t)b << shift;
+            imask |= (uint32_t)(nb - 1) << shift;
+        }
+        ilast = ipre;
+    }
+    // ---- 3. gather (any order), sort, write
+    if (tid == 0) s_cnt = 0;
+#ifdef LDP_PHASE_CLOCKS
+    if (tid == 0) ws.dbgclk[(size_t)r * 32 + 2] = clock64();
+#endif
+    int n2 = 1;
+    while (n2 < M) n2 <<= 1;
+    for (int i = M + tid; i < n2; i += T) keys[i] = 0ull;
+    __syncthreads();
+    for (int q00 = 0; q00 < N4; q00 += KT_UNROLL * T) {
+        float4 vv[KT_UNROLL];
+#pragma unroll
+        for (int u = 0; u < KT_UNROLL; ++u) {
+            const int q = q00 + u * T + tid;
+            vv[u] = (q < N4) ? __ldcg(reinterpret_cast<const float4*>(w) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < KT_UNROLL; ++u) {
+        const int q = q00 + u * T + tid;
+        const float4 v = vv[u];
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t i = (uint32_t)(4 * q + j), k = f32_order_key(e[j]);
+            const bool take = q < N4 && i < (uint32_t)N && (k > kth || (k == kth && i <= ilast));
+            const unsigned m = __ballot_sync(0xffffffffu, take);
+            if (m) {
+                int basep = 0;
+                if ((tid & 31) == 0) basep = atomicAdd(&s_cnt, __popc(m));
+                basep = __shfl_sync(0xffffffffu, basep, 0);
+                if (take) {
+                    const int pos = basep + __popc(m & ((1u << (tid & 31)) - 1u));
+                    if (pos < n2) keys[pos] = ((unsigned long long)k << 32) | (0xFFFFFFFFu - i);
+                }
+            }
+        }
+        }
+    }
+#ifdef LDP_PHASE_CLOCKS
+    if (tid == 0) ws.dbgclk[(size_t)r * 32 + 3] = clock64();
+#endif
+    __syncthreads();
+    bitonic_sort_desc(keys, n2);
+#ifdef LDP_PHASE_CLOCKS
+    if (tid == 0) ws.dbgclk[(size_t)r * 32 + 4] = clock64();
+#endif
     for (int i = tid; i < M; i += T) sel[i] = (int)(0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull));
     if (tid == 0) {
         out.status[r] = LDP_REF_OK;
