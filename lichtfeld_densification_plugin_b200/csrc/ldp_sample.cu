@@ -53,13 +53,12 @@ __device__ __forceinline__ unsigned long long cov_key(float p, int idx) {
 __device__ void bitonic_sort_desc(unsigned long long* a, int n) {
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const unsigned long long x = a[i], y = a[l];
-                    const bool desc = ((i & k) == 0);
-                    if (desc ? (x < y) : (x > y)) { a[i] = y; a[l] = x; }
-                }
+            // one compare-exchange per thread and step: pair p -> elements (i, i + j), i = p with a zero inserted at bit log2(j)
+            for (int p = threadIdx.x; p < (n >> 1); p += blockDim.x) {
+                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i + j;
+                const unsigned long long x = a[i], y = a[l];
+                const bool desc = ((i & k) == 0);
+                if (desc ? (x < y) : (x > y)) { a[i] = y; a[l] = x; }
             }
             __syncthreads();
         }
