@@ -302,9 +302,45 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
               (void)cudaFuncSetAttribute(ldp::ldp_topm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
               topm_configured = true;
           }
-          if (n2 * 8 <= K1_SMEM_BUDGET - 16 * 1024 && !getenv("LDP_TOPM_GENERIC"))     // keys sorted in shared memory
-              (void)launch_k(ldp::ldp_topm_kernel, dim3(nsubrefs), dim3(ldp::K1_THREADS), n2 * 8, st, *p, refs, plan.ws, *out, plan.geom);
-          else
+          // dynamic shared memory of a CTA: its sort buffer(s) + one tie count per 128-pixel row of its slice
+          const size_t n4 = plan.ws.n_pad / 4;
+          auto topm_smem = [&](int c) {
+              const size_t keys_cap = std::max(n2 / (size_t)c, std::min(n2, (size_t)1024));
+              const size_t per = (((n4 + c - 1) / c) + 31) & ~(size_t)31;
+              return (c > 1 ? 2 : 1) * keys_cap * 8 + (per / 32) * 4;
+          };
+          if (topm_smem(1) <= K1_SMEM_BUDGET && !getenv("LDP_TOPM_GENERIC")) {
+              // one cluster of C CTAs per view: the largest C that keeps every view's cluster in one wave (one CTA per SM)
+              int csize = 1;
+              for (int c = 8; c > 1; c >>= 1)
+                  if ((long long)nsubrefs * c <= sm_count() && (size_t)c * 1024 <= n2) { csize = c; break; }
+              static const int env_c = [] { const char* e = getenv("LDP_TOPM_CLUSTER"); return e ? atoi(e) : 0; }();
+              if ((env_c == 1 || env_c == 2 || env_c == 4 || env_c == 8) && (size_t)env_c <= n2) csize = env_c;
+              const int fc = g_force_cluster;              // test hook
+              if ((fc == 1 || fc == 2 || fc == 4 || fc == 8) && (size_t)fc <= n2) csize = fc;
+              while (csize > 1 && topm_smem(csize) > K1_SMEM_BUDGET) csize >>= 1;
+              static const int pdl = [] { const char* e = getenv("LDP_PDL"); return e ? atoi(e) : 1; }();
+              for (;;) {
+                  cudaLaunchConfig_t cfg = {};
+                  cfg.gridDim = dim3((unsigned)(nsubrefs * csize));
+                  cfg.blockDim = dim3(ldp::K1_THREADS);
+                  cfg.dynamicSmemBytes = topm_smem(csize);
+                  cfg.stream = st;
+                  cudaLaunchAttribute attr[2];
+                  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                  attr[0].val.programmaticStreamSerializationAllowed = pdl;
+                  attr[1].id = cudaLaunchAttributeClusterDimension;
+                  attr[1].val.clusterDim.x = (unsigned)csize;
+                  attr[1].val.clusterDim.y = 1;
+                  attr[1].val.clusterDim.z = 1;
+                  cfg.attrs = attr;
+                  cfg.numAttrs = csize > 1 ? 2 : 1;
+                  if (cudaLaunchKernelEx(&cfg, ldp::ldp_topm_kernel, *p, refs, plan.ws, *out, plan.geom, csize) == cudaSuccess || csize == 1) break;
+                  (void)cudaGetLastError();
+                  csize >>= 1;                             // cluster not schedulable: smaller one
+              }
+              g_last_cluster = csize;
+          } else
               (void)launch_k(ldp::ldp_topm_generic_kernel, dim3(nsubrefs), dim3(ldp::K1_THREADS), 0, st, *p, refs, plan.ws, *out, plan.geom); }
         ++g_launches;
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_topm_kernel");

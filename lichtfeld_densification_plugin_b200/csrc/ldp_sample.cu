@@ -1290,195 +1290,458 @@ ldp_topm_generic_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ ref
 }
 
 // ---------------------------------------------------------------------------------------------
-// no_filter, fast variant (M <= 16384): same result as ldp_topm_generic_kernel, one CTA per view, everything after
-// the selection in shared memory.
-//   1. 3-pass radix select (11 + 11 + 10 bits) of the M-th largest key: coalesced reads, one shared atomic per
-//      distinct bin and warp (__match_any_sync: certainties saturated at the cap would otherwise serialise on one bin),
-//      the crossing bin found by a block-wide suffix scan;
+// no_filter, fast variant (M <= 16384): same result as ldp_topm_generic_kernel.  One thread-block CLUSTER of C CTAs per
+// view (C = 1, 2, 4 or 8, chosen by the host so that the views fill the SMs): every pass over the view's pixels is
+// split between the CTAs (contiguous slices of quads), the histograms meet through distributed shared memory, and the
+// M selected keys are sorted by a bitonic network whose 64-bit keys live in the shared memory of the C CTAs.
+//   1. 3-pass radix select (11 + 11 + 10 bits) of the M-th largest key: coalesced reads; one shared atomic per 128-pixel
+//      row, per quad or per pixel depending on how many pixels share a bin (certainties saturated at the cap would
+//      otherwise serialise on one bin); every CTA sums the C histograms and finds the crossing bin by a suffix scan;
 //   2. if more pixels tie at that key than are needed, the ones with the lowest indices win (np.argsort is unstable in
 //      the reference; ours is "ascending index"): the index of the last one taken is found by the same radix select
-//      over the pixel index of the tied pixels;
-//   3. unordered gather of the M keys into shared memory (warp-aggregated counter), bitonic sort there, write out.
+//      over the pixel index of the tied pixels (skipped when every tied pixel is taken);
+//   3. unordered gather of the M keys (one counter in CTA 0, one atomic per warp, keys stored straight into the owning
+//      CTA's slice), bitonic sort (two butterfly stages per shared-memory pass; the stages whose partner lives in
+//      another CTA read it over DSMEM into a second buffer), write out.
 // ---------------------------------------------------------------------------------------------
 constexpr int KT_BINS = 2048;
 constexpr int KT_UNROLL = 4;
-__device__ __forceinline__ void topm_hist_add(int* hist, bool take, int bin) {
-    // one atomic for the whole warp when every lane hits the same bin (certainties saturated at the cap: the common
-    // heavy-contention case); plain shared atomics otherwise (__match_any_sync costs a loop over the distinct values)
-    const int v = take ? bin : -1;
-    const int v0 = __shfl_sync(0xffffffffu, v, 0);
-    if (__all_sync(0xffffffffu, v == v0)) {
-        if (take && (threadIdx.x & 31) == 0) atomicAdd(&hist[bin], 32);
-    } else if (take) {
-        atomicAdd(&hist[bin], 1);
+// bins of the four pixels of a thread's quad (-1: not counted)
+__device__ __forceinline__ void topm_hist_add4(int* hist, int b0, int b1, int b2, int b3) {
+    const bool uni = (b0 == b1) && (b1 == b2) && (b2 == b3);
+    const int v0 = __shfl_sync(0xffffffffu, b0, 0);
+    if (__all_sync(0xffffffffu, uni && b0 == v0)) {                 // the warp's whole 128-pixel row in one bin (or in none)
+        if (v0 >= 0 && (threadIdx.x & 31) == 0) atomicAdd(&hist[v0], 128);
+    } else if (uni) {
+        if (b0 >= 0) atomicAdd(&hist[b0], 4);
+    } else {
+        if (b0 >= 0) atomicAdd(&hist[b0], 1);
+        if (b1 >= 0) atomicAdd(&hist[b1], 1);
+        if (b2 >= 0) atomicAdd(&hist[b2], 1);
+        if (b3 >= 0) atomicAdd(&hist[b3], 1);
     }
 }
-// Finds, scanning the bins from the top (DESC) or from the bottom, the bin in which the running count reaches `rem`;
-// returns the bin and leaves in *rem_out how many are still needed inside it.  All threads get the result.
+// Same, for passes in which a warp's 128 pixels fall into very few distinct bins (the most significant key digit of
+// certainties in [0, 1]; digits of the pixel index): one ballot count and one atomic per distinct bin instead of up to
+// 32 atomics colliding on one address; whatever is left after 8 bins takes the plain atomics.
+__device__ __forceinline__ void topm_hist_add4_few(int* hist, int b0, int b1, int b2, int b3) {
+    const int lane = threadIdx.x & 31;
+    for (int round = 0; ; ++round) {
+        const int mine = b0 >= 0 ? b0 : (b1 >= 0 ? b1 : (b2 >= 0 ? b2 : b3));
+        const unsigned pend = __ballot_sync(0xffffffffu, mine >= 0);
+        if (!pend) break;
+        if (round == 8) {
+            if (b0 >= 0) atomicAdd(&hist[b0], 1);
+            if (b1 >= 0) atomicAdd(&hist[b1], 1);
+            if (b2 >= 0) atomicAdd(&hist[b2], 1);
+            if (b3 >= 0) atomicAdd(&hist[b3], 1);
+            break;
+        }
+        const int piv = __shfl_sync(0xffffffffu, mine, __ffs(pend) - 1);
+        const int c = __popc(__ballot_sync(0xffffffffu, b0 == piv)) + __popc(__ballot_sync(0xffffffffu, b1 == piv)) +
+                      __popc(__ballot_sync(0xffffffffu, b2 == piv)) + __popc(__ballot_sync(0xffffffffu, b3 == piv));
+        if (lane == 0) atomicAdd(&hist[piv], c);
+        b0 = (b0 == piv) ? -1 : b0; b1 = (b1 == piv) ? -1 : b1; b2 = (b2 == piv) ? -1 : b2; b3 = (b3 == piv) ? -1 : b3;
+    }
+}
+// Waits for the C local histograms of the pass, sums them, and finds - scanning the bins from the top (DESC) or from the
+// bottom - the bin in which the running count reaches `rem`; returns the bin, how many are still needed inside it
+// (*rem_out) and how many it holds (*binc_out).  Every thread of every CTA gets the same result.
 template <bool DESC>
-__device__ __forceinline__ int topm_crossing_bin(const int* hist, int nbins, int rem, int* red_i, int* s_bin, int* s_rem, int* rem_out) {
-    const int tid = threadIdx.x;                         // nbins <= 2 * blockDim.x
+__device__ __forceinline__ int topm_crossing_bin(cooperative_groups::cluster_group& cl, int C, int* hist, int nbins, int rem,
+                                                 int* red_i, int* s3, int* rem_out, int* binc_out) {
+    if (C > 1) cl.sync(); else __syncthreads();
+    const int tid = threadIdx.x;                         // nbins is even and <= 2 * blockDim.x
     const int b0 = 2 * tid, b1 = 2 * tid + 1;
     const int i0 = DESC ? nbins - 1 - b0 : b0, i1 = DESC ? nbins - 1 - b1 : b1;
-    const int h0 = (b0 < nbins) ? hist[i0] : 0, h1 = (b1 < nbins) ? hist[i1] : 0;
+    int h0 = 0, h1 = 0;
+    if (b1 < nbins) {
+        if (C > 1) {
+            for (int c = 0; c < C; ++c) { const int* rh = cl.map_shared_rank(hist, c); h0 += rh[i0]; h1 += rh[i1]; }
+        } else { h0 = hist[i0]; h1 = hist[i1]; }
+    }
     int total;
     const int before = block_exclusive_scan(h0 + h1, red_i, &total);
-    if (before < rem && rem <= before + h0) { *s_bin = i0; *s_rem = rem - before; }
-    else if (before + h0 < rem && rem <= before + h0 + h1) { *s_bin = i1; *s_rem = rem - before - h0; }
+    if (before < rem && rem <= before + h0) { s3[0] = i0; s3[1] = rem - before; s3[2] = h0; }
+    else if (before + h0 < rem && rem <= before + h0 + h1) { s3[0] = i1; s3[1] = rem - before - h0; s3[2] = h1; }
     __syncthreads();
-    *rem_out = *s_rem;
-    const int b = *s_bin;
+    *rem_out = s3[1];
+    *binc_out = s3[2];
+    const int b = s3[0];
     __syncthreads();
     return b;
+}
+__device__ __forceinline__ void topm_cx(unsigned long long& x, unsigned long long& y, bool desc) {
+    const bool sw = desc ? (x < y) : (x > y);
+    const unsigned long long t = x;
+    x = sw ? y : x;
+    y = sw ? t : y;
+}
+
+// Stages jstart, jstart / 2, .., 1 (jstart <= 64) of merge k on a warp's 128-key block: x[m] is key e = lane + 32 m of
+// the block, g0 the global position of key e = lane.
+__device__ __forceinline__ void topm_tail(unsigned long long (&x)[4], int g0, int lane, int k, int jstart) {
+#pragma unroll
+    for (int j = 64; j >= 32; j >>= 1) {
+        if (j > jstart) continue;
+        const int mb = j >> 5;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            if ((m & mb) == 0) topm_cx(x[m], x[m | mb], ((g0 + 32 * m) & k) == 0);
+    }
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        if (j > jstart) continue;
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const unsigned long long y = __shfl_xor_sync(0xffffffffu, x[m], j);
+            const bool desc = ((g0 + 32 * m) & k) == 0;
+            const bool take_max = (desc == lower);
+            x[m] = ((x[m] > y) == take_max) ? x[m] : y;
+        }
+    }
+}
+
+// rows[rho] = number of pixels of row rho (32 consecutive quads = 128 pixels of the CTA's slice) whose key is `key`
+__device__ __forceinline__ void topm_count_rows(const float* __restrict__ w, int q_lo, int q_hi, int N, uint32_t key, int* rows) {
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+    for (int qb = q_lo; qb < q_hi; qb += KT_UNROLL * T) {
+        float4 v[KT_UNROLL];
+#pragma unroll
+        for (int u = 0; u < KT_UNROLL; ++u) {
+            const int q = qb + u * T + tid;
+            v[u] = (q < q_hi) ? __ldcg(reinterpret_cast<const float4*>(w) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < KT_UNROLL; ++u) {
+            const int qw = qb + u * T + (tid & ~31);                 // the row's first quad: warp-uniform
+            if (qw >= q_hi) break;
+            const int q = qw + lane;
+            const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c += (4 * q + j < N && f32_order_key(e[j]) == key) ? 1 : 0;
+            const int tot = __popc(__ballot_sync(0xffffffffu, c & 1)) + 2 * __popc(__ballot_sync(0xffffffffu, c & 2)) +
+                            4 * __popc(__ballot_sync(0xffffffffu, c & 4));
+            if (lane == 0) rows[(qw - q_lo) >> 5] = tot;
+        }
+    }
+    __syncthreads();
+}
+// rows[] -> exclusive prefix sums in place; returns the CTA's total
+__device__ __forceinline__ int topm_rows_prefix(int* rows, int nrows, int* red_i) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int per_t = (nrows + T - 1) / T, r0 = min(tid * per_t, nrows), r1 = min(r0 + per_t, nrows);
+    int s = 0;
+    for (int i = r0; i < r1; ++i) s += rows[i];
+    int total;
+    int ex = block_exclusive_scan(s, red_i, &total);
+    for (int i = r0; i < r1; ++i) { const int c = rows[i]; rows[i] = ex; ex += c; }
+    __syncthreads();
+    return total;
 }
 
 __global__ void __launch_bounds__(K1_THREADS, 1)
 ldp_topm_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws,
-                const ldp_outputs out, const SampleGeom G)
+                const ldp_outputs out, const SampleGeom G, const int C)
 {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);       // [n2]
-    __shared__ int hist[KT_BINS];
+    __shared__ int hist2[2][KT_BINS];
     __shared__ int red_i[32];
-    __shared__ int s_bin, s_rem, s_cnt;
+    __shared__ int s3[3];
+    __shared__ int s_cnt, s_tot;
     grid_dependency_sync();
-    const int r = blockIdx.x + G.ref0, tid = threadIdx.x, T = blockDim.x, N = G.N;
+    const int rank = (C > 1) ? (int)cl.block_rank() : 0;
+    const int r = (int)(blockIdx.x / (unsigned)C) + G.ref0, tid = threadIdx.x, T = blockDim.x, N = G.N, lane = tid & 31;
     const float* __restrict__ w = ws.w + (size_t)r * ws.n_pad;
     int32_t* __restrict__ sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
     const int M = min(P.matches_per_ref, N);
-    if (refs[r].nn <= 0 || M <= 0) {
-        if (tid == 0) { out.status[r] = (refs[r].nn <= 0) ? LDP_REF_NO_NEIGHBOURS : LDP_REF_EMPTY; out.n_samples[r] = 0; }
+    if (refs[r].nn <= 0 || M <= 0) {                    // the same for every CTA of the cluster
+        if (tid == 0 && rank == 0) { out.status[r] = (refs[r].nn <= 0) ? LDP_REF_NO_NEIGHBOURS : LDP_REF_EMPTY; out.n_samples[r] = 0; }
         return;
     }
+    int n2 = 1;
+    while (n2 < M) n2 <<= 1;
+    const int keys_cap = max(n2 / C, min(n2, 1024));    // keys per sort buffer (same formula on the host)
+    unsigned long long* cur = reinterpret_cast<unsigned long long*>(smem_raw);        // [keys_cap]
+    unsigned long long* nxt = cur + keys_cap;                                         // [keys_cap], only when C > 1
+    int* rows = reinterpret_cast<int*>(cur + (C > 1 ? 2 : 1) * (size_t)keys_cap);     // [nrows] tie counts per 128-pixel row
     const int N4 = (int)(ws.n_pad / 4);                 // rows are padded to a multiple of 256 floats (padding is zero)
+    const int per = (((N4 + C - 1) / C) + 31) & ~31;    // quads per CTA: whole warps
+    const int q_lo = min(rank * per, N4), q_hi = min(q_lo + per, N4);
+    const int nrows = (q_hi - q_lo) >> 5;
+    if (tid == 0) s_cnt = 0;
 #ifdef LDP_PHASE_CLOCKS
-    if (tid == 0) ws.dbgclk[(size_t)r * 32 + 0] = clock64();
+    if (tid == 0 && rank == 0) ws.dbgclk[(size_t)r * 32 + 0] = clock64();
 #endif
-    // ---- 1. the M-th largest key
-    uint32_t prefix = 0u, pmask = 0u;
-    int rem = M;
-    const int shifts[3] = {21, 10, 0}, widths[3] = {11, 11, 10};
-    for (int pass = 0; pass < 3; ++pass) {
-        const int shift = shifts[pass], nb = 1 << widths[pass];
-        for (int i = tid; i < KT_BINS; i += T) hist[i] = 0;
-        __syncthreads();
-        for (int q0 = tid; q0 < N4; q0 += KT_UNROLL * T) {           // KT_UNROLL loads in flight per thread: one CTA streams the view
-            float4 v[KT_UNROLL];
-#pragma unroll
-            for (int u = 0; u < KT_UNROLL; ++u) {
-                const int q = q0 + u * T;
-                v[u] = (q < N4) ? __ldcg(reinterpret_cast<const float4*>(w) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < KT_UNROLL; ++u) {
-                const int q = q0 + u * T;
-                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t k = f32_order_key(e[j]);
-                    topm_hist_add(hist, (4 * q + j < N) && (k & pmask) == prefix, (int)((k >> shift) & (uint32_t)(nb - 1)));
-                }
-            }
-        }
-        __syncthreads();
-        const int b = topm_crossing_bin<true>(hist, nb, rem, red_i, &s_bin, &s_rem, &rem);
-        prefix |= (uint32_t)b << shift;
-        pmask |= (uint32_t)(nb - 1) << shift;
-    }
-    const uint32_t kth = prefix;
-    const int need_eq = rem;                             // pixels with key == kth that are taken (lowest indices first)
-#ifdef LDP_PHASE_CLOCKS
-    if (tid == 0) ws.dbgclk[(size_t)r * 32 + 1] = clock64();
-#endif
-    // ---- 2. index of the last tied pixel taken
-    uint32_t ilast = 0xFFFFFFFFu;
+    // ---- 0. certainties saturate at the cap (w = min(certainty, cap)): if at least M pixels sit there, the M-th largest
+    // key is the cap itself and nothing is strictly greater - no selection and no sort, only the ordered emission of 3b.
+    const uint32_t capkey = f32_order_key(P.sample_cap);
+    uint32_t kth = capkey;
+    int need_eq = M;                                     // pixels with key == kth that are taken (lowest indices first)
+    int before_eq = 0;                                   // tied pixels in the slices of the lower-ranked CTAs
+    int pc = 0;                                          // pass counter; pass p counts into hist2[p & 1]
+    topm_count_rows(w, q_lo, q_hi, N, capkey, rows);
     {
-        int idx_bits = 0;
-        while ((1u << idx_bits) < (uint32_t)N) ++idx_bits;
-        uint32_t ipre = 0u, imask = 0u;
-        int irem = need_eq;
-        for (int top = idx_bits; top > 0; top -= 11) {
-            const int width = min(11, top), shift = top - width, nb = 1 << width;
+        const int mine = topm_rows_prefix(rows, nrows, red_i);
+        int all = mine;
+        if (C > 1) {
+            if (tid == 0) s_tot = mine;
+            cl.sync();
+            all = 0;
+            for (int c = 0; c < C; ++c) { const int t = *cl.map_shared_rank(&s_tot, c); all += t; before_eq += (c < rank) ? t : 0; }
+        }
+        if (all < M) need_eq = -1;                       // not enough: find the M-th largest key
+    }
+    if (need_eq < 0) {
+        // ---- 1. the M-th largest key
+        uint32_t prefix = 0u, pmask = 0u;
+        int rem = M, binc = 0;
+        const int shifts[3] = {21, 10, 0}, widths[3] = {11, 11, 10};
+        for (int pass = 0; pass < 3; ++pass, ++pc) {
+            const int shift = shifts[pass], nb = 1 << widths[pass];
+            int* hist = hist2[pc & 1];                  // its readers of pass pc - 2 are past the barrier of pass pc - 1
             for (int i = tid; i < KT_BINS; i += T) hist[i] = 0;
             __syncthreads();
-            for (int q0 = tid; q0 < N4; q0 += KT_UNROLL * T) {
+            int ncap = 0;
+            for (int qb = q_lo; qb < q_hi; qb += KT_UNROLL * T) {        // KT_UNROLL loads in flight per thread
                 float4 v[KT_UNROLL];
 #pragma unroll
                 for (int u = 0; u < KT_UNROLL; ++u) {
-                    const int q = q0 + u * T;
-                    v[u] = (q < N4) ? __ldcg(reinterpret_cast<const float4*>(w) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int q = qb + u * T + tid;
+                    v[u] = (q < q_hi) ? __ldcg(reinterpret_cast<const float4*>(w) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int u = 0; u < KT_UNROLL; ++u) {
-                    const int q = q0 + u * T;
+                    const int q = qb + u * T + tid;
+                    if (qb + u * T + (tid & ~31) >= q_hi) break;         // warp-uniform: the row lies beyond the slice
                     const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                    int b[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint32_t i = (uint32_t)(4 * q + j);
-                        topm_hist_add(hist, q < N4 && i < (uint32_t)N && f32_order_key(e[j]) == kth && (i & imask) == ipre, (int)((i >> shift) & (uint32_t)(nb - 1)));
+                        const uint32_t k = f32_order_key(e[j]);
+                        const bool in = (4 * q + j < N) && (k & pmask) == prefix;
+                        ncap += (in && k == capkey) ? 1 : 0;               // saturated certainties: counted in a register
+                        b[j] = (in && k != capkey) ? (int)((k >> shift) & (uint32_t)(nb - 1)) : -1;
+                    }
+                    if (pass == 0) topm_hist_add4_few(hist, b[0], b[1], b[2], b[3]);
+                    else topm_hist_add4(hist, b[0], b[1], b[2], b[3]);
+                }
+            }
+            ncap = warp_sum(ncap);
+            if (lane == 0 && ncap > 0) atomicAdd(&hist[(capkey >> shift) & (uint32_t)(nb - 1)], ncap);
+            const int bsel = topm_crossing_bin<true>(cl, C, hist, nb, rem, red_i, s3, &rem, &binc);
+            prefix |= (uint32_t)bsel << shift;
+            pmask |= (uint32_t)(nb - 1) << shift;
+        }
+        kth = prefix;
+        need_eq = rem;
+#ifdef LDP_PHASE_CLOCKS
+        if (tid == 0 && rank == 0) ws.dbgclk[(size_t)r * 32 + 1] = clock64();
+#endif
+        // ---- 2. where the pixels tied at that key lie (they are emitted in pixel order, the first need_eq of them)
+        topm_count_rows(w, q_lo, q_hi, N, kth, rows);
+        const int mine = topm_rows_prefix(rows, nrows, red_i);
+        before_eq = 0;
+        if (C > 1) {
+            if (tid == 0) s_tot = mine;                  // its readers of step 0 are past the barriers of step 1
+            cl.sync();
+            for (int c = 0; c < rank; ++c) before_eq += *cl.map_shared_rank(&s_tot, c);
+        }
+    }
+#ifdef LDP_PHASE_CLOCKS
+    else if (tid == 0 && rank == 0) ws.dbgclk[(size_t)r * 32 + 1] = clock64();
+    if (tid == 0 && rank == 0) ws.dbgclk[(size_t)r * 32 + 2] = clock64();
+#endif
+    // ---- 3. the n_gt keys above kth are sorted; they go (any order) into the sort buffers: the CTAs share them when
+    // there are enough keys, otherwise CTA 0 sorts alone
+    const int n_gt = M - need_eq;
+    int n2s = 1;
+    while (n2s < n_gt) n2s <<= 1;
+    const int Cs = (n2s >= 128 * C) ? C : 1;
+    const int L = n2s / Cs, gbase = (Cs > 1 ? rank : 0) * L;
+    int logL = 0;
+    while ((1 << logL) < L) ++logL;
+    const bool sorter = n_gt > 0 && (Cs > 1 || rank == 0);
+    if (sorter) for (int i = tid; i < L; i += T) if (gbase + i >= n_gt) cur[i] = 0ull;      // padding sorts last
+    int pos = 0;
+    if (n_gt > 0) {                                      // 3a. slots for this thread's keys: one reservation per warp
+        int cnt = 0;
+        for (int qb = q_lo; qb < q_hi; qb += KT_UNROLL * T) {
+            float4 v[KT_UNROLL];
+#pragma unroll
+            for (int u = 0; u < KT_UNROLL; ++u) {
+                const int q = qb + u * T + tid;
+                v[u] = (q < q_hi) ? __ldcg(reinterpret_cast<const float4*>(w) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < KT_UNROLL; ++u) {
+                const int q = qb + u * T + tid;
+                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    cnt += (q < q_hi && 4 * q + j < N && f32_order_key(e[j]) > kth) ? 1 : 0;
+            }
+        }
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        int base = 0;
+        if (lane == 31 && inc > 0) base = atomicAdd((C > 1) ? cl.map_shared_rank(&s_cnt, 0) : &s_cnt, inc);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        pos = base + inc - cnt;
+    }
+    // 3b. one sweep: keys above kth into their slots; tied pixels straight to their final place, in pixel order:
+    // rows[] holds how many tied pixels precede each 128-pixel row, ballots count the ones before a lane inside the row
+    for (int qb = q_lo; qb < q_hi; qb += KT_UNROLL * T) {
+        float4 v[KT_UNROLL];
+#pragma unroll
+        for (int u = 0; u < KT_UNROLL; ++u) {
+            const int q = qb + u * T + tid;
+            v[u] = (q < q_hi) ? __ldcg(reinterpret_cast<const float4*>(w) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < KT_UNROLL; ++u) {
+            const int qw = qb + u * T + (tid & ~31);
+            if (qw >= q_hi) break;
+            const int q = qw + lane;
+            const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            uint32_t kk[4];
+            bool eq[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                kk[j] = f32_order_key(e[j]);
+                eq[j] = (4 * q + j < N) && kk[j] == kth;
+            }
+            const unsigned m0 = __ballot_sync(0xffffffffu, eq[0]), m1 = __ballot_sync(0xffffffffu, eq[1]),
+                           m2 = __ballot_sync(0xffffffffu, eq[2]), m3 = __ballot_sync(0xffffffffu, eq[3]);
+            if (m0 | m1 | m2 | m3) {
+                const unsigned lt = (1u << lane) - 1u;
+                int ord = before_eq + rows[(qw - q_lo) >> 5] + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (eq[j]) { if (ord < need_eq) sel[n_gt + ord] = 4 * q + j; ++ord; }
+            }
+            if (n_gt > 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if ((4 * q + j < N) && kk[j] > kth) {
+                        if (pos < n_gt) {
+                            const int owner = pos >> logL, li = pos & (L - 1);
+                            unsigned long long* dst = (Cs > 1) ? cl.map_shared_rank(cur, owner) : ((C > 1) ? cl.map_shared_rank(cur, 0) : cur);
+                            dst[li] = ((unsigned long long)kk[j] << 32) | (0xFFFFFFFFu - (uint32_t)(4 * q + j));
+                        }
+                        ++pos;
                     }
                 }
             }
-            __syncthreads();
-            const int b = topm_crossing_bin<false>(hist, nb, irem, red_i, &s_bin, &s_rem, &irem);
-            ipre |= (uint32_t)b << shift;
-            imask |= (uint32_t)(nb - 1) << shift;
-        }
-        ilast = ipre;
-    }
-    // ---- 3. gather (any order), sort, write
-    if (tid == 0) s_cnt = 0;
-#ifdef LDP_PHASE_CLOCKS
-    if (tid == 0) ws.dbgclk[(size_t)r * 32 + 2] = clock64();
-#endif
-    int n2 = 1;
-    while (n2 < M) n2 <<= 1;
-    for (int i = M + tid; i < n2; i += T) keys[i] = 0ull;
-    __syncthreads();
-    for (int q00 = 0; q00 < N4; q00 += KT_UNROLL * T) {
-        float4 vv[KT_UNROLL];
-#pragma unroll
-        for (int u = 0; u < KT_UNROLL; ++u) {
-            const int q = q00 + u * T + tid;
-            vv[u] = (q < N4) ? __ldcg(reinterpret_cast<const float4*>(w) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < KT_UNROLL; ++u) {
-        const int q = q00 + u * T + tid;
-        const float4 v = vv[u];
-        const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t i = (uint32_t)(4 * q + j), k = f32_order_key(e[j]);
-            const bool take = q < N4 && i < (uint32_t)N && (k > kth || (k == kth && i <= ilast));
-            const unsigned m = __ballot_sync(0xffffffffu, take);
-            if (m) {
-                int basep = 0;
-                if ((tid & 31) == 0) basep = atomicAdd(&s_cnt, __popc(m));
-                basep = __shfl_sync(0xffffffffu, basep, 0);
-                if (take) {
-                    const int pos = basep + __popc(m & ((1u << (tid & 31)) - 1u));
-                    if (pos < n2) keys[pos] = ((unsigned long long)k << 32) | (0xFFFFFFFFu - i);
-                }
-            }
-        }
         }
     }
 #ifdef LDP_PHASE_CLOCKS
-    if (tid == 0) ws.dbgclk[(size_t)r * 32 + 3] = clock64();
+    if (tid == 0 && rank == 0) ws.dbgclk[(size_t)r * 32 + 3] = clock64();
 #endif
-    __syncthreads();
-    bitonic_sort_desc(keys, n2);
-#ifdef LDP_PHASE_CLOCKS
-    if (tid == 0) ws.dbgclk[(size_t)r * 32 + 4] = clock64();
-#endif
-    for (int i = tid; i < M; i += T) sel[i] = (int)(0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull));
-    if (tid == 0) {
+    if (tid == 0 && rank == 0) {
         out.status[r] = LDP_REF_OK;
         out.n_samples[r] = M;
         if (out.uniforms_used) out.uniforms_used[r] = 0;
         if (out.rounds) out.rounds[r] = 0;
     }
+#ifdef LDP_PHASE_CLOCKS
+    if (tid == 0 && rank == 0 && n_gt == 0) ws.dbgclk[(size_t)r * 32 + 4] = clock64();
+#endif
+    if (n_gt == 0) return;                               // every CTA of the cluster takes this exit together
+    if (C > 1) cl.sync(); else __syncthreads();          // every key is in its slice
+    if (!sorter) return;                                 // CTA 0 sorts alone: nobody touches the others' memory any more
+    // ---- bitonic sort, descending, over the Cs slices (element g = rank * L + i).  Stages by partner distance j:
+    //   j >= L        partner in another CTA: read over DSMEM into the second buffer;
+    //   128 <= j < L  two stages (j, j / 2) per shared-memory pass, 4 keys per thread, conflict-free;
+    //   j <= 64       ("tail") a warp holds a 128-key block, key e = lane + 32 m in register m of lane: stages 64 and 32
+    //                 are between registers, 16..1 between lanes (shuffles) - 7 stages in one conflict-free pass, and
+    //                 the whole of the merges k <= 128 in the first one.
+    const bool tails = L >= 128;
+    if (tails) {
+        for (int blk = (tid >> 5) * 128; blk < L; blk += (T >> 5) * 128) {
+            unsigned long long x[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) x[m] = cur[blk + lane + 32 * m];
+            const int g0 = gbase + blk + lane;
+            for (int k = 2; k <= 128 && k <= n2s; k <<= 1) topm_tail(x, g0, lane, k, k >> 1);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) cur[blk + lane + 32 * m] = x[m];
+        }
+        __syncthreads();
+    }
+    for (int k = tails ? 256 : 2; k <= n2s; k <<= 1) {
+        int j = k >> 1;
+        if (j >= L) {                                    // partner in another CTA (Cs > 1 only)
+            cl.sync();                                   // the partner's local stages of the previous merge are done
+            for (; j >= L; j >>= 1) {
+                const unsigned long long* rem_buf = cl.map_shared_rank(cur, rank ^ (j >> logL));
+                for (int i = tid; i < L; i += T) {
+                    const int g = gbase + i;
+                    const unsigned long long x = cur[i], y = rem_buf[i];
+                    const bool desc = (g & k) == 0, lower = (g & j) == 0;
+                    const unsigned long long mx = x > y ? x : y, mn = x > y ? y : x;
+                    nxt[i] = (desc == lower) ? mx : mn;
+                }
+                cl.sync();                               // everybody has read `cur`; `nxt` is complete
+                unsigned long long* t = cur; cur = nxt; nxt = t;
+            }
+        }
+        const int jstop = tails ? 128 : 2;               // stages below jstop are the tail's (or the single j == 1 stage)
+        while (j >= jstop) {
+            if (j >= 2 * jstop || !tails) {              // stages j and j / 2 in one shared-memory pass: 4 keys per thread
+                const int h = j >> 1;
+                for (int p = tid; p < (L >> 2); p += T) {
+                    const int i0 = ((p & ~(h - 1)) << 2) | (p & (h - 1));
+                    unsigned long long a = cur[i0], b = cur[i0 + h], c = cur[i0 + j], d = cur[i0 + j + h];
+                    const bool desc = ((gbase + i0) & k) == 0;
+                    topm_cx(a, c, desc); topm_cx(b, d, desc);
+                    topm_cx(a, b, desc); topm_cx(c, d, desc);
+                    cur[i0] = a; cur[i0 + h] = b; cur[i0 + j] = c; cur[i0 + j + h] = d;
+                }
+                j >>= 2;
+            } else {                                     // j == 128 alone
+                for (int p = tid; p < (L >> 1); p += T) {
+                    const int i0 = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                    unsigned long long a = cur[i0], b = cur[i0 + j];
+                    topm_cx(a, b, ((gbase + i0) & k) == 0);
+                    cur[i0] = a; cur[i0 + j] = b;
+                }
+                j >>= 1;
+            }
+            __syncthreads();
+        }
+        if (tails) {
+            for (int blk = (tid >> 5) * 128; blk < L; blk += (T >> 5) * 128) {
+                unsigned long long x[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) x[m] = cur[blk + lane + 32 * m];
+                topm_tail(x, gbase + blk + lane, lane, k, 64);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) cur[blk + lane + 32 * m] = x[m];
+            }
+            __syncthreads();
+        } else if (j == 1) {
+            for (int p = tid; p < (L >> 1); p += T) {
+                const int i0 = 2 * p;
+                unsigned long long a = cur[i0], b = cur[i0 + 1];
+                topm_cx(a, b, ((gbase + i0) & k) == 0);
+                cur[i0] = a; cur[i0 + 1] = b;
+            }
+            __syncthreads();
+        }
+    }
+#ifdef LDP_PHASE_CLOCKS
+    if (tid == 0 && rank == 0) ws.dbgclk[(size_t)r * 32 + 4] = clock64();
+#endif
+    for (int i = tid; i < L; i += T) if (gbase + i < n_gt) sel[gbase + i] = (int)(0xFFFFFFFFu - (uint32_t)(cur[i] & 0xFFFFFFFFull));
 }
 
 }  // namespace ldp

@@ -342,3 +342,66 @@ def test_more_views_than_sms(engine):
                    weight_sums=[res.taps["s"]])
     rep = G.compare_ref(g1, 0, res, c, scene)
     assert rep.ok(), rep
+
+
+def test_no_filter_cluster_sizes_and_tie_rule(engine, fast_scene):
+    """no_filter top-M: one cluster of 1/2/4/8 CTAs per view gives the same, fully determined order
+    (descending capped certainty, ascending pixel index among equal certainties = a stable argsort)."""
+    scene, inputs = fast_scene
+    lib = engine.lib
+    used = []
+    try:
+        for M in (10000, 777, 3):
+            c = dict(M=M, no_filter=True, wm=scene.w_match, hm=scene.h_match)
+            for cs in (1, 2, 4, 8):
+                assert lib.ldp_debug_set_cluster(cs) == 0
+                g = G.run_gpu(engine, scene, inputs[:3], G.path_cfg(c))
+                used.append(lib.ldp_debug_last_cluster())
+                for r in range(3):
+                    capped = np.minimum(inputs[r]["cert"].max(dim=0).values.numpy().reshape(-1), np.float32(0.9))
+                    want = np.argsort(-capped, kind="stable")[:M]
+                    assert np.array_equal(g.sel_idx[r], want), (M, cs, r)
+    finally:
+        lib.ldp_debug_set_cluster(0)
+    print("top-M cluster sizes launched:", used)
+    assert max(used) >= 2
+
+
+def test_no_filter_ties_cut_inside_a_plateau(engine):
+    """More pixels tie at the M-th certainty than are needed: the lowest pixel indices win, whichever CTA holds them."""
+    H = W = 96
+    rs = np.random.RandomState(5)
+
+    def cert_fn(cert):
+        v = rs.choice(np.array([0.3, 0.5, 0.7, 0.95, 0.99], np.float32), size=cert.shape).astype(np.float32)
+        return torch.from_numpy(v)
+    for M in (50, 4000, 9000):
+        scene, inp, c = _mk_single((H, W), 2, cert_fn, M)
+        c = dict(c, no_filter=True)
+        capped = np.minimum(inp["cert"].max(dim=0).values.numpy().reshape(-1), np.float32(0.9))
+        want = np.argsort(-capped, kind="stable")[:min(M, H * W)]
+        try:
+            for cs in (1, 2, 4, 8):
+                engine.lib.ldp_debug_set_cluster(cs)
+                g = G.run_gpu(engine, scene, [inp], G.path_cfg(c))
+                assert np.array_equal(g.sel_idx[0], want), (M, cs)
+        finally:
+            engine.lib.ldp_debug_set_cluster(0)
+
+
+def test_no_filter_distinct_certainties_cluster_sizes(engine):
+    """Tie-free certainties (nothing saturated): the generic path - radix select, gather, cluster-wide bitonic sort."""
+    from lichtfeld_densification_plugin_b200 import synth
+    scene = synth.make_scene(40, "fast", ref_fraction=0.2, nn=4)
+    inputs = [synth.synth_ref_inputs(scene, rp, cert_family="T", seed=6) for rp in range(2)]
+    try:
+        for M in (10000, 16384, 130, 1):
+            c = dict(M=M, no_filter=True, wm=scene.w_match, hm=scene.h_match)
+            for cs in (1, 2, 4, 8):
+                engine.lib.ldp_debug_set_cluster(cs)
+                g = G.run_gpu(engine, scene, inputs, G.path_cfg(c))
+                for r in range(2):
+                    capped = np.minimum(inputs[r]["cert"].max(dim=0).values.numpy().reshape(-1), np.float32(0.9))
+                    assert np.array_equal(g.sel_idx[r], np.argsort(-capped, kind="stable")[:M]), (M, cs, r)
+    finally:
+        engine.lib.ldp_debug_set_cluster(0)
