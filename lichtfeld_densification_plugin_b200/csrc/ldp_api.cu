@@ -259,6 +259,10 @@ void launch_stream(const ldp_params* p, const ldp_ref_desc* refs, Plan& plan, cu
           case 2: (void)launch_k(ldp::ldp_stream_kernel<2, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
           case 3: (void)launch_k(ldp::ldp_stream_kernel<3, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
           case 4: (void)launch_k(ldp::ldp_stream_kernel<4, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 5: (void)launch_k(ldp::ldp_stream_kernel<5, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 6: (void)launch_k(ldp::ldp_stream_kernel<6, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 7: (void)launch_k(ldp::ldp_stream_kernel<7, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 8: (void)launch_k(ldp::ldp_stream_kernel<8, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
           default: (void)launch_k(ldp::ldp_stream_kernel<0, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
       }
 }

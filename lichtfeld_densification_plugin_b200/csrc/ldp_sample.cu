@@ -91,11 +91,12 @@ __device__ __forceinline__ void quad_border_weights(float wv[4], int px, int x, 
 #ifndef KS_MIN_BLOCKS
 #define KS_MIN_BLOCKS 5
 #endif
-// NNMAX 1..4: plane pointers held in registers, loop fully unrolled; 0: any nn (pointers in shared memory).
+// NNMAX 1..4: plane pointers held in registers, loop fully unrolled, two quads per step; 5..8: one quad per step, NNMAX loads
+// in flight; 0: any nn (pointers in shared memory).
 // PRO: the planes are raw matcher outputs and the reference's post-processing (core/pipeline.py:405-430) is applied
 //      to every value as it is read (ldp_device.cuh:prologue_cert).
 template <int NNMAX, bool PRO>
-__global__ void __launch_bounds__(KS_THREADS, PRO ? 3 : KS_MIN_BLOCKS)      // PRO holds the warp rows too: more registers
+__global__ void __launch_bounds__(KS_THREADS, PRO ? 3 : (NNMAX > 4 ? 4 : KS_MIN_BLOCKS))      // PRO holds the warp rows too: more registers
 ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const SampleGeom G)
 {
     grid_dependency_sync();
@@ -182,7 +183,21 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
                 c.z = __fmul_rn(c.z, warped_mask(mb, g2)); c.w = __fmul_rn(c.w, warped_mask(mb, g3));
             }
         };
-        if (G.vec && NNMAX > 0) {
+        if (G.vec && NNMAX > 4 && !PRO) {
+            // 5..8 neighbours: one quad per step, all NNMAX 128-bit loads issued before any of them is consumed
+            for (int it = 0; it < KS_SPAN / (KS_THREADS * 4); ++it) {
+                const int px = base + (it * KS_THREADS + tid) * 4;
+                if (px >= N) break;
+                float4 a[NNMAX > 4 ? NNMAX : 1];
+#pragma unroll
+                for (int k = 0; k < NNMAX; ++k) a[k] = ld_stream4(s_cert[min(k, nn - 1)] + px);    // clamp: a duplicate load, not a branch
+                float wv[4] = {a[0].x, a[0].y, a[0].z, a[0].w};
+                int bi[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int k = 1; k < NNMAX; ++k) if (k < nn) take(a[k], k, wv, bi);
+                finish_quad(px, wv, bi);
+            }
+        } else if (G.vec && NNMAX > 0 && NNMAX <= 4) {
             // two quads per step: all 2*NNMAX 128-bit loads are issued before any of them is consumed
             constexpr int STEP = KS_THREADS * 4;
             for (int it = 0; it < KS_SPAN / STEP; it += 2) {
