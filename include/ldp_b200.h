@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LDP_ABI_VERSION 8
+#define LDP_ABI_VERSION 9
 #define LDP_MAX_NN 16          /* neighbours per reference view (the panel clamps to 10) */
 #define LDP_MAX_BINS 4096      /* coverage tiles per map: ceil(W/tile)*ceil(H/tile), tile = max(1, W/24) */
 
@@ -172,6 +172,33 @@ int ldp_triangulate_samples(const ldp_params* params, const ldp_ref_desc* refs,
  * ignored (the step is always applied); certainty_floor, H, W, n_refs are read. */
 int ldp_postprocess_certainty(const ldp_params* params, const ldp_ref_desc* refs, float* out,
                               size_t ref_stride, size_t plane_stride, void* stream);
+
+/* ---- output contract on the device ---------------------------------
+ * The reference converts colours with to_uint8_rgb (core/image_utils.py:24-26: clip(round(rgb * 255), 0, 255), half to
+ * even) and writes one struct.pack per point (core/writers.py:15-46).  These build the same bytes where the points are:
+ * the caller copies the records to the host and writes header + records (byte-identical files).
+ * xyz, rgb: [n,3] f32 device; err: [n] f32 device or NULL (zeros, like errors=None); n_dev: optional DEVICE pointer
+ * to the actual point count (then n is an upper bound that sizes the launch and min(n, *n_dev) records are written:
+ * no host synchronisation between the path and the packing); records_out: device, n * 15 / n * 43 bytes.
+ *   ldp_pack_ply_records       per vertex  <fff xyz, BBB rgb                           core/writers.py:44-45
+ *   ldp_pack_points3d_records  per point   <Q first_id + i, <ddd xyz, <BBB rgb, <d err  core/writers.py:23-26
+ *                              (first_id = 1 for a whole file; a rank writing rows [a, b) passes a + 1)
+ *   ldp_rgb_to_uint8           to_uint8_rgb on n_values floats                         core/image_utils.py:24-26
+ *   ldp_gather_points          xyz[sel], rgb[sel], err[sel] for the int64 indices the point cap drew on the host
+ *                              (densify.py:110-120, np.random.default_rng(seed).choice(n, m, replace=False));
+ *                              negative indices wrap like numpy's; an index outside [-n, n) sets *bad_index_flag
+ *                              (device int32, may be NULL) and leaves the row unwritten. */
+int ldp_pack_ply_records(const float* xyz, const float* rgb, int64_t n, const int64_t* n_dev, uint8_t* records_out, void* stream);
+int ldp_pack_points3d_records(const float* xyz, const float* rgb, const float* err, int64_t n, const int64_t* n_dev,
+                              uint64_t first_id, uint8_t* records_out, void* stream);
+int ldp_rgb_to_uint8(const float* rgb, int64_t n_values, uint8_t* out, void* stream);
+int ldp_gather_points(const float* xyz, const float* rgb, const float* err, const int64_t* sel, int64_t m, int64_t n,
+                      float* xyz_out, float* rgb_out, float* err_out, int32_t* bad_index_flag, void* stream);
+
+/* out[i,:] = src[sel[i],:] for rows of row_floats f32 values: the debug preview's subsample of the kept matches [K,4]
+ * and their normalised certainties [K] (core/pipeline.py:573-582; indices from default_rng(pair seed).choice on the host). */
+int ldp_gather_rows(const float* src, int32_t row_floats, const int64_t* sel, int64_t m, int64_t n, float* out,
+                    int32_t* bad_index_flag, void* stream);
 
 /* Kernel launches enqueued by the last ldp_* call on this thread (for bench.py's gpu_launches). */
 int ldp_last_launch_count(void);

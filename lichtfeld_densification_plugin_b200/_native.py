@@ -13,7 +13,7 @@ import numpy as np
 
 from . import build as _build
 
-LDP_ABI_VERSION = 8
+LDP_ABI_VERSION = 9
 LDP_MAX_NN = 16
 LDP_MAX_BINS = 4096
 
@@ -96,6 +96,7 @@ EXPORTS = [
     "ldp_abi_version", "ldp_last_error_string", "ldp_sel_capacity", "ldp_workspace_bytes",
     "ldp_densify_refs", "ldp_sample_refs", "ldp_triangulate_samples", "ldp_postprocess_certainty", "ldp_last_launch_count",
     "ldp_struct_size", "ldp_profile_enable", "ldp_profile_read", "ldp_profile_name", "ldp_debug_set_cluster", "ldp_debug_last_cluster", "ldp_debug_set_subbatches", "ldp_debug_read_clocks", "ldp_debug_launch_stream",
+    "ldp_pack_ply_records", "ldp_pack_points3d_records", "ldp_rgb_to_uint8", "ldp_gather_points", "ldp_gather_rows",
 ]
 
 _lock = threading.Lock()
@@ -158,6 +159,18 @@ def load(build_if_missing: bool = False):
         lib.ldp_debug_launch_stream.argtypes = [C.POINTER(LdpParams), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
         lib.ldp_postprocess_certainty.restype = C.c_int
         lib.ldp_postprocess_certainty.argtypes = [C.POINTER(LdpParams), C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+        lib.ldp_pack_ply_records.restype = C.c_int
+        lib.ldp_pack_ply_records.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ldp_pack_points3d_records.restype = C.c_int
+        lib.ldp_pack_points3d_records.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_uint64,
+                                                  C.c_void_p, C.c_void_p]
+        lib.ldp_rgb_to_uint8.restype = C.c_int
+        lib.ldp_rgb_to_uint8.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        lib.ldp_gather_points.restype = C.c_int
+        lib.ldp_gather_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ldp_gather_rows.restype = C.c_int
+        lib.ldp_gather_rows.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         if lib.ldp_abi_version() != LDP_ABI_VERSION:
             raise NativeLibraryError(f"ABI version mismatch: library {lib.ldp_abi_version()}, binding {LDP_ABI_VERSION}")
         for which, struct in enumerate((LdpParams, LdpRefDesc, LdpOutputs)):

@@ -9,6 +9,7 @@
 
 #include "ldp_sample.cu"
 #include "ldp_geometry.cu"
+#include "ldp_output.cu"
 
 namespace {
 
@@ -601,6 +602,82 @@ int ldp_debug_set_cluster(int csize) {
 }
 
 const char* ldp_profile_name(int i) { return (i >= 0 && i < g_prof_n) ? g_prof_name[i] : ""; }
+
+// ---- output contract on the device (ldp_output.cu)
+static int pack_records(int format, const float* xyz, const float* rgb, const float* err, int64_t n, const int64_t* n_dev,
+                        uint64_t first_id, uint8_t* out, void* stream) {
+    if (n < 0) return fail(LDP_ERR_INVALID, "negative point count");
+    g_launches = 0;
+    if (n == 0) return LDP_OK;
+    if (!xyz || !rgb || !out) return fail(LDP_ERR_INVALID, "null pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((n + ldp::KO_THREADS - 1) / ldp::KO_THREADS);
+    const int aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    if (format == 0)
+        (void)launch_k(ldp::ldp_records_kernel<0>, dim3(grid), dim3(ldp::KO_THREADS), 0, st, xyz, rgb, err, (long long)n,
+                       reinterpret_cast<const long long*>(n_dev), (unsigned long long)first_id, out, aligned);
+    else
+        (void)launch_k(ldp::ldp_records_kernel<1>, dim3(grid), dim3(ldp::KO_THREADS), 0, st, xyz, rgb, err, (long long)n,
+                       reinterpret_cast<const long long*>(n_dev), (unsigned long long)first_id, out, aligned);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ldp_records_kernel");
+    return LDP_OK;
+}
+
+int ldp_pack_ply_records(const float* xyz, const float* rgb, int64_t n, const int64_t* n_dev, uint8_t* records_out, void* stream) {
+    return pack_records(0, xyz, rgb, nullptr, n, n_dev, 0, records_out, stream);
+}
+
+int ldp_pack_points3d_records(const float* xyz, const float* rgb, const float* err, int64_t n, const int64_t* n_dev,
+                              uint64_t first_id, uint8_t* records_out, void* stream) {
+    return pack_records(1, xyz, rgb, err, n, n_dev, first_id, records_out, stream);
+}
+
+int ldp_rgb_to_uint8(const float* rgb, int64_t n_values, uint8_t* out, void* stream) {
+    if (n_values < 0) return fail(LDP_ERR_INVALID, "negative count");
+    g_launches = 0;
+    if (n_values == 0) return LDP_OK;
+    if (!rgb || !out) return fail(LDP_ERR_INVALID, "null pointer");
+    const long long blocks = (n_values + ldp::KO_THREADS - 1) / ldp::KO_THREADS;
+    const unsigned grid = (unsigned)std::min<long long>(blocks, (long long)sm_count() * 16);
+    (void)launch_k(ldp::ldp_rgb_u8_kernel, dim3(grid), dim3(ldp::KO_THREADS), 0, reinterpret_cast<cudaStream_t>(stream), rgb, (long long)n_values, out);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ldp_rgb_u8_kernel");
+    return LDP_OK;
+}
+
+int ldp_gather_points(const float* xyz, const float* rgb, const float* err, const int64_t* sel, int64_t m, int64_t n,
+                      float* xyz_out, float* rgb_out, float* err_out, int32_t* bad_index_flag, void* stream) {
+    if (m < 0 || n < 0) return fail(LDP_ERR_INVALID, "negative count");
+    g_launches = 0;
+    if (m == 0) return LDP_OK;
+    if (!xyz || !rgb || !sel || !xyz_out || !rgb_out) return fail(LDP_ERR_INVALID, "null pointer");
+    const unsigned grid = (unsigned)((m + ldp::KO_THREADS - 1) / ldp::KO_THREADS);
+    (void)launch_k(ldp::ldp_gather_rows_kernel, dim3(grid), dim3(ldp::KO_THREADS), 0, reinterpret_cast<cudaStream_t>(stream), xyz, rgb, err,
+                   reinterpret_cast<const long long*>(sel), (long long)m, (long long)n, xyz_out, rgb_out, err_out, (int*)bad_index_flag);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ldp_gather_rows_kernel");
+    return LDP_OK;
+}
+
+int ldp_gather_rows(const float* src, int32_t row_floats, const int64_t* sel, int64_t m, int64_t n, float* out,
+                    int32_t* bad_index_flag, void* stream) {
+    if (m < 0 || n < 0 || row_floats <= 0) return fail(LDP_ERR_INVALID, "bad row gather shape");
+    g_launches = 0;
+    if (m == 0) return LDP_OK;
+    if (!src || !sel || !out) return fail(LDP_ERR_INVALID, "null pointer");
+    const long long blocks = (m * row_floats + ldp::KO_THREADS - 1) / ldp::KO_THREADS;
+    const unsigned grid = (unsigned)std::min<long long>(blocks, (long long)sm_count() * 16);
+    (void)launch_k(ldp::ldp_gather_f32_rows_kernel, dim3(grid), dim3(ldp::KO_THREADS), 0, reinterpret_cast<cudaStream_t>(stream), src,
+                   (int)row_floats, reinterpret_cast<const long long*>(sel), (long long)m, (long long)n, out, (int*)bad_index_flag);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ldp_gather_f32_rows_kernel");
+    return LDP_OK;
+}
 
 int64_t ldp_struct_size(int which) {
     switch (which) {

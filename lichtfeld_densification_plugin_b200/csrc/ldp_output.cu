@@ -1,0 +1,118 @@
+// Output contract on the device: the reference turns the path's float colours into
+// uint8 (core/image_utils.py:24-26) and writes one struct.pack per point (core/writers.py:15-46).  Here the records
+// are built where the points are - 15 bytes per vertex for the binary PLY, 43 bytes per point for COLMAP's
+// points3D.bin - so a caller copies n * 15 bytes to the host and appends them to the header with one write; and the
+// rows a point cap keeps (densify.py:110-120; the indices stay numpy's default_rng(seed).choice on the host) are
+// gathered on the device.  Included by ldp_api.cu (unity build).
+#include "ldp_device.cuh"
+
+namespace ldp {
+
+constexpr int KO_THREADS = 256;       // points per CTA: 256 * 15 and 256 * 43 bytes are multiples of 16
+
+// np.clip(np.round(c * 255.0), 0, 255).astype(np.uint8) on a float32 colour: the product stays float32 (NEP 50),
+// np.round is half-to-even
+__device__ __forceinline__ uint8_t to_u8(float c) {
+    const float v = rintf(__fmul_rn(c, 255.0f));
+    return (uint8_t)fminf(fmaxf(v, 0.0f), 255.0f);
+}
+__device__ __forceinline__ void put_bytes(uint8_t* dst, const void* src, int n) {
+    const uint8_t* s = reinterpret_cast<const uint8_t*>(src);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i < n) dst[i] = s[i];
+}
+// copies `bytes` staged bytes to out (any alignment of the total; the CTA's first byte is 16-byte aligned when the
+// buffer is)
+__device__ __forceinline__ void flush_records(const uint8_t* smem, uint8_t* out, int bytes, bool aligned) {
+    const int tid = threadIdx.x;
+    if (aligned) {
+        const int nw = bytes >> 2;
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(smem);
+        uint32_t* o = reinterpret_cast<uint32_t*>(out);
+        for (int i = tid; i < nw; i += KO_THREADS) o[i] = s[i];
+        for (int i = (nw << 2) + tid; i < bytes; i += KO_THREADS) out[i] = smem[i];
+    } else {
+        for (int i = tid; i < bytes; i += KO_THREADS) out[i] = smem[i];
+    }
+}
+
+// FORMAT 0: PLY vertex  <fff BBB            (core/writers.py:44-45)
+// FORMAT 1: points3D    <Q id <ddd <BBB <d  (core/writers.py:23-26; ids are first_id + i, first_id = 1 for a whole file)
+template <int FORMAT>
+__global__ void __launch_bounds__(KO_THREADS)
+ldp_records_kernel(const float* __restrict__ xyz, const float* __restrict__ rgb, const float* __restrict__ err,
+                   long long n_max, const long long* __restrict__ n_dev, unsigned long long first_id,
+                   uint8_t* __restrict__ out, int aligned)
+{
+    constexpr int REC = (FORMAT == 0) ? 15 : 43;
+    __shared__ __align__(16) uint8_t rec[KO_THREADS * REC];
+    grid_dependency_sync();
+    long long n = n_max;
+    if (n_dev) { const long long nd = *n_dev; n = nd < n ? nd : n; }
+    const long long p0 = (long long)blockIdx.x * KO_THREADS;
+    if (p0 >= n) return;
+    const int cnt = (int)((n - p0 < KO_THREADS) ? (n - p0) : KO_THREADS), tid = threadIdx.x;
+    if (tid < cnt) {
+        const long long i = p0 + tid;
+        const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        const uint8_t r8 = to_u8(rgb[3 * i]), g8 = to_u8(rgb[3 * i + 1]), b8 = to_u8(rgb[3 * i + 2]);
+        uint8_t* d = rec + tid * REC;
+        if (FORMAT == 0) {
+            put_bytes(d, &x, 4); put_bytes(d + 4, &y, 4); put_bytes(d + 8, &z, 4);
+            d[12] = r8; d[13] = g8; d[14] = b8;
+        } else {
+            const unsigned long long id = first_id + (unsigned long long)i;
+            const double xd = (double)x, yd = (double)y, zd = (double)z, ed = err ? (double)err[i] : 0.0;
+            put_bytes(d, &id, 8); put_bytes(d + 8, &xd, 8); put_bytes(d + 16, &yd, 8); put_bytes(d + 24, &zd, 8);
+            d[32] = r8; d[33] = g8; d[34] = b8;
+            put_bytes(d + 35, &ed, 8);
+        }
+    }
+    __syncthreads();
+    flush_records(rec, out + p0 * REC, cnt * REC, aligned != 0);
+}
+
+__global__ void __launch_bounds__(KO_THREADS)
+ldp_rgb_u8_kernel(const float* __restrict__ rgb, long long n_values, uint8_t* __restrict__ out)
+{
+    grid_dependency_sync();
+    for (long long i = (long long)blockIdx.x * KO_THREADS + threadIdx.x; i < n_values; i += (long long)gridDim.x * KO_THREADS)
+        out[i] = to_u8(rgb[i]);
+}
+
+// rows sel[0..m) of (xyz, rgb, err): xyz[sel], rgb[sel], err[sel] (densify.py:118-119)
+__global__ void __launch_bounds__(KO_THREADS)
+ldp_gather_rows_kernel(const float* __restrict__ xyz, const float* __restrict__ rgb, const float* __restrict__ err,
+                       const long long* __restrict__ sel, long long m, long long n,
+                       float* __restrict__ xyz_out, float* __restrict__ rgb_out, float* __restrict__ err_out, int* __restrict__ bad)
+{
+    grid_dependency_sync();
+    const long long i = (long long)blockIdx.x * KO_THREADS + threadIdx.x;
+    if (i >= m) return;
+    long long s = sel[i];
+    if (s < 0) s += n;                                   // numpy's negative indices
+    if (s < 0 || s >= n) { if (bad) atomicExch(bad, 1); return; }
+    xyz_out[3 * i] = xyz[3 * s]; xyz_out[3 * i + 1] = xyz[3 * s + 1]; xyz_out[3 * i + 2] = xyz[3 * s + 2];
+    rgb_out[3 * i] = rgb[3 * s]; rgb_out[3 * i + 1] = rgb[3 * s + 1]; rgb_out[3 * i + 2] = rgb[3 * s + 2];
+    if (err && err_out) err_out[i] = err[s];
+}
+
+// out[i, :] = src[sel[i], :] for rows of `row_floats` floats (the debug preview's subsample of matches [K,4] and
+// normalised certainties [K], core/pipeline.py:577-582)
+__global__ void __launch_bounds__(KO_THREADS)
+ldp_gather_f32_rows_kernel(const float* __restrict__ src, int row_floats, const long long* __restrict__ sel, long long m, long long n,
+                           float* __restrict__ out, int* __restrict__ bad)
+{
+    grid_dependency_sync();
+    const long long total = m * row_floats;
+    for (long long e = (long long)blockIdx.x * KO_THREADS + threadIdx.x; e < total; e += (long long)gridDim.x * KO_THREADS) {
+        const long long i = e / row_floats;
+        const int c = (int)(e - i * row_floats);
+        long long s = sel[i];
+        if (s < 0) s += n;
+        if (s < 0 || s >= n) { if (bad) atomicExch(bad, 1); continue; }
+        out[e] = src[s * row_floats + c];
+    }
+}
+
+}  // namespace ldp

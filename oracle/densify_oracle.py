@@ -538,3 +538,28 @@ def points3d_bin_bytes(xyz: np.ndarray, rgb_u8: np.ndarray, errors: Optional[np.
         parts.append(struct.pack("<BBB", int(rgb_u8[i, 0]), int(rgb_u8[i, 1]), int(rgb_u8[i, 2])))
         parts.append(struct.pack("<d", float(errors[i])))
     return b"".join(parts)
+
+
+# ---------------------------------------------------------------------------------------------
+# Reducers after the path -- pinned by tests/golden/output_reducers.npz, which
+# tests/golden/make_output_golden.py froze from the live reference functions.
+# ---------------------------------------------------------------------------------------------
+def apply_point_cap(xyz: np.ndarray, rgb: np.ndarray, err: np.ndarray, max_points: int, seed: int):
+    """densify.py:110-120: a PCG64 ``default_rng(seed).choice`` without replacement, then three gathers."""
+    if max_points > 0 and xyz.shape[0] > max_points:
+        sel = np.random.default_rng(seed).choice(xyz.shape[0], size=max_points, replace=False)
+        return xyz[sel], rgb[sel], err[sel]
+    return xyz, rgb, err
+
+
+def preview_subsample(matches: np.ndarray, cert_norm: np.ndarray, ref_id: int, nbr_id: int, max_matches: int = 10000):
+    """core/pipeline.py:569-582: at most ``max_matches`` of a pair's kept matches, seeded by the pair's ids."""
+    matches = np.asarray(matches, dtype=np.float32)
+    cert_norm = np.asarray(cert_norm, dtype=np.float32)
+    if matches.shape[0] > max_matches > 0:
+        seed = ((int(ref_id) & 0xFFFF_FFFF) * 73856093) ^ ((int(nbr_id) & 0xFFFF_FFFF) * 19349663)
+        rng = np.random.default_rng(seed & 0xFFFF_FFFF)
+        sel_idx = rng.choice(matches.shape[0], size=max_matches, replace=False)
+        matches = matches[sel_idx]
+        cert_norm = cert_norm[sel_idx]
+    return matches, cert_norm

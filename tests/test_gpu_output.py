@@ -1,0 +1,137 @@
+"""GPU: the output contract and the post-path reducers on the device produce the
+reference's bytes / rows: against goldens frozen from the live reference writers, `_apply_point_cap` and
+`_build_filtered_match_preview`, and against the oracle's struct.pack restatement on random data."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import densify_oracle as O
+from tests.golden.make_output_golden import CAP_CASES, PREVIEW_CASES, cap_inputs, preview_inputs
+from tests.helpers import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def out_mod():
+    from lichtfeld_densification_plugin_b200 import output
+    return output
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_records_equal_reference_writer_golden(out_mod, tmp_path):
+    z = np.load(os.path.join(GOLDEN_DIR, "writers.npz"))
+    xyz, rgb, err = _dev(z["xyz"]), _dev(z["rgb"]), _dev(z["err"])
+    assert np.array_equal(out_mod.to_uint8_rgb(rgb).cpu().numpy(), z["rgb_u8"])
+    out_mod.write_ply(str(tmp_path / "a.ply"), xyz, rgb)
+    out_mod.write_points3D_bin(str(tmp_path / "a.bin"), xyz, rgb, err)
+    out_mod.write_points3D_bin(str(tmp_path / "b.bin"), xyz, rgb, None)
+    assert (tmp_path / "a.ply").read_bytes() == z["ply"].tobytes()
+    assert (tmp_path / "a.bin").read_bytes() == z["bin"].tobytes()
+    assert (tmp_path / "b.bin").read_bytes() == z["bin_noerr"].tobytes()
+
+
+@pytest.mark.parametrize("n", [0, 1, 255, 256, 257, 1000, 100003])
+def test_records_random_sizes_against_struct_pack(out_mod, n):
+    rs = np.random.RandomState(n + 1)
+    xyz = (rs.standard_normal((n, 3)) * 10).astype(np.float32)
+    rgb = (rs.random_sample((n, 3)) * 1.2 - 0.1).astype(np.float32)          # also below 0 and above 1: clipped
+    if n > 8:
+        rgb[:8, 0] = (np.arange(8, dtype=np.float32) + 0.5) / 255.0          # .5 cases: half to even
+    err = rs.random_sample((n,)).astype(np.float32)
+    u8 = O.to_uint8_rgb(rgb)
+    m = min(n, 3000)                                                         # the struct.pack oracle is slow: check a prefix ...
+    ply = out_mod.ply_records(_dev(xyz), _dev(rgb)).cpu().numpy().tobytes()
+    b3d = out_mod.points3d_records(_dev(xyz), _dev(rgb), _dev(err)).cpu().numpy().tobytes()
+    assert len(ply) == 15 * n and len(b3d) == 43 * n
+    ref_ply = O.ply_bytes(xyz[:m], u8[:m])
+    head = len(ref_ply) - 15 * m
+    assert ply[:15 * m] == ref_ply[head:]
+    assert b3d[:43 * m] == O.points3d_bin_bytes(xyz[:m], u8[:m], err[:m])[8:]
+    if n:                                                                    # ... and everything against the vectorised writer
+        from lichtfeld_densification_plugin_b200.core import writers as W
+        rec = np.frombuffer(ply, dtype=W._PLY_VERTEX)
+        assert np.array_equal(rec["x"], xyz[:, 0]) and np.array_equal(rec["z"], xyz[:, 2]) and np.array_equal(rec["g"], u8[:, 1])
+        rec = np.frombuffer(b3d, dtype=W._BIN_POINT)
+        assert np.array_equal(rec["id"], np.arange(1, n + 1, dtype=np.uint64)) and np.array_equal(rec["err"], err.astype(np.float64))
+        assert np.array_equal(rec["y"], xyz[:, 1].astype(np.float64)) and np.array_equal(rec["b"], u8[:, 2])
+
+
+def test_records_device_count_unaligned_buffer_and_first_id(out_mod):
+    n, k = 5000, 1777
+    rs = np.random.RandomState(3)
+    xyz, rgb = rs.standard_normal((n, 3)).astype(np.float32), rs.random_sample((n, 3)).astype(np.float32)
+    want = out_mod.ply_records(_dev(xyz[:k]), _dev(rgb[:k])).cpu().numpy()
+    buf = torch.full((n * 15 + 1,), 0xAB, dtype=torch.uint8, device="cuda")
+    n_dev = torch.tensor([k], dtype=torch.int64, device="cuda")
+    out_mod.ply_records(_dev(xyz), _dev(rgb), n_dev=n_dev, out=buf[1:])                # misaligned destination, device-side count
+    got = buf.cpu().numpy()
+    assert np.array_equal(got[1:1 + 15 * k], want) and np.all(got[1 + 15 * k:] == 0xAB) and got[0] == 0xAB
+    a = out_mod.points3d_records(_dev(xyz[100:200]), _dev(rgb[100:200]), None, first_id=101).cpu().numpy()
+    b = out_mod.points3d_records(_dev(xyz[:200]), _dev(rgb[:200]), None).cpu().numpy()
+    assert np.array_equal(a, b[100 * 43:])                                              # a rank writing rows [100, 200)
+
+
+def test_point_cap_equals_reference_golden(out_mod):
+    z = np.load(os.path.join(GOLDEN_DIR, "output_reducers.npz"))
+    for i, c in enumerate(CAP_CASES):
+        xyz, rgb, err = cap_inputs(c["n"], c["data_seed"])
+        a, b, e = out_mod.apply_point_cap(_dev(xyz), _dev(rgb), _dev(err), c["max_points"], c["seed"])
+        assert np.array_equal(a.cpu().numpy(), z[f"cap{i}_xyz"]) and np.array_equal(b.cpu().numpy(), z[f"cap{i}_rgb"])
+        assert np.array_equal(e.cpu().numpy(), z[f"cap{i}_err"])
+
+
+def test_preview_subsample_equals_reference_golden(out_mod):
+    z = np.load(os.path.join(GOLDEN_DIR, "output_reducers.npz"))
+    for i, c in enumerate(PREVIEW_CASES):
+        m, cn = preview_inputs(c["k"], c["data_seed"])
+        a, b = out_mod.subsample_preview_matches(_dev(m), _dev(cn), c["ref_id"], c["nbr_id"], c["max_matches"])
+        assert np.array_equal(a.cpu().numpy(), z[f"pv{i}_matches"]) and np.array_equal(b.cpu().numpy(), z[f"pv{i}_cert"])
+    with pytest.raises(IndexError):
+        out_mod.gather_rows(_dev(np.zeros((4, 2), np.float32)), torch.tensor([0, 4], device="cuda"))
+    assert out_mod.gather_rows(_dev(np.arange(8, dtype=np.float32).reshape(4, 2)), torch.tensor([-1], device="cuda")).tolist() == [[6.0, 7.0]]
+
+
+def test_incremental_ply_equals_rewriting_everything(out_mod, tmp_path):
+    from lichtfeld_densification_plugin_b200.core import writers as W
+    rs = np.random.RandomState(8)
+    inc = out_mod.IncrementalPly()
+    xs, cs = [], []
+    for step, n in enumerate([300, 0, 1, 4097]):
+        xyz, rgb = rs.standard_normal((n, 3)).astype(np.float32), rs.random_sample((n, 3)).astype(np.float32)
+        xs.append(xyz); cs.append(rgb)
+        inc.append(_dev(xyz), _dev(rgb))
+        inc.emit(str(tmp_path / f"i{step}.ply"))
+        W.write_ply(str(tmp_path / f"w{step}.ply"), np.concatenate(xs), W.to_uint8_rgb(np.concatenate(cs)))   # core/pipeline.py:523-526
+        assert (tmp_path / f"i{step}.ply").read_bytes() == (tmp_path / f"w{step}.ply").read_bytes()
+
+
+def test_path_outputs_to_ply_without_host_sync(out_mod):
+    """The path's packed outputs go to PLY records with the device-side point count (ref_offset[-1])."""
+    from lichtfeld_densification_plugin_b200 import synth
+    from lichtfeld_densification_plugin_b200.engine import DensifyEngine, PathConfig
+    from lichtfeld_densification_plugin_b200.core import writers as W
+    eng = DensifyEngine()
+    scene = synth.make_scene(12, "turbo", 0.25, 2)
+    b = eng.new_batch(scene.H, scene.W, scene.w_match, scene.h_match)
+    for rp in range(scene.n_refs):
+        inp = synth.synth_ref_inputs(scene, rp, device=eng.device, cert_family="R", seed=2)
+        k = len(inp["nbr_indices"])
+        b.add([inp["cert"][q] for q in range(k)], [inp["warp"][q] for q in range(k)], inp["image"], scene.cameras[inp["ref_index"]],
+              [scene.cameras[j] for j in inp["nbr_indices"]], rng_stream=rp)
+    out = eng.densify(b, PathConfig(matches_per_ref=3000))
+    cap = int(out.err.shape[0])
+    rec = out_mod.ply_records(out.xyz, out.rgb, n=cap, n_dev=out.ref_offset[-1:])
+    K = out.total_points()
+    assert 0 < K < cap
+    xyz, rgb = out.xyz[:K].cpu().numpy(), out.rgb[:K].cpu().numpy()
+    want = np.empty(K, dtype=W._PLY_VERTEX)
+    want["x"], want["y"], want["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    u8 = W.to_uint8_rgb(rgb)
+    want["r"], want["g"], want["b"] = u8[:, 0], u8[:, 1], u8[:, 2]
+    assert rec[:15 * K].cpu().numpy().tobytes() == want.tobytes()
