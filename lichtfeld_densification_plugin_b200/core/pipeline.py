@@ -17,6 +17,7 @@ raise (no CPU fallback).
 """
 from __future__ import annotations
 
+import os
 import time
 from dataclasses import dataclass, field
 from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
@@ -98,6 +99,7 @@ class _TriangulatedReference:
     err: np.ndarray
     debug_matches_by_nbr: Dict[int, np.ndarray]
     debug_cert_by_nbr: Dict[int, np.ndarray]
+    ply_records: Optional[np.ndarray] = None      # extra: this view's 15-byte PLY vertex records, packed on the device
 
 
 def _build_camera_lookup(camera_records: Sequence[CameraRecord]) -> _CameraLookup:
@@ -178,12 +180,17 @@ def _split_reference(out: DensifyOutputs, host: dict, r: int, nbr_uids: List[int
                 dbg_m[nbr_uids[g]] = host["dbg_matches"][pos:pos + cnt].copy()
                 dbg_c[nbr_uids[g]] = host["dbg_cert"][pos:pos + cnt].copy()
             pos += cnt
+    rec = host["ply"][15 * a:15 * b].copy() if "ply" in host else None
     return _TriangulatedReference(xyz=host["xyz"][a:b].copy(), rgb=host["rgb"][a:b].copy(), err=host["err"][a:b].copy(),
-                                  debug_matches_by_nbr=dbg_m, debug_cert_by_nbr=dbg_c)
+                                  debug_matches_by_nbr=dbg_m, debug_cert_by_nbr=dbg_c, ply_records=rec)
 
 
-def _download(out: DensifyOutputs, collect_debug: bool) -> dict:
+def _download(out: DensifyOutputs, collect_debug: bool, ply_records: bool = False) -> dict:
     """One synchronising device->host read of everything the host needs."""
+    rec = None
+    if ply_records and out.n_refs:      # packed before the first host read: the point count is taken on the device
+        from .. import output as _output
+        rec = _output.ply_records(out.xyz, out.rgb, n=int(out.err.shape[0]), n_dev=out.ref_offset[-1:])
     meta = {"ref_offset": out.ref_offset.cpu().numpy()}
     total = int(meta["ref_offset"][-1]) if out.n_refs else 0
     meta["status"] = out.status.cpu().numpy()
@@ -196,6 +203,8 @@ def _download(out: DensifyOutputs, collect_debug: bool) -> dict:
     if collect_debug:
         meta["dbg_matches"] = out.dbg_matches[:total].cpu().numpy()
         meta["dbg_cert"] = out.dbg_cert[:total].cpu().numpy()
+    if rec is not None:
+        meta["ply"] = rec[:15 * total].cpu().numpy()
     return meta
 
 
@@ -210,12 +219,13 @@ def triangulate_refs(matched_refs: Sequence[_MatchedReference], tri_ctx: _Triang
                      collect_debug_matches: bool = False, *, rng_streams: Optional[Sequence[int]] = None,
                      uniforms: Optional[np.ndarray] = None,
                      weight_sums: Optional[Sequence[float]] = None,
-                     errors: Optional[list] = None) -> List[Optional[_TriangulatedReference]]:
+                     errors: Optional[list] = None, ply_records: bool = False) -> List[Optional[_TriangulatedReference]]:
     """Batched ``_triangulate_ref``: every view of ``matched_refs`` in one launch sequence.
 
     RNG: ``uniforms`` (f64 [n, U], explicit parity stream per view) or Philox keyed by
     (config.seed, rng_streams[i]).  Views the reference would skip (None return / exception) come back as
     None; the exception a per-view call would raise is appended to ``errors`` as (index, exc).
+    ``ply_records``: also return every view's PLY vertex records (built on the device, 15 bytes per point).
     """
     n = len(matched_refs)
     if n == 0:
@@ -254,7 +264,7 @@ def triangulate_refs(matched_refs: Sequence[_MatchedReference], tri_ctx: _Triang
     if uniforms is not None:
         u_dev = torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float64)).to(dev)
     out = eng.densify(batch, pcfg, uniforms=u_dev, collect_debug=collect_debug_matches)
-    host = _download(out, collect_debug_matches)
+    host = _download(out, collect_debug_matches, ply_records)
     results: List[Optional[_TriangulatedReference]] = []
     for r in range(n):
         try:
@@ -341,6 +351,40 @@ def _collect_reference_matches(packed: _PackedReferenceBatch, matcher, config: D
 MatchSource = Callable[[int], Optional[_MatchedReference]]
 
 
+def _prepare_intermediate_ply_base(output_path: str, viz_interval: int,
+                                   on_sequential_viz: Optional[Callable[[str], None]]) -> Optional[str]:
+    """reference core/pipeline.py:296-306"""
+    if not on_sequential_viz or viz_interval <= 0:
+        return None
+    output_dir = os.path.dirname(output_path)
+    base_no_ext = os.path.splitext(os.path.basename(output_path))[0]
+    os.makedirs(output_dir, exist_ok=True)
+    return os.path.join(output_dir, f"{base_no_ext}_intermediate")
+
+
+def _ply_records_host(xyz: np.ndarray, rgb: np.ndarray) -> np.ndarray:
+    from . import writers as _w
+    rec = np.empty(int(xyz.shape[0]), dtype=_w._PLY_VERTEX)
+    rec["x"], rec["y"], rec["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    u8 = _w.to_uint8_rgb(rgb)
+    rec["r"], rec["g"], rec["b"] = u8[:, 0], u8[:, 1], u8[:, 2]
+    return rec.view(np.uint8)
+
+
+def _emit_intermediate_ply(path: str, n_points: int, parts: List[np.ndarray],
+                           on_sequential_viz: Callable[[str], None]) -> None:
+    """reference core/pipeline.py:523-530: same file bytes as write_ply(path, concat(xyz), to_uint8_rgb(concat(rgb)))."""
+    from . import writers as _w
+    try:
+        with open(path, "wb") as f:
+            f.write(_w.ply_header(n_points))
+            for p in parts:
+                p.tofile(f)
+        on_sequential_viz(path)
+    except Exception:                                          # the reference logs and carries on (:531-532)
+        pass
+
+
 def _is_cancelled(cancel_requested: Optional[Callable[[], bool]]) -> bool:
     if cancel_requested is None:
         return False
@@ -369,7 +413,7 @@ def run_dense_pipeline(
     ``ref_local -> _MatchedReference | None`` standing in for pack loader + RoMa matcher (out of scope here;
     an integrator wraps ``RomaMatcher.match_grids_batch`` and may keep its outputs on the GPU).
     Views are processed ``config.refs_per_launch`` at a time (0 = all in one launch)."""
-    del on_sequential_viz, debug_state, nn_table
+    del debug_state, nn_table
     if match_source is None:
         raise RuntimeError("run_dense_pipeline needs a match_source: the RoMa matcher is not part of this package")
     from .config import ROMA_PRESETS
@@ -385,6 +429,12 @@ def run_dense_pipeline(
     step = int(getattr(config, "refs_per_launch", 0)) or max(1, len(refs_local))
     parts_xyz, parts_rgb, parts_err = [], [], []
     pairs = 0
+    # live update (core/pipeline.py:296-306,508-532): every viz_interval views the reference re-concatenates and re-packs
+    # all points so far; here every view's PLY records are packed once, on the device, and an emission is a bulk write
+    viz_interval = int(getattr(config, "viz_interval", 0))
+    ply_base = _prepare_intermediate_ply_base(config.output_path, viz_interval, on_sequential_viz)
+    ply_parts: List[np.ndarray] = []
+    ply_points = 0
     total = len(refs_local)
     for lo in range(0, total, step):
         if _is_cancelled(cancel_requested):
@@ -402,7 +452,8 @@ def run_dense_pipeline(
                 except Exception:
                     outs.append(None)
         else:
-            outs = triangulate_refs([m for _, m in matched], tri_ctx, rng_streams=[int(r) for r, _ in matched])
+            outs = triangulate_refs([m for _, m in matched], tri_ctx, rng_streams=[int(r) for r, _ in matched],
+                                    ply_records=ply_base is not None)
         for tri in outs:
             if tri is None:
                 continue
@@ -410,6 +461,14 @@ def run_dense_pipeline(
             parts_rgb.append(tri.rgb)
             parts_err.append(tri.err)
             pairs += 1
+            if ply_base is not None:
+                rec = tri.ply_records
+                if rec is None:                               # numpy-RNG mode goes through _triangulate_ref: pack on the host
+                    rec = _ply_records_host(tri.xyz, tri.rgb)
+                ply_parts.append(rec)
+                ply_points += int(tri.xyz.shape[0])
+                if pairs % viz_interval == 0:
+                    _emit_intermediate_ply(f"{ply_base}_{pairs}.ply", ply_points, ply_parts, on_sequential_viz)
         if progress_callback:
             done = min(total, lo + step)
             progress_callback(10.0 + 80.0 * done / max(1, total), f"Matching {done}/{total} references")

@@ -135,3 +135,48 @@ def test_path_outputs_to_ply_without_host_sync(out_mod):
     u8 = W.to_uint8_rgb(rgb)
     want["r"], want["g"], want["b"] = u8[:, 0], u8[:, 1], u8[:, 2]
     assert rec[:15 * K].cpu().numpy().tobytes() == want.tobytes()
+
+
+def test_run_dense_pipeline_live_updates_write_the_reference_files(tmp_path):
+    """run_dense_pipeline (reference signature) with a synthetic match source: the PipelineResult equals the per-view
+    calls, and every intermediate PLY (core/pipeline.py:508-532: one every viz_interval views) holds exactly the bytes
+    write_ply(concat(xyz so far), to_uint8_rgb(concat(rgb so far))) would - from records packed once on the device."""
+    from lichtfeld_densification_plugin_b200 import synth
+    from lichtfeld_densification_plugin_b200.core import pipeline as P
+    from lichtfeld_densification_plugin_b200.core import writers as W
+    from lichtfeld_densification_plugin_b200.core.config import DensePipelineConfig
+    scene = synth.make_scene(24, "turbo", ref_fraction=0.3, nn=3)
+    cams = scene.cameras
+
+    def match_source(rp):
+        inp = synth.synth_ref_inputs(scene, rp, cert_family="R", seed=4)
+        ri, nb = inp["ref_index"], inp["nbr_indices"]
+        packed = P._PackedReferenceBatch(ref_id=cams[ri].uid, ref_path="", imA_np=inp["image"].numpy(), maskA_np=None,
+                                         wA_cam=cams[ri].width, hA_cam=cams[ri].height, nn_ids=[cams[j].uid for j in nb],
+                                         nn_masks=[None] * len(nb), nn_arrays=[None] * len(nb))
+        return P._MatchedReference(packed=packed, warp_list_cpu=[inp["warp"][k] for k in range(len(nb))],
+                                   cert_list_cpu=[inp["cert"][k] for k in range(len(nb))], pair_index_by_nbr={}, image_by_nbr={})
+    refs = list(range(scene.n_refs))
+    assert len(refs) >= 6
+    for per_launch in (0, 4):
+        out_dir = tmp_path / f"run{per_launch}"
+        cfg = DensePipelineConfig(output_path=str(out_dir / "dense.ply"), matches_per_ref=2000, viz_interval=2, refs_per_launch=per_launch)
+        emitted = []
+        res = P.run_dense_pipeline(cams, refs, None, cfg, on_sequential_viz=emitted.append, match_source=match_source,
+                                   w_match=scene.w_match, h_match=scene.h_match)
+        assert res.pairs_processed == len(refs) and res.xyz.shape[0] > 1000
+        assert [os.path.basename(p) for p in emitted] == [f"dense_intermediate_{k}.ply" for k in range(2, len(refs) + 1, 2)]
+        # per-view sizes: the same views one at a time (Philox streams are keyed by the view, not by the launch)
+        ctx = P._TriangulationContext(cameras=P._build_camera_lookup(cams), config=cfg, matcher_sample_cap=0.9,
+                                      w_match=scene.w_match, h_match=scene.h_match)
+        sizes = [P.triangulate_refs([match_source(r)], ctx, rng_streams=[r])[0].xyz.shape[0] for r in refs]
+        assert sum(sizes) == res.xyz.shape[0]
+        for k, path in zip(range(2, len(refs) + 1, 2), emitted):
+            n = sum(sizes[:k])
+            W.write_ply(str(out_dir / "want.ply"), res.xyz[:n], W.to_uint8_rgb(res.rgb[:n]))
+            assert open(path, "rb").read() == (out_dir / "want.ply").read_bytes(), (per_launch, k)
+    # no callback / interval 0: nothing is written
+    cfg = DensePipelineConfig(output_path=str(tmp_path / "none" / "dense.ply"), matches_per_ref=2000, viz_interval=0)
+    P.run_dense_pipeline(cams, refs[:2], None, cfg, on_sequential_viz=emitted.append, match_source=match_source,
+                         w_match=scene.w_match, h_match=scene.h_match)
+    assert not (tmp_path / "none").exists()
