@@ -200,6 +200,21 @@ int ldp_gather_points(const float* xyz, const float* rgb, const float* err, cons
 int ldp_gather_rows(const float* src, int32_t row_floats, const int64_t* sel, int64_t m, int64_t n, float* out,
                     int32_t* bad_index_flag, void* stream);
 
+/* ---- pair generation on the device ---------------------------------------------
+ * flat_poses: [n,16] f32 device, the row-major 4x4 world-to-camera transforms (CameraRecord.flat_pose()).
+ *   ldp_select_kcenters    core/selection.py:36-54 select_cameras_kcenters: normalise the columns (mean, std + 1e-8), start
+ *                          from the row of largest norm, then k - 1 greedy farthest-point picks.  numpy's float32
+ *                          operation order is mirrored, so the picks are numpy's.  scratch: [n,16] f32 device.
+ *                          centers_sorted [k] = sorted(centers) (what the reference returns); centers_order [k] = pick order.
+ *                          1 <= k <= n <= 8192 (the reference clamps k the same way before the loop).
+ *   ldp_nearest_neighbors  core/selection.py:57-70 nearest_neighbors: for every view the k nearest other views by Euclidean
+ *                          distance of the poses, ascending (ties: lower index).  idx_out [n,k] int64.  k <= min(n - 1, 16).
+ *                          Distances are formed from differences (torch.cdist uses |x|^2 + |y|^2 - 2 x.y, ~1e-3 absolute
+ *                          error here), so views at near-equal distance may be ordered differently from torch. */
+int ldp_select_kcenters(const float* flat_poses, int32_t n, int32_t k, float* scratch, int32_t* centers_sorted,
+                        int32_t* centers_order, void* stream);
+int ldp_nearest_neighbors(const float* flat_poses, int32_t n, int32_t k, int64_t* idx_out, void* stream);
+
 /* Kernel launches enqueued by the last ldp_* call on this thread (for bench.py's gpu_launches). */
 int ldp_last_launch_count(void);
 

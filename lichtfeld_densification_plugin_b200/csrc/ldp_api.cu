@@ -10,6 +10,7 @@
 #include "ldp_sample.cu"
 #include "ldp_geometry.cu"
 #include "ldp_output.cu"
+#include "ldp_select.cu"
 
 namespace {
 
@@ -676,6 +677,36 @@ int ldp_gather_rows(const float* src, int32_t row_floats, const int64_t* sel, in
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ldp_gather_f32_rows_kernel");
+    return LDP_OK;
+}
+
+// ---- pair generation on the device (ldp_select.cu)
+int ldp_select_kcenters(const float* flat_poses, int32_t n, int32_t k, float* scratch, int32_t* centers_sorted,
+                        int32_t* centers_order, void* stream) {
+    g_launches = 0;
+    if (n <= 0 || k <= 0 || k > n) return fail(LDP_ERR_INVALID, "k-centres needs 1 <= k <= n");
+    if (n > ldp::KC_THREADS * ldp::KC_MAX_PER_THREAD) return fail(LDP_ERR_INVALID, "k-centres: more than 8192 views");
+    if (!flat_poses || !scratch || !centers_sorted || !centers_order) return fail(LDP_ERR_INVALID, "null pointer");
+    (void)launch_k(ldp::ldp_kcenters_kernel, dim3(1), dim3(ldp::KC_THREADS), 0, reinterpret_cast<cudaStream_t>(stream), flat_poses,
+                   (int)n, (int)k, scratch, centers_sorted, centers_order);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ldp_kcenters_kernel");
+    return LDP_OK;
+}
+
+int ldp_nearest_neighbors(const float* flat_poses, int32_t n, int32_t k, int64_t* idx_out, void* stream) {
+    g_launches = 0;
+    if (n < 0 || k < 0) return fail(LDP_ERR_INVALID, "negative size");
+    if (n <= 1 || k == 0) return LDP_OK;
+    if (k > n - 1 || k > ldp::KNN_MAX_K) return fail(LDP_ERR_INVALID, "nearest neighbours needs k <= min(n - 1, 16)");
+    if (!flat_poses || !idx_out) return fail(LDP_ERR_INVALID, "null pointer");
+    const unsigned grid = (unsigned)((n + 7) / 8);
+    (void)launch_k(ldp::ldp_knn_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), flat_poses, (int)n, (int)k,
+                   reinterpret_cast<long long*>(idx_out));
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ldp_knn_kernel");
     return LDP_OK;
 }
 

@@ -1670,7 +1670,10 @@ ldp_topm_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
 #ifdef LDP_PHASE_CLOCKS
     if (tid == 0 && rank == 0 && n_gt == 0) ws.dbgclk[(size_t)r * 32 + 4] = clock64();
 #endif
-    if (n_gt == 0) return;                               // every CTA of the cluster takes this exit together
+    if (n_gt == 0) {                                     // every CTA of the cluster takes this exit together ...
+        if (C > 1) cl.sync();                            // ... and none before the others have read its s_tot (DSMEM of an exited CTA is gone)
+        return;
+    }
     if (C > 1) cl.sync(); else __syncthreads();          // every key is in its slice
     if (!sorter) return;                                 // CTA 0 sorts alone: nobody touches the others' memory any more
     // ---- bitonic sort, descending, over the Cs slices (element g = rank * L + i).  Stages by partner distance j:

@@ -563,3 +563,62 @@ def preview_subsample(matches: np.ndarray, cert_norm: np.ndarray, ref_id: int, n
         matches = matches[sel_idx]
         cert_norm = cert_norm[sel_idx]
     return matches, cert_norm
+
+
+# ---------------------------------------------------------------------------------------------
+# Pair generation -- pinned by tests/golden/selection.npz (tests/golden/make_selection_golden.py
+# froze the live reference's select_cameras_kcenters / nearest_neighbors on synthetic camera sets).
+# ---------------------------------------------------------------------------------------------
+def _row_sum16_f32(a: np.ndarray) -> np.ndarray:
+    """np.add.reduce over 16 contiguous float32 values, as numpy evaluates it: 8 running sums, then a fixed tree
+    (measured: equals np.linalg.norm(.., axis=1) ** 2 bit for bit)."""
+    r = a[:, :8] + a[:, 8:16]
+    return ((r[:, 0] + r[:, 1]) + (r[:, 2] + r[:, 3])) + ((r[:, 4] + r[:, 5]) + (r[:, 6] + r[:, 7]))
+
+
+def select_cameras_kcenters(flat_poses: np.ndarray, k: int, explicit: bool = True):
+    """core/selection.py:36-54 with the float32 operation order written out (the order the CUDA kernel mirrors):
+    column mean / std accumulate row by row; row norms are the 8-accumulator pairwise sum.  Returns (sorted centres,
+    pick order).  The very first pick is an np.einsum row reduction in the reference, whose summation order is
+    build-specific; the row of largest norm is normally far from a tie."""
+    f32 = np.float32
+    X = np.asarray(flat_poses, dtype=f32)
+    n = X.shape[0]
+    k = max(1, min(int(k), n))
+    s = np.zeros(X.shape[1], f32)
+    for i in range(n):
+        s = s + X[i]
+    mu = s / f32(n)
+    d = X - mu
+    d2 = d * d
+    s2 = np.zeros(X.shape[1], f32)
+    for i in range(n):
+        s2 = s2 + d2[i]
+    sigma = np.sqrt(s2 / f32(n)) + f32(1e-8)
+    Xn = (X - mu) / sigma
+    first = int(np.argmax(_row_sum16_f32(Xn * Xn)))
+    centers = [first]
+    diff = Xn - Xn[first]
+    dist = np.sqrt(_row_sum16_f32(diff * diff))
+    dist[first] = -np.inf
+    for _ in range(1, k):
+        nxt = int(np.argmax(dist))
+        centers.append(nxt)
+        diff = Xn - Xn[nxt]
+        dist = np.minimum(dist, np.sqrt(_row_sum16_f32(diff * diff)))
+        dist[nxt] = -np.inf
+    return sorted(centers), centers
+
+
+def nearest_neighbors_exact(flat_poses: np.ndarray, k: int):
+    """core/selection.py:57-70 with distances formed from differences in float64 (what torch.cdist approximates with one
+    float32 sgemm): indices [n, k] ascending by (distance, index), and the distances."""
+    X = np.asarray(flat_poses, dtype=np.float32).astype(np.float64)
+    n = X.shape[0]
+    if n <= 1:
+        return np.empty((n, 0), dtype=np.int64), np.empty((n, 0))
+    k = max(1, min(int(k), n - 1))
+    D = np.sqrt(((X[:, None, :] - X[None, :, :]) ** 2).sum(-1))
+    np.fill_diagonal(D, np.inf)
+    idx = np.argsort(D, axis=1, kind="stable")[:, :k]
+    return idx.astype(np.int64), np.take_along_axis(D, idx, axis=1)

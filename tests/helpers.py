@@ -14,7 +14,7 @@ from oracle import densify_oracle as O
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = sorted(os.path.splitext(os.path.basename(p))[0]
-                      for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not p.endswith(("writers.npz", "output_reducers.npz")))
+                      for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not p.endswith(("writers.npz", "output_reducers.npz", "selection.npz")))
 
 
 def golden_scene(c) -> synth.SynthScene:

@@ -1,0 +1,66 @@
+"""GPU: pair generation on the device against the live reference's frozen outputs and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import densify_oracle as O
+from tests.golden.make_selection_golden import selection_cases
+from tests.helpers import GOLDEN_DIR
+from tests.test_oracle_selection import nn_equivalent
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    from lichtfeld_densification_plugin_b200.core import selection
+    return selection
+
+
+def test_kcenters_equal_reference_golden(S):
+    z = np.load(os.path.join(GOLDEN_DIR, "selection.npz"))
+    for name, (flat, kc, _) in selection_cases().items():
+        got = S.select_cameras_kcenters(flat, kc)
+        assert isinstance(got, list) and got == z[f"{name}_centers"].tolist(), name
+        _, order_dev = S.select_cameras_kcenters_device(flat, kc)
+        assert order_dev.cpu().tolist() == O.select_cameras_kcenters(flat, kc)[1], name           # same greedy sequence
+
+
+def test_kcenters_every_k_and_more_views_than_threads(S):
+    rs = np.random.RandomState(5)
+    flat = rs.standard_normal((2500, 16)).astype(np.float32)                                    # 3 views per thread
+    flat[:, 12:] = [0, 0, 0, 1]
+    for k in (1, 2, 17, 2500, 9999):
+        want, order = O.select_cameras_kcenters(flat, k)
+        assert S.select_cameras_kcenters(flat, k) == want, k
+    small = flat[:5]
+    for k in range(1, 7):
+        assert S.select_cameras_kcenters(small, k) == O.select_cameras_kcenters(small, k)[0]
+
+
+def test_nearest_neighbours_equal_reference_golden(S):
+    z = np.load(os.path.join(GOLDEN_DIR, "selection.npz"))
+    for name, (flat, _, kn) in selection_cases().items():
+        got = S.nearest_neighbors(flat, kn)
+        ref = z[f"{name}_nn"]
+        assert got.dtype == np.int64 and got.shape == ref.shape, name
+        assert nn_equivalent(got, ref, flat, 5e-3), name                                        # cdist noise, see the oracle test
+        exact, _ = O.nearest_neighbors_exact(flat, kn)
+        assert nn_equivalent(got, exact, flat, 1e-5), name
+        if name.startswith("random"):                   # generic poses: identical except where two float32 distances round together
+            assert int((got != ref).any(axis=1).sum()) <= max(1, got.shape[0] // 500), name
+
+
+def test_pairs_feed_the_path(S):
+    """Selection -> neighbour table -> the views a launch processes (the device-resident front of the 1000-view config)."""
+    from lichtfeld_densification_plugin_b200 import synth
+    scene = synth.make_scene(40, "turbo", 0.25, 3)
+    flat = np.stack([c.flat_pose() for c in scene.cameras], 0)
+    refs = S.select_cameras_kcenters(flat, 10)
+    nn = S.nearest_neighbors(flat, 3)
+    assert len(refs) == 10 and nn.shape == (40, 3)
+    assert S._estimate_total_pairs(refs, nn, list(range(40)), 3) == 30
+    with pytest.raises(Exception):
+        S.nearest_neighbors(flat, 17) if False else S.nearest_neighbors_device(np.zeros((40, 15), np.float32), 3)
