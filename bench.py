@@ -389,7 +389,7 @@ def gpu_arm(args) -> None:
     # ---- e2e through the public API from host buffers.  The views are handed over in E2E_CHUNKS groups: the pinned
     #      host->device copy of group g+1 (copy stream) overlaps the kernels of group g, whose warp rows are gathered
     #      straight from pinned host memory over PCIe (the 0.77 GB of warp planes are never uploaded).
-    E2E_CHUNKS = 4 if R >= 8 else 1
+    E2E_CHUNKS = int(os.environ.get("BENCH_E2E_CHUNKS", "4")) if R >= 8 else 1
     h_cert = cert.cpu().pin_memory()
     h_img = image.cpu().pin_memory()
     h_warp = warp.cpu().pin_memory()

@@ -1336,27 +1336,22 @@ __device__ __forceinline__ void topm_hist_add4(int* hist, int b0, int b1, int b2
         if (b3 >= 0) atomicAdd(&hist[b3], 1);
     }
 }
-// Same, for passes in which a warp's 128 pixels fall into very few distinct bins (the most significant key digit of
-// certainties in [0, 1]; digits of the pixel index): one ballot count and one atomic per distinct bin instead of up to
-// 32 atomics colliding on one address; whatever is left after 8 bins takes the plain atomics.
+// Same, for passes in which a warp's 128 pixels fall into few distinct bins (the most significant key digit of
+// certainties in [0, 1]): lanes with the same bin are found with match.any and their leader adds the group's count - one
+// conflict-free atomic per distinct bin instead of up to 32 atomics colliding on one address.
 __device__ __forceinline__ void topm_hist_add4_few(int* hist, int b0, int b1, int b2, int b3) {
     const int lane = threadIdx.x & 31;
-    for (int round = 0; ; ++round) {
-        const int mine = b0 >= 0 ? b0 : (b1 >= 0 ? b1 : (b2 >= 0 ? b2 : b3));
-        const unsigned pend = __ballot_sync(0xffffffffu, mine >= 0);
-        if (!pend) break;
-        if (round == 8) {
-            if (b0 >= 0) atomicAdd(&hist[b0], 1);
-            if (b1 >= 0) atomicAdd(&hist[b1], 1);
-            if (b2 >= 0) atomicAdd(&hist[b2], 1);
-            if (b3 >= 0) atomicAdd(&hist[b3], 1);
-            break;
-        }
-        const int piv = __shfl_sync(0xffffffffu, mine, __ffs(pend) - 1);
-        const int c = __popc(__ballot_sync(0xffffffffu, b0 == piv)) + __popc(__ballot_sync(0xffffffffu, b1 == piv)) +
-                      __popc(__ballot_sync(0xffffffffu, b2 == piv)) + __popc(__ballot_sync(0xffffffffu, b3 == piv));
-        if (lane == 0) atomicAdd(&hist[piv], c);
-        b0 = (b0 == piv) ? -1 : b0; b1 = (b1 == piv) ? -1 : b1; b2 = (b2 == piv) ? -1 : b2; b3 = (b3 == piv) ? -1 : b3;
+    const bool uni = (b0 == b1) && (b1 == b2) && (b2 == b3);
+    if (__all_sync(0xffffffffu, uni)) {                                // every thread's quad in one bin: one match for the four
+        const unsigned m = __match_any_sync(0xffffffffu, b0);
+        if (b0 >= 0 && (__ffs(m) - 1) == lane) atomicAdd(&hist[b0], 4 * __popc(m));
+        return;
+    }
+    const int b[4] = {b0, b1, b2, b3};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned m = __match_any_sync(0xffffffffu, b[j]);
+        if (b[j] >= 0 && (__ffs(m) - 1) == lane) atomicAdd(&hist[b[j]], __popc(m));
     }
 }
 // Waits for the C local histograms of the pass, sums them, and finds - scanning the bins from the top (DESC) or from the
@@ -1419,8 +1414,10 @@ __device__ __forceinline__ void topm_tail(unsigned long long (&x)[4], int g0, in
 }
 
 // rows[rho] = number of pixels of row rho (32 consecutive quads = 128 pixels of the CTA's slice) whose key is `key`
-__device__ __forceinline__ void topm_count_rows(const float* __restrict__ w, int q_lo, int q_hi, int N, uint32_t key, int* rows) {
+// returns how many of this thread's pixels have a larger key
+__device__ __forceinline__ int topm_count_rows(const float* __restrict__ w, int q_lo, int q_hi, int N, uint32_t key, int* rows) {
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+    int n_above = 0;
     for (int qb = q_lo; qb < q_hi; qb += KT_UNROLL * T) {
         float4 v[KT_UNROLL];
 #pragma unroll
@@ -1436,13 +1433,18 @@ __device__ __forceinline__ void topm_count_rows(const float* __restrict__ w, int
             const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
             int c = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) c += (4 * q + j < N && f32_order_key(e[j]) == key) ? 1 : 0;
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t k = f32_order_key(e[j]);
+                c += (4 * q + j < N && k == key) ? 1 : 0;
+                n_above += (4 * q + j < N && k > key) ? 1 : 0;
+            }
             const int tot = __popc(__ballot_sync(0xffffffffu, c & 1)) + 2 * __popc(__ballot_sync(0xffffffffu, c & 2)) +
                             4 * __popc(__ballot_sync(0xffffffffu, c & 4));
             if (lane == 0) rows[(qw - q_lo) >> 5] = tot;
         }
     }
     __syncthreads();
+    return n_above;
 }
 // rows[] -> exclusive prefix sums in place; returns the CTA's total
 __device__ __forceinline__ int topm_rows_prefix(int* rows, int nrows, int* red_i) {
@@ -1499,7 +1501,7 @@ ldp_topm_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     int need_eq = M;                                     // pixels with key == kth that are taken (lowest indices first)
     int before_eq = 0;                                   // tied pixels in the slices of the lower-ranked CTAs
     int pc = 0;                                          // pass counter; pass p counts into hist2[p & 1]
-    topm_count_rows(w, q_lo, q_hi, N, capkey, rows);
+    int cnt_gt = topm_count_rows(w, q_lo, q_hi, N, capkey, rows);      // 0: nothing exceeds the cap
     {
         const int mine = topm_rows_prefix(rows, nrows, red_i);
         int all = mine;
@@ -1558,7 +1560,7 @@ ldp_topm_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
         if (tid == 0 && rank == 0) ws.dbgclk[(size_t)r * 32 + 1] = clock64();
 #endif
         // ---- 2. where the pixels tied at that key lie (they are emitted in pixel order, the first need_eq of them)
-        topm_count_rows(w, q_lo, q_hi, N, kth, rows);
+        cnt_gt = topm_count_rows(w, q_lo, q_hi, N, kth, rows);
         const int mine = topm_rows_prefix(rows, nrows, red_i);
         before_eq = 0;
         if (C > 1) {
@@ -1583,24 +1585,8 @@ ldp_topm_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     const bool sorter = n_gt > 0 && (Cs > 1 || rank == 0);
     if (sorter) for (int i = tid; i < L; i += T) if (gbase + i >= n_gt) cur[i] = 0ull;      // padding sorts last
     int pos = 0;
-    if (n_gt > 0) {                                      // 3a. slots for this thread's keys: one reservation per warp
-        int cnt = 0;
-        for (int qb = q_lo; qb < q_hi; qb += KT_UNROLL * T) {
-            float4 v[KT_UNROLL];
-#pragma unroll
-            for (int u = 0; u < KT_UNROLL; ++u) {
-                const int q = qb + u * T + tid;
-                v[u] = (q < q_hi) ? __ldcg(reinterpret_cast<const float4*>(w) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < KT_UNROLL; ++u) {
-                const int q = qb + u * T + tid;
-                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    cnt += (q < q_hi && 4 * q + j < N && f32_order_key(e[j]) > kth) ? 1 : 0;
-            }
-        }
+    if (n_gt > 0) {                                      // 3a. slots for this thread's keys (counted by step 2's sweep): one reservation per warp
+        const int cnt = cnt_gt;
         int inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
