@@ -47,34 +47,51 @@ def exchange_counts(n_points: torch.Tensor, group=None) -> Tuple[torch.Tensor, t
     return counts, torch.cumsum(counts, 0) - counts
 
 
-def write_ply_sharded(path_out: str, xyz, rgb_uint8, row_offset: int, total_rows: int, rank: int, group=None) -> None:
-    """Every rank writes its own rows of ONE binary PLY file, byte-identical to ``core.writers.write_ply`` of the
-    rank-order concatenation: rank 0 writes the header for ``total_rows`` vertices, each rank writes 15-byte records at
-    header + 15 * row_offset.  ``xyz`` / ``rgb_uint8``: this rank's numpy arrays.  Needs a file system all ranks share."""
+def _write_sharded(path_out: str, header: bytes, payload: bytes, byte_offset: int, total_bytes: int, rank: int, group) -> None:
     import os
-
-    import numpy as np
-
-    from .core.writers import _PLY_VERTEX, ply_header
-
-    header = ply_header(int(total_rows))
-    n = int(xyz.shape[0])
-    rec = np.empty(n, dtype=_PLY_VERTEX)
-    rec["x"], rec["y"], rec["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
-    rec["r"], rec["g"], rec["b"] = rgb_uint8[:, 0], rgb_uint8[:, 1], rgb_uint8[:, 2]
     if rank == 0:
         with open(path_out, "wb") as f:
             f.write(header)
-            f.truncate(len(header) + 15 * int(total_rows))
+            f.truncate(len(header) + int(total_bytes))
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.barrier(group=group)                    # the file exists with its final size before anybody seeks into it
     fd = os.open(path_out, os.O_WRONLY)
     try:
-        os.pwrite(fd, rec.tobytes(), len(header) + 15 * int(row_offset))
+        os.pwrite(fd, payload, len(header) + int(byte_offset))
     finally:
         os.close(fd)
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.barrier(group=group)
+
+
+def write_ply_sharded(path_out: str, xyz, rgb_uint8, row_offset: int, total_rows: int, rank: int, group=None,
+                      records=None) -> None:
+    """Every rank writes its own rows of ONE binary PLY file, byte-identical to ``core.writers.write_ply`` of the
+    rank-order concatenation: rank 0 writes the header for ``total_rows`` vertices, each rank writes 15-byte records at
+    header + 15 * row_offset.  ``xyz`` / ``rgb_uint8``: this rank's numpy arrays - or ``records``: the rank's records
+    already packed on the device (``output.ply_records(...).cpu().numpy()``, uint8 [15 * n]).  Needs a file system all
+    ranks share."""
+    import numpy as np
+
+    from .core.writers import _PLY_VERTEX, ply_header
+
+    if records is None:
+        n = int(xyz.shape[0])
+        rec = np.empty(n, dtype=_PLY_VERTEX)
+        rec["x"], rec["y"], rec["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+        rec["r"], rec["g"], rec["b"] = rgb_uint8[:, 0], rgb_uint8[:, 1], rgb_uint8[:, 2]
+        payload = rec.tobytes()
+    else:
+        payload = np.ascontiguousarray(records, dtype=np.uint8).tobytes()
+    _write_sharded(path_out, ply_header(int(total_rows)), payload, 15 * int(row_offset), 15 * int(total_rows), rank, group)
+
+
+def write_points3D_bin_sharded(path_out: str, records, row_offset: int, total_rows: int, rank: int, group=None) -> None:
+    """Same for COLMAP's points3D.bin (reference core/writers.py:15-26): ``records`` are this rank's 43-byte records
+    packed with ``output.points3d_records(..., first_id=row_offset + 1)`` (ids are global row numbers + 1)."""
+    import numpy as np
+    payload = np.ascontiguousarray(records, dtype=np.uint8).tobytes()
+    _write_sharded(path_out, np.uint64(int(total_rows)).tobytes(), payload, 43 * int(row_offset), 43 * int(total_rows), rank, group)
 
 
 def all_gather_points(xyz: torch.Tensor, rgb: torch.Tensor, err: torch.Tensor, n_valid: Optional[int] = None,

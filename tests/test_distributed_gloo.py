@@ -85,11 +85,28 @@ def _worker_sharded_write(rank, world, port, tmp, q):
         assert counts.tolist() == [377, 623] and offs.tolist() == [0, 377]
         path = os.path.join(tmp, "sharded.ply")
         D.write_ply_sharded(path, xyz_all[lo:hi], rgb_all[lo:hi], int(offs[rank]), int(counts.sum()), rank)
+        # the same files from pre-packed records (what the device packers hand over), and the points3D.bin variant
+        from lichtfeld_densification_plugin_b200.core import writers as W
+        rec = np.empty(hi - lo, dtype=W._PLY_VERTEX)
+        rec["x"], rec["y"], rec["z"] = xyz_all[lo:hi, 0], xyz_all[lo:hi, 1], xyz_all[lo:hi, 2]
+        rec["r"], rec["g"], rec["b"] = rgb_all[lo:hi, 0], rgb_all[lo:hi, 1], rgb_all[lo:hi, 2]
+        path2 = os.path.join(tmp, "sharded_records.ply")
+        D.write_ply_sharded(path2, None, None, int(offs[rank]), int(counts.sum()), rank, records=rec.view(np.uint8))
+        brec = np.empty(hi - lo, dtype=W._BIN_POINT)
+        brec["id"] = np.arange(lo + 1, hi + 1, dtype=np.uint64)
+        brec["x"], brec["y"], brec["z"] = xyz_all[lo:hi, 0], xyz_all[lo:hi, 1], xyz_all[lo:hi, 2]
+        brec["r"], brec["g"], brec["b"] = rgb_all[lo:hi, 0], rgb_all[lo:hi, 1], rgb_all[lo:hi, 2]
+        brec["err"] = 0.0
+        path3 = os.path.join(tmp, "sharded.bin")
+        D.write_points3D_bin_sharded(path3, brec.view(np.uint8), int(offs[rank]), int(counts.sum()), rank)
         if rank == 0:
-            from lichtfeld_densification_plugin_b200.core.writers import write_ply
             ref = os.path.join(tmp, "whole.ply")
-            write_ply(ref, xyz_all, rgb_all)
-            q.put(open(path, "rb").read() == open(ref, "rb").read())
+            W.write_ply(ref, xyz_all, rgb_all)
+            refb = os.path.join(tmp, "whole.bin")
+            W.write_points3D_bin(refb, xyz_all, rgb_all)
+            want = open(ref, "rb").read()
+            q.put(open(path, "rb").read() == want and open(path2, "rb").read() == want
+                  and open(path3, "rb").read() == open(refb, "rb").read())
     finally:
         dist.destroy_process_group()
 

@@ -405,3 +405,14 @@ def test_no_filter_distinct_certainties_cluster_sizes(engine):
                     assert np.array_equal(g.sel_idx[r], np.argsort(-capped, kind="stable")[:M]), (M, cs, r)
     finally:
         engine.lib.ldp_debug_set_cluster(0)
+
+
+def test_no_filter_more_matches_than_the_shared_memory_sort_holds(engine, fast_scene):
+    """M > 16384: the one-CTA kernel that sorts in global memory (same order rule)."""
+    scene, inputs = fast_scene
+    M = 20000
+    c = dict(M=M, no_filter=True, wm=scene.w_match, hm=scene.h_match)
+    g = G.run_gpu(engine, scene, inputs[:2], G.path_cfg(c))
+    for r in range(2):
+        capped = np.minimum(inputs[r]["cert"].max(dim=0).values.numpy().reshape(-1), np.float32(0.9))
+        assert np.array_equal(g.sel_idx[r], np.argsort(-capped, kind="stable")[:M])
