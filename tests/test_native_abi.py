@@ -53,3 +53,21 @@ def test_no_cpu_fallback():
     from lichtfeld_densification_plugin_b200.engine import DensifyEngine
     with pytest.raises(_native.NativeLibraryError):
         DensifyEngine()
+
+
+def test_no_cpu_fallback_around_the_path():
+    """The device output contract and pair generation refuse to run without a GPU as well."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from lichtfeld_densification_plugin_b200 import output
+    from lichtfeld_densification_plugin_b200.core import selection
+    with pytest.raises(_native.NativeLibraryError):
+        output.ply_records(torch.zeros((4, 3)), torch.zeros((4, 3)))
+    with pytest.raises(_native.NativeLibraryError):
+        output.apply_point_cap(torch.zeros((4, 3)), torch.zeros((4, 3)), torch.zeros((4,)), 2, 0)
+    with pytest.raises(_native.NativeLibraryError):
+        selection.select_cameras_kcenters(np.zeros((4, 16), np.float32), 2)
+    with pytest.raises(_native.NativeLibraryError):
+        selection.nearest_neighbors(np.zeros((4, 16), np.float32), 2)
