@@ -215,6 +215,18 @@ int ldp_select_kcenters(const float* flat_poses, int32_t n, int32_t k, float* sc
                         int32_t* centers_order, void* stream);
 int ldp_nearest_neighbors(const float* flat_poses, int32_t n, int32_t k, int64_t* idx_out, void* stream);
 
+/* ---- voxel-grid downsample -------------------------------------------------------
+ * densify.py:29-50 _voxel_downsample = Open3D's PointCloud::voxel_down_sample: voxel index
+ * floor((p - (min_bound - voxel_size / 2)) / voxel_size) per axis in f64, every voxel replaced by the f64 mean (in point
+ * order) of its points and colours, cast to f32; colours are divided by 255 first when their maximum exceeds 1
+ * (densify.py:41-44).  PARITY UNPINNED: Open3D is not in the reference tree nor in this image; the algorithm is restated
+ * from its published source.  Open3D emits voxels in std::unordered_map order; here in order of each voxel's first point.
+ * xyz, rgb [n,3] f32 device; xyz_out, rgb_out [n,3] f32 device (first status_out[1] rows are written);
+ * status_out: device int32[2] = {1 if a voxel index does not fit 21 bits per axis or a coordinate is NaN, voxel count}. */
+int ldp_voxel_workspace_bytes(int64_t n, size_t* bytes_out);
+int ldp_voxel_downsample(const float* xyz, const float* rgb, int64_t n, double voxel_size, float* xyz_out, float* rgb_out,
+                         int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Kernel launches enqueued by the last ldp_* call on this thread (for bench.py's gpu_launches). */
 int ldp_last_launch_count(void);
 

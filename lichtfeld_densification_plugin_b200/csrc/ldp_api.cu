@@ -11,6 +11,7 @@
 #include "ldp_geometry.cu"
 #include "ldp_output.cu"
 #include "ldp_select.cu"
+#include "ldp_voxel.cu"
 
 namespace {
 
@@ -707,6 +708,94 @@ int ldp_nearest_neighbors(const float* flat_poses, int32_t n, int32_t k, int64_t
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ldp_knn_kernel");
+    return LDP_OK;
+}
+
+// ---- voxel-grid downsample (ldp_voxel.cu)
+static size_t voxel_cap(int64_t n) {
+    size_t cap = 1024;
+    while (cap < (size_t)n * 2) cap <<= 1;
+    return cap;
+}
+static int voxel_plan(int64_t n, void* base, ldp::VoxelWs* ws, size_t* bytes) {
+    if (n < 0 || n > 500000000ll) return fail(LDP_ERR_INVALID, "voxel downsample: bad point count");
+    const size_t cap = voxel_cap(n), N = (size_t)std::max<int64_t>(n, 1);
+    size_t off = 0;
+    auto carve = [&](size_t b) { void* p = base ? static_cast<char*>(base) + off : nullptr; off += align_up(b, 256); return p; };
+    ws->bounds = reinterpret_cast<double*>(carve(8 * sizeof(double)));
+    ws->bounds_u = reinterpret_cast<unsigned int*>(carve(4 * sizeof(unsigned int)));
+    ws->keys = reinterpret_cast<unsigned long long*>(carve(cap * sizeof(unsigned long long)));
+    ws->first = reinterpret_cast<int*>(carve(cap * sizeof(int)));
+    ws->slot = reinterpret_cast<int*>(carve(N * sizeof(int)));
+    ws->flag = reinterpret_cast<int*>(carve(N * sizeof(int)));
+    ws->rank = reinterpret_cast<int*>(carve(N * sizeof(int)));
+    ws->count = reinterpret_cast<int*>(carve((N + 1) * sizeof(int)));
+    ws->cursor = reinterpret_cast<int*>(carve(N * sizeof(int)));
+    ws->seg = reinterpret_cast<int*>(carve(N * sizeof(int)));
+    ws->members = reinterpret_cast<int*>(carve(N * sizeof(int)));
+    ws->block_tot = reinterpret_cast<int*>(carve((N / ldp::SC_THREADS + 2) * sizeof(int)));
+    ws->large = reinterpret_cast<int*>(carve((N + 2) * sizeof(int)));
+    ws->status = nullptr;
+    ws->cap_mask = cap - 1;
+    *bytes = off;
+    return LDP_OK;
+}
+
+int ldp_voxel_workspace_bytes(int64_t n, size_t* bytes_out) {
+    if (!bytes_out) return fail(LDP_ERR_INVALID, "null bytes_out");
+    ldp::VoxelWs ws;
+    return voxel_plan(n, nullptr, &ws, bytes_out);
+}
+
+static int scan_exclusive(const int* in, int* out, int64_t n, int* block_tot, int* grand_total, cudaStream_t st) {
+    const int nblocks = (int)((n + ldp::SC_THREADS - 1) / ldp::SC_THREADS);
+    (void)launch_k(ldp::ldp_scan_blocks_kernel, dim3(nblocks), dim3(ldp::SC_THREADS), 0, st, in, out, (long long)n, block_tot);
+    (void)launch_k(ldp::ldp_scan_totals_kernel, dim3(1), dim3(ldp::SC_THREADS), 0, st, block_tot, nblocks, grand_total);
+    (void)launch_k(ldp::ldp_scan_add_kernel, dim3(nblocks), dim3(ldp::SC_THREADS), 0, st, out, (long long)n, (const int*)block_tot);
+    g_launches += 3;
+    return LDP_OK;
+}
+
+int ldp_voxel_downsample(const float* xyz, const float* rgb, int64_t n, double voxel_size, float* xyz_out, float* rgb_out,
+                         int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    if (!(voxel_size > 0.0)) return fail(LDP_ERR_INVALID, "voxel_size must be positive");       // Open3D: "voxel_size <= 0."
+    if (!status_out) return fail(LDP_ERR_INVALID, "null status_out");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(status_out, 0, 2 * sizeof(int32_t), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(status)");
+    if (n == 0) return LDP_OK;
+    if (!xyz || !rgb || !xyz_out || !rgb_out || !workspace) return fail(LDP_ERR_INVALID, "null pointer");
+    ldp::VoxelWs ws;
+    size_t need = 0;
+    int rc = voxel_plan(n, workspace, &ws, &need);
+    if (rc != LDP_OK) return rc;
+    if (workspace_bytes < need) return fail(LDP_ERR_INVALID, "voxel workspace too small");
+    ws.status = status_out;
+    const size_t cap = (size_t)ws.cap_mask + 1;
+    e = cudaMemsetAsync(ws.bounds_u, 0xFF, 3 * sizeof(unsigned int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws.bounds_u + 3, 0, sizeof(unsigned int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws.keys, 0xFF, cap * sizeof(unsigned long long), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws.first, 0x7F, cap * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws.count, 0, ((size_t)n + 1) * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws.cursor, 0, (size_t)n * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws.large, 0, 2 * sizeof(int), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(voxel workspace)");
+    const unsigned grid = (unsigned)((n + ldp::KV_THREADS - 1) / ldp::KV_THREADS);
+    const unsigned rgrid = (unsigned)std::min<long long>(grid, (long long)sm_count() * 8);
+    (void)launch_k(ldp::ldp_voxel_bounds_kernel, dim3(rgrid), dim3(ldp::KV_THREADS), 0, st, xyz, rgb, (long long)n, ws);
+    (void)launch_k(ldp::ldp_voxel_insert_kernel, dim3(grid), dim3(ldp::KV_THREADS), 0, st, xyz, (long long)n, voxel_size, ws);
+    (void)launch_k(ldp::ldp_voxel_flag_kernel, dim3(grid), dim3(ldp::KV_THREADS), 0, st, (long long)n, ws);
+    g_launches += 3;
+    scan_exclusive(ws.flag, ws.rank, n, ws.block_tot, ws.status + 1, st);
+    (void)launch_k(ldp::ldp_voxel_count_kernel, dim3(grid), dim3(ldp::KV_THREADS), 0, st, (long long)n, ws);
+    ++g_launches;
+    scan_exclusive(ws.count, ws.seg, n, ws.block_tot, nullptr, st);
+    (void)launch_k(ldp::ldp_voxel_group_kernel, dim3(grid), dim3(ldp::KV_THREADS), 0, st, (long long)n, ws, (const int*)ws.seg);
+    (void)launch_k(ldp::ldp_voxel_mean_kernel, dim3(grid), dim3(ldp::KV_THREADS), 0, st, xyz, rgb, ws, (const int*)ws.seg, xyz_out, rgb_out);
+    (void)launch_k(ldp::ldp_voxel_large_kernel, dim3((unsigned)sm_count()), dim3(ldp::SC_THREADS), 0, st, xyz, rgb, ws, (const int*)ws.seg, xyz_out, rgb_out);
+    g_launches += 3;
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "voxel downsample kernels");
     return LDP_OK;
 }
 

@@ -5,6 +5,7 @@ Mirrors, on tensors that stay on the GPU
 * ``to_uint8_rgb``                     reference core/image_utils.py:24-26
 * ``write_ply`` / ``write_points3D_bin``   reference core/writers.py:15-46 (files byte-identical; the records are built by
   ``ldp_pack_ply_records`` / ``ldp_pack_points3d_records`` and reach the host as one copy of 15 / 43 bytes per point)
+* ``voxel_downsample``                 reference densify.py:29-50 (Open3D voxel grid mean; parity unpinned, see the function)
 * ``apply_point_cap``                  reference densify.py:110-120 (the indices are numpy's own
   ``default_rng(seed).choice`` on the host - PCG64 + a sequential shuffle, microseconds; only the gather is device work)
 * ``subsample_preview_matches``        reference core/pipeline.py:573-582 (debug preview subsample of the kept matches)
@@ -137,6 +138,30 @@ def apply_point_cap(xyz: torch.Tensor, rgb: torch.Tensor, err: torch.Tensor, max
                                   C.c_void_p(sel_dev.data_ptr()), m, n, C.c_void_p(o_xyz.data_ptr()), C.c_void_p(o_rgb.data_ptr()),
                                   C.c_void_p(o_err.data_ptr()), C.c_void_p(0), C.c_void_p(stream)), "ldp_gather_points")
     return o_xyz, o_rgb, o_err
+
+
+def voxel_downsample(xyz: torch.Tensor, rgb: torch.Tensor, voxel_size: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """reference densify.py:29-50 (Open3D ``voxel_down_sample``) on device tensors: one point per occupied voxel, the f64
+    mean of the voxel's points and colours (colours above 1 are taken as 0..255 and scaled), float32 out.
+    PARITY UNPINNED (Open3D is not installed here; see include/ldp_b200.h).  Voxels come out in the order of their first
+    point.  Synchronises once to learn the voxel count."""
+    xyz, rgb = _f32c(xyz, "xyz"), _f32c(rgb[:, :3], "rgb")
+    lib, stream = _lib_and_stream(xyz)
+    n = int(xyz.shape[0])
+    if n == 0:
+        return xyz, rgb
+    need = C.c_size_t(0)
+    N.check(lib.ldp_voxel_workspace_bytes(n, C.byref(need)), "ldp_voxel_workspace_bytes")
+    ws = torch.empty((need.value,), dtype=torch.uint8, device=xyz.device)
+    o_xyz, o_rgb = torch.empty_like(xyz), torch.empty_like(rgb)
+    status = torch.zeros((2,), dtype=torch.int32, device=xyz.device)
+    N.check(lib.ldp_voxel_downsample(C.c_void_p(xyz.data_ptr()), C.c_void_p(rgb.data_ptr()), n, C.c_double(float(voxel_size)),
+                                     C.c_void_p(o_xyz.data_ptr()), C.c_void_p(o_rgb.data_ptr()), C.c_void_p(status.data_ptr()),
+                                     C.c_void_p(ws.data_ptr()), C.c_size_t(need.value), C.c_void_p(stream)), "ldp_voxel_downsample")
+    bad, nv = (int(v) for v in status.cpu().tolist())
+    if bad:
+        raise ValueError("voxel_size is too small for the extent of the cloud (or a coordinate is not finite)")
+    return o_xyz[:nv], o_rgb[:nv]
 
 
 PREVIEW_MAX_MATCHES = 10000       # reference core/pipeline.py:50 _PREVIEW_MAX_MATCHES

@@ -622,3 +622,26 @@ def nearest_neighbors_exact(flat_poses: np.ndarray, k: int):
     np.fill_diagonal(D, np.inf)
     idx = np.argsort(D, axis=1, kind="stable")[:, :k]
     return idx.astype(np.int64), np.take_along_axis(D, idx, axis=1)
+
+
+def voxel_downsample(xyz: np.ndarray, rgb: np.ndarray, voxel_size: float):
+    """densify.py:29-50 with Open3D's voxel_down_sample restated from its published source
+    (open3d/geometry/PointCloud.cpp: VoxelDownSample, AccumulatedPoint).  PARITY UNPINNED: Open3D is neither in the
+    reference tree nor installed here, so this restatement could not be run against it.  Voxels are returned in the order
+    of their first point (Open3D: std::unordered_map iteration order, implementation-defined)."""
+    pts = np.asarray(xyz).astype(np.float64)
+    rgb = np.asarray(rgb)
+    cols = rgb[:, :3].astype(np.float64) / 255.0 if rgb.max() > 1.0 else rgb[:, :3].astype(np.float64)      # :41-44
+    vmin = pts.min(axis=0) - float(voxel_size) * 0.5
+    idx = np.floor((pts - vmin) / float(voxel_size)).astype(np.int64)
+    uniq, first, inv = np.unique(idx, axis=0, return_index=True, return_inverse=True)
+    inv = np.asarray(inv).reshape(-1)
+    rank = np.empty(len(uniq), dtype=np.int64)
+    rank[np.argsort(first, kind="stable")] = np.arange(len(uniq))
+    v = rank[inv]
+    acc_p = np.zeros((len(uniq), 3))
+    acc_c = np.zeros((len(uniq), 3))
+    np.add.at(acc_p, v, pts)            # unbuffered: accumulates in point order, like Open3D's loop
+    np.add.at(acc_c, v, cols)
+    cnt = np.bincount(v, minlength=len(uniq)).astype(np.float64)[:, None]
+    return (acc_p / cnt).astype(np.float32), (acc_c / cnt).astype(np.float32)

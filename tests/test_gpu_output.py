@@ -180,3 +180,30 @@ def test_run_dense_pipeline_live_updates_write_the_reference_files(tmp_path):
     P.run_dense_pipeline(cams, refs[:2], None, cfg, on_sequential_viz=emitted.append, match_source=match_source,
                          w_match=scene.w_match, h_match=scene.h_match)
     assert not (tmp_path / "none").exists()
+
+
+@pytest.mark.parametrize("n,vs,scale255", [(1, 0.5, False), (2000, 0.25, False), (50000, 0.05, True), (30000, 100.0, False), (4097, 1e-3, False)])
+def test_voxel_downsample_equals_the_restated_open3d_algorithm(out_mod, n, vs, scale255):
+    """PARITY UNPINNED against Open3D itself (not installed); exact against the oracle's restatement of its algorithm:
+    same voxels, f64 means accumulated in point order, first-appearance order."""
+    rs = np.random.RandomState(n)
+    xyz = (rs.standard_normal((n, 3)) * 2).astype(np.float32)
+    rgb = rs.random_sample((n, 3)).astype(np.float32) * (255.0 if scale255 else 1.0)
+    want_xyz, want_rgb = O.voxel_downsample(xyz, rgb, vs)
+    got_xyz, got_rgb = out_mod.voxel_downsample(_dev(xyz), _dev(rgb), vs)
+    assert got_xyz.shape == want_xyz.shape and 1 <= got_xyz.shape[0] <= n
+    assert np.array_equal(got_xyz.cpu().numpy(), want_xyz) and np.array_equal(got_rgb.cpu().numpy(), want_rgb)
+    if vs == 100.0:
+        assert got_xyz.shape[0] == 1                      # everything in one voxel: 30 000 points summed in order
+    # idempotence-like property: every output point lies inside the voxel of the points it averages
+    again_xyz, _ = out_mod.voxel_downsample(got_xyz, got_rgb, vs)
+    assert again_xyz.shape[0] <= got_xyz.shape[0]
+
+
+def test_voxel_downsample_rejects_bad_sizes(out_mod):
+    xyz = _dev(np.array([[0, 0, 0], [1e6, 0, 0]], np.float32))
+    rgb = _dev(np.zeros((2, 3), np.float32))
+    with pytest.raises(Exception):
+        out_mod.voxel_downsample(xyz, rgb, 0.0)
+    with pytest.raises(ValueError):
+        out_mod.voxel_downsample(xyz, rgb, 1e-3)          # 1e9 voxels along x: does not fit 21 bits
