@@ -688,8 +688,18 @@ int ldp_select_kcenters(const float* flat_poses, int32_t n, int32_t k, float* sc
     if (n <= 0 || k <= 0 || k > n) return fail(LDP_ERR_INVALID, "k-centres needs 1 <= k <= n");
     if (n > ldp::KC_THREADS * ldp::KC_MAX_PER_THREAD) return fail(LDP_ERR_INVALID, "k-centres: more than 8192 views");
     if (!flat_poses || !scratch || !centers_sorted || !centers_order) return fail(LDP_ERR_INVALID, "null pointer");
-    (void)launch_k(ldp::ldp_kcenters_kernel, dim3(1), dim3(ldp::KC_THREADS), 0, reinterpret_cast<cudaStream_t>(stream), flat_poses,
-                   (int)n, (int)k, scratch, centers_sorted, centers_order);
+    const size_t smem = (size_t)n * ldp::KC_PAD * sizeof(float);
+    if (smem <= K1_SMEM_BUDGET) {                        // the poses fit in shared memory (n <= 3011)
+        static bool configured = false;
+        if (!configured) {
+            (void)cudaFuncSetAttribute(ldp::ldp_kcenters_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
+            configured = true;
+        }
+        (void)launch_k(ldp::ldp_kcenters_kernel<true>, dim3(1), dim3(ldp::KC_THREADS), smem, reinterpret_cast<cudaStream_t>(stream),
+                       flat_poses, (int)n, (int)k, scratch, centers_sorted, centers_order);
+    } else
+        (void)launch_k(ldp::ldp_kcenters_kernel<false>, dim3(1), dim3(ldp::KC_THREADS), 0, reinterpret_cast<cudaStream_t>(stream),
+                       flat_poses, (int)n, (int)k, scratch, centers_sorted, centers_order);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ldp_kcenters_kernel");

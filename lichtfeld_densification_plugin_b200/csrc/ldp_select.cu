@@ -26,10 +26,16 @@ __device__ __forceinline__ void argmax_merge(float& v, int& i, float ov, int oi)
     if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
 }
 
+// SMEM: the poses live in shared memory (rows padded to 17 floats: conflict-free row reads), n * 68 bytes; otherwise the
+// normalised rows go to the caller's scratch in global memory.
+constexpr int KC_PAD = KC_DIM + 1;
+template <bool SMEM>
 __global__ void __launch_bounds__(KC_THREADS, 1)
 ldp_kcenters_kernel(const float* __restrict__ X, int n, int k, float* __restrict__ Xn, int32_t* __restrict__ out_sorted,
                     int32_t* __restrict__ out_order)
 {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* xs = reinterpret_cast<float*>(smem_raw);                  // [n][KC_PAD] when SMEM
     __shared__ float s_mu[KC_DIM], s_sigma[KC_DIM], s_c[KC_DIM];
     __shared__ float s_v[32];
     __shared__ int s_i[32];
@@ -37,17 +43,24 @@ ldp_kcenters_kernel(const float* __restrict__ X, int n, int k, float* __restrict
     __shared__ int red_i[32];
     grid_dependency_sync();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rs = SMEM ? KC_PAD : KC_DIM;                           // row stride of the working copy
+    float* R = SMEM ? xs : Xn;
+    if (SMEM) {
+        for (int e = tid; e < n * KC_DIM; e += KC_THREADS) xs[(e >> 4) * KC_PAD + (e & 15)] = X[e];
+        __syncthreads();
+    }
+    const float* src = SMEM ? xs : X;
     // ---- mu = X.mean(axis=0), sigma = X.std(axis=0) + 1e-8: column sums run over the rows in order (numpy reduces the
     // outer axis of a C-contiguous array row by row)
     if (tid < KC_DIM) {
         float s = 0.f;
 #pragma unroll 8
-        for (int i = 0; i < n; ++i) s = __fadd_rn(s, X[(size_t)i * KC_DIM + tid]);
+        for (int i = 0; i < n; ++i) s = __fadd_rn(s, src[(size_t)i * rs + tid]);
         const float mu = __fdiv_rn(s, (float)n);
         float s2 = 0.f;
 #pragma unroll 8
         for (int i = 0; i < n; ++i) {
-            const float d = __fsub_rn(X[(size_t)i * KC_DIM + tid], mu);
+            const float d = __fsub_rn(src[(size_t)i * rs + tid], mu);
             s2 = __fadd_rn(s2, __fmul_rn(d, d));
         }
         s_mu[tid] = mu;
@@ -66,8 +79,8 @@ ldp_kcenters_kernel(const float* __restrict__ X, int n, int k, float* __restrict
             float a[KC_DIM];
 #pragma unroll
             for (int j = 0; j < KC_DIM; ++j) {
-                const float v = __fdiv_rn(__fsub_rn(X[(size_t)i * KC_DIM + j], s_mu[j]), s_sigma[j]);
-                Xn[(size_t)i * KC_DIM + j] = v;
+                const float v = __fdiv_rn(__fsub_rn(src[(size_t)i * rs + j], s_mu[j]), s_sigma[j]);
+                R[(size_t)i * rs + j] = v;                            // a thread rewrites only its own rows
                 a[j] = __fmul_rn(v, v);
             }
             argmax_merge(bv, bi, pairwise16(a), i);
@@ -95,11 +108,11 @@ ldp_kcenters_kernel(const float* __restrict__ X, int n, int k, float* __restrict
         __syncthreads();
         return s_pick;
     };
-    int c = block_argmax(bv, bi);
+    int c = block_argmax(bv, bi);                                     // (its barriers also publish the normalised rows)
     // ---- greedy k-centres: dist = min(dist, |Xn - Xn[c]|), picked views drop to -inf
     for (int it = 0; it < k; ++it) {
         if (tid == 0) out_order[it] = c;
-        if (tid < KC_DIM) s_c[tid] = Xn[(size_t)c * KC_DIM + tid];     // written by this CTA: plain load after the barrier below
+        if (tid < KC_DIM) s_c[tid] = R[(size_t)c * rs + tid];
         __syncthreads();
         bv = -INFINITY; bi = 0x7fffffff;
 #pragma unroll
@@ -109,7 +122,7 @@ ldp_kcenters_kernel(const float* __restrict__ X, int n, int k, float* __restrict
                 float a[KC_DIM];
 #pragma unroll
                 for (int j = 0; j < KC_DIM; ++j) {
-                    const float d = __fsub_rn(Xn[(size_t)i * KC_DIM + j], s_c[j]);
+                    const float d = __fsub_rn(R[(size_t)i * rs + j], s_c[j]);
                     a[j] = __fmul_rn(d, d);
                 }
                 const float d = __fsqrt_rn(pairwise16(a));

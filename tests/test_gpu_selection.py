@@ -35,6 +35,9 @@ def test_kcenters_every_k_and_more_views_than_threads(S):
     for k in (1, 2, 17, 2500, 9999):
         want, order = O.select_cameras_kcenters(flat, k)
         assert S.select_cameras_kcenters(flat, k) == want, k
+    big = np.concatenate([flat, flat[::-1] * np.float32(1.5)])[:4000]                          # beyond the shared-memory copy: global rows
+    for k in (3, 40):
+        assert S.select_cameras_kcenters(big, k) == O.select_cameras_kcenters(big, k)[0], k
     small = flat[:5]
     for k in range(1, 7):
         assert S.select_cameras_kcenters(small, k) == O.select_cameras_kcenters(small, k)[0]
