@@ -216,7 +216,7 @@ def gpu_arm(args) -> None:
     import torch
     import torch.distributed as dist
     from lichtfeld_densification_plugin_b200 import synth
-    from lichtfeld_densification_plugin_b200.engine import DensifyEngine, PathConfig
+    from lichtfeld_densification_plugin_b200.engine import DensifyRing, PathConfig
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -224,7 +224,8 @@ def gpu_arm(args) -> None:
         dist.init_process_group("nccl", device_id=dev)
         # the collective of the previous step runs beside the kernels: keep a few SMs free for it, or the one-CTA-per-SM
         # draw kernel splits into two waves (the counts exchange is one small CTA; gathering all points needs channels)
-        os.environ.setdefault("LDP_SM_RESERVE", "16" if int(os.environ.get("BENCH_GATHER_POINTS", "0")) else "4")
+        if int(os.environ.get("BENCH_PIPELINE_DEPTH", "3")) <= 1:      # (with steps in flight DensifyRing reserves 16 SMs itself)
+            os.environ.setdefault("LDP_SM_RESERVE", "16" if int(os.environ.get("BENCH_GATHER_POINTS", "0")) else "4")
 
     scene = synth.make_scene(WORKLOAD["n_views"], WORKLOAD["setting"], WORKLOAD["ref_fraction"], WORKLOAD["nn"])
     R, nn, H, W = scene.n_refs, scene.nn, scene.H, scene.W
@@ -239,7 +240,12 @@ def gpu_arm(args) -> None:
         nbr_table.append((inp["ref_index"], inp["nbr_indices"]))
     torch.cuda.synchronize()
 
-    eng = DensifyEngine(dev)
+    # Consecutive steps are independent batches: DEPTH of them are kept in flight (engine.DensifyRing: one workspace and
+    # one CUDA stream per slot), so the HBM-bound first kernel of one step runs beside the latency-bound draw / geometry
+    # kernels of another.  BENCH_PIPELINE_DEPTH=1 times one launch sequence at a time (also measured and reported below).
+    DEPTH = max(1, int(os.environ.get("BENCH_PIPELINE_DEPTH", "3")))
+    ring = DensifyRing(dev, DEPTH)
+    eng = ring.engines[0]
     cfg = PathConfig(matches_per_ref=WORKLOAD["M"], seed=0)
     cams = scene.cameras
 
@@ -254,7 +260,8 @@ def gpu_arm(args) -> None:
     batch = make_batch(cert, warp, image)
     descs = eng.upload_descs(batch)
     sel_cap = eng.sel_capacity(cfg.matches_per_ref)
-    outs = [eng.alloc_outputs(R, sel_cap) for _ in range(2)]
+    NBUF = max(2, DEPTH)
+    outs = [eng.alloc_outputs(R, sel_cap) for _ in range(NBUF)]
     cap = R * sel_cap
 
     # multi-GPU: the views are sharded, the points stay on the rank that made them (as they stay in HBM at N = 1); what
@@ -265,25 +272,28 @@ def gpu_arm(args) -> None:
     gather_points = bool(int(os.environ.get("BENCH_GATHER_POINTS", "0")))
     if world > 1:
         if gather_points:
-            gathered = [torch.empty((world, outs[0].packed.numel()), dtype=torch.uint8, device=dev) for _ in range(2)]
-        counts_all = [torch.zeros((world,), dtype=torch.int64, device=dev) for _ in range(2)]
-        gather_done = [torch.cuda.Event() for _ in range(2)]
-        step_done = [torch.cuda.Event() for _ in range(2)]
+            gathered = [torch.empty((world, outs[0].packed.numel()), dtype=torch.uint8, device=dev) for _ in range(NBUF)]
+        counts_all = [torch.zeros((world,), dtype=torch.int64, device=dev) for _ in range(NBUF)]
+        gather_done = [torch.cuda.Event() for _ in range(NBUF)]
+        step_done = [torch.cuda.Event() for _ in range(NBUF)]
 
-    def step(i: int):
-        o = outs[i % 2]
-        main = torch.cuda.current_stream(dev)
-        if world > 1 and i >= 2:
-            main.wait_event(gather_done[i % 2])          # buffers of step i-2 are free again
-        eng.densify(batch, cfg, descs_dev=descs, outputs=o)
-        if world > 1:
-            step_done[i % 2].record(main)
-            with torch.cuda.stream(comm):
-                comm.wait_event(step_done[i % 2])
-                dist.all_gather_into_tensor(counts_all[i % 2], o.ref_offset[-1:])
-                if gather_points:      # offsets | xyz | rgb | err of a rank are one allocation: a single collective
-                    dist.all_gather_into_tensor(gathered[i % 2], o.packed)
-                gather_done[i % 2].record(comm)
+    def step(i: int, depth: int):
+        k = i % NBUF
+        o = outs[k]
+        st = ring.streams[i % depth] if depth > 1 else torch.cuda.current_stream(dev)
+        e = ring.engines[i % depth] if depth > 1 else eng
+        with torch.cuda.stream(st):
+            if world > 1 and i >= NBUF:
+                st.wait_event(gather_done[k])            # buffers of step i-NBUF are free again
+            e.densify(batch, cfg, descs_dev=descs, outputs=o)
+            if world > 1:
+                step_done[k].record(st)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(step_done[k])
+                    dist.all_gather_into_tensor(counts_all[k], o.ref_offset[-1:])
+                    if gather_points:      # offsets | xyz | rgb | err of a rank are one allocation: a single collective
+                        dist.all_gather_into_tensor(gathered[k], o.packed)
+                    gather_done[k].record(comm)
         return o
 
     def barrier():
@@ -292,22 +302,44 @@ def gpu_arm(args) -> None:
         torch.cuda.synchronize(dev)
 
     _dbg("setup done")
-    for i in range(max(3, args.warmup)):
-        step(i)
-    barrier()
-    _dbg("warmup done")
+
+    def timed(depth: int, n_steps: int):
+        """n_steps steps, `depth` in flight, between two events on the main stream; returns (ms, last outputs)."""
+        main = torch.cuda.current_stream(dev)
+        for i in range(max(3, args.warmup)):
+            step(i, depth)
+        if depth > 1:
+            for st in ring.streams:
+                main.wait_stream(st)
+        if world > 1:
+            main.wait_stream(comm)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if depth > 1:
+            for st in ring.streams:
+                st.wait_event(e0)
+        last = None
+        for i in range(n_steps):
+            last = step(i, depth)
+        if depth > 1:
+            for st in ring.streams:
+                main.wait_stream(st)
+        if world > 1:
+            main.wait_stream(comm)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), last
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-        o = step(i)
-    if world > 1:
-        torch.cuda.current_stream(dev).wait_stream(comm)
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    if DEPTH > 1 and world == 1:
+        eng.lib.ldp_set_sm_reserve(0)                    # alone on the device the first draw kernel takes every SM
+    ms_single, o = timed(1, args.steps)                  # one launch sequence at a time
+    ms_total = ms_single
+    if DEPTH > 1:
+        eng.lib.ldp_set_sm_reserve(16)                   # DensifyRing's setting: SMs for the other steps in flight
+        ms_total, o = timed(DEPTH, args.steps)           # the headline: DEPTH steps in flight
     _dbg("timed loop done")
     # keep the GPU under the same load a little longer so the clock sampler sees the loaded state
     t_end = time.time() + (0.0 if args.quick else max(0.0, 0.6 - ms_total / 1e3))
@@ -326,15 +358,16 @@ def gpu_arm(args) -> None:
     total_pts = o.total_points()
     S_total = int(o.n_samples.sum().item())
     if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_total, ms_single], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+        ms_total, ms_single = float(t[0].item()), float(t[1].item())
         c = torch.tensor([total_pts, S_total], dtype=torch.int64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         total_pts_all, S_all = int(c[0].item()), int(c[1].item())
     else:
         total_pts_all, S_all = total_pts, S_total
     ms_step = ms_total / args.steps
+    ms_single_step = ms_single / args.steps
     value = total_pts_all / (ms_step / 1e3)
     pairs_per_s = world * scene.n_pairs / (ms_step / 1e3)
 
@@ -468,10 +501,12 @@ def gpu_arm(args) -> None:
             "dtype": "f32 geometry / f64 cdf, sampson, colour", "data": "synthetic",
             "config": {"workload": WORKLOAD["name"], "refs_per_gpu": R, "pairs_per_gpu": scene.n_pairs,
                        "l2_policy": "inputs larger than L2 (0.97 GB per step vs 126 MB)",
+                       "steps_in_flight": DEPTH,
                        "rng": "philox4x32-10", "multi_gpu": (("per-step NCCL all-gather of every rank's packed points (28 B/point) on a side stream" if gather_points else
                                       "views sharded, points stay on their rank; per-step NCCL all-gather of the per-rank kept-point "
                                       "counts (global row offsets) on a side stream") if world > 1 else "none")},
             "pairs_per_sec": pairs_per_s, "points_per_step": total_pts_all, "samples_per_step": S_all,
+            "ms_per_step_one_launch_at_a_time": ms_single_step,
             "gpu_launches": launches_per_step * args.steps,
             "kernels_ms": kdict,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LDP_ABI_VERSION 9
+#define LDP_ABI_VERSION 10
 #define LDP_MAX_NN 16          /* neighbours per reference view (the panel clamps to 10) */
 #define LDP_MAX_BINS 4096      /* coverage tiles per map: ceil(W/tile)*ceil(H/tile), tile = max(1, W/24) */
 
@@ -226,6 +226,12 @@ int ldp_nearest_neighbors(const float* flat_poses, int32_t n, int32_t k, int64_t
 int ldp_voxel_workspace_bytes(int64_t n, size_t* bytes_out);
 int ldp_voxel_downsample(const float* xyz, const float* rgb, int64_t n, double voxel_size, float* xyz_out, float* rgb_out,
                          int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* SMs the one-CTA-per-SM first draw kernel leaves free (process-wide; default 0; the environment variable
+ * LDP_SM_RESERVE, when set, wins).  With several launches in flight on different streams (engine.DensifyRing) or a
+ * collective running beside the path, the free SMs let the other kernels make progress: measured 0.1445 -> 0.1420 ms per
+ * step at 3 launches in flight with 16. */
+int ldp_set_sm_reserve(int n_sms);
 
 /* Kernel launches enqueued by the last ldp_* call on this thread (for bench.py's gpu_launches). */
 int ldp_last_launch_count(void);

@@ -77,6 +77,7 @@ int cuda_fail(cudaError_t e, const char* where) {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int g_force_cluster = 0;      // test hook (ldp_debug_set_cluster)
+int g_sm_reserve = 0;         // ldp_set_sm_reserve
 int g_last_cluster = 0;
 
 int sm_count() {
@@ -377,8 +378,9 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_prep_kernel");
     // ---- round 1: independent CTAs, as many per view as the device has SMs for (one CTA per SM: the table fills it)
-    static const int sm_reserve = [] { const char* e = getenv("LDP_SM_RESERVE"); return e ? atoi(e) : 0; }();   // SMs left to concurrent
-    int c_first = (sm_count() - sm_reserve) / nsubrefs;                                                            // (communication) kernels
+    static const int env_reserve = [] { const char* e = getenv("LDP_SM_RESERVE"); return e ? atoi(e) : -1; }();   // SMs left to concurrent
+    const int sm_reserve = env_reserve >= 0 ? env_reserve : g_sm_reserve;                                             // kernels (other launches in
+    int c_first = (sm_count() - sm_reserve) / nsubrefs;                                                            // flight, communication)
     if (c_first < 1) c_first = 1;
     if (c_first > (int)plan.ws.draw_cmax) c_first = (int)plan.ws.draw_cmax;
     if (g_force_cluster > 0) c_first = g_force_cluster;
@@ -806,6 +808,12 @@ int ldp_voxel_downsample(const float* xyz, const float* rgb, int64_t n, double v
     (void)launch_k(ldp::ldp_voxel_large_kernel, dim3((unsigned)sm_count()), dim3(ldp::SC_THREADS), 0, st, xyz, rgb, ws, (const int*)ws.seg, xyz_out, rgb_out);
     g_launches += 3;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "voxel downsample kernels");
+    return LDP_OK;
+}
+
+int ldp_set_sm_reserve(int n_sms) {
+    if (n_sms < 0 || n_sms >= sm_count()) return fail(LDP_ERR_INVALID, "sm reserve out of range");
+    g_sm_reserve = n_sms;
     return LDP_OK;
 }
 

@@ -225,6 +225,7 @@ class DensifyOutputs:
     sample_xyzerr: Optional[torch.Tensor] = None
     launches: int = 0
     packed: Optional[torch.Tensor] = None      # the u8 allocation behind ref_offset | xyz | rgb | err
+    ready: Optional[torch.cuda.Event] = None   # DensifyRing: recorded on the ring stream after the launch sequence
 
     def total_points(self) -> int:
         """Synchronises."""
@@ -399,3 +400,49 @@ class DensifyEngine:
             out.sample_flags = torch.zeros((R, sel_cap), dtype=torch.uint8, device=dev)
             out.sample_xyzerr = torch.zeros((R, sel_cap, 4), **f32)
         return out
+
+
+class DensifyRing:
+    """Several launches in flight: a caller with more than one batch of views (a large scene cut into launches, or one
+    scene after another) submits them round-robin to ``depth`` engines, each with its own workspace and CUDA stream.
+    The kernels of a launch sequence are bound by different things - the first streams HBM, the draw and geometry
+    kernels are latency / issue bound and leave most of the memory system idle - so consecutive launches overlap:
+    measured 175 -> 152 -> 145 us per 46-view launch at depth 1 / 2 / 3 (``scratch/two_streams.py``).  Results are
+    those of ``DensifyEngine.densify`` (same kernels, same RNG streams); only the scheduling differs."""
+
+    def __init__(self, device=None, depth: int = 3, sm_reserve: int = 16) -> None:
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.engines = [DensifyEngine(device) for _ in range(depth)]
+        if depth > 1:      # process-wide: the first draw kernel leaves SMs to the other launches in flight
+            N.check(self.engines[0].lib.ldp_set_sm_reserve(int(sm_reserve)), "ldp_set_sm_reserve")
+        self.device = self.engines[0].device
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(depth)]
+        self.depth = depth
+        self._n = 0
+
+    def slot(self) -> int:
+        """Index of the engine / stream the next ``submit`` uses."""
+        return self._n % self.depth
+
+    def submit(self, batch: RefBatch, cfg: PathConfig, **kw) -> DensifyOutputs:
+        """Enqueue ``DensifyEngine.densify(batch, cfg, **kw)`` on the next ring stream, ordered after the work already on
+        the caller's current stream (which produced the inputs).  ``outputs.ready`` is recorded behind it."""
+        j = self._n % self.depth
+        self._n += 1
+        st = self.streams[j]
+        st.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(st):
+            out = self.engines[j].densify(batch, cfg, **kw)
+            out.ready = torch.cuda.Event()
+            out.ready.record(st)
+        return out
+
+    def wait(self, out: DensifyOutputs) -> None:
+        """Order the caller's current stream after ``out``."""
+        if out.ready is not None:
+            torch.cuda.current_stream(self.device).wait_event(out.ready)
+
+    def synchronize(self) -> None:
+        for st in self.streams:
+            st.synchronize()

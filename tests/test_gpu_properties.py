@@ -416,3 +416,36 @@ def test_no_filter_more_matches_than_the_shared_memory_sort_holds(engine, fast_s
     for r in range(2):
         capped = np.minimum(inputs[r]["cert"].max(dim=0).values.numpy().reshape(-1), np.float32(0.9))
         assert np.array_equal(g.sel_idx[r], np.argsort(-capped, kind="stable")[:M])
+
+
+def test_ring_of_launches_gives_the_same_results(engine, fast_scene):
+    """DensifyRing: launches in flight on several streams / workspaces produce exactly what one engine produces."""
+    from lichtfeld_densification_plugin_b200.engine import DensifyRing, PathConfig
+    scene, inputs = fast_scene
+    dev = engine.device
+    cfg = PathConfig(matches_per_ref=10000, seed=11)
+
+    def batch_for(eng, lo, hi):
+        b = eng.new_batch(scene.H, scene.W, scene.w_match, scene.h_match)
+        for rp in range(lo, hi):
+            inp = inputs[rp]
+            k = len(inp["nbr_indices"])
+            b.add([inp["cert"][q].to(dev) for q in range(k)], [inp["warp"][q].to(dev) for q in range(k)], inp["image"].to(dev),
+                  scene.cameras[inp["ref_index"]], [scene.cameras[j] for j in inp["nbr_indices"]], rng_stream=rp)
+        return b
+    n = len(inputs)
+    cuts = [(0, n // 3), (n // 3, 2 * n // 3), (2 * n // 3, n), (0, n)]
+    want = []
+    for lo, hi in cuts:
+        o = engine.densify(batch_for(engine, lo, hi), cfg)
+        k = o.total_points()
+        want.append((o.xyz[:k].clone(), o.rgb[:k].clone(), o.ref_offset.clone()))
+    ring = DensifyRing(dev, depth=3)
+    outs = [ring.submit(batch_for(ring.engines[0], lo, hi), cfg) for _ in range(2) for lo, hi in cuts]     # 8 launches, 3 in flight
+    for o in outs:
+        ring.wait(o)
+    torch.cuda.synchronize()
+    for idx, o in enumerate(outs):
+        xyz, rgb, off = want[idx % len(cuts)]
+        k = int(off[-1])
+        assert torch.equal(o.ref_offset, off) and torch.equal(o.xyz[:k], xyz) and torch.equal(o.rgb[:k], rgb), idx
