@@ -277,15 +277,19 @@ def gpu_arm(args) -> None:
         gather_done = [torch.cuda.Event() for _ in range(NBUF)]
         step_done = [torch.cuda.Event() for _ in range(NBUF)]
 
+    prepared = {}      # (engine slot, output buffer) -> PreparedLaunch: the host side of a step is one C call
+
     def step(i: int, depth: int):
         k = i % NBUF
         o = outs[k]
-        st = ring.streams[i % depth] if depth > 1 else torch.cuda.current_stream(dev)
-        e = ring.engines[i % depth] if depth > 1 else eng
+        j = i % depth if depth > 1 else 0
+        st = ring.streams[j] if depth > 1 else torch.cuda.current_stream(dev)
+        if (j, k) not in prepared:
+            prepared[(j, k)] = ring.engines[j].prepare(batch, cfg, descs_dev=descs, outputs=o)
         with torch.cuda.stream(st):
             if world > 1 and i >= NBUF:
                 st.wait_event(gather_done[k])            # buffers of step i-NBUF are free again
-            e.densify(batch, cfg, descs_dev=descs, outputs=o)
+            prepared[(j, k)].launch()
             if world > 1:
                 step_done[k].record(st)
                 with torch.cuda.stream(comm):

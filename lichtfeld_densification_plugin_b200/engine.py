@@ -284,11 +284,12 @@ class DensifyEngine:
         host = torch.from_numpy(arr.view(np.uint8).reshape(-1))
         return host.to(self.device, non_blocking=False)
 
-    def densify(self, batch: RefBatch, cfg: PathConfig, uniforms: Optional[torch.Tensor] = None,
+    def prepare(self, batch: RefBatch, cfg: PathConfig, uniforms: Optional[torch.Tensor] = None,
                 collect_debug: bool = False, taps: bool = False, descs_dev: Optional[torch.Tensor] = None,
-                outputs: Optional[DensifyOutputs] = None) -> DensifyOutputs:
-        """Run the whole path for ``batch``.  ``uniforms``: f64 [n_refs, U] device tensor selects the
-        explicit (parity) RNG mode; otherwise Philox keyed by (cfg.seed, rng_stream)."""
+                outputs: Optional[DensifyOutputs] = None) -> "PreparedLaunch":
+        """Everything ``densify`` does on the host except the call itself: parameter block, workspace, descriptor upload,
+        output allocation.  ``PreparedLaunch.launch()`` can then be repeated (same batch, same outputs) at the cost of one
+        C call - for callers that re-run a batch or keep several launches in flight."""
         R = len(batch)
         dev = self.device
         rng_mode = N.LDP_RNG_PHILOX
@@ -317,14 +318,15 @@ class DensifyEngine:
             o.sel_idx = out.sel_idx.data_ptr()
         if out.sample_flags is not None:
             o.sample_flags, o.sample_xyzerr = out.sample_flags.data_ptr(), out.sample_xyzerr.data_ptr()
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = self.lib.ldp_densify_refs(C.byref(params), C.c_void_p(descs_dev.data_ptr()),
-                                       C.c_void_p(uniforms.data_ptr() if uniforms is not None else 0), C.byref(o),
-                                       C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()), C.c_void_p(stream))
-        N.check(rc, "ldp_densify_refs")
-        out.launches = int(self.lib.ldp_last_launch_count())
         out._keep = (descs_dev, uniforms, batch)      # keep inputs alive until the stream is done with them
-        return out
+        return PreparedLaunch(self, params, o, out, descs_dev, uniforms, ws)
+
+    def densify(self, batch: RefBatch, cfg: PathConfig, uniforms: Optional[torch.Tensor] = None,
+                collect_debug: bool = False, taps: bool = False, descs_dev: Optional[torch.Tensor] = None,
+                outputs: Optional[DensifyOutputs] = None) -> DensifyOutputs:
+        """Run the whole path for ``batch``.  ``uniforms``: f64 [n_refs, U] device tensor selects the
+        explicit (parity) RNG mode; otherwise Philox keyed by (cfg.seed, rng_stream)."""
+        return self.prepare(batch, cfg, uniforms, collect_debug, taps, descs_dev, outputs).launch()
 
     def postprocess_certainty(self, batch: RefBatch, certainty_floor: float) -> torch.Tensor:
         """``ldp_postprocess_certainty``: the reference's certainty post-processing alone (core/pipeline.py:405-430).
@@ -400,6 +402,28 @@ class DensifyEngine:
             out.sample_flags = torch.zeros((R, sel_cap), dtype=torch.uint8, device=dev)
             out.sample_xyzerr = torch.zeros((R, sel_cap, 4), **f32)
         return out
+
+
+class PreparedLaunch:
+    """A launch of the path with its host-side arguments frozen (``DensifyEngine.prepare``)."""
+
+    def __init__(self, engine: "DensifyEngine", params, c_outputs, outputs: DensifyOutputs, descs_dev, uniforms, workspace) -> None:
+        self.engine, self.params, self.c_outputs, self.outputs = engine, params, c_outputs, outputs
+        self.descs_dev, self.uniforms, self.workspace = descs_dev, uniforms, workspace
+        self._args = (C.byref(params), C.c_void_p(descs_dev.data_ptr()),
+                      C.c_void_p(uniforms.data_ptr() if uniforms is not None else 0), C.byref(c_outputs),
+                      C.c_void_p(workspace.data_ptr()), C.c_size_t(workspace.numel()))
+
+    def launch(self) -> DensifyOutputs:
+        """Enqueue the launch sequence on the current torch CUDA stream."""
+        eng = self.engine
+        if eng._workspace is not self.workspace:
+            raise RuntimeError("the engine's workspace was re-allocated for a larger launch: prepare() again")
+        stream = torch.cuda.current_stream(eng.device).cuda_stream
+        rc = eng.lib.ldp_densify_refs(*self._args, C.c_void_p(stream))
+        N.check(rc, "ldp_densify_refs")
+        self.outputs.launches = int(eng.lib.ldp_last_launch_count())
+        return self.outputs
 
 
 class DensifyRing:
