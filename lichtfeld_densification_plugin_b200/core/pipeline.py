@@ -144,6 +144,23 @@ def get_engine(device: Optional[torch.device] = None) -> DensifyEngine:
     return eng
 
 
+_rings: Dict[int, "DensifyRing"] = {}
+
+
+def get_ring(device: Optional[torch.device] = None, depth: int = 3):
+    """Per-device ring of engines for callers that keep several launches in flight (run_dense_pipeline with
+    ``config.refs_per_launch``)."""
+    from ..engine import DensifyRing
+    if not torch.cuda.is_available():
+        raise N.NativeLibraryError("the densification path needs a CUDA device (there is no CPU fallback)")
+    idx = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    ring = _rings.get(idx)
+    if ring is None or ring.depth != depth:
+        ring = DensifyRing(torch.device("cuda", idx), depth)
+        _rings[idx] = ring
+    return ring
+
+
 def _to_device(t, device, dtype) -> torch.Tensor:
     if isinstance(t, np.ndarray):
         t = torch.from_numpy(t)
@@ -215,22 +232,24 @@ def _mt_stream_from_global(n: int) -> np.ndarray:
     return rs.random_sample(n)
 
 
-def triangulate_refs(matched_refs: Sequence[_MatchedReference], tri_ctx: _TriangulationContext,
-                     collect_debug_matches: bool = False, *, rng_streams: Optional[Sequence[int]] = None,
-                     uniforms: Optional[np.ndarray] = None,
-                     weight_sums: Optional[Sequence[float]] = None,
-                     errors: Optional[list] = None, ply_records: bool = False) -> List[Optional[_TriangulatedReference]]:
-    """Batched ``_triangulate_ref``: every view of ``matched_refs`` in one launch sequence.
+@dataclass
+class _PendingLaunch:
+    """A submitted launch of ``triangulate_refs`` whose results have not been read back yet."""
+    out: DensifyOutputs
+    batch: RefBatch
+    n: int
+    collect_debug: bool
+    ply_records: bool
 
-    RNG: ``uniforms`` (f64 [n, U], explicit parity stream per view) or Philox keyed by
-    (config.seed, rng_streams[i]).  Views the reference would skip (None return / exception) come back as
-    None; the exception a per-view call would raise is appended to ``errors`` as (index, exc).
-    ``ply_records``: also return every view's PLY vertex records (built on the device, 15 bytes per point).
-    """
+
+def submit_refs(matched_refs: Sequence[_MatchedReference], tri_ctx: _TriangulationContext,
+                collect_debug_matches: bool = False, *, rng_streams: Optional[Sequence[int]] = None,
+                uniforms: Optional[np.ndarray] = None, weight_sums: Optional[Sequence[float]] = None,
+                ply_records: bool = False, ring=None) -> _PendingLaunch:
+    """First half of ``triangulate_refs``: upload what is not on the device yet and enqueue the launch sequence - on the
+    next stream of ``ring`` (a ``DensifyRing``: several launches in flight) or on the current stream."""
     n = len(matched_refs)
-    if n == 0:
-        return []
-    eng = get_engine()
+    eng = get_engine() if ring is None else ring.engines[ring.slot()]
     dev = eng.device
     cfg = tri_ctx.config
     pcfg = PathConfig.from_pipeline_config(cfg, sample_cap=tri_ctx.matcher_sample_cap)
@@ -263,13 +282,24 @@ def triangulate_refs(matched_refs: Sequence[_MatchedReference], tri_ctx: _Triang
     u_dev = None
     if uniforms is not None:
         u_dev = torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float64)).to(dev)
-    out = eng.densify(batch, pcfg, uniforms=u_dev, collect_debug=collect_debug_matches)
-    host = _download(out, collect_debug_matches, ply_records)
+    if ring is None:
+        out = eng.densify(batch, pcfg, uniforms=u_dev, collect_debug=collect_debug_matches)
+    else:
+        out = ring.submit(batch, pcfg, uniforms=u_dev, collect_debug=collect_debug_matches)
+    return _PendingLaunch(out=out, batch=batch, n=n, collect_debug=collect_debug_matches, ply_records=ply_records)
+
+
+def collect_refs(pending: _PendingLaunch, errors: Optional[list] = None, ring=None) -> List[Optional[_TriangulatedReference]]:
+    """Second half: one synchronising read of the launch's results, split per view."""
+    out, batch = pending.out, pending.batch
+    if ring is not None:
+        ring.wait(out)                                 # the current stream (which does the read-back) follows the ring stream
+    host = _download(out, pending.collect_debug, pending.ply_records)
     results: List[Optional[_TriangulatedReference]] = []
-    for r in range(n):
+    for r in range(pending.n):
         try:
             _raise_for_status(int(host["status"][r]))
-            results.append(_split_reference(out, host, r, batch.nbr_uids[r], collect_debug_matches))
+            results.append(_split_reference(out, host, r, batch.nbr_uids[r], pending.collect_debug))
         except Exception as exc:      # the reference's caller logs and skips (core/pipeline.py:874-879)
             if errors is not None:
                 errors.append((r, exc))
@@ -277,6 +307,25 @@ def triangulate_refs(matched_refs: Sequence[_MatchedReference], tri_ctx: _Triang
     triangulate_refs.last_uniforms_used = host["uniforms_used"]
     triangulate_refs.last_launches = out.launches
     return results
+
+
+def triangulate_refs(matched_refs: Sequence[_MatchedReference], tri_ctx: _TriangulationContext,
+                     collect_debug_matches: bool = False, *, rng_streams: Optional[Sequence[int]] = None,
+                     uniforms: Optional[np.ndarray] = None,
+                     weight_sums: Optional[Sequence[float]] = None,
+                     errors: Optional[list] = None, ply_records: bool = False) -> List[Optional[_TriangulatedReference]]:
+    """Batched ``_triangulate_ref``: every view of ``matched_refs`` in one launch sequence.
+
+    RNG: ``uniforms`` (f64 [n, U], explicit parity stream per view) or Philox keyed by
+    (config.seed, rng_streams[i]).  Views the reference would skip (None return / exception) come back as
+    None; the exception a per-view call would raise is appended to ``errors`` as (index, exc).
+    ``ply_records``: also return every view's PLY vertex records (built on the device, 15 bytes per point).
+    """
+    if len(matched_refs) == 0:
+        return []
+    pending = submit_refs(matched_refs, tri_ctx, collect_debug_matches, rng_streams=rng_streams, uniforms=uniforms,
+                          weight_sums=weight_sums, ply_records=ply_records)
+    return collect_refs(pending, errors)
 
 
 def _triangulate_ref(matched_ref: _MatchedReference, tri_ctx: _TriangulationContext,
@@ -436,24 +485,12 @@ def run_dense_pipeline(
     ply_parts: List[np.ndarray] = []
     ply_points = 0
     total = len(refs_local)
-    for lo in range(0, total, step):
-        if _is_cancelled(cancel_requested):
-            raise PipelineCancelled("Cancelled")
-        chunk = refs_local[lo:lo + step]
-        matched = [(r, match_source(r)) for r in chunk]
-        matched = [(r, m) for r, m in matched if m is not None]
-        if not matched:
-            continue
-        if getattr(config, "rng_mode", RNG_PHILOX) == RNG_NUMPY_GLOBAL:
-            outs = []
-            for _, m in matched:
-                try:
-                    outs.append(_triangulate_ref(m, tri_ctx))
-                except Exception:
-                    outs.append(None)
-        else:
-            outs = triangulate_refs([m for _, m in matched], tri_ctx, rng_streams=[int(r) for r, _ in matched],
-                                    ply_records=ply_base is not None)
+    n_chunks = (total + step - 1) // step
+    ring = get_ring() if (n_chunks > 1 and getattr(config, "rng_mode", RNG_PHILOX) != RNG_NUMPY_GLOBAL) else None
+    in_flight: List[Tuple[int, _PendingLaunch]] = []      # (views done when this launch is collected, launch)
+
+    def consume(outs, done: int) -> None:
+        nonlocal pairs, ply_points
         for tri in outs:
             if tri is None:
                 continue
@@ -470,8 +507,37 @@ def run_dense_pipeline(
                 if pairs % viz_interval == 0:
                     _emit_intermediate_ply(f"{ply_base}_{pairs}.ply", ply_points, ply_parts, on_sequential_viz)
         if progress_callback:
-            done = min(total, lo + step)
             progress_callback(10.0 + 80.0 * done / max(1, total), f"Matching {done}/{total} references")
+
+    for lo in range(0, total, step):
+        if _is_cancelled(cancel_requested):
+            raise PipelineCancelled("Cancelled")
+        chunk = refs_local[lo:lo + step]
+        done = min(total, lo + step)
+        matched = [(r, match_source(r)) for r in chunk]
+        matched = [(r, m) for r, m in matched if m is not None]
+        if not matched:
+            continue
+        if getattr(config, "rng_mode", RNG_PHILOX) == RNG_NUMPY_GLOBAL:
+            outs = []
+            for _, m in matched:
+                try:
+                    outs.append(_triangulate_ref(m, tri_ctx))
+                except Exception:
+                    outs.append(None)
+            consume(outs, done)
+        elif ring is None:
+            consume(triangulate_refs([m for _, m in matched], tri_ctx, rng_streams=[int(r) for r, _ in matched],
+                                     ply_records=ply_base is not None), done)
+        else:
+            # several launches in flight: the next chunk is uploaded and enqueued before the oldest one is read back
+            in_flight.append((done, submit_refs([m for _, m in matched], tri_ctx, rng_streams=[int(r) for r, _ in matched],
+                                                ply_records=ply_base is not None, ring=ring)))
+            if len(in_flight) >= ring.depth:
+                d, pend = in_flight.pop(0)
+                consume(collect_refs(pend, ring=ring), d)
+    for d, pend in in_flight:
+        consume(collect_refs(pend, ring=ring), d)
     if _is_cancelled(cancel_requested):
         raise PipelineCancelled("Cancelled")
     if progress_callback:

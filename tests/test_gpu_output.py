@@ -158,13 +158,15 @@ def test_run_dense_pipeline_live_updates_write_the_reference_files(tmp_path):
                                    cert_list_cpu=[inp["cert"][k] for k in range(len(nb))], pair_index_by_nbr={}, image_by_nbr={})
     refs = list(range(scene.n_refs))
     assert len(refs) >= 6
-    for per_launch in (0, 4):
+    results = {}
+    for per_launch in (0, 4, 2):                      # one launch; 2 and 4 launches kept in flight on the ring of engines
         out_dir = tmp_path / f"run{per_launch}"
         cfg = DensePipelineConfig(output_path=str(out_dir / "dense.ply"), matches_per_ref=2000, viz_interval=2, refs_per_launch=per_launch)
         emitted = []
         res = P.run_dense_pipeline(cams, refs, None, cfg, on_sequential_viz=emitted.append, match_source=match_source,
                                    w_match=scene.w_match, h_match=scene.h_match)
         assert res.pairs_processed == len(refs) and res.xyz.shape[0] > 1000
+        results[per_launch] = res
         assert [os.path.basename(p) for p in emitted] == [f"dense_intermediate_{k}.ply" for k in range(2, len(refs) + 1, 2)]
         # per-view sizes: the same views one at a time (Philox streams are keyed by the view, not by the launch)
         ctx = P._TriangulationContext(cameras=P._build_camera_lookup(cams), config=cfg, matcher_sample_cap=0.9,
@@ -175,6 +177,9 @@ def test_run_dense_pipeline_live_updates_write_the_reference_files(tmp_path):
             n = sum(sizes[:k])
             W.write_ply(str(out_dir / "want.ply"), res.xyz[:n], W.to_uint8_rgb(res.rgb[:n]))
             assert open(path, "rb").read() == (out_dir / "want.ply").read_bytes(), (per_launch, k)
+    for per_launch in (4, 2):                         # cutting the views into launches changes nothing
+        assert np.array_equal(results[0].xyz, results[per_launch].xyz) and np.array_equal(results[0].rgb, results[per_launch].rgb)
+        assert np.array_equal(results[0].err, results[per_launch].err)
     # no callback / interval 0: nothing is written
     cfg = DensePipelineConfig(output_path=str(tmp_path / "none" / "dense.ply"), matches_per_ref=2000, viz_interval=0)
     P.run_dense_pipeline(cams, refs[:2], None, cfg, on_sequential_viz=emitted.append, match_source=match_source,
