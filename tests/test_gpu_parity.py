@@ -206,3 +206,28 @@ def test_randomised_shapes(engine, case):
         assert rep.ok(), (case, H, W, hm, wm, nn, M, fam, rep)
         if not no_filter:
             assert g.uniforms_used[r] == res.taps["uniforms_used"] and g.rounds[r] == res.taps["rounds"]
+
+
+def test_neighbours_with_their_own_camera_sizes(engine):
+    """the pixel scales of a neighbour use ITS camera's (width, height) (core/pipeline.py:697-699); here every
+    third camera is a different sensor (other size, other intrinsics), as neighbour and as reference view."""
+    from lichtfeld_densification_plugin_b200 import synth
+    from lichtfeld_densification_plugin_b200.core.camera_models import CameraRecord
+    scene = synth.make_scene(16, "turbo", ref_fraction=0.25, nn=3)
+    for i, cam in enumerate(scene.cameras):
+        if i % 3 == 1:
+            w2, h2 = 973, 1111
+            K2 = np.array([[0.9 * w2, 0.0, w2 / 2.0 + 3.0], [0.0, 0.85 * w2, h2 / 2.0 - 2.0], [0.0, 0.0, 1.0]], dtype=np.float32)
+            scene.cameras[i] = CameraRecord.from_KRt(cam.uid, w2, h2, K2, cam.R, cam.t, image_path=cam.image_path)
+    c = dict(M=6000, no_filter=False, wm=scene.w_match, hm=scene.h_match)
+    inputs = [synth.synth_ref_inputs(scene, rp, cert_family="T", seed=33) for rp in range(scene.n_refs)]
+    sizes = {(scene.cameras[j].width, scene.cameras[j].height) for inp in inputs for j in list(inp["nbr_indices"]) + [inp["ref_index"]]}
+    assert len(sizes) == 2
+    U = np.stack([np.random.RandomState(900 + r).random_sample(3 * c["M"]) for r in range(len(inputs))])
+    ress = [G.run_oracle_ref(scene, inp, c, uniforms=U[r], collect_debug=True) for r, inp in enumerate(inputs)]
+    g = G.run_gpu(engine, scene, inputs, G.path_cfg(c), uniforms=U, weight_sums=[res.taps["s"] for res in ress], collect_debug=True)
+    for r in range(len(inputs)):
+        rep = G.compare_ref(g, r, ress[r], c, scene)
+        _report(f"mixed-sensors/ref{r}", rep)
+        assert rep.ok(), rep
+        assert rep.n_kept_ref > 1000
