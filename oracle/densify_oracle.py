@@ -30,6 +30,8 @@ __all__ = [
     "OracleCamera",
     "OracleConfig",
     "legacy_choice_no_replace",
+    "philox4x32_10",
+    "philox_uniforms",
     "sample_weights",
     "coverage_picks",
     "select_samples",
@@ -138,6 +140,56 @@ def legacy_choice_no_replace(p32: np.ndarray, size: int, uniforms: np.ndarray) -
         found[have:have + hit.size] = hit
         have += hit.size
     return found, used, rounds
+
+
+# ----------------------------------------------------------------------------------------------
+# production uniforms: the product's counter-based stream restated on the host, so that a Philox-mode GPU
+# run can be compared value for value with ``legacy_choice_no_replace`` fed the same doubles.
+# (Not reference code: the reference draws from numpy's global MT19937, core/sampling.py:32.  What is
+# restated here is lichtfeld_densification_plugin_b200/csrc/ldp_device.cuh:philox4x32_10 / philox_uniform.)
+# ----------------------------------------------------------------------------------------------
+_PHILOX_M0, _PHILOX_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PHILOX_W0, _PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+
+
+def philox4x32_10(counter: np.ndarray, key: Sequence[int]) -> np.ndarray:
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11;
+    Random123 ``philox4x32_R(10, ctr, key)``).  ``counter``: uint32 [..., 4]; ``key``: two 32-bit words.
+    Returns uint32 [..., 4].  Known-answer vectors of Random123's ``kat_vectors`` are in tests/test_oracle_philox.py."""
+    c = np.asarray(counter, dtype=np.uint32).astype(np.uint64)
+    c0, c1, c2, c3 = c[..., 0], c[..., 1], c[..., 2], c[..., 3]
+    k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    mask = np.uint64(0xFFFFFFFF)
+    sh = np.uint64(32)
+    for _ in range(10):
+        p0 = _PHILOX_M0 * c0                     # 32 x 32 -> 64 bit products
+        p1 = _PHILOX_M1 * c2
+        hi0, lo0 = p0 >> sh, p0 & mask
+        hi1, lo1 = p1 >> sh, p1 & mask
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0 = (k0 + _PHILOX_W0) & 0xFFFFFFFF
+        k1 = (k1 + _PHILOX_W1) & 0xFFFFFFFF
+    return np.stack([c0, c1, c2, c3], axis=-1).astype(np.uint32)
+
+
+PHILOX_DOMAIN_TAG = 0x4C445031                   # "LDP1": fourth counter word of the sampler's stream
+
+
+def philox_uniforms(seed: int, stream: int, n: int, first: int = 0) -> np.ndarray:
+    """Draws ``first .. first + n - 1`` of view ``stream``'s production stream, as the kernels build them
+    (ldp_device.cuh:philox_uniform): draw d uses Philox counter (d >> 1, 0, stream, "LDP1") under key
+    (seed & 2^32-1, seed >> 32); even d takes output words (0, 1), odd d words (2, 3); the double is numpy's
+    ``random_sample`` construction ((a >> 5) * 2^26 + (b >> 6)) / 2^53, so both modes share one lattice."""
+    d = np.arange(first, first + n, dtype=np.uint64)
+    ctr = np.zeros((n, 4), dtype=np.uint32)
+    ctr[:, 0] = (d >> np.uint64(1)).astype(np.uint32)
+    ctr[:, 2] = np.uint32(int(stream) & 0xFFFFFFFF)
+    ctr[:, 3] = np.uint32(PHILOX_DOMAIN_TAG)
+    r = philox4x32_10(ctr, (int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF))
+    odd = (d & np.uint64(1)).astype(bool)
+    a = np.where(odd, r[:, 2], r[:, 0]).astype(np.uint64)
+    b = np.where(odd, r[:, 3], r[:, 1]).astype(np.uint64)
+    return ((a >> np.uint64(5)).astype(np.float64) * 67108864.0 + (b >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
 
 
 def sample_weights(best_cert: torch.Tensor, cap: float, border: int) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -13,8 +13,18 @@ from tests.helpers import oracle_cam
 
 XYZ_RTOL, XYZ_ATOL = 1e-4, 1e-5          # BASELINE.json north_star tolerance for XYZ / colour
 ERR_ATOL = 1e-3                          # reprojection error: the reference's own f32-SVD noise reaches 2.4e-4 px
-NEAR_REPROJ = 2e-3                       # px: a keep flip is "near threshold" if |err - thr| below this
-NEAR_PARALLAX = 5e-3                     # degrees
+# Keep masks must be bit-exact.  The ONE admitted exception, always listed with its distances: the reference solves the
+# 4x4 DLT system with LAPACK's float32 SVD, whose result moves from build to build (SURVEY.md 7-5 / App. B measured
+# 1.1e-5 px / 9.2e-4 degrees on its probes; on the 46-view bench batch the same noise reaches 6e-5 px, see
+# tests/test_gpu_parity.py::test_bench_batch_philox_mode_vs_oracle).  A flip is therefore tolerated only if
+#   (a) the GPU's verdict equals the verdict of the REFERENCE'S OWN filter code (oracle restatement, float32, same
+#       operation order) applied to the exactly solved point (float64 SVD of the same float32 DLT matrix, rounded once
+#       to float32) -- i.e. it is the reference's solver noise, not ours, that crossed the threshold; and
+#   (b) that exact point lies within the reference's documented solver noise of a threshold:
+NEAR_REPROJ = 2.5e-4                     # px   (reference f32-SVD noise on the reprojection error reaches 2.4e-4 px)
+NEAR_PARALLAX = 9.2e-4                   # degrees
+# north_star's 1e-6 band is narrower than the reference's own irreproducibility; what is enforced instead is (a), which
+# admits no error of ours at any distance.  The golden cases (tie-free and realistic) assert ZERO flips.
 
 
 def path_cfg(c: dict, seed: int = 0) -> PathConfig:
@@ -222,15 +232,11 @@ def compare_ref(g: GpuRun, r: int, res, c, scene) -> ParityReport:
     # keep flags
     flips = np.nonzero((keep_gpu_all != keep_ref) & common)[0]
     for i in flips:
-        d_reproj = abs(float(xe[i, 3]) - float(thr_r))
-        d_ref = abs(float(e_ref[i]) - float(thr_r)) if have[i] else float("inf")
-        near = min(d_reproj, d_ref) < NEAR_REPROJ
-        info = {"sample": int(i), "pixel": int(sel_gpu[i]), "err_gpu": float(xe[i, 3]), "err_ref": float(e_ref[i]), "dist_reproj": min(d_reproj, d_ref)}
-        if not near and c.get("parallax", 0.5) > 0 and have[i]:
-            # parallax angle recomputed in f64 from the oracle's point
-            info["parallax_checked"] = True
-            near = _parallax_near(res, scene, int(m[i]), X_ref[i], c)
-        info["near_threshold"] = bool(near)
+        info = _explain_flip(res, scene, int(m[i]), c)
+        info.update(sample=int(i), pixel=int(sel_gpu[i]), keep_gpu=bool(keep_gpu_all[i]), keep_ref=bool(keep_ref[i]),
+                    err_gpu=float(xe[i, 3]), err_ref=float(e_ref[i]) if have[i] else None)
+        near = bool(info.pop("explained")) and info["keep_exact"] == bool(keep_gpu_all[i])
+        info["near_threshold"] = near
         rep.keep_flips.append(info)
         if not near:
             rep.keep_flips_far += 1
@@ -263,22 +269,42 @@ def compare_ref(g: GpuRun, r: int, res, c, scene) -> ParityReport:
     return rep
 
 
-def _parallax_near(res, scene, i, X, c) -> bool:
-    """Is the f64 parallax angle of oracle point X (sample i) within NEAR_PARALLAX of the threshold?"""
-    uid = None
+def _explain_flip(res, scene, i, c) -> dict:
+    """Verdict of the reference's filter code (oracle restatement) on the EXACTLY solved point of oracle sample ``i``:
+    float64 SVD of the same float32 DLT matrix, dehomogenised, rounded once to float32.  ``explained`` is True when that
+    point is within the reference's solver noise of the threshold that decides it."""
     for gt in res.taps["groups"]:
-        if "pos" in gt and (gt["pos"] == i).any():
-            uid = gt["uid"]
-            break
-    if uid is None:
-        return False
-    cams = {cam.uid: cam for cam in scene.cameras}
-    C1 = cams[res.taps["ref_uid"]].C.astype(np.float64)
-    C2 = cams[uid].C.astype(np.float64)
-    a, b = X - C1, X - C2
-    cosv = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
-    ang = np.degrees(np.arccos(np.clip(cosv, -1, 1)))
-    return abs(ang - c.get("parallax", 0.5)) < NEAR_PARALLAX
+        if "pos" not in gt:
+            continue
+        hit = np.nonzero(gt["pos"] == i)[0]
+        if hit.size == 0:
+            continue
+        j = int(hit[0])
+        uvA, uvB, P1, P2 = gt["uvA"][j:j + 1], gt["uvB"][j:j + 1], gt["P1"], gt["P2"]
+        A = np.empty((4, 4), dtype=np.float32)
+        A[0] = uvA[0, 0] * P1[2] - P1[0]
+        A[1] = uvA[0, 1] * P1[2] - P1[1]
+        A[2] = uvB[0, 0] * P2[2] - P2[0]
+        A[3] = uvB[0, 1] * P2[2] - P2[1]
+        v = np.linalg.svd(A.astype(np.float64))[2][-1]
+        X = np.concatenate([(v[:3] / v[3]).astype(np.float32), np.ones(1, dtype=np.float32)])[None, :]
+        e = float(np.maximum(O.reprojection_error(P1, X, uvA), O.reprojection_error(P2, X, uvB))[0])
+        thr = float(np.float32(c.get("reproj", 0.8)))
+        keep = bool(np.float32(e) <= np.float32(thr)) and bool(O.in_front(P1, X)[0]) and bool(O.in_front(P2, X)[0])
+        out = {"err_exact": e, "dist_reproj": abs(e - thr)}
+        explained = abs(e - thr) < NEAR_REPROJ
+        min_deg = c.get("parallax", 0.5)
+        if min_deg > 0:
+            cams = {cam.uid: cam for cam in scene.cameras}
+            C1, C2 = cams[res.taps["ref_uid"]].C, cams[gt["uid"]].C
+            keep = keep and bool(O.parallax_ok(C1, C2, X.copy(), min_deg)[0])
+            a, b = X[0, :3].astype(np.float64) - C1.astype(np.float64), X[0, :3].astype(np.float64) - C2.astype(np.float64)
+            ang = float(np.degrees(np.arccos(np.clip(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)), -1, 1))))
+            out["dist_parallax_deg"] = abs(ang - min_deg)
+            explained = explained or abs(ang - min_deg) < NEAR_PARALLAX
+        out.update(keep_exact=keep, explained=explained)
+        return out
+    return {"keep_exact": None, "explained": False}
 
 
 def expected_pack_order(flags: np.ndarray) -> np.ndarray:
