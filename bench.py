@@ -8,14 +8,22 @@ Workload (config.workload): BASELINE.json configs[1] -- MipNeRF360-garden-shaped
 per reference, all filters on; synthetic matcher outputs (the RoMa network is out of scope).  One "step" = one pass
 of sample -> triangulate -> filter -> colour over all 46 reference views (one launch sequence of the C-ABI call).
 
-value      filtered 3D points / s, inputs resident in HBM, CUDA-event timed, max over ranks (weak scaling: every
-           rank processes its own 46-view scene; for N > 1 the per-step NCCL all-gather of the kept-point counts is
-           enqueued on a side stream and is inside the timed region).
-e2e        same metric through the public batched API from HOST buffers: certainty planes + reference images are
-           copied host->device from pinned memory every step, the warp planes stay in pinned host memory and are
-           gathered over PCIe at the sampled pixels only (zero-copy), results are read back device->host.
-roofline   dominant kernel (ldp_stream_kernel): algorithmic bytes = nn*H*W*4 per view (every certainty read once),
-           duration from CUDA events recorded around the kernel on its launch stream (ldp_profile_*).
+value      filtered 3D points / s, inputs resident in HBM, CUDA-event timed, max over ranks.  Weak scaling: every rank
+           processes its own 46-view batches, each step in flight reads its OWN input tensors, and there is NO collective
+           per step: the points stay on the rank that made them; the ranks' kept-point counts (what a rank needs to place
+           its slice in the global output) are exchanged ONCE, after the last step, inside the timed region.
+e2e        same metric through the public batched API from HOST buffers (pinned): certainty planes + reference images
+           are copied host->device every step, the warp planes stay in pinned host memory and are gathered over PCIe at
+           the sampled pixels only (zero-copy), results are read back device->host.
+api        the drop-in entry point an integrator calls, core.pipeline.triangulate_refs (descriptors rebuilt per call,
+           results returned as numpy arrays), with device-resident matcher outputs and with pageable host tensors.
+roofline   dominant kernel (the fused front kernel: every certainty value read once, nn*H*W*4 bytes per view), duration
+           from back-to-back launches of that kernel alone between two CUDA events; by_kernel: every kernel of the step
+           (event-bracketed inside the step); path_frac: SURVEY 8d bytes of the whole step / step time / peak.
+config5    BASELINE.json configs[4]: 1000-view scene, 'base' 640x640, 250 reference views sharded over the ranks
+           (distributed.shard_bounds), Philox keyed by the global view index; timed region = every launch of the rank +
+           ONE final point all-gather (single NCCL collective of the rank's packed cloud, counts in its header) + the
+           device-side concatenation in rank order; checked bit-exact against the single-GPU result.
 cpu_baseline / --impl reference
            the oracle port of the reference's CPU path (oracle/densify_oracle.py, bit-identical to the reference in
            the build container) on the host cores, one process per core, bounded sample.
@@ -23,6 +31,7 @@ cpu_baseline / --impl reference
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import multiprocessing as mp
 import os
@@ -38,8 +47,11 @@ import numpy as np  # noqa: E402
 
 WORKLOAD = dict(name="garden-shaped 185 views, RoMa fast 512x512, ref_fraction 0.25 (46 refs), 4 nn/ref (184 pairs), "
                      "M=10000, all filters on", n_views=185, setting="fast", ref_fraction=0.25, nn=4, M=10000)
+CONFIG5 = dict(name="1000 views, RoMa base 640x640, ref_fraction 0.25 (250 refs), 4 nn/ref (1000 pairs), M=10000, all filters on",
+               n_views=1000, setting="base", ref_fraction=0.25, nn=4, M=10000, refs_per_launch=32)
 METRIC = "filtered_points_per_sec"
 UNIT = "points/s"
+CPU_SAMPLE = dict(steps=8, warmup=3)          # cpu_baseline inside the GPU arm: same code and sample shape as --impl reference
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -101,21 +113,30 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def cpu_sample_text(workers: int, steps: int, warmup: int) -> str:
+    return (f"{workers} processes (one per host core, torch threads = 1) x {steps} timed reference views each of the workload "
+            f"after {warmup} warm-up views (1 view per step per process)")
+
+
 def reference_arm(args) -> None:
+    """The reference's CPU implementation of the path (oracle port; the reference is pure Python and was checked
+    bit-identical against it in the build container) on every host core.  --steps / --warmup are honoured as given:
+    a step is one reference view per worker process (a bounded sample of the 46-view workload)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     workers = max(1, min(host_cores(), 32))
-    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
+    steps = max(1, args.steps if args.steps is not None else 20)
+    warmup = max(0, args.warmup if args.warmup is not None else 3)
     r = run_cpu_arm(workers, steps, warmup)
-    sample = f"{workers} processes x {steps} timed reference views each of the workload (1 view per step per process)"
     line = {
         "impl": "reference", "metric": METRIC, "value": r["points_per_s"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * r["wall_s"] / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 geometry / f64 cdf, sampson, colour", "data": "synthetic",
         "config": {"workload": WORKLOAD["name"]},
         "pairs_per_sec": r["pairs_per_s"],
-        "cpu_baseline": {"value": r["points_per_s"], "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": r["points_per_s"], "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": cpu_sample_text(workers, steps, warmup),
                          "ms_per_ref_single_core": r["ms_per_ref_single_core"]},
         "e2e": {"value": r["points_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -199,18 +220,227 @@ def _dbg(msg: str) -> None:
         print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
 
 
+class SceneInputs:
+    """Synthetic matcher outputs of `n` reference views of a scene, resident on one device."""
+
+    def __init__(self, scene, ref_positions, dev, seed: int):
+        import torch
+        from lichtfeld_densification_plugin_b200 import synth
+        n, nn, H, W = len(ref_positions), scene.nn, scene.H, scene.W
+        self.cert = torch.empty((n, nn, H, W), dtype=torch.float32, device=dev)
+        self.warp = torch.empty((n, nn, H, W, 4), dtype=torch.float32, device=dev)
+        self.image = torch.empty((n, scene.h_match, scene.w_match, 3), dtype=torch.uint8, device=dev)
+        self.table, self.positions = [], list(ref_positions)
+        for i, rp in enumerate(ref_positions):
+            inp = synth.synth_ref_inputs(scene, rp, device=dev, cert_family="R", seed=seed)
+            self.cert[i], self.warp[i], self.image[i] = inp["cert"], inp["warp"], inp["image"]
+            self.table.append((inp["ref_index"], inp["nbr_indices"]))
+
+    def batch(self, eng, scene, lo: int, hi: int, stream_base: int, cert=None, warp=None, image=None):
+        cert = self.cert if cert is None else cert
+        warp = self.warp if warp is None else warp
+        image = self.image if image is None else image
+        cams, nn = scene.cameras, scene.nn
+        b = eng.new_batch(scene.H, scene.W, scene.w_match, scene.h_match)
+        for i in range(lo, hi):
+            ri, nb = self.table[i]
+            b.add([cert[i, k] for k in range(nn)], [warp[i, k] for k in range(nn)], image[i], cams[ri],
+                  [cams[j] for j in nb], rng_stream=stream_base + self.positions[i])
+        return b
+
+
+def config5_block(args, dev, rank: int, world: int, ring) -> dict:
+    """BASELINE.json configs[4]: the sharded scene with the final point all-gather (see the module docstring)."""
+    import torch
+    import torch.distributed as dist
+    from lichtfeld_densification_plugin_b200 import distributed as D
+    from lichtfeld_densification_plugin_b200 import synth
+    from lichtfeld_densification_plugin_b200.engine import PathConfig
+    from lichtfeld_densification_plugin_b200.output import ConcatPlan, PackedCloud
+
+    scene = synth.make_scene(CONFIG5["n_views"], CONFIG5["setting"], CONFIG5["ref_fraction"], CONFIG5["nn"])
+    R_all, per = scene.n_refs, CONFIG5["refs_per_launch"]
+    cfg = PathConfig(matches_per_ref=CONFIG5["M"], seed=5)
+    eng0 = ring.engines[0]
+    sel_cap = eng0.sel_capacity(cfg.matches_per_ref)
+    depth = ring.depth
+
+    class Shard:
+        def __init__(self, lo, hi, cap_refs):
+            self.lo, self.hi = lo, hi
+            self.inputs = SceneInputs(scene, list(range(lo, hi)), dev, seed=500)
+            self.chunks = [(a, min(a + per, hi - lo)) for a in range(0, hi - lo, per)]
+            self.outs = [eng0.alloc_outputs(b - a, sel_cap) for a, b in self.chunks]
+            self.prepared = []
+            for c, (a, b) in enumerate(self.chunks):
+                j = c % depth
+                batch = self.inputs.batch(ring.engines[j], scene, a, b, stream_base=0)
+                descs = ring.engines[j].upload_descs(batch)
+                self.prepared.append((j, ring.engines[j].prepare(batch, cfg, descs_dev=descs, outputs=self.outs[c])))
+            self.cloud = PackedCloud(cap_refs * sel_cap, dev)            # the SAME capacity on every rank: one padded collective
+            self.plan = ConcatPlan([o.xyz for o in self.outs], [o.rgb for o in self.outs], [o.err for o in self.outs],
+                                   [o.ref_offset[o.n_refs:o.n_refs + 1] for o in self.outs], per * sel_cap)
+
+        def launch_all(self):
+            """every launch of the shard on the ring streams, then the rank's cloud on the main stream"""
+            main = torch.cuda.current_stream(dev)
+            for st in ring.streams:
+                st.wait_stream(main)
+            for j, p in self.prepared:
+                with torch.cuda.stream(ring.streams[j]):
+                    p.launch()
+            for st in ring.streams:
+                main.wait_stream(st)
+            self.plan.run(self.cloud)
+
+    cap_refs = max(D.shard_bounds(R_all, q, world)[1] - D.shard_bounds(R_all, q, world)[0] for q in range(world))
+    lo, hi = D.shard_bounds(R_all, rank, world)
+    shard = Shard(lo, hi, cap_refs)
+    gathered = PackedCloud(world * shard.cloud.capacity, dev) if world > 1 else None
+    scratch = torch.empty((world, shard.cloud.packed.numel()), dtype=torch.uint8, device=dev) if world > 1 else None
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_pass():
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        shard.launch_all()
+        e[1].record()
+        total, offsets = D.all_gather_cloud(shard.cloud, out=gathered, scratch=scratch)
+        e[2].record()
+        return e, total, offsets
+
+    passes = max(3, min(10, args.steps))
+    for _ in range(2):
+        one_pass()
+    barrier()
+    ms_all, ms_compute, ms_gather = [], [], []
+    total = offsets = None
+    for _ in range(passes):
+        barrier()
+        e, total, offsets = one_pass()
+        torch.cuda.synchronize(dev)
+        ms_all.append(e[0].elapsed_time(e[2]))
+        ms_compute.append(e[0].elapsed_time(e[1]))
+        ms_gather.append(e[1].elapsed_time(e[2]))
+    t = torch.tensor([float(np.median(ms_all)), float(np.median(ms_compute)), float(np.median(ms_gather))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_c, ms_g = (float(x) for x in t.tolist())
+    n_total = int(offsets[-1].item())
+    # ---- bit-exact check against the single-GPU result: rank 0 recomputes the whole scene alone (outside the timed region)
+    same = None
+    sha = None
+    if rank == 0:
+        if world > 1:
+            whole = Shard(0, R_all, R_all)
+            whole.launch_all()
+            torch.cuda.synchronize(dev)
+            ref_cloud = whole.cloud
+        else:                                   # N = 1: another cut into launches (46 views per launch) must give the same cloud
+            per_alt = 46
+            outs, preps = [], []
+            for a in range(0, R_all, per_alt):
+                b = min(a + per_alt, R_all)
+                batch = shard.inputs.batch(eng0, scene, a, b, stream_base=0)
+                o = eng0.alloc_outputs(b - a, sel_cap)
+                preps.append(eng0.prepare(batch, cfg, outputs=o))
+                preps[-1].launch()
+                torch.cuda.synchronize(dev)
+                outs.append(o)
+            from lichtfeld_densification_plugin_b200.output import concat_launches
+            ref_cloud = concat_launches(outs)
+            torch.cuda.synchronize(dev)
+        k = ref_cloud.total_points()
+        same = bool(k == n_total and torch.equal(ref_cloud.xyz[:k], total.xyz[:k]) and torch.equal(ref_cloud.rgb[:k], total.rgb[:k])
+                    and torch.equal(ref_cloud.err[:k], total.err[:k]))
+        h = hashlib.sha1()
+        for a in (total.xyz[:n_total], total.rgb[:n_total], total.err[:n_total]):
+            h.update(a.cpu().numpy().tobytes())
+        sha = h.hexdigest()
+    pad_bytes = int(shard.cloud.packed.numel())
+    return {
+        "workload": CONFIG5["name"], "refs_total": R_all, "refs_this_rank": hi - lo, "refs_per_launch": per,
+        "launches_per_rank": len(shard.chunks), "steps_in_flight": depth, "passes_timed": passes,
+        "ms": ms, "ms_launches_and_local_concat": ms_c, "ms_all_gather_and_concat": ms_g,
+        "points": n_total, "points_per_sec": n_total / (ms * 1e-3), "pairs_per_sec": R_all * scene.nn / (ms * 1e-3),
+        "all_gather": {"collective": "ncclAllGather (one call: count header + xyz | rgb | err, padded to capacity)" if world > 1 else "none (N = 1)",
+                       "bytes_sent_per_rank": pad_bytes if world > 1 else 0, "bytes_received_per_rank": pad_bytes * (world - 1),
+                       "payload_bytes_total": 28 * n_total, "ms": ms_g,
+                       "bus_gb_per_s": (pad_bytes * (world - 1) / (ms_g * 1e-3) / 1e9) if world > 1 and ms_g > 0 else None},
+        "limiter": ("all-gather" if ms_g > ms_c else "launches") if world > 1 else "launches",
+        "equals_single_gpu_result": same if world > 1 else None,
+        "equals_other_cut_into_launches": same if world == 1 else None,
+        "cloud_sha1": sha, "timing": "CUDA events on the main stream, median over the passes, max over ranks; host sync only between passes",
+    }
+
+
+def api_block(args, dev, scene, inputs, cfg_M: int) -> dict:
+    """The drop-in entry point: core.pipeline.triangulate_refs on _MatchedReference objects (descriptors rebuilt per call,
+    numpy results), with the matcher outputs on the device and with pageable host tensors (what the reference's
+    .to('cpu') leaves behind, core/pipeline.py:432-442)."""
+    import torch
+    from lichtfeld_densification_plugin_b200.core import pipeline as PL
+    from lichtfeld_densification_plugin_b200.core.config import DensePipelineConfig
+    cams = scene.cameras
+    cfg = DensePipelineConfig(output_path="/tmp/bench_api.ply", matches_per_ref=cfg_M)
+    ctx = PL._TriangulationContext(cameras=PL._build_camera_lookup(cams), config=cfg, matcher_sample_cap=0.9,
+                                   w_match=scene.w_match, h_match=scene.h_match)
+
+    def matched(cert, warp, image_np):
+        out = []
+        for i, (ri, nb) in enumerate(inputs.table):
+            packed = PL._PackedReferenceBatch(ref_id=cams[ri].uid, ref_path="", imA_np=image_np[i], maskA_np=None,
+                                              wA_cam=cams[ri].width, hA_cam=cams[ri].height, nn_ids=[cams[j].uid for j in nb],
+                                              nn_masks=[None] * len(nb), nn_arrays=[])
+            out.append(PL._MatchedReference(packed=packed, warp_list_cpu=[warp[i, k] for k in range(len(nb))],
+                                            cert_list_cpu=[cert[i, k] for k in range(len(nb))], pair_index_by_nbr={}, image_by_nbr={}))
+        return out
+
+    def run(mrs, n):
+        streams = [int(mr.packed.ref_id) for mr in mrs]
+        pts = 0
+        for _ in range(2):
+            PL.triangulate_refs(mrs, ctx, rng_streams=streams)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            res = PL.triangulate_refs(mrs, ctx, rng_streams=streams)
+            pts = sum(0 if r is None else int(r.xyz.shape[0]) for r in res)
+        torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) / n, pts
+
+    image_dev_np = inputs.image            # device tensor: _to_device accepts tensors as well as numpy arrays
+    n = max(3, min(args.steps, 20))
+    s_dev, pts = run(matched(inputs.cert, inputs.warp, image_dev_np), n)
+    h_cert, h_warp, h_img = inputs.cert.cpu(), inputs.warp.cpu(), inputs.image.cpu().numpy()
+    s_host, pts_h = run(matched(h_cert, h_warp, h_img), max(2, min(n, 5)))
+    return {"entry_point": "core.pipeline.triangulate_refs (46 _MatchedReference per call, numpy results)",
+            "device_resident_inputs": {"ms_per_step": 1e3 * s_dev, "points_per_sec": pts / s_dev},
+            "pageable_host_inputs": {"ms_per_step": 1e3 * s_host, "points_per_sec": pts_h / s_host,
+                                     "h2d_bytes_per_step": int(h_cert.numel() * 4 + h_warp.numel() * 4 + h_img.size)},
+            "points_per_step": pts}
+
+
 def gpu_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    steps = max(1, args.steps if args.steps is not None else 1000)
+    warmup = max(3, args.warmup if args.warmup is not None else 10)
+    args.steps, args.warmup = steps, warmup
 
     cpu_base = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline and not args.quick:
         # before CUDA is initialised in this process (workers are forked)
         workers = max(1, min(host_cores(), 32))
-        r = run_cpu_arm(workers, steps=2, warmup=1)
+        r = run_cpu_arm(workers, steps=CPU_SAMPLE["steps"], warmup=CPU_SAMPLE["warmup"])
         cpu_base = {"value": r["points_per_s"], "unit": UNIT, "cores": workers, "kind": "port",
-                    "sample": f"{workers} processes x 2 timed reference views each of the workload",
+                    "sample": cpu_sample_text(workers, CPU_SAMPLE["steps"], CPU_SAMPLE["warmup"]),
                     "ms_per_ref_single_core": r["ms_per_ref_single_core"], "pairs_per_sec": r["pairs_per_s"]}
 
     import torch
@@ -222,83 +452,37 @@ def gpu_arm(args) -> None:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        # the collective of the previous step runs beside the kernels: keep a few SMs free for it, or the one-CTA-per-SM
-        # draw kernel splits into two waves (the counts exchange is one small CTA; gathering all points needs channels)
-        if int(os.environ.get("BENCH_PIPELINE_DEPTH", "3")) <= 1:      # (with steps in flight DensifyRing reserves 16 SMs itself)
-            os.environ.setdefault("LDP_SM_RESERVE", "16" if int(os.environ.get("BENCH_GATHER_POINTS", "0")) else "4")
 
     scene = synth.make_scene(WORKLOAD["n_views"], WORKLOAD["setting"], WORKLOAD["ref_fraction"], WORKLOAD["nn"])
     R, nn, H, W = scene.n_refs, scene.nn, scene.H, scene.W
-    hm, wm = scene.h_match, scene.w_match
-    cert = torch.empty((R, nn, H, W), dtype=torch.float32, device=dev)
-    warp = torch.empty((R, nn, H, W, 4), dtype=torch.float32, device=dev)
-    image = torch.empty((R, hm, wm, 3), dtype=torch.uint8, device=dev)
-    nbr_table = []
-    for rp in range(R):
-        inp = synth.synth_ref_inputs(scene, rp, device=dev, cert_family="R", seed=100 + rank)
-        cert[rp], warp[rp], image[rp] = inp["cert"], inp["warp"], inp["image"]
-        nbr_table.append((inp["ref_index"], inp["nbr_indices"]))
-    torch.cuda.synchronize()
 
     # Consecutive steps are independent batches: DEPTH of them are kept in flight (engine.DensifyRing: one workspace and
-    # one CUDA stream per slot), so the HBM-bound first kernel of one step runs beside the latency-bound draw / geometry
-    # kernels of another.  BENCH_PIPELINE_DEPTH=1 times one launch sequence at a time (also measured and reported below).
+    # one CUDA stream per slot), each slot with its OWN input tensors (different synthetic matcher outputs), so the
+    # HBM-bound first kernel of one step runs beside the latency-bound draw / geometry kernels of another and no step
+    # can hit another step's lines in L2.  BENCH_PIPELINE_DEPTH=1 times one launch sequence at a time only.
     DEPTH = max(1, int(os.environ.get("BENCH_PIPELINE_DEPTH", "3")))
     ring = DensifyRing(dev, DEPTH)
     eng = ring.engines[0]
     cfg = PathConfig(matches_per_ref=WORKLOAD["M"], seed=0)
-    cams = scene.cameras
-
-    def make_batch(cert_t, warp_t, image_t):
-        b = eng.new_batch(H, W, wm, hm)
-        for rp in range(R):
-            ri, nb = nbr_table[rp]
-            b.add([cert_t[rp, k] for k in range(nn)], [warp_t[rp, k] for k in range(nn)], image_t[rp], cams[ri],
-                  [cams[j] for j in nb], rng_stream=rank * R + rp)
-        return b
-
-    batch = make_batch(cert, warp, image)
-    descs = eng.upload_descs(batch)
+    slots = [SceneInputs(scene, list(range(R)), dev, seed=100 + rank + 1000 * j) for j in range(DEPTH)]
+    torch.cuda.synchronize(dev)
+    batches = [slots[j].batch(ring.engines[j], scene, 0, R, stream_base=rank * R) for j in range(DEPTH)]
+    descs = [ring.engines[j].upload_descs(batches[j]) for j in range(DEPTH)]
     sel_cap = eng.sel_capacity(cfg.matches_per_ref)
-    NBUF = max(2, DEPTH)      # output buffers in rotation (8 at N = 2 measured slower: 0.158 vs 0.153 ms per step)
+    NBUF = max(2, DEPTH)      # output buffers in rotation
     outs = [eng.alloc_outputs(R, sel_cap) for _ in range(NBUF)]
-    cap = R * sel_cap
-
-    # multi-GPU: the views are sharded, the points stay on the rank that made them (as they stay in HBM at N = 1); what
-    # the ranks exchange every step is their kept-point COUNT (distributed.exchange_counts semantics: one int64 per rank,
-    # NCCL all-gather on a side stream), which gives each rank the global row offset of its slice of the output
-    # (distributed.write_ply_sharded).  BENCH_GATHER_POINTS=1 ships every point to every rank instead (28 B/point).
-    comm = torch.cuda.Stream(dev) if world > 1 else None
-    gather_points = bool(int(os.environ.get("BENCH_GATHER_POINTS", "0")))
-    if world > 1:
-        if gather_points:
-            gathered = [torch.empty((world, outs[0].packed.numel()), dtype=torch.uint8, device=dev) for _ in range(NBUF)]
-        counts_all = [torch.zeros((world,), dtype=torch.int64, device=dev) for _ in range(NBUF)]
-        gather_done = [torch.cuda.Event() for _ in range(NBUF)]
-        step_done = [torch.cuda.Event() for _ in range(NBUF)]
-
     prepared = {}      # (engine slot, output buffer) -> PreparedLaunch: the host side of a step is one C call
+    counts_all = torch.zeros((world, NBUF), dtype=torch.int64, device=dev) if world > 1 else None
 
     def step(i: int, depth: int):
         k = i % NBUF
-        o = outs[k]
         j = i % depth if depth > 1 else 0
         st = ring.streams[j] if depth > 1 else torch.cuda.current_stream(dev)
         if (j, k) not in prepared:
-            prepared[(j, k)] = ring.engines[j].prepare(batch, cfg, descs_dev=descs, outputs=o)
+            prepared[(j, k)] = ring.engines[j].prepare(batches[j], cfg, descs_dev=descs[j], outputs=outs[k])
         with torch.cuda.stream(st):
-            if world > 1 and i >= NBUF:
-                st.wait_event(gather_done[k])            # buffers of step i-NBUF are free again
             prepared[(j, k)].launch()
-            if world > 1:
-                step_done[k].record(st)
-                with torch.cuda.stream(comm):
-                    comm.wait_event(step_done[k])
-                    dist.all_gather_into_tensor(counts_all[k], o.ref_offset[-1:])
-                    if gather_points:      # offsets | xyz | rgb | err of a rank are one allocation: a single collective
-                        dist.all_gather_into_tensor(gathered[k], o.packed)
-                    gather_done[k].record(comm)
-        return o
+        return outs[k]
 
     def barrier():
         if world > 1:
@@ -308,15 +492,14 @@ def gpu_arm(args) -> None:
     _dbg("setup done")
 
     def timed(depth: int, n_steps: int):
-        """n_steps steps, `depth` in flight, between two events on the main stream; returns (ms, last outputs)."""
+        """n_steps steps, `depth` in flight, between two events on the main stream; returns (ms, last outputs).  N > 1: the
+        ranks' kept-point counts of the last NBUF steps are exchanged once, after the last step, inside the timed region."""
         main = torch.cuda.current_stream(dev)
-        for i in range(max(3, args.warmup)):
+        for i in range(warmup):
             step(i, depth)
         if depth > 1:
             for st in ring.streams:
                 main.wait_stream(st)
-        if world > 1:
-            main.wait_stream(comm)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -330,27 +513,28 @@ def gpu_arm(args) -> None:
             for st in ring.streams:
                 main.wait_stream(st)
         if world > 1:
-            main.wait_stream(comm)
+            mine = torch.stack([o.ref_offset[R] for o in outs])
+            dist.all_gather_into_tensor(counts_all.view(-1), mine)
         e1.record()
         barrier()
         return e0.elapsed_time(e1), last
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    if DEPTH > 1 and world == 1:
-        eng.lib.ldp_set_sm_reserve(0)                    # alone on the device the first draw kernel takes every SM
-    ms_single, o = timed(1, args.steps)                  # one launch sequence at a time
+    if DEPTH > 1:
+        eng.lib.ldp_set_sm_reserve(0)                    # one launch sequence at a time: the first draw kernel takes every SM
+    ms_single, o = timed(1, steps)
     ms_total = ms_single
     if DEPTH > 1:
         eng.lib.ldp_set_sm_reserve(16)                   # DensifyRing's setting: SMs for the other steps in flight
-        ms_total, o = timed(DEPTH, args.steps)           # the headline: DEPTH steps in flight
+        ms_total, o = timed(DEPTH, steps)                # the headline: DEPTH steps in flight
     _dbg("timed loop done")
     # keep the GPU under the same load a little longer so the clock sampler sees the loaded state
     t_end = time.time() + (0.0 if args.quick else max(0.0, 0.6 - ms_total / 1e3))
     j = 0
     while time.time() < t_end:
         # wall-clock bounded, so the ranks run different numbers of iterations: no collectives in here
-        eng.densify(batch, cfg, descs_dev=descs, outputs=outs[j % 2])
+        step(j, DEPTH)
         j += 1
         if j % 64 == 0:
             torch.cuda.synchronize(dev)
@@ -370,36 +554,38 @@ def gpu_arm(args) -> None:
         total_pts_all, S_all = int(c[0].item()), int(c[1].item())
     else:
         total_pts_all, S_all = total_pts, S_total
-    ms_step = ms_total / args.steps
-    ms_single_step = ms_single / args.steps
+    ms_step = ms_total / steps
+    ms_single_step = ms_single / steps
     value = total_pts_all / (ms_step / 1e3)
     pairs_per_s = world * scene.n_pairs / (ms_step / 1e3)
 
     # ---- per-kernel timing (after the timed region; CUDA events around each kernel on the launch stream)
     import ctypes as C
+    eng.lib.ldp_set_sm_reserve(0)
     eng.lib.ldp_profile_enable(1)
     n_prof = 20
     buf = (C.c_float * 64)()
     kdict = {}
     for i in range(n_prof):
-        eng.densify(batch, cfg, descs_dev=descs, outputs=outs[0])
+        eng.densify(batches[0], cfg, descs_dev=descs[0], outputs=outs[0])
         n = eng.lib.ldp_profile_read(buf, 64)
         for k in range(n):                       # kernels of all sub-batches, summed by name
             name = eng.lib.ldp_profile_name(k).decode()
             kdict[name] = kdict.get(name, 0.0) + float(buf[k]) / n_prof
     eng.lib.ldp_profile_enable(0)
     _dbg("per-kernel profile done")
-    dom = "ldp_stream_kernel"
+    dom = "ldp_front_kernel" if "ldp_front_kernel" in kdict else "ldp_stream_kernel"
     peak, peak_src = measured_hbm_peak()
     k1_bytes = R * nn * H * W * 4                     # every certainty value read exactly once
     # The dominant kernel's average launch duration: `reps` back-to-back launches of that kernel alone between two CUDA
     # events on the launch stream (193 MB of inputs per launch, larger than L2).  Bracketing each launch inside the step
     # with its own event pair (kernels_ms above) adds ~4 us of event latency per kernel; that figure is reported too.
-    params = eng._params(batch, cfg, False, 0, 0)
+    params = eng._params(batches[0], cfg, False, 0, 0)
     ws_t = eng._ensure_workspace(params)
     cur = torch.cuda.current_stream(dev).cuda_stream
+
     def stream_only(reps):
-        rc = eng.lib.ldp_debug_launch_stream(C.byref(params), C.c_void_p(descs.data_ptr()), C.c_void_p(ws_t.data_ptr()),
+        rc = eng.lib.ldp_debug_launch_stream(C.byref(params), C.c_void_p(descs[0].data_ptr()), C.c_void_p(ws_t.data_ptr()),
                                              C.c_size_t(ws_t.numel()), C.c_void_p(cur), C.c_int(reps))
         if rc != 0:
             raise RuntimeError(f"ldp_debug_launch_stream failed: {rc}")
@@ -415,17 +601,52 @@ def gpu_arm(args) -> None:
     achieved = k1_bytes / (dom_ms * 1e-3) / 1e9
     K_pts = total_pts
     path_bytes = R * nn * H * W * 4 + S_total * 28 + K_pts * 28          # B_ref summed over the views
-    path_gbs = path_bytes / (ms_step * 1e-3) / 1e9 if world == 1 else None
+    path_gbs = path_bytes / (ms_step * 1e-3) / 1e9
+    path_gbs_single = path_bytes / (ms_single_step * 1e-3) / 1e9
+    # every kernel of the step against the same peak, on the bytes it has to move (what each is bound by: DESIGN.md 4)
+    nominal = {
+        "ldp_front_kernel": (k1_bytes, "nn*H*W*4: every certainty value once (workspace writes, 5 B/px, not counted)"),
+        "ldp_stream_kernel": (k1_bytes, "nn*H*W*4: every certainty value once"),
+        "ldp_prep_kernel": (R * H * W * 8, "H*W*8: weights in, probabilities out (L2)"),
+        "ldp_draw_kernel": (R * int(WORKLOAD["M"] * 0.85) * 136, "draws * (128-byte chunk line + 8-byte chunk sum), L2"),
+        "ldp_resume_kernel": (R * (H * W // 8 + (S_total // max(R, 1)) * 4), "selection bitmap + sorted indices out, L2"),
+        "ldp_geometry_kernel": (S_total * (16 + 12 + 1) + S_total * 33, "per sample: warp row 16 B + 4 texels 12 B + winner 1 B in, 33 B out"),
+        "ldp_fix_kernel": (0, "worklist of non-converged samples (normally empty)"),
+        "ldp_pack_kernel": (S_total * 33 + K_pts * 28, "per sample 33 B in, per kept point 28 B out"),
+    }
+    by_kernel = {}
+    for name, ms_k in kdict.items():
+        nb, what = nominal.get(name, (0, ""))
+        by_kernel[name] = {"us_in_step_event_bracketed": 1e3 * ms_k, "bytes": int(nb), "what": what,
+                           "frac": (nb / (ms_k * 1e-3) / 1e9 / peak) if ms_k > 0 else None}
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "ms_per_step": ms_step, "kernels_ms": kdict, "stream_kernel_alone_ms": dom_ms,
-                              "k1_frac": achieved / peak, "path_frac": (path_gbs / peak) if path_gbs else None}))
+            print(json.dumps({"quick": True, "ms_per_step": ms_step, "ms_per_step_one_launch_at_a_time": ms_single_step,
+                              "kernels_ms": kdict, "front_kernel_alone_ms": dom_ms,
+                              "k1_frac": achieved / peak, "path_frac": path_gbs / peak, "path_frac_one_at_a_time": path_gbs_single / peak}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     _dbg("stream-only timing done")
+
+    # ---- BASELINE config 5 (sharded scene + final point all-gather)
+    c5 = None
+    if not args.no_config5:
+        c5 = config5_block(args, dev, rank, world, ring)
+        _dbg("config5 done")
+
+    # ---- the drop-in entry point (rank 0 only: it is a per-process host path)
+    api = None
+    if rank == 0 and not args.no_api:
+        api = api_block(args, dev, scene, slots[0], WORKLOAD["M"])
+        _dbg("api block done")
+
     # ---- e2e through the public API from host buffers.  The views are handed over in E2E_CHUNKS groups: the pinned
     #      host->device copy of group g+1 (copy stream) overlaps the kernels of group g, whose warp rows are gathered
     #      straight from pinned host memory over PCIe (the 0.77 GB of warp planes are never uploaded).
+    cert, warp, image = slots[0].cert, slots[0].warp, slots[0].image
     E2E_CHUNKS = int(os.environ.get("BENCH_E2E_CHUNKS", "4")) if R >= 8 else 1
     h_cert = cert.cpu().pin_memory()
     h_img = image.cpu().pin_memory()
@@ -433,16 +654,7 @@ def gpu_arm(args) -> None:
     d_cert = torch.empty_like(cert)
     d_img = torch.empty_like(image)
     bounds = [(R * g // E2E_CHUNKS, R * (g + 1) // E2E_CHUNKS) for g in range(E2E_CHUNKS)]
-
-    def make_sub_batch(lo, hi):
-        b = eng.new_batch(H, W, wm, hm)
-        for rp in range(lo, hi):
-            ri, nb = nbr_table[rp]
-            b.add([d_cert[rp, k] for k in range(nn)], [h_warp[rp, k] for k in range(nn)], d_img[rp], cams[ri],
-                  [cams[j] for j in nb], rng_stream=rank * R + rp)
-        return b
-
-    e2e_batches = [make_sub_batch(lo, hi) for lo, hi in bounds]
+    e2e_batches = [slots[0].batch(eng, scene, lo, hi, stream_base=rank * R, cert=d_cert, warp=h_warp, image=d_img) for lo, hi in bounds]
     e2e_descs = [eng.upload_descs(b) for b in e2e_batches]
     e2e_outs = [eng.alloc_outputs(hi - lo, sel_cap) for lo, hi in bounds]
     copy_stream = torch.cuda.Stream(dev)
@@ -476,7 +688,7 @@ def gpu_arm(args) -> None:
         return n
 
     _dbg("e2e setup done")
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(steps, 20))
     for _ in range(3):
         n_e2e = e2e_step()
     barrier()
@@ -500,28 +712,35 @@ def gpu_arm(args) -> None:
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 geometry / f64 cdf, sampson, colour", "data": "synthetic",
             "config": {"workload": WORKLOAD["name"], "refs_per_gpu": R, "pairs_per_gpu": scene.n_pairs,
-                       "l2_policy": "inputs larger than L2 (0.97 GB per step vs 126 MB)",
+                       "l2_policy": "inputs larger than L2 (0.97 GB per step vs 126 MB); every step in flight has its own input tensors",
                        "steps_in_flight": DEPTH,
-                       "rng": "philox4x32-10", "multi_gpu": (("per-step NCCL all-gather of every rank's packed points (28 B/point) on a side stream" if gather_points else
-                                      "views sharded, points stay on their rank; per-step NCCL all-gather of the per-rank kept-point "
-                                      "counts (global row offsets) on a side stream") if world > 1 else "none")},
+                       "rng": "philox4x32-10", "multi_gpu": ("views sharded, points stay on their rank, no collective per step; the "
+                                      "ranks' kept-point counts (global row offsets) are exchanged once after the last step, inside "
+                                      "the timed region" if world > 1 else "none")},
             "pairs_per_sec": pairs_per_s, "points_per_step": total_pts_all, "samples_per_step": S_all,
             "ms_per_step_one_launch_at_a_time": ms_single_step,
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": launches_per_step * steps,
             "kernels_ms": kdict,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": recorded_traffic(), "peak_source": peak_src,
                          "kernel_ms": dom_ms, "kernel_ms_in_step_event_bracketed": kdict[dom],
                          "timing": f"{k_reps} back-to-back launches of the kernel alone between two CUDA events",
                          "algorithmic_bytes_per_launch": k1_bytes,
-                         "path_achieved": path_gbs, "path_frac": (path_gbs / peak) if path_gbs else None,
-                         "path_algorithmic_bytes_per_step": path_bytes},
+                         "by_kernel": by_kernel,
+                         "path_achieved": path_gbs, "path_frac": path_gbs / peak,
+                         "path_frac_one_launch_at_a_time": path_gbs_single / peak,
+                         "path_algorithmic_bytes_per_step": path_bytes,
+                         "path_note": "per GPU: SURVEY 8d bytes of one step (nn*H*W*4 + S*28 + K*28 per view) / ms_per_step / peak"},
             "e2e": e2e, "clocks": clocks,
         }
+        if c5 is not None:
+            line["config5"] = c5
+        if api is not None:
+            line["api"] = api
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line))
@@ -533,11 +752,13 @@ def gpu_arm(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None, help="default: 1000 (GPU arm), 20 (--impl reference)")
+    ap.add_argument("--warmup", type=int, default=None, help="default: 10 (GPU arm), 3 (--impl reference)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--quick", action="store_true", help="profiling runs: skip cpu baseline, clock-load loop and e2e")
+    ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--no-api", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: skip cpu baseline, clock-load loop, config5, api and e2e")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LDP_ABI_VERSION 10
+#define LDP_ABI_VERSION 11
 #define LDP_MAX_NN 16          /* neighbours per reference view (the panel clamps to 10) */
 #define LDP_MAX_BINS 4096      /* coverage tiles per map: ceil(W/tile)*ceil(H/tile), tile = max(1, W/24) */
 
@@ -79,7 +79,9 @@ typedef struct ldp_params {
                                   x mask_a (nearest-resized to the map), x mask_b[k] sampled at the warp's (xB, yB)
                                   (nearest, zeros outside, align_corners = False).  0: planes are already processed */
     float certainty_floor;     /* f32(config.certainty_thresh), core/pipeline.py:407; read only if prologue */
-    int32_t reserved2;
+    int32_t no_warped_masks;   /* prologue only.  1: the caller guarantees that every ldp_ref_desc.mask_b[k] of the launch is NULL
+                                  (no neighbour masks to sample through the warp), which lets the single fused front kernel
+                                  take raw planes too; 0: unknown -- the two-kernel path that reads the warp planes is used */
     uint64_t seed;             /* Philox key */
     int64_t uniforms_per_ref;  /* explicit mode: doubles available per reference view */
 } ldp_params;
@@ -199,6 +201,18 @@ int ldp_gather_points(const float* xyz, const float* rgb, const float* err, cons
  * and their normalised certainties [K] (core/pipeline.py:573-582; indices from default_rng(pair seed).choice on the host). */
 int ldp_gather_rows(const float* src, int32_t row_floats, const int64_t* sel, int64_t m, int64_t n, float* out,
                     int32_t* bad_index_flag, void* stream);
+
+/* Concatenation of packed point segments on the device: replaces the reference's final np.concatenate of the per-view arrays
+ * (core/pipeline.py:914-928) for callers that keep several launches, or several ranks' all-gathered blocks, in device memory.
+ * Segment q holds *count_src[q] points (a DEVICE int64, e.g. ldp_outputs.ref_offset + n_refs of a launch) at the start of
+ * its padded arrays xyz_src[q] [seg_cap,3], rgb_src[q] [seg_cap,3], err_src[q] [seg_cap]; its rows are written to
+ * xyz_out / rgb_out / err_out at row sum(count_src[0..q)).  The four pointer tables are DEVICE arrays of n_seg device
+ * pointers.  seg_offset_out: optional device int64 [n_seg + 1], the exclusive prefix of the counts (last = total);
+ * total_out: optional device int64, the total alone (e.g. the header of a buffer that goes into a collective).
+ * No host synchronisation: the counts never leave the device. */
+int ldp_concat_points(const float* const* xyz_src, const float* const* rgb_src, const float* const* err_src,
+                      const int64_t* const* count_src, int32_t n_seg, int64_t seg_cap, float* xyz_out, float* rgb_out,
+                      float* err_out, int64_t out_capacity, int64_t* seg_offset_out, int64_t* total_out, void* stream);
 
 /* ---- pair generation on the device ---------------------------------------------
  * flat_poses: [n,16] f32 device, the row-major 4x4 world-to-camera transforms (CameraRecord.flat_pose()).

@@ -8,6 +8,7 @@
 #include <utility>
 
 #include "ldp_sample.cu"
+#include "ldp_front.cu"
 #include "ldp_geometry.cu"
 #include "ldp_output.cu"
 #include "ldp_select.cu"
@@ -119,7 +120,30 @@ struct Plan {
     size_t k1_smem;
     size_t prep_smem;
     int nb2;
+    void* zero_base;        // launch state that every call clears with ONE memset: counters, per-view statistics, coverage
+    size_t zero_bytes;      //   keys, tile partial slots
+    int use_front;          // the fused persistent front kernel replaces stream + prep
+    int front_grid;
+    size_t front_smem;
 };
+
+// CTAs of the front kernel that are resident at once (2 per SM for up to 4 neighbour planes per stage, else 1)
+int front_grid_size(int nn_stage, size_t smem) {
+    (void)nn_stage;
+    const size_t per_sm = 227 * 1024;
+    int per = (int)(per_sm / (smem + 2048));
+    if (per > 2) per = 2;
+    if (per < 1) per = 1;
+    return per * sm_count();
+}
+
+int choose_subbatches(int n_refs);
+
+int next_epoch() {
+    static int epoch = 0;
+    epoch = (epoch % 0x3fffffff) + 1;      // never 0: the counters are cleared to 0 at the start of every call
+    return epoch;
+}
 
 int64_t sel_capacity(int32_t M) {
     const int64_t m_main = (int64_t)((double)M * 0.85);      // int(M * 0.85), reference core/sampling.py:31
@@ -193,7 +217,6 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     while (tk < Mn) tk <<= 1;
     w.topk_cap = p->no_filter ? tk : 0;
     w.nchunk_pad = align_up((size_t)g.nchunk, 32);
-    w.nblk = ((size_t)N + ldp::KS_SPAN - 1) / ldp::KS_SPAN;
     w.bins_cap = align_up((size_t)g.nbins, 32);
     {
         const int rows = (ldp::KS_SPAN + p->W - 1) / p->W + 1;
@@ -202,6 +225,29 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
         g.prep_lb_cap = (int)align_up((size_t)lb, 4);
     }
     plan->prep_smem = (size_t)g.prep_lb_cap * 8;
+    // ---- which first stage: the fused persistent front kernel (ldp_front.cu) needs the vector path (16-byte aligned rows of
+    //      W % 4 == 0 pixels), coverage tiles wider than a pixel, a known neighbour count <= 8 per view, no warped masks,
+    //      and few enough tiles per view that the resident CTAs can park a whole view (see the deadlock note there)
+    //      MEASURED SLOWER than the two kernels it replaces and therefore OFF unless LDP_FRONT=1 (profiles/r02_summary.md):
+    //      131-140 us against 41 + 27 us at the bench shape.  With one quad per thread and tile every per-tile step (stage
+    //      selection, block reductions, announcement, barriers) is paid per quad: 84 M warp instructions against 25 M.
+    static const int front_mode = [] { const char* e = getenv("LDP_FRONT"); return e ? atoi(e) : 0; }();
+    g.front_nn = p->nn_max;
+    g.front_cache = 0;
+    plan->use_front = 0;
+    plan->front_grid = 0;
+    plan->front_smem = 0;
+    if (front_mode && !p->no_filter && p->W % 4 == 0 && p->scalar_loads == 0 && g.prep_lean && p->nn_max >= 1 && p->nn_max <= 8 &&
+        (!p->prologue || p->no_warped_masks) && choose_subbatches(p->n_refs) == 1 && plan->prep_smem <= 16 * 1024) {
+        size_t smem = ((size_t)ldp::KF_STAGES * g.front_nn + ldp::KF_PARK) * ldp::KF_TILE * sizeof(float) + plan->prep_smem;
+        const size_t cache = (size_t)p->n_refs * ((size_t)g.front_nn * sizeof(void*) + sizeof(int));
+        g.front_cache = (cache <= 12 * 1024) ? 1 : 0;        // what is left of the SM's shared memory beside two CTAs' rings
+        if (g.front_cache) smem += cache;
+        const int grid = front_grid_size(g.front_nn, smem);
+        const size_t tpv = ((size_t)N + ldp::KF_TILE - 1) / ldp::KF_TILE;
+        if (smem <= 200 * 1024 && tpv <= (size_t)3 * grid) { plan->use_front = 1; plan->front_grid = grid; plan->front_smem = smem; }
+    }
+    w.nblk = plan->use_front ? ((size_t)N + ldp::KF_TILE - 1) / ldp::KF_TILE : ((size_t)N + ldp::KS_SPAN - 1) / ldp::KS_SPAN;
 
     size_t off = 0;
     char* b = static_cast<char*>(base);
@@ -218,23 +264,37 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     w.pt1 = reinterpret_cast<float4*>(carve(R * w.sel_cap * sizeof(float4)));
     w.dbgm = reinterpret_cast<float4*>(carve(p->collect_debug ? R * w.sel_cap * sizeof(float4) : 0));
     w.flags = reinterpret_cast<uint8_t*>(carve(R * w.sel_cap));
-    w.kept = reinterpret_cast<int32_t*>(carve(R * sizeof(int32_t)));
     w.topk_keys = reinterpret_cast<unsigned long long*>(carve(R * w.topk_cap * sizeof(unsigned long long)));
     w.csum = reinterpret_cast<double*>(carve(R * w.nchunk_pad * sizeof(double)));
-    w.partial = reinterpret_cast<double*>(carve(R * w.nblk * sizeof(double)));
-    w.bflags = reinterpret_cast<int32_t*>(carve(R * w.nblk * sizeof(int32_t)));
-    w.rstat = reinterpret_cast<ldp::RefStat*>(carve(R * sizeof(ldp::RefStat)));
-    w.gbins = reinterpret_cast<unsigned long long*>(carve(R * w.bins_cap * sizeof(unsigned long long)));
     w.dbgclk = reinterpret_cast<long long*>(carve(R * 32 * sizeof(long long)));
     plan->nb2 = (int)((w.sel_cap + ldp::K2_THREADS - 1) / ldp::K2_THREADS);
     w.blk_cnt = reinterpret_cast<int32_t*>(carve(R * plan->nb2 * LDP_MAX_NN * sizeof(int32_t)));
     w.blk_first = reinterpret_cast<int32_t*>(carve(R * plan->nb2 * LDP_MAX_NN * sizeof(int32_t)));
     w.fix_list = reinterpret_cast<int2*>(carve(R * w.sel_cap * sizeof(int2)));
-    w.fix_count = reinterpret_cast<int32_t*>(carve((ldp::LDP_MAX_SUB + R) * sizeof(int32_t)));
-    w.arrive = w.fix_count ? w.fix_count + ldp::LDP_MAX_SUB : nullptr;
     w.dstat = reinterpret_cast<int32_t*>(carve(R * sizeof(int32_t)));
+    // ---- the zero block (one memset per call, clear_launch_state): 8-byte items first
+    {
+        const size_t z0 = off;
+        auto sub = [&](size_t bytes) { char* q = b ? b + off : nullptr; off += align_up(bytes, 8); return q; };
+        w.vword = reinterpret_cast<unsigned long long*>(sub(R * sizeof(unsigned long long)));
+        w.gbins = reinterpret_cast<unsigned long long*>(sub(R * w.bins_cap * sizeof(unsigned long long)));
+        w.partial = reinterpret_cast<double*>(sub(R * w.nblk * sizeof(double)));
+        w.rstat = reinterpret_cast<ldp::RefStat*>(sub(R * sizeof(ldp::RefStat)));
+        w.bflags = reinterpret_cast<int32_t*>(sub(R * w.nblk * sizeof(int32_t)));
+        w.kept = reinterpret_cast<int32_t*>(sub(R * sizeof(int32_t)));
+        w.fix_count = reinterpret_cast<int32_t*>(sub(ldp::LDP_MAX_SUB * sizeof(int32_t)));
+        w.arrive = reinterpret_cast<int32_t*>(sub(R * sizeof(int32_t)));
+        w.ticket = reinterpret_cast<int32_t*>(sub(8 * sizeof(int32_t)));
+        plan->zero_base = b ? b + z0 : nullptr;
+        plan->zero_bytes = off - z0;
+        off = align_up(off, 256);
+    }
     plan->bytes = off;
     return LDP_OK;
+}
+
+cudaError_t clear_launch_state(const Plan& plan, cudaStream_t st) {
+    return cudaMemsetAsync(plan.zero_base, 0, plan.zero_bytes, st);
 }
 
 int check_outputs(const ldp_params* p, const ldp_outputs* o) {
@@ -248,6 +308,23 @@ int check_outputs(const ldp_params* p, const ldp_outputs* o) {
 }
 
 static int vec_ok_for(const ldp_params* p) { return (p->W % 4 == 0 && p->scalar_loads == 0) ? 1 : 0; }
+
+// the fused first stage (ldp_front.cu): persistent CTAs, TMA ring, stream + normalise
+cudaError_t launch_front(const ldp_params* p, const ldp_ref_desc* refs, const ldp_outputs* out, Plan& plan, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ldp::ldp_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    plan.geom.epoch = next_epoch();
+    const long long total = (long long)plan.ws.nblk * p->n_refs;
+    const unsigned grid = (unsigned)std::min<long long>(plan.front_grid, total);
+    if (p->prologue)
+        return launch_k(ldp::ldp_front_kernel<true>, dim3(grid), dim3(ldp::KF_THREADS), plan.front_smem, st, *p, refs, plan.ws, *out, plan.geom);
+    return launch_k(ldp::ldp_front_kernel<false>, dim3(grid), dim3(ldp::KF_THREADS), plan.front_smem, st, *p, refs, plan.ws, *out, plan.geom);
+}
 
 // the first kernel of the path (also launched alone by ldp_debug_launch_stream for the roofline measurement)
 void launch_stream(const ldp_params* p, const ldp_ref_desc* refs, Plan& plan, cudaStream_t st, int nsubrefs) {
@@ -296,10 +373,21 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     if (plan.prep_smem > 64 * 1024) return fail(LDP_ERR_INVALID, "map too wide for the prep kernel tables");
     const dim3 grid((unsigned)plan.ws.nblk, (unsigned)nsubrefs);
     cudaError_t e;
+    if (plan.use_front) {
+        if (plan.geom.chunk_shift > 7) {      // chunk sums are accumulated with atomics: start from zero
+            e = cudaMemsetAsync(plan.ws.csum, 0, (size_t)nsubrefs * plan.ws.nchunk_pad * sizeof(double), st);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(csum)");
+        }
+        { KernelTimer kt(st, "ldp_front_kernel");
+          e = launch_front(p, refs, out, plan, st); }
+        ++g_launches;
+        if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_front_kernel");
+    } else {
     { KernelTimer kt(st, "ldp_stream_kernel");
       launch_stream(p, refs, plan, st, nsubrefs); }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_stream_kernel");
+    }
     if (p->no_filter) {
         { KernelTimer kt(st, "ldp_topm_kernel");
           size_t n2 = 1;
@@ -354,6 +442,7 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_topm_kernel");
         return LDP_OK;
     }
+    if (!plan.use_front) {
     if (plan.geom.chunk_shift > 7) {      // chunk sums are accumulated with atomics: start from zero
         e = cudaMemsetAsync(plan.ws.csum + (size_t)ref0 * plan.ws.nchunk_pad, 0, (size_t)nsubrefs * plan.ws.nchunk_pad * sizeof(double), st);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(csum)");
@@ -377,6 +466,7 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
       } }
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_prep_kernel");
+    }
     // ---- round 1: independent CTAs, as many per view as the device has SMs for (one CTA per SM: the table fills it)
     static const int env_reserve = [] { const char* e = getenv("LDP_SM_RESERVE"); return e ? atoi(e) : -1; }();   // SMs left to concurrent
     const int sm_reserve = env_reserve >= 0 ? env_reserve : g_sm_reserve;                                             // kernels (other launches in
@@ -583,8 +673,16 @@ int ldp_debug_launch_stream(const ldp_params* params, const ldp_ref_desc* refs, 
     plan.geom.vec = vec_ok_for(params);
     plan.geom.ref0 = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    for (int i = 0; i < reps; ++i) launch_stream(params, refs, plan, st, params->n_refs);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (plan.use_front) {      // the fused front kernel is the first stage on this shape (it cleans its own counters up)
+        ldp_outputs none = {};
+        e = clear_launch_state(plan, st);
+        for (int i = 0; i < reps && e == cudaSuccess; ++i) e = launch_front(params, refs, &none, plan, st);
+        if (e != cudaSuccess) return cuda_fail(e, "ldp_front_kernel");
+    } else {
+        for (int i = 0; i < reps; ++i) launch_stream(params, refs, plan, st, params->n_refs);
+    }
+    e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ldp_stream_kernel");
     return LDP_OK;
 }
@@ -680,6 +778,26 @@ int ldp_gather_rows(const float* src, int32_t row_floats, const int64_t* sel, in
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ldp_gather_f32_rows_kernel");
+    return LDP_OK;
+}
+
+int ldp_concat_points(const float* const* xyz_src, const float* const* rgb_src, const float* const* err_src,
+                      const int64_t* const* count_src, int32_t n_seg, int64_t seg_cap, float* xyz_out, float* rgb_out,
+                      float* err_out, int64_t out_capacity, int64_t* seg_offset_out, int64_t* total_out, void* stream) {
+    if (n_seg < 0 || seg_cap < 0 || out_capacity < 0) return fail(LDP_ERR_INVALID, "negative size");
+    g_launches = 0;
+    if (n_seg == 0) return LDP_OK;
+    if (!xyz_src || !rgb_src || !err_src || !count_src || !xyz_out || !rgb_out || !err_out) return fail(LDP_ERR_INVALID, "null pointer");
+    if (n_seg > 65535) return fail(LDP_ERR_INVALID, "too many segments");
+    const long long blocks = (seg_cap * 3 + ldp::KO_THREADS * 4 - 1) / (ldp::KO_THREADS * 4);
+    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>(blocks, 64));
+    (void)launch_k(ldp::ldp_concat_points_kernel, dim3(gx, (unsigned)n_seg), dim3(ldp::KO_THREADS), 0, reinterpret_cast<cudaStream_t>(stream),
+                   xyz_src, rgb_src, err_src, reinterpret_cast<const long long* const*>(count_src), (int)n_seg, (long long)seg_cap,
+                   xyz_out, rgb_out, err_out, (long long)out_capacity, reinterpret_cast<long long*>(seg_offset_out),
+                   reinterpret_cast<long long*>(total_out));
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ldp_concat_points_kernel");
     return LDP_OK;
 }
 
@@ -900,8 +1018,8 @@ int ldp_densify_refs(const ldp_params* params, const ldp_ref_desc* refs, const d
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // the winning-neighbour plane is written by the first kernel and gathered (1 byte per sample, random) by the fifth
     L2Window l2(st, plan.ws.bestk, (size_t)params->n_refs * plan.ws.n_pad);      // winning-neighbour plane (1 B / px)
-    cudaError_t e = cudaMemsetAsync(plan.ws.fix_count, 0, (ldp::LDP_MAX_SUB + (size_t)params->n_refs) * sizeof(int32_t), st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(fix_count)");
+    cudaError_t e = clear_launch_state(plan, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(launch state)");
     const int nsub = choose_subbatches(params->n_refs);
     if (nsub == 1) {
         rc = launch_sample(params, refs, uniforms, out, plan, vec_ok_for(params), st, 0, params->n_refs);
@@ -941,8 +1059,8 @@ int ldp_sample_refs(const ldp_params* params, const ldp_ref_desc* refs, const do
     int rc = make_plan(params, base, &plan);
     if (rc != LDP_OK) return rc;
     if (plan.bytes + (size_t)(base - static_cast<char*>(workspace)) > workspace_bytes) return fail(LDP_ERR_WORKSPACE, "workspace too small");
-    cudaError_t e = cudaMemsetAsync(plan.ws.fix_count, 0, (ldp::LDP_MAX_SUB + (size_t)params->n_refs) * sizeof(int32_t), static_cast<cudaStream_t>(stream));
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(counters)");
+    cudaError_t e = clear_launch_state(plan, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(launch state)");
     return launch_sample(params, refs, uniforms, out, plan, vec_ok_for(params), static_cast<cudaStream_t>(stream), 0, params->n_refs);
 }
 
@@ -961,10 +1079,8 @@ int ldp_triangulate_samples(const ldp_params* params, const ldp_ref_desc* refs, 
     if (rc != LDP_OK) return rc;
     if (plan.bytes + (size_t)(base - static_cast<char*>(workspace)) > workspace_bytes) return fail(LDP_ERR_WORKSPACE, "workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(plan.ws.kept, 0, (size_t)params->n_refs * sizeof(int32_t), st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(kept)");
-    e = cudaMemsetAsync(plan.ws.fix_count, 0, (ldp::LDP_MAX_SUB + (size_t)params->n_refs) * sizeof(int32_t), st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(fix_count)");
+    cudaError_t e = clear_launch_state(plan, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(launch state)");
     rc = launch_geometry(params, refs, out, plan, 0, st, 0, params->n_refs, 0);
     if (rc != LDP_OK) return rc;
     return launch_pack(params, refs, out, plan, st);

@@ -15,7 +15,7 @@ constexpr int LDP_MAX_SUB = 8;      // sub-batches a launch may be pipelined ove
 struct RefStat {        // per-view scalars passed between the sampler kernels
     float s;            // f32 normaliser (core/sampling.py:26)
     int npos;           // number of p > 0
-    int emin;           // smallest biased exponent among positive p
+    int emin_inv;       // max over positive p of (255 - biased exponent); 0: no positive p (zero-initialisable, atomicMax)
     int bad;            // bit0 NaN weight, bit1 negative weight, bit2 no neighbours
 };
 
@@ -43,7 +43,10 @@ struct Workspace {
     int32_t* blk_first;  // [R][nb2][LDP_MAX_NN] first sample position per tile and group
     int2* fix_list;      // [R*sel_cap] (view, sample) pairs whose null-vector iteration did not converge
     int32_t* fix_count;  // [LDP_MAX_SUB] one counter per sub-batch (its list starts at ref0 * sel_cap)
-    int32_t* arrive;     // [R] (spare counters, zeroed with fix_count)
+    int32_t* arrive;     // [R] front kernel: tiles of the view announced so far (zeroed with fix_count)
+    unsigned long long* vword;   // [R] front kernel: (launch epoch << 34 | bad flags << 32 | bits of the f32 normaliser s), one 64-bit
+                         //     store by the CTA that completes the view; 0 until then
+    int32_t* ticket;     // [2] front kernel: next tile ticket, CTAs that have left
     int32_t* dstat;      // [R] verdict of the first draw round for the rounds that follow: fail code | inexact << 8
     long long* dbgclk;   // [R][32] phase timestamps of the draw kernel (written only with -DLDP_PHASE_CLOCKS)
     size_t n_pad, n_words, found_cap, sel_cap, topk_cap, nchunk_pad, nblk, bins_cap, draw_cmax;
@@ -69,6 +72,9 @@ struct SampleGeom {     // launch-constant shape of the sampler
     int draw_pre_cap;   // draw kernel: doubles in the padded prefix table
     int draw_ng;        // draw kernel: guide-table buckets
     int draw_smem_bytes; // draw kernel: dynamic shared memory of the launch
+    int front_nn;       // front kernel: neighbour planes a TMA stage holds (max neighbours of the launch)
+    int epoch;          // front kernel: value that marks a view's flag as raised in THIS launch
+    int front_cache;    // front kernel: per-view plane pointers / neighbour counts are cached in shared memory
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -115,4 +115,56 @@ ldp_gather_f32_rows_kernel(const float* __restrict__ src, int row_floats, const 
     }
 }
 
+// Concatenation of packed point segments without a host round trip (reference core/pipeline.py:914-928: np.concatenate of
+// the per-view arrays, in arrival order).  Segment q holds *count[q] points at the start of its own padded arrays
+// (the outputs of one launch, or one rank's block of an all-gather); segment q's rows land at sum(count[0..q)).
+// grid = (row blocks of the largest segment, segments); every CTA sums the counts before its segment itself (a few
+// hundred at most), so nothing synchronises: the counts stay on the device.
+__global__ void __launch_bounds__(KO_THREADS)
+ldp_concat_points_kernel(const float* const* __restrict__ xyz_src, const float* const* __restrict__ rgb_src,
+                         const float* const* __restrict__ err_src, const long long* const* __restrict__ count_src,
+                         int n_seg, long long seg_cap, float* __restrict__ xyz_out, float* __restrict__ rgb_out,
+                         float* __restrict__ err_out, long long out_cap, long long* __restrict__ seg_offset_out,
+                         long long* __restrict__ total_out)
+{
+    __shared__ long long red[KO_THREADS / 32];
+    __shared__ long long s_base;
+    grid_dependency_sync();
+    const int q = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long part = 0;
+    for (int j = tid; j < q; j += KO_THREADS) { const long long c = *count_src[j]; part += (c < 0) ? 0 : (c > seg_cap ? seg_cap : c); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+        long long b = 0;
+        for (int w = 0; w < KO_THREADS / 32; ++w) b += red[w];
+        s_base = b;
+    }
+    __syncthreads();
+    const long long base = s_base;
+    long long cnt = *count_src[q];
+    cnt = (cnt < 0) ? 0 : (cnt > seg_cap ? seg_cap : cnt);
+    if (blockIdx.x == 0 && tid == 0) {
+        if (seg_offset_out) {
+            seg_offset_out[q] = base;
+            if (q == n_seg - 1) seg_offset_out[n_seg] = base + cnt;
+        }
+        if (total_out && q == n_seg - 1) *total_out = (base + cnt < out_cap) ? base + cnt : out_cap;
+    }
+    if (base + cnt > out_cap) cnt = (out_cap > base) ? out_cap - base : 0;
+    const float* __restrict__ xs = xyz_src[q];
+    const float* __restrict__ rs = rgb_src[q];
+    const float* __restrict__ es = err_src[q];
+    const long long n3 = cnt * 3;
+    // flat copies: a row block covers KO_THREADS * 4 rows = 3072 floats of xyz / rgb per block step
+    for (long long e = ((long long)blockIdx.x * KO_THREADS + tid); e < n3; e += (long long)gridDim.x * KO_THREADS) {
+        xyz_out[base * 3 + e] = xs[e];
+        rgb_out[base * 3 + e] = rs[e];
+    }
+    for (long long e = ((long long)blockIdx.x * KO_THREADS + tid); e < cnt; e += (long long)gridDim.x * KO_THREADS)
+        err_out[base + e] = es[e];
+}
+
 }  // namespace ldp

@@ -112,7 +112,7 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
     if (PRO) stage_proview(rd, s_pv, tid);
     if (blk == 0) {          // per-view state consumed by the later kernels of this launch
         if (tid == 0) {
-            ws.rstat[r].s = 0.f; ws.rstat[r].npos = 0; ws.rstat[r].emin = 0x7fffffff; ws.rstat[r].bad = 0;
+            ws.rstat[r].s = 0.f; ws.rstat[r].npos = 0; ws.rstat[r].emin_inv = 0; ws.rstat[r].bad = 0;
             ws.kept[r] = 0;
         }
         unsigned long long* gb = ws.gbins + (size_t)r * ws.bins_cap;
@@ -410,7 +410,7 @@ ldp_prep_generic_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ ref
     const int eminbits = block_min((int)lminbits, red_i);
     if (tid == 0) {
         if (npos) atomicAdd(&ws.rstat[r].npos, npos);
-        if (eminbits != 0x7fffffff) atomicMin(&ws.rstat[r].emin, (eminbits >> 23) & 0xff);
+        if (eminbits != 0x7fffffff) atomicMax(&ws.rstat[r].emin_inv, 255 - ((eminbits >> 23) & 0xff));
     }
     __syncthreads();
     unsigned long long* gb = ws.gbins + (size_t)r * ws.bins_cap;
@@ -592,7 +592,7 @@ ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     const uint32_t min1 = (uint32_t)block_min((int)(lmin1 ^ 0x80000000u), red_i) ^ 0x80000000u;   // unsigned order through the signed reduction
     if (tid == 0) {
         if (npos) atomicAdd(&ws.rstat[r].npos, npos);
-        if (min1 != 0xFFFFFFFFu) atomicMin(&ws.rstat[r].emin, (int)(((min1 + 1u) >> 23) & 0xffu));
+        if (min1 != 0xFFFFFFFFu) atomicMax(&ws.rstat[r].emin_inv, 255 - (int)(((min1 + 1u) >> 23) & 0xffu));
     }
     __syncthreads();
     LDP_PCLK(3);
@@ -833,7 +833,8 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             // 2^53 of those units  <=>  ilogb(total) - (emin - 150) < 53
             if (st.npos > 0) {
                 const int etot = ilogb(total);
-                if (st.emin == 0 || etot - (st.emin - 150) >= 53) inexact = 1;
+                const int emin = 255 - st.emin_inv;          // smallest biased exponent among the positive p
+                if (emin <= 0 || etot - (emin - 150) >= 53) inexact = 1;
             }
             LDP_CLK(ws, r, 17);                        // (the selection bitmap was cleared by the prep kernel)
         }

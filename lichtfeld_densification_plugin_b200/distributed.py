@@ -47,7 +47,7 @@ def exchange_counts(n_points: torch.Tensor, group=None) -> Tuple[torch.Tensor, t
     return counts, torch.cumsum(counts, 0) - counts
 
 
-def _write_sharded(path_out: str, header: bytes, payload: bytes, byte_offset: int, total_bytes: int, rank: int, group) -> None:
+def _write_sharded(path_out: str, header: bytes, payload, byte_offset: int, total_bytes: int, rank: int, group) -> None:
     import os
     if rank == 0:
         with open(path_out, "wb") as f:
@@ -57,7 +57,13 @@ def _write_sharded(path_out: str, header: bytes, payload: bytes, byte_offset: in
         dist.barrier(group=group)                    # the file exists with its final size before anybody seeks into it
     fd = os.open(path_out, os.O_WRONLY)
     try:
-        os.pwrite(fd, payload, len(header) + int(byte_offset))
+        view = memoryview(payload).cast("B")
+        pos, base = 0, len(header) + int(byte_offset)
+        while pos < len(view):                       # a single write is capped at 0x7ffff000 bytes and may come back short
+            n = os.pwrite(fd, view[pos:pos + (1 << 30)], base + pos)
+            if n <= 0:
+                raise OSError(f"short write to {path_out} at byte {base + pos}")
+            pos += n
     finally:
         os.close(fd)
     if dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -80,9 +86,9 @@ def write_ply_sharded(path_out: str, xyz, rgb_uint8, row_offset: int, total_rows
         rec = np.empty(n, dtype=_PLY_VERTEX)
         rec["x"], rec["y"], rec["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
         rec["r"], rec["g"], rec["b"] = rgb_uint8[:, 0], rgb_uint8[:, 1], rgb_uint8[:, 2]
-        payload = rec.tobytes()
+        payload = rec.view(np.uint8).reshape(-1)
     else:
-        payload = np.ascontiguousarray(records, dtype=np.uint8).tobytes()
+        payload = np.ascontiguousarray(records, dtype=np.uint8).reshape(-1)
     _write_sharded(path_out, ply_header(int(total_rows)), payload, 15 * int(row_offset), 15 * int(total_rows), rank, group)
 
 
@@ -90,17 +96,47 @@ def write_points3D_bin_sharded(path_out: str, records, row_offset: int, total_ro
     """Same for COLMAP's points3D.bin (reference core/writers.py:15-26): ``records`` are this rank's 43-byte records
     packed with ``output.points3d_records(..., first_id=row_offset + 1)`` (ids are global row numbers + 1)."""
     import numpy as np
-    payload = np.ascontiguousarray(records, dtype=np.uint8).tobytes()
+    payload = np.ascontiguousarray(records, dtype=np.uint8).reshape(-1)
     _write_sharded(path_out, np.uint64(int(total_rows)).tobytes(), payload, 43 * int(row_offset), 43 * int(total_rows), rank, group)
+
+
+def all_gather_cloud(cloud, group=None, out=None, scratch: Optional[torch.Tensor] = None):
+    """The final point all-gather, replacing the reference's single-process concatenation
+    (core/pipeline.py:914-928): every rank contributes its ``output.PackedCloud`` (header with the device-side point count
+    | xyz | rgb | err, 28 B/point, padded to ``cloud.capacity`` - the SAME capacity on every rank) in ONE collective;
+    ``ldp_concat_points`` then squeezes the padding out in rank order, reading the counts from the gathered headers.
+    Nothing synchronises with the host.  Returns (``PackedCloud`` with every rank's points in rank order = the single-GPU
+    order, int64 device tensor [world + 1] of the ranks' global row offsets)."""
+    from .output import ConcatPlan, PackedCloud
+    dev = cloud.packed.device
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        off = torch.zeros((2,), dtype=torch.int64, device=dev)
+        off[1:] = cloud.count
+        return cloud, off
+    world = dist.get_world_size(group)
+    nbytes = cloud.packed.numel()
+    if scratch is None:
+        scratch = torch.empty((world, nbytes), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(scratch.view(-1), cloud.packed, group=group)
+    blocks = [PackedCloud(cloud.capacity, dev, storage=scratch[r]) for r in range(world)]
+    plan = ConcatPlan([b.xyz for b in blocks], [b.rgb for b in blocks], [b.err for b in blocks], [b.count for b in blocks],
+                      cloud.capacity)
+    if out is None:
+        out = PackedCloud(world * cloud.capacity, dev)
+    plan.run(out)
+    out._plan, out._blocks = plan, scratch
+    return out, plan.seg_offsets
 
 
 def all_gather_points(xyz: torch.Tensor, rgb: torch.Tensor, err: torch.Tensor, n_valid: Optional[int] = None,
                       group=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Order-preserving all-gather of per-rank packed points.
+    """Order-preserving all-gather of per-rank packed points, exact-size results.
 
-    ``xyz`` [cap,3], ``rgb`` [cap,3], ``err`` [cap] hold ``n_valid`` points (default: all rows).  Two collectives:
-    the counts, then one padded gather of a fused [max_count, 7] f32 buffer (28 B per point).  Returns the
-    concatenation in rank order plus the per-rank counts.
+    ``xyz`` [cap,3], ``rgb`` [cap,3], ``err`` [cap] hold ``n_valid`` points (default: all rows).  Returns the
+    concatenation in rank order plus the per-rank counts.  On CUDA tensors this is ``all_gather_cloud`` (one padded
+    collective + the device-side concatenation) followed by the single host read that sizing the returned tensors needs;
+    callers that can keep capacity-sized buffers use ``all_gather_cloud`` directly and never synchronise.  On CPU tensors
+    (gloo, the host-logic tests) the same protocol runs with torch indexing.
     """
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         n = xyz.shape[0] if n_valid is None else int(n_valid)
@@ -108,17 +144,27 @@ def all_gather_points(xyz: torch.Tensor, rgb: torch.Tensor, err: torch.Tensor, n
     world = dist.get_world_size(group)
     n = xyz.shape[0] if n_valid is None else int(n_valid)
     dev = xyz.device
+    if xyz.is_cuda:
+        from .output import PackedCloud
+        caps = torch.tensor([int(xyz.shape[0])], dtype=torch.int64, device=dev)
+        dist.all_reduce(caps, op=dist.ReduceOp.MAX, group=group)          # one capacity for every rank (set-up, not data path)
+        cloud = PackedCloud(int(caps.item()), dev)
+        cloud.xyz[:n], cloud.rgb[:n], cloud.err[:n] = xyz[:n], rgb[:n], err[:n]
+        cloud.count.fill_(n)
+        total, offsets = all_gather_cloud(cloud, group=group)
+        k = int(offsets[-1].item())
+        return total.xyz[:k], total.rgb[:k], total.err[:k], offsets[1:] - offsets[:-1]
     counts = torch.zeros(world, dtype=torch.int64, device=dev)
     mine = torch.tensor([n], dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(counts, mine, group=group)
-    cmax = int(counts.max().item())
-    fused = torch.zeros((max(cmax, 1), 7), dtype=torch.float32, device=dev)
+    cmax = max(int(counts.max()), 1)
+    fused = torch.zeros((cmax, 7), dtype=torch.float32, device=dev)
     fused[:n, 0:3] = xyz[:n]
     fused[:n, 3:6] = rgb[:n]
     fused[:n, 6] = err[:n]
-    gathered = torch.empty((world * max(cmax, 1) * 7,), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world * cmax * 7,), dtype=torch.float32, device=dev)
     dist.all_gather_into_tensor(gathered, fused.reshape(-1), group=group)
-    gathered = gathered.view(world, max(cmax, 1), 7)
-    parts = [gathered[r, : int(counts[r].item())] for r in range(world)]
-    allp = torch.cat(parts, dim=0) if parts else fused[:0]
+    gathered = gathered.view(world, cmax, 7)
+    cl = counts.tolist()
+    allp = torch.cat([gathered[r, :cl[r]] for r in range(world)], dim=0)
     return allp[:, 0:3].contiguous(), allp[:, 3:6].contiguous(), allp[:, 6].contiguous(), counts

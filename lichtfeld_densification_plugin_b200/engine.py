@@ -78,6 +78,7 @@ class RefBatch:
         self.nbr_uids: List[List[int]] = []
         self.ref_uids: List[int] = []
         self.force_scalar_loads = False
+        self.has_warped_masks = False        # some neighbour mask (mask_b) was registered: the warp planes are read per pixel
         self.pairs = pair_cache or PairConstantCache()
 
     def __len__(self) -> int:
@@ -169,6 +170,7 @@ class RefBatch:
                 row["mask_a"] = m.data_ptr()
             else:
                 row["mask_b"][j - 1] = m.data_ptr()
+                self.has_warped_masks = True
         if shape is not None:
             mh, mw = shape
             row["mask_w"], row["mask_h"] = mw, mh
@@ -264,6 +266,7 @@ class DensifyEngine:
         p.nn_max = max((len(u) for u in batch.nbr_uids), default=0)
         p.prologue = 0 if cfg.certainty_floor is None else 1
         p.certainty_floor = float(np.float32(cfg.certainty_floor if cfg.certainty_floor is not None else 0.0))
+        p.no_warped_masks = 0 if batch.has_warped_masks else 1
         p.seed = int(cfg.seed) & 0xFFFFFFFFFFFFFFFF
         p.uniforms_per_ref = int(uniforms_per_ref)
         return p

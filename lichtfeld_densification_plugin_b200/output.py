@@ -30,6 +30,85 @@ PLY_RECORD_BYTES = 15
 POINTS3D_RECORD_BYTES = 43
 
 
+class PackedCloud:
+    """A point cloud in ONE device allocation: 16-byte header (int64 point count) | xyz [cap,3] | rgb [cap,3] | err [cap],
+    all float32 - so that a rank's whole cloud goes into a single collective (``distributed.all_gather_points``) and a
+    launch sequence can append to it without the host learning any count."""
+    HEADER_BYTES = 16
+
+    def __init__(self, capacity: int, device, storage: Optional[torch.Tensor] = None) -> None:
+        self.capacity = cap = self.round_capacity(capacity)
+        nbytes = self.nbytes(cap)
+        self.packed = storage if storage is not None else torch.zeros((nbytes,), dtype=torch.uint8, device=device)
+        if self.packed.numel() != nbytes or self.packed.dtype != torch.uint8:
+            raise ValueError("storage must be a uint8 tensor of PackedCloud.nbytes(capacity) bytes")
+        h = self.HEADER_BYTES
+        self.count = self.packed[:8].view(torch.int64)                       # [1], stays on the device
+        self.xyz = self.packed[h:h + 12 * cap].view(torch.float32).view(cap, 3)
+        self.rgb = self.packed[h + 12 * cap:h + 24 * cap].view(torch.float32).view(cap, 3)
+        self.err = self.packed[h + 24 * cap:h + 28 * cap].view(torch.float32)
+
+    @staticmethod
+    def round_capacity(capacity: int) -> int:
+        return (max(1, int(capacity)) + 3) // 4 * 4          # blocks of a gathered [world, nbytes] buffer stay 16-byte aligned
+
+    @classmethod
+    def nbytes(cls, capacity: int) -> int:
+        return cls.HEADER_BYTES + 28 * cls.round_capacity(capacity)
+
+    def total_points(self) -> int:
+        """Synchronises."""
+        return int(self.count.item())
+
+
+class ConcatPlan:
+    """``ldp_concat_points`` with its pointer tables built once: concatenates the first ``*count[q]`` rows of every segment
+    (the outputs of a launch, or a rank's block of an all-gather) into a ``PackedCloud``, in segment order - the
+    reference's final ``np.concatenate`` (core/pipeline.py:914-928) without a host round trip."""
+
+    def __init__(self, xyz, rgb, err, counts, seg_cap: int) -> None:
+        n = len(xyz)
+        if not (n == len(rgb) == len(err) == len(counts)) or n == 0:
+            raise ValueError("one xyz / rgb / err / count tensor per segment")
+        dev = xyz[0].device
+        if not xyz[0].is_cuda:
+            raise N.NativeLibraryError("device tensors required (there is no CPU fallback)")
+        for t in list(xyz) + list(rgb) + list(err):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
+                raise ValueError("segments must be contiguous float32 tensors on one device")
+        for c in counts:
+            if c.dtype != torch.int64 or c.device != dev or c.numel() < 1:
+                raise ValueError("counts must be int64 device tensors")
+        self.n_seg, self.seg_cap, self.device = n, int(seg_cap), dev
+        self._keep = (list(xyz), list(rgb), list(err), list(counts))
+        tab = np.array([[t.data_ptr() for t in lst] for lst in self._keep], dtype=np.int64)        # [4, n_seg] device pointers
+        self.tables = torch.from_numpy(tab).to(dev)
+        self.seg_offsets = torch.zeros((n + 1,), dtype=torch.int64, device=dev)
+
+    def run(self, dst: PackedCloud) -> PackedCloud:
+        lib = N.load()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        t = self.tables
+        N.check(lib.ldp_concat_points(C.c_void_p(t[0].data_ptr()), C.c_void_p(t[1].data_ptr()), C.c_void_p(t[2].data_ptr()),
+                                      C.c_void_p(t[3].data_ptr()), self.n_seg, self.seg_cap, C.c_void_p(dst.xyz.data_ptr()),
+                                      C.c_void_p(dst.rgb.data_ptr()), C.c_void_p(dst.err.data_ptr()), dst.capacity,
+                                      C.c_void_p(self.seg_offsets.data_ptr()), C.c_void_p(dst.count.data_ptr()),
+                                      C.c_void_p(stream)), "ldp_concat_points")
+        return dst
+
+
+def concat_launches(outs, dst: Optional[PackedCloud] = None) -> PackedCloud:
+    """Kept points of several launches (``DensifyOutputs``, launch order) as one packed cloud."""
+    seg_cap = max(int(o.err.shape[0]) for o in outs)
+    plan = ConcatPlan([o.xyz for o in outs], [o.rgb for o in outs], [o.err for o in outs],
+                      [o.ref_offset[o.n_refs:o.n_refs + 1] for o in outs], seg_cap)
+    if dst is None:
+        dst = PackedCloud(sum(int(o.err.shape[0]) for o in outs), outs[0].xyz.device)
+    plan.run(dst)
+    dst._plan = plan                     # keeps the pointer tables alive until the stream is done with them
+    return dst
+
+
 def _lib_and_stream(t: torch.Tensor):
     if not t.is_cuda:
         raise N.NativeLibraryError("device tensors required (there is no CPU fallback)")
