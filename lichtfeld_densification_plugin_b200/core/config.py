@@ -50,7 +50,10 @@ class DensePipelineConfig:
     pack_workers: int = 4
     # --- B200 path, opt-in ---
     rng_mode: str = RNG_PHILOX
-    refs_per_launch: int = 0         # 0 = all reference views of a rank in one launch
+    refs_per_launch: int = 32        # reference views per launch sequence (launches are kept in flight on a ring of engines, so
+                                     # memory, cancellation latency and progress granularity are bounded by this); 0 = all in one launch
+    viz_every_emission: bool = False # live update: True writes every intermediate PLY the reference would (one per viz_interval
+                                     # views, each a rewrite of all points so far); False only the latest one per collected launch
 
     def validate(self) -> "DensePipelineConfig":
         if self.matches_per_ref < 0:

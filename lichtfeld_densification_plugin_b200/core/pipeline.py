@@ -44,6 +44,26 @@ class PipelineCancelled(RuntimeError):
     """Raised when a running dense pipeline is cancelled."""
 
 
+_DEBUG_PREVIEW_INTERVAL = 3          # reference core/pipeline.py:34
+_PREVIEW_MAX_MATCHES = 10000         # reference core/pipeline.py:50
+
+
+@dataclass
+class MatchPreview:
+    """reference core/debug_viz.py:13-26 (what ``MatchDebugState.submit_preview`` receives)."""
+    ref_id: int
+    nbr_id: int
+    ref_label: str
+    nbr_label: str
+    left_image: np.ndarray
+    right_image: np.ndarray
+    matches: np.ndarray
+    cert_norm: np.ndarray
+    match_count: int
+    pair_index: int
+    total_pairs: int
+
+
 @dataclass
 class _PackedReferenceBatch:
     ref_id: int
@@ -118,14 +138,30 @@ def _build_camera_lookup(camera_records: Sequence[CameraRecord]) -> _CameraLooku
     )
 
 
-def _record_for(cameras: _CameraLookup, uid: int) -> CameraRecord:
-    rec = cameras.record_by.get(uid) if cameras.record_by else None
-    if rec is None:       # a lookup built by the reference's own helper has no record_by
+_side_tables: Dict[int, tuple] = {}      # lookups built by the reference's own helper carry no record_by: (pinned lookup, table)
+
+
+def _record_for(cameras, uid: int, size: Optional[Tuple[int, int]] = None) -> CameraRecord:
+    """The ``CameraRecord`` of ``uid`` - always the SAME object for the same (lookup, uid, size), so that the engine's
+    per-pair constant cache (keyed by record identity) hits.  ``size``: the (width, height) a packed reference view carries
+    when it differs from the camera's own (``packed.wA_cam`` / ``hA_cam``, reference core/pipeline.py:681-682)."""
+    table = getattr(cameras, "record_by", None)
+    if table is None:
+        table = _side_tables.setdefault(id(cameras), (cameras, {}))[1]
+    rec = table.get(uid)
+    if rec is None:
         w, h = cameras.size_by[uid]
         rec = CameraRecord(uid=uid, image_path=cameras.path_by.get(uid, ""), width=w, height=h, K=cameras.K_by[uid],
                            R=cameras.R_by[uid], t=cameras.t_by[uid], P=cameras.P_by[uid], C=cameras.C_by[uid])
-        if cameras.record_by is not None:
-            cameras.record_by[uid] = rec
+        table[uid] = rec
+    if size is not None and (rec.width, rec.height) != (int(size[0]), int(size[1])):
+        key = (uid, int(size[0]), int(size[1]))
+        sized = table.get(key)
+        if sized is None:
+            sized = CameraRecord(uid=rec.uid, image_path=rec.image_path, width=int(size[0]), height=int(size[1]),
+                                 K=rec.K, R=rec.R, t=rec.t, P=rec.P, C=rec.C)
+            table[key] = sized
+        rec = sized
     return rec
 
 
@@ -202,24 +238,39 @@ def _split_reference(out: DensifyOutputs, host: dict, r: int, nbr_uids: List[int
                                   debug_matches_by_nbr=dbg_m, debug_cert_by_nbr=dbg_c, ply_records=rec)
 
 
-def _download(out: DensifyOutputs, collect_debug: bool, ply_records: bool = False) -> dict:
-    """One synchronising device->host read of everything the host needs."""
+def _download(out: DensifyOutputs, collect_debug: bool, ply_records: bool = False, engine: Optional[DensifyEngine] = None) -> dict:
+    """ONE device->host copy of the launch's packed result (offsets, per-view status words, xyz, rgb, err and, when asked
+    for, the debug rows: ``DensifyOutputs.packed``) into page-locked memory, one synchronisation; every array of the
+    returned dict is a view of that host buffer (callers copy what they keep)."""
     rec = None
     if ply_records and out.n_refs:      # packed before the first host read: the point count is taken on the device
         from .. import output as _output
         rec = _output.ply_records(out.xyz, out.rgb, n=int(out.err.shape[0]), n_dev=out.ref_offset[-1:])
-    meta = {"ref_offset": out.ref_offset.cpu().numpy()}
-    total = int(meta["ref_offset"][-1]) if out.n_refs else 0
-    meta["status"] = out.status.cpu().numpy()
-    meta["uniforms_used"] = out.uniforms_used.cpu().numpy()
-    meta["group_order"] = out.group_order.cpu().numpy()
-    meta["group_count"] = out.group_count.cpu().numpy()
-    meta["xyz"] = out.xyz[:total].cpu().numpy()
-    meta["rgb"] = out.rgb[:total].cpu().numpy()
-    meta["err"] = out.err[:total].cpu().numpy()
+    eng = engine if engine is not None else get_engine(out.packed.device)
+    host_t = eng.pinned_like(out.packed)
+    host_t.copy_(out.packed, non_blocking=True)
+    torch.cuda.current_stream(out.packed.device).synchronize()
+    host = host_t.numpy()
+    R, NN = out.n_refs, N.LDP_MAX_NN
+    L = out.layout
+
+    def arr(name, dtype, shape):
+        a, n = L[name]
+        return host[a:a + n].view(dtype).reshape(shape)
+
+    meta = {"ref_offset": arr("ref_offset", np.int64, (R + 1,))}
+    total = int(meta["ref_offset"][-1]) if R else 0
+    cap = int(out.err.shape[0])
+    meta["status"] = arr("status", np.int32, (R,))
+    meta["uniforms_used"] = arr("uniforms_used", np.int32, (R,))
+    meta["group_order"] = arr("group_order", np.int32, (R, NN))
+    meta["group_count"] = arr("group_count", np.int32, (R, NN))
+    meta["xyz"] = arr("xyz", np.float32, (cap, 3))[:total]
+    meta["rgb"] = arr("rgb", np.float32, (cap, 3))[:total]
+    meta["err"] = arr("err", np.float32, (cap,))[:total]
     if collect_debug:
-        meta["dbg_matches"] = out.dbg_matches[:total].cpu().numpy()
-        meta["dbg_cert"] = out.dbg_cert[:total].cpu().numpy()
+        meta["dbg_matches"] = arr("dbg_matches", np.float32, (cap, 4))[:total]
+        meta["dbg_cert"] = arr("dbg_cert", np.float32, (cap,))[:total]
     if rec is not None:
         meta["ply"] = rec[:15 * total].cpu().numpy()
     return meta
@@ -266,10 +317,7 @@ def submit_refs(matched_refs: Sequence[_MatchedReference], tri_ctx: _Triangulati
         certs = [_to_device(c, dev, torch.float32) for c in mr.cert_list_cpu]
         warps = [_to_device(w, dev, torch.float32) for w in mr.warp_list_cpu]
         image = _to_device(packed.imA_np, dev, torch.uint8)
-        ref_cam = _record_for(tri_ctx.cameras, packed.ref_id)
-        if (ref_cam.width, ref_cam.height) != (packed.wA_cam, packed.hA_cam):
-            ref_cam = CameraRecord(uid=ref_cam.uid, image_path=ref_cam.image_path, width=packed.wA_cam, height=packed.hA_cam,
-                                   K=ref_cam.K, R=ref_cam.R, t=ref_cam.t, P=ref_cam.P, C=ref_cam.C)
+        ref_cam = _record_for(tri_ctx.cameras, packed.ref_id, size=(packed.wA_cam, packed.hA_cam))
         nbrs = [_record_for(tri_ctx.cameras, uid) for uid in packed.nn_ids]
         mask_a = masks_b = None
         if raw[i]:
@@ -295,6 +343,7 @@ def collect_refs(pending: _PendingLaunch, errors: Optional[list] = None, ring=No
     if ring is not None:
         ring.wait(out)                                 # the current stream (which does the read-back) follows the ring stream
     host = _download(out, pending.collect_debug, pending.ply_records)
+    triangulate_refs.last_uniforms_used = host["uniforms_used"].copy()
     results: List[Optional[_TriangulatedReference]] = []
     for r in range(pending.n):
         try:
@@ -304,7 +353,6 @@ def collect_refs(pending: _PendingLaunch, errors: Optional[list] = None, ring=No
             if errors is not None:
                 errors.append((r, exc))
             results.append(None)
-    triangulate_refs.last_uniforms_used = host["uniforms_used"]
     triangulate_refs.last_launches = out.launches
     return results
 
@@ -396,6 +444,52 @@ def _collect_reference_matches(packed: _PackedReferenceBatch, matcher, config: D
                              image_by_nbr=image_by_nbr, raw_certainty=True), pair_counter
 
 
+def _build_filtered_match_preview(imA_np, imB_np, matches, cert_norm, ref_id: int, nbr_id: int, ref_label: str, nbr_label: str,
+                                  pair_index: int, total_pairs: int, match_count: int,
+                                  max_matches: int = _PREVIEW_MAX_MATCHES) -> Optional[MatchPreview]:
+    """reference core/pipeline.py:551-599: at most ``max_matches`` of the kept matches, drawn with the pair's own seed."""
+    if matches is None or cert_norm is None or matches.size == 0 or cert_norm.size == 0:
+        return None
+    matches = np.asarray(matches, dtype=np.float32)
+    cert_norm = np.asarray(cert_norm, dtype=np.float32)
+    total = int(match_count if match_count > 0 else matches.shape[0])
+    if matches.shape[0] > max_matches > 0:
+        from ..output import preview_seed
+        sel = np.random.default_rng(preview_seed(ref_id, nbr_id)).choice(matches.shape[0], size=max_matches, replace=False)
+        matches, cert_norm = matches[sel], cert_norm[sel]
+    return MatchPreview(ref_id=ref_id, nbr_id=nbr_id, ref_label=ref_label, nbr_label=nbr_label, left_image=imA_np,
+                        right_image=imB_np, matches=matches, cert_norm=cert_norm.astype(np.float32, copy=False),
+                        match_count=total, pair_index=int(pair_index), total_pairs=int(total_pairs))
+
+
+def _emit_debug_previews(matched_ref: _MatchedReference, tri_ref: _TriangulatedReference, debug_state, cameras: _CameraLookup,
+                         total_pairs_est: int, pair_counter: int, cancel_requested: Optional[Callable[[], bool]]) -> None:
+    """reference core/pipeline.py:458-505: one preview per neighbour of the view (every third pair when auto-stepping)."""
+    if debug_state is None:
+        return
+    packed = matched_ref.packed
+    total_pairs_val = total_pairs_est if total_pairs_est > 0 else max(pair_counter, 1)
+    for nbr_id, matches in tri_ref.debug_matches_by_nbr.items():
+        if _is_cancelled(cancel_requested):
+            raise PipelineCancelled("Cancelled")
+        imB_np = matched_ref.image_by_nbr.get(nbr_id)
+        pair_idx = matched_ref.pair_index_by_nbr.get(nbr_id)
+        cert_norm = tri_ref.debug_cert_by_nbr.get(nbr_id)
+        if imB_np is None or pair_idx is None or cert_norm is None:
+            continue
+        auto = debug_state.is_auto_step() if hasattr(debug_state, "is_auto_step") else True
+        if auto and _DEBUG_PREVIEW_INTERVAL > 0 and pair_idx % _DEBUG_PREVIEW_INTERVAL != 1:
+            continue
+        try:
+            preview = _build_filtered_match_preview(packed.imA_np, imB_np, matches, cert_norm, packed.ref_id, nbr_id,
+                                                    os.path.basename(packed.ref_path), os.path.basename(cameras.path_by.get(nbr_id, "")),
+                                                    pair_idx, total_pairs_val, match_count=int(matches.shape[0]))
+            if preview:
+                debug_state.submit_preview(preview)
+        except Exception:                                      # the reference logs and carries on (:503-504)
+            pass
+
+
 # ------------------------------------------------------------------------------------------------
 MatchSource = Callable[[int], Optional[_MatchedReference]]
 
@@ -461,43 +555,63 @@ def run_dense_pipeline(
     """Reference signature (core/pipeline.py:783-792) + ``match_source``: a callable
     ``ref_local -> _MatchedReference | None`` standing in for pack loader + RoMa matcher (out of scope here;
     an integrator wraps ``RomaMatcher.match_grids_batch`` and may keep its outputs on the GPU).
-    Views are processed ``config.refs_per_launch`` at a time (0 = all in one launch)."""
-    del debug_state, nn_table
+
+    Views are processed ``config.refs_per_launch`` at a time (default 32; 0 = all in one launch): ``match_source`` is
+    asked for one launch worth of views, the launch is enqueued on a ring of engines, and the oldest launch in flight is
+    read back - so device memory holds the matcher outputs of at most ring-depth launches, ``cancel_requested`` is polled
+    before every launch and ``progress_callback`` fires after every collected launch.
+    ``debug_state`` (reference ``MatchDebugState``: ``is_enabled``, ``set_total_pairs``, ``is_auto_step``,
+    ``submit_preview``, ``release_waiters``): when enabled, the launches collect the kept matches per neighbour and a
+    ``MatchPreview`` per pair is submitted exactly as the reference does (core/pipeline.py:866-893)."""
     if match_source is None:
         raise RuntimeError("run_dense_pipeline needs a match_source: the RoMa matcher is not part of this package")
     from .config import ROMA_PRESETS
+    from .selection import _estimate_total_pairs
     if w_match is None or h_match is None:
         h_lr, _ = ROMA_PRESETS[config.roma_setting]
         w_match = h_match = h_lr
     if getattr(config, "rng_mode", RNG_PHILOX) == RNG_NUMPY_GLOBAL:
         np.random.seed(config.seed)                                    # core/pipeline.py:793
     cameras = _build_camera_lookup(camera_records)
+    total_pairs_est = 0
+    if debug_state is not None and nn_table is not None:
+        try:
+            total_pairs_est = int(_estimate_total_pairs(refs_local, nn_table, cameras.img_ids, config.nns_per_ref))
+        except Exception:
+            total_pairs_est = 0
+        debug_state.set_total_pairs(total_pairs_est)                   # core/pipeline.py:796-798
     tri_ctx = _TriangulationContext(cameras=cameras, config=config, matcher_sample_cap=sample_cap,
                                     w_match=int(w_match), h_match=int(h_match))
     t0 = time.time()
-    step = int(getattr(config, "refs_per_launch", 0)) or max(1, len(refs_local))
+    step = int(getattr(config, "refs_per_launch", 32)) or max(1, len(refs_local))
     parts_xyz, parts_rgb, parts_err = [], [], []
     pairs = 0
+    pair_counter = 0
     # live update (core/pipeline.py:296-306,508-532): every viz_interval views the reference re-concatenates and re-packs
     # all points so far; here every view's PLY records are packed once, on the device, and an emission is a bulk write
     viz_interval = int(getattr(config, "viz_interval", 0))
     ply_base = _prepare_intermediate_ply_base(config.output_path, viz_interval, on_sequential_viz)
+    every_emission = bool(getattr(config, "viz_every_emission", False))
     ply_parts: List[np.ndarray] = []
     ply_points = 0
     total = len(refs_local)
     n_chunks = (total + step - 1) // step
     ring = get_ring() if (n_chunks > 1 and getattr(config, "rng_mode", RNG_PHILOX) != RNG_NUMPY_GLOBAL) else None
-    in_flight: List[Tuple[int, _PendingLaunch]] = []      # (views done when this launch is collected, launch)
+    in_flight: List[tuple] = []      # (views done when this launch is collected, launch, its matched references)
 
-    def consume(outs, done: int) -> None:
-        nonlocal pairs, ply_points
-        for tri in outs:
+    def consume(outs, done: int, matched_refs) -> None:
+        nonlocal pairs, ply_points, pair_counter
+        latest = None                 # (file name, points, parts) of the newest due emission of this launch
+        for tri, mr in zip(outs, matched_refs):
+            pair_counter = max([pair_counter] + list(mr.pair_index_by_nbr.values()))
             if tri is None:
                 continue
             parts_xyz.append(tri.xyz)
             parts_rgb.append(tri.rgb)
             parts_err.append(tri.err)
             pairs += 1
+            if tri.debug_matches_by_nbr and debug_state is not None:
+                _emit_debug_previews(mr, tri, debug_state, cameras, total_pairs_est, pair_counter, cancel_requested)
             if ply_base is not None:
                 rec = tri.ply_records
                 if rec is None:                               # numpy-RNG mode goes through _triangulate_ref: pack on the host
@@ -505,39 +619,52 @@ def run_dense_pipeline(
                 ply_parts.append(rec)
                 ply_points += int(tri.xyz.shape[0])
                 if pairs % viz_interval == 0:
-                    _emit_intermediate_ply(f"{ply_base}_{pairs}.ply", ply_points, ply_parts, on_sequential_viz)
+                    if every_emission:
+                        _emit_intermediate_ply(f"{ply_base}_{pairs}.ply", ply_points, ply_parts, on_sequential_viz)
+                    else:
+                        latest = (f"{ply_base}_{pairs}.ply", ply_points, len(ply_parts))
+        if latest is not None:
+            _emit_intermediate_ply(latest[0], latest[1], ply_parts[:latest[2]], on_sequential_viz)
         if progress_callback:
             progress_callback(10.0 + 80.0 * done / max(1, total), f"Matching {done}/{total} references")
 
-    for lo in range(0, total, step):
-        if _is_cancelled(cancel_requested):
-            raise PipelineCancelled("Cancelled")
-        chunk = refs_local[lo:lo + step]
-        done = min(total, lo + step)
-        matched = [(r, match_source(r)) for r in chunk]
-        matched = [(r, m) for r, m in matched if m is not None]
-        if not matched:
-            continue
-        if getattr(config, "rng_mode", RNG_PHILOX) == RNG_NUMPY_GLOBAL:
-            outs = []
-            for _, m in matched:
-                try:
-                    outs.append(_triangulate_ref(m, tri_ctx))
-                except Exception:
-                    outs.append(None)
-            consume(outs, done)
-        elif ring is None:
-            consume(triangulate_refs([m for _, m in matched], tri_ctx, rng_streams=[int(r) for r, _ in matched],
-                                     ply_records=ply_base is not None), done)
-        else:
-            # several launches in flight: the next chunk is uploaded and enqueued before the oldest one is read back
-            in_flight.append((done, submit_refs([m for _, m in matched], tri_ctx, rng_streams=[int(r) for r, _ in matched],
-                                                ply_records=ply_base is not None, ring=ring)))
-            if len(in_flight) >= ring.depth:
-                d, pend = in_flight.pop(0)
-                consume(collect_refs(pend, ring=ring), d)
-    for d, pend in in_flight:
-        consume(collect_refs(pend, ring=ring), d)
+    try:
+        for lo in range(0, total, step):
+            if _is_cancelled(cancel_requested):
+                raise PipelineCancelled("Cancelled")
+            chunk = refs_local[lo:lo + step]
+            done = min(total, lo + step)
+            matched = [(r, match_source(r)) for r in chunk]
+            matched = [(r, m) for r, m in matched if m is not None]
+            if not matched:
+                continue
+            mrs = [m for _, m in matched]
+            collect_debug = debug_state is not None and bool(debug_state.is_enabled())      # core/pipeline.py:866
+            if getattr(config, "rng_mode", RNG_PHILOX) == RNG_NUMPY_GLOBAL:
+                outs = []
+                for m in mrs:
+                    try:
+                        outs.append(_triangulate_ref(m, tri_ctx, collect_debug))
+                    except Exception:
+                        outs.append(None)
+                consume(outs, done, mrs)
+            elif ring is None:
+                consume(triangulate_refs(mrs, tri_ctx, collect_debug, rng_streams=[int(r) for r, _ in matched],
+                                         ply_records=ply_base is not None), done, mrs)
+            else:
+                # several launches in flight: the next chunk is uploaded and enqueued before the oldest one is read back
+                in_flight.append((done, submit_refs(mrs, tri_ctx, collect_debug, rng_streams=[int(r) for r, _ in matched],
+                                                    ply_records=ply_base is not None, ring=ring), mrs))
+                if len(in_flight) >= ring.depth:
+                    d, pend, pm = in_flight.pop(0)
+                    consume(collect_refs(pend, ring=ring), d, pm)
+        for d, pend, pm in in_flight:
+            if _is_cancelled(cancel_requested):
+                raise PipelineCancelled("Cancelled")
+            consume(collect_refs(pend, ring=ring), d, pm)
+    finally:
+        if debug_state is not None and hasattr(debug_state, "release_waiters"):
+            debug_state.release_waiters()                              # core/pipeline.py:547-548
     if _is_cancelled(cancel_requested):
         raise PipelineCancelled("Cancelled")
     if progress_callback:

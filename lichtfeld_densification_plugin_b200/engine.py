@@ -51,10 +51,23 @@ class PathConfig:
 
 class PairConstantCache:
     """Per (reference, neighbour) camera constants, computed once on the host with the reference's
-    float32 numpy arithmetic (reference core/geometry.py:122-130)."""
+    float32 numpy arithmetic (reference core/geometry.py:122-130), and whole descriptor rows with every camera constant of a
+    (reference view, neighbour list) filled in.  Keys are object identities (the records are pinned so an id cannot be
+    recycled): two scenes may reuse camera uids with other poses."""
+    MAX_ROWS = 8192
 
     def __init__(self) -> None:
         self._F: Dict[Tuple[int, int], tuple] = {}
+        self._rows: Dict[tuple, tuple] = {}
+
+    def row_template(self, key: tuple, pins: tuple, make):
+        hit = self._rows.get(key)
+        if hit is None:
+            if len(self._rows) >= self.MAX_ROWS:
+                self._rows.clear()
+            hit = (make(), pins)
+            self._rows[key] = hit
+        return hit[0]
 
     def fundamental(self, a: CameraRecord, b: CameraRecord) -> np.ndarray:
         key = (id(a), id(b))
@@ -111,46 +124,57 @@ class RefBatch:
             raise ValueError("cert_planes, warp_planes and nbr_cams must have the same length")
         if nn > N.LDP_MAX_NN:
             raise ValueError(f"at most {N.LDP_MAX_NN} neighbours per reference view")
-        row = np.zeros((), dtype=N.REF_DESC_DTYPE)
-        for k in range(nn):
-            c = self._check_plane(cert_planes[k], (self.H, self.W), "certainty plane", allow_pinned_host=True)
-            w = self._check_plane(warp_planes[k], (self.H, self.W, 4), "warp plane", allow_pinned_host=True)
-            if c.data_ptr() % 16 != 0:
-                self.force_scalar_loads = True
-            if w.data_ptr() % 16 != 0:
-                raise ValueError("warp planes must be 16-byte aligned")
-            row["cert"][k] = c.data_ptr()
-            row["warp"][k] = w.data_ptr()
-            self._keep_alive += [c, w]
         if image.device != self.device or image.dtype != torch.uint8 or image.dim() != 3 or image.shape[2] != 3:
             raise ValueError("image must be a uint8 [h, w, 3] tensor on the batch device")
         image = image.contiguous()
-        self._keep_alive.append(image)
         ih, iw = int(image.shape[0]), int(image.shape[1])
-        wm, hm = float(self.w_match), float(self.h_match)
+        uids = [int(c.uid) for c in nbr_cams]
+
+        def make_template():
+            """every camera constant of this (reference view, neighbour list): computed once, copied per call"""
+            t = np.zeros((), dtype=N.REF_DESC_DTYPE)
+            wm, hm = float(self.w_match), float(self.h_match)
+            t["nn"] = nn
+            t["img_w"], t["img_h"] = iw, ih
+            # python-float scale factors rounded to f32 at the multiply (NEP 50), reference core/pipeline.py:662-663,681-682
+            t["sxA"], t["syA"] = np.float32(ref_cam.width / wm), np.float32(ref_cam.height / hm)
+            t["sx_img"], t["sy_img"] = np.float32(iw / wm), np.float32(ih / hm)
+            t["P1"] = np.asarray(ref_cam.P, dtype=np.float32).reshape(12)
+            t["C1"] = np.asarray(ref_cam.C, dtype=np.float32).reshape(3)
+            for k, cam in enumerate(nbr_cams):
+                t["P2"][k] = np.asarray(cam.P, dtype=np.float32).reshape(12)
+                t["C2"][k] = np.asarray(cam.C, dtype=np.float32).reshape(3)
+                t["F"][k] = self.pairs.fundamental(ref_cam, cam).reshape(9)
+                t["sxB"][k], t["syB"][k] = np.float32(cam.width / wm), np.float32(cam.height / hm)
+                t["group"][k] = uids.index(uids[k])          # the reference groups by neighbour uid
+            return t
+
+        key = (id(ref_cam), tuple(id(c) for c in nbr_cams), self.w_match, self.h_match, iw, ih)
+        row = self.pairs.row_template(key, (ref_cam, tuple(nbr_cams)), make_template).copy()
+        cert_ptrs, warp_ptrs = row["cert"], row["warp"]
+        for k in range(nn):
+            c = self._check_plane(cert_planes[k], (self.H, self.W), "certainty plane", allow_pinned_host=True)
+            w = self._check_plane(warp_planes[k], (self.H, self.W, 4), "warp plane", allow_pinned_host=True)
+            cp, wp = c.data_ptr(), w.data_ptr()
+            if cp % 16 != 0:
+                self.force_scalar_loads = True
+            if wp % 16 != 0:
+                raise ValueError("warp planes must be 16-byte aligned")
+            cert_ptrs[k] = cp
+            warp_ptrs[k] = wp
+            self._keep_alive += [c, w]
+        self._keep_alive.append(image)
         row["image"] = image.data_ptr()
-        row["nn"] = nn
-        row["img_w"], row["img_h"] = iw, ih
         row["rng_stream"] = np.uint32(int(rng_stream) & 0xFFFFFFFF)
         row["weight_sum_override"] = np.float32(weight_sum_override)
-        # python-float scale factors rounded to f32 at the multiply (NEP 50), reference core/pipeline.py:662-663,681-682
-        row["sxA"], row["syA"] = np.float32(ref_cam.width / wm), np.float32(ref_cam.height / hm)
-        row["sx_img"], row["sy_img"] = np.float32(iw / wm), np.float32(ih / hm)
-        row["P1"] = np.asarray(ref_cam.P, dtype=np.float32).reshape(12)
-        row["C1"] = np.asarray(ref_cam.C, dtype=np.float32).reshape(3)
-        uids = [int(c.uid) for c in nbr_cams]
-        for k, cam in enumerate(nbr_cams):
-            row["P2"][k] = np.asarray(cam.P, dtype=np.float32).reshape(12)
-            row["C2"][k] = np.asarray(cam.C, dtype=np.float32).reshape(3)
-            row["F"][k] = self.pairs.fundamental(ref_cam, cam).reshape(9)
-            row["sxB"][k], row["syB"][k] = np.float32(cam.width / wm), np.float32(cam.height / hm)
-            row["group"][k] = uids.index(uids[k])          # the reference groups by neighbour uid
         self._add_masks(row, nn, mask_a, masks_b)
         self._rows.append(row)
         self.nbr_uids.append(uids)
         self.ref_uids.append(int(ref_cam.uid))
 
     def _add_masks(self, row, nn: int, mask_a, masks_b) -> None:
+        if mask_a is None and masks_b is None:
+            return
         masks = [mask_a] + list(masks_b if masks_b is not None else [])
         if len(masks) - 1 not in (0, nn):
             raise ValueError("masks_b must have one entry (tensor or None) per neighbour")
@@ -226,7 +250,8 @@ class DensifyOutputs:
     sample_flags: Optional[torch.Tensor] = None
     sample_xyzerr: Optional[torch.Tensor] = None
     launches: int = 0
-    packed: Optional[torch.Tensor] = None      # the u8 allocation behind ref_offset | xyz | rgb | err
+    packed: Optional[torch.Tensor] = None      # the u8 allocation behind ref_offset | status words | xyz | rgb | err [| debug]
+    layout: Optional[dict] = None              # name -> (byte offset, bytes) inside ``packed``
     ready: Optional[torch.cuda.Event] = None   # DensifyRing: recorded on the ring stream after the launch sequence
 
     def total_points(self) -> int:
@@ -243,6 +268,7 @@ class DensifyEngine:
         self.lib = N.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self._workspace: Optional[torch.Tensor] = None
+        self._pinned: Optional[torch.Tensor] = None
         self.pairs = PairConstantCache()
 
     def new_batch(self, H: int, W: int, w_match: int, h_match: int) -> RefBatch:
@@ -378,33 +404,57 @@ class DensifyEngine:
         return sel, n_samples, status, used
 
     def alloc_outputs(self, R: int, sel_cap: int, collect_debug: bool = False, taps: bool = False) -> DensifyOutputs:
+        """Everything a caller reads back lives in ONE allocation (``packed``): ref_offset | per-view status words | xyz | rgb |
+        err [| debug matches | debug certainties] - a rank hands its whole result to a single collective
+        (``distributed`` / bench.py) and the drop-in path reads it back with a single device->host copy."""
         dev = self.device
         cap = max(1, R * sel_cap)
         i32 = dict(dtype=torch.int32, device=dev)
-        f32 = dict(dtype=torch.float32, device=dev)
-        # ref_offset | xyz | rgb | err live in ONE allocation (`packed`), so that a rank can hand its whole packed result
-        # to a single collective (distributed.all_gather_packed / bench.py) instead of one per array
-        off_bytes = (8 * (R + 1) + 15) // 16 * 16
-        packed = torch.zeros((off_bytes + 28 * cap,), dtype=torch.uint8, device=dev)
-        xyz_b, rgb_b, err_b = off_bytes, off_bytes + 12 * cap, off_bytes + 24 * cap
+        NN = N.LDP_MAX_NN
+        sizes = [("ref_offset", 8 * (R + 1)), ("status", 4 * R), ("n_samples", 4 * R), ("uniforms_used", 4 * R), ("rounds", 4 * R),
+                 ("weight_sum", 4 * R), ("group_count", 4 * R * NN), ("group_order", 4 * R * NN),
+                 ("xyz", 12 * cap), ("rgb", 12 * cap), ("err", 4 * cap)]
+        if collect_debug:
+            sizes += [("dbg_matches", 16 * cap), ("dbg_cert", 4 * cap)]
+        off, layout = 0, {}
+        for name, nbytes in sizes:
+            off = (off + 15) // 16 * 16
+            layout[name] = (off, nbytes)
+            off += nbytes
+        packed = torch.zeros((off,), dtype=torch.uint8, device=dev)
+
+        def view(name, dtype, shape):
+            a, n = layout[name]
+            return packed[a:a + n].view(dtype).view(*shape)
+
         out = DensifyOutputs(
             n_refs=R, sel_cap=sel_cap,
-            xyz=packed[xyz_b:rgb_b].view(torch.float32).view(cap, 3), rgb=packed[rgb_b:err_b].view(torch.float32).view(cap, 3),
-            err=packed[err_b:err_b + 4 * cap].view(torch.float32),
-            ref_offset=packed[:8 * (R + 1)].view(torch.int64),
-            status=torch.zeros((R,), **i32), n_samples=torch.zeros((R,), **i32),
-            group_count=torch.zeros((R, N.LDP_MAX_NN), **i32), group_order=torch.full((R, N.LDP_MAX_NN), -1, **i32),
-            uniforms_used=torch.zeros((R,), **i32), rounds=torch.zeros((R,), **i32), weight_sum=torch.zeros((R,), **f32),
+            xyz=view("xyz", torch.float32, (cap, 3)), rgb=view("rgb", torch.float32, (cap, 3)), err=view("err", torch.float32, (cap,)),
+            ref_offset=view("ref_offset", torch.int64, (R + 1,)),
+            status=view("status", torch.int32, (R,)), n_samples=view("n_samples", torch.int32, (R,)),
+            group_count=view("group_count", torch.int32, (R, NN)), group_order=view("group_order", torch.int32, (R, NN)),
+            uniforms_used=view("uniforms_used", torch.int32, (R,)), rounds=view("rounds", torch.int32, (R,)),
+            weight_sum=view("weight_sum", torch.float32, (R,)),
         )
+        out.group_order.fill_(-1)
         out.packed = packed
+        out.layout = layout
         if collect_debug:
-            out.dbg_matches = torch.empty((cap, 4), **f32)
-            out.dbg_cert = torch.empty((cap,), **f32)
+            out.dbg_matches = view("dbg_matches", torch.float32, (cap, 4))
+            out.dbg_cert = view("dbg_cert", torch.float32, (cap,))
         if taps:
             out.sel_idx = torch.zeros((R, sel_cap), **i32)
             out.sample_flags = torch.zeros((R, sel_cap), dtype=torch.uint8, device=dev)
-            out.sample_xyzerr = torch.zeros((R, sel_cap, 4), **f32)
+            out.sample_xyzerr = torch.zeros((R, sel_cap, 4), dtype=torch.float32, device=dev)
         return out
+
+    def pinned_like(self, packed: torch.Tensor) -> torch.Tensor:
+        """A page-locked host buffer for device->host reads of ``packed`` (cached, grown on demand; its contents are valid
+        until the next read through it)."""
+        n = int(packed.numel())
+        if self._pinned is None or self._pinned.numel() < n:
+            self._pinned = torch.empty((max(n, 1 << 20),), dtype=torch.uint8).pin_memory()
+        return self._pinned[:n]
 
 
 class PreparedLaunch:

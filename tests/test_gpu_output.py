@@ -161,7 +161,8 @@ def test_run_dense_pipeline_live_updates_write_the_reference_files(tmp_path):
     results = {}
     for per_launch in (0, 4, 2):                      # one launch; 2 and 4 launches kept in flight on the ring of engines
         out_dir = tmp_path / f"run{per_launch}"
-        cfg = DensePipelineConfig(output_path=str(out_dir / "dense.ply"), matches_per_ref=2000, viz_interval=2, refs_per_launch=per_launch)
+        cfg = DensePipelineConfig(output_path=str(out_dir / "dense.ply"), matches_per_ref=2000, viz_interval=2, refs_per_launch=per_launch,
+                                  viz_every_emission=True)
         emitted = []
         res = P.run_dense_pipeline(cams, refs, None, cfg, on_sequential_viz=emitted.append, match_source=match_source,
                                    w_match=scene.w_match, h_match=scene.h_match)
@@ -212,3 +213,85 @@ def test_voxel_downsample_rejects_bad_sizes(out_mod):
         out_mod.voxel_downsample(xyz, rgb, 0.0)
     with pytest.raises(ValueError):
         out_mod.voxel_downsample(xyz, rgb, 1e-3)          # 1e9 voxels along x: does not fit 21 bits
+
+
+def test_run_dense_pipeline_debug_state_and_latest_only_live_update(tmp_path):
+    """run_dense_pipeline honours ``debug_state`` like the reference (core/pipeline.py:866-893): with it enabled, every launch
+    collects the kept matches per neighbour and one MatchPreview per due pair is submitted - the same previews the
+    per-view drop-in call yields; by default only the newest due intermediate PLY of each collected launch is written."""
+    from lichtfeld_densification_plugin_b200 import synth
+    from lichtfeld_densification_plugin_b200.core import pipeline as P
+    from lichtfeld_densification_plugin_b200.core import writers as W
+    from lichtfeld_densification_plugin_b200.core.config import DensePipelineConfig
+    scene = synth.make_scene(24, "turbo", ref_fraction=0.3, nn=3)
+    cams = scene.cameras
+    counter = {"pairs": 0}
+    made = {}
+
+    def match_source(rp):
+        if rp in made:
+            return made[rp]
+        inp = synth.synth_ref_inputs(scene, rp, cert_family="R", seed=4)
+        ri, nb = inp["ref_index"], inp["nbr_indices"]
+        nn_ids = [cams[j].uid for j in nb]
+        packed = P._PackedReferenceBatch(ref_id=cams[ri].uid, ref_path=f"img/{ri}.png", imA_np=inp["image"].numpy(), maskA_np=None,
+                                         wA_cam=cams[ri].width, hA_cam=cams[ri].height, nn_ids=nn_ids,
+                                         nn_masks=[None] * len(nb), nn_arrays=[None] * len(nb))
+        pair_idx = {}
+        for u in nn_ids:
+            counter["pairs"] += 1
+            pair_idx[u] = counter["pairs"]
+        made[rp] = P._MatchedReference(packed=packed, warp_list_cpu=[inp["warp"][k] for k in range(len(nb))],
+                                       cert_list_cpu=[inp["cert"][k] for k in range(len(nb))], pair_index_by_nbr=pair_idx,
+                                       image_by_nbr={u: np.zeros((4, 4, 3), np.uint8) + i for i, u in enumerate(nn_ids)})
+        return made[rp]
+
+    class DebugState:
+        def __init__(self, enabled):
+            self.enabled, self.previews, self.total, self.released = enabled, [], None, False
+        def is_enabled(self): return self.enabled
+        def is_auto_step(self): return True
+        def set_total_pairs(self, n): self.total = n
+        def submit_preview(self, p): self.previews.append(p)
+        def release_waiters(self): self.released = True
+
+    refs = list(range(scene.n_refs))
+    nn_table = scene.nn_table
+    cfg = DensePipelineConfig(output_path=str(tmp_path / "dbg" / "dense.ply"), matches_per_ref=2000, viz_interval=2, refs_per_launch=3,
+                              nns_per_ref=3)
+    ds = DebugState(True)
+    emitted, progress = [], []
+    res = P.run_dense_pipeline(cams, refs, nn_table, cfg, progress_callback=lambda p, m: progress.append(p),
+                               on_sequential_viz=emitted.append, debug_state=ds, match_source=match_source,
+                               w_match=scene.w_match, h_match=scene.h_match)
+    assert ds.released and ds.total is not None and ds.total > 0
+    assert len(progress) >= (len(refs) + 2) // 3                                       # one progress report per collected launch
+    # the previews the per-view drop-in call gives for the same views (pairs 1, 4, 7, ... when auto-stepping)
+    ctx = P._TriangulationContext(cameras=P._build_camera_lookup(cams), config=cfg, matcher_sample_cap=0.9,
+                                  w_match=scene.w_match, h_match=scene.h_match)
+    want = []
+    for r in refs:
+        mr = match_source(r)
+        tri = P.triangulate_refs([mr], ctx, True, rng_streams=[r])[0]
+        for nbr_id, m in tri.debug_matches_by_nbr.items():
+            if mr.pair_index_by_nbr[nbr_id] % 3 == 1:
+                want.append((mr.packed.ref_id, nbr_id, mr.pair_index_by_nbr[nbr_id], m, tri.debug_cert_by_nbr[nbr_id]))
+    assert len(ds.previews) == len(want) > 0
+    for pv, (rid, nid, pidx, m, c) in zip(ds.previews, want):
+        assert (pv.ref_id, pv.nbr_id, pv.pair_index, pv.total_pairs) == (rid, nid, pidx, ds.total)
+        assert pv.match_count == m.shape[0] and np.array_equal(pv.matches, m) and np.array_equal(pv.cert_norm, c)
+        assert pv.ref_label == f"{rid}.png" or pv.ref_label.endswith(".png")
+    # live update, default: the newest due file of every collected launch only, each byte-identical to the reference's rewrite
+    names = [os.path.basename(p) for p in emitted]
+    assert names == sorted(set(names), key=names.index) and 0 < len(names) <= (len(refs) + 2) // 3
+    sizes = [P.triangulate_refs([match_source(r)], ctx, rng_streams=[r])[0].xyz.shape[0] for r in refs]
+    for path in emitted:
+        k = int(os.path.basename(path).split("_")[-1].split(".")[0])
+        assert k % 2 == 0
+        n = sum(sizes[:k])
+        W.write_ply(str(tmp_path / "want.ply"), res.xyz[:n], W.to_uint8_rgb(res.rgb[:n]))
+        assert open(path, "rb").read() == (tmp_path / "want.ply").read_bytes(), k
+    # disabled debug state: nothing is collected, nothing submitted
+    ds2 = DebugState(False)
+    P.run_dense_pipeline(cams, refs[:3], nn_table, cfg, debug_state=ds2, match_source=match_source, w_match=scene.w_match, h_match=scene.h_match)
+    assert not ds2.previews and ds2.released
