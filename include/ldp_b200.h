@@ -222,9 +222,12 @@ int ldp_concat_points(const float* const* xyz_src, const float* const* rgb_src, 
  *                          centers_sorted [k] = sorted(centers) (what the reference returns); centers_order [k] = pick order.
  *                          1 <= k <= n <= 8192 (the reference clamps k the same way before the loop).
  *   ldp_nearest_neighbors  core/selection.py:57-70 nearest_neighbors: for every view the k nearest other views by Euclidean
- *                          distance of the poses, ascending (ties: lower index).  idx_out [n,k] int64.  k <= min(n - 1, 16).
- *                          Distances are formed from differences (torch.cdist uses |x|^2 + |y|^2 - 2 x.y, ~1e-3 absolute
- *                          error here), so views at near-equal distance may be ordered differently from torch. */
+ *                          distance of the poses, ascending.  idx_out [n,k] int64.  k <= min(n - 1, 16).  The distances are
+ *                          torch.cdist's own float32 values (|x|^2 + |y|^2 - 2 x.y as ONE K = 18 dot product of float32
+ *                          FMAs in index order, row norms as eight lanes added left to right; measured against torch), so
+ *                          near-equal distances - the left / right neighbours of a ring camera - come out in the
+ *                          reference's order.  EXACTLY equal float32 distances: lower index first (torch.topk leaves that
+ *                          order to std::nth_element / std::partial_sort). */
 int ldp_select_kcenters(const float* flat_poses, int32_t n, int32_t k, float* scratch, int32_t* centers_sorted,
                         int32_t* centers_order, void* stream);
 int ldp_nearest_neighbors(const float* flat_poses, int32_t n, int32_t k, int64_t* idx_out, void* stream);

@@ -152,9 +152,23 @@ ldp_kcenters_kernel(const float* __restrict__ X, int n, int k, float* __restrict
 }
 
 // One warp per view: distances to every other view, the k smallest in ascending order (ties: lower index first).
-// torch.cdist computes |x|^2 + |y|^2 - 2 x.y with one sgemm (absolute error ~1e-3 on poses of norm ~10); here the
-// differences are taken first, so near-equal distances may come out in another order than torch's (documented).
+// The distances are torch.cdist's own float32 values (reference core/selection.py:66; ATen _euclidean_dist, used above 25 rows):
+//   d(i, j) = sqrt(max(x1_[i] . x2_[j], 0)),  x1_ = [-2 x, |x|^2, 1],  x2_ = [x, 1, |x|^2]
+// with the K = 18 dot product accumulated as a chain of float32 FMAs in index order (what the sgemm does) and the row norms
+// summed as eight lanes (a[i] + a[i + 8]) added left to right -- both orders measured against torch 2.11 (oracle:
+// cdist_squared_f32).  The cancellation error of this formula (~1e-6 on poses of norm ~10) is what decides the order of the
+// left / right neighbours of a ring camera, so it is reproduced, not avoided.  Where two float32 distances are EXACTLY equal
+// the reference's order is whatever std::nth_element / std::partial_sort leave (torch.topk); here the lower index comes first.
 constexpr int KNN_MAX_K = 16;
+__device__ __forceinline__ float cdist_row_norm16(const float* __restrict__ x) {
+    float l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) l[i] = __fadd_rn(__fmul_rn(x[i], x[i]), __fmul_rn(x[i + 8], x[i + 8]));
+    float s = l[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s = __fadd_rn(s, l[i]);
+    return s;
+}
 __global__ void __launch_bounds__(256)
 ldp_knn_kernel(const float* __restrict__ X, int n, int k, long long* __restrict__ out)
 {
@@ -164,16 +178,25 @@ ldp_knn_kernel(const float* __restrict__ X, int n, int k, long long* __restrict_
     float xi[KC_DIM];
 #pragma unroll
     for (int j = 0; j < KC_DIM; ++j) xi[j] = X[(size_t)row * KC_DIM + j];
+    const float ni = cdist_row_norm16(xi);
+#pragma unroll
+    for (int j = 0; j < KC_DIM; ++j) xi[j] = __fmul_rn(xi[j], -2.0f);      // x1.mul(-2): exact
     float bv[KNN_MAX_K];
     int bi[KNN_MAX_K];
 #pragma unroll
     for (int t = 0; t < KNN_MAX_K; ++t) { bv[t] = INFINITY; bi[t] = 0x7fffffff; }
     for (int j = lane; j < n; j += 32) {
         if (j == row) continue;                                    // dist.fill_diagonal_(inf)
-        float a[KC_DIM];
+        float xj[KC_DIM];
 #pragma unroll
-        for (int c = 0; c < KC_DIM; ++c) { const float d = __fsub_rn(xi[c], X[(size_t)j * KC_DIM + c]); a[c] = __fmul_rn(d, d); }
-        float v = __fsqrt_rn(pairwise16(a));
+        for (int c = 0; c < KC_DIM; ++c) xj[c] = X[(size_t)j * KC_DIM + c];
+        const float nj = cdist_row_norm16(xj);
+        float acc = __fmul_rn(xi[0], xj[0]);                       // fma(a, b, 0)
+#pragma unroll
+        for (int c = 1; c < KC_DIM; ++c) acc = __fmaf_rn(xi[c], xj[c], acc);
+        acc = __fmaf_rn(ni, 1.0f, acc);
+        acc = __fmaf_rn(1.0f, nj, acc);
+        float v = __fsqrt_rn(fmaxf(acc, 0.0f));                    // clamp_min_(0).sqrt_()
         int vi = j;
         // insert into this lane's ascending list (indices ascend within a lane, so ties keep the earlier one first)
 #pragma unroll

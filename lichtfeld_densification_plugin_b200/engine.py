@@ -20,6 +20,12 @@ from . import _native as N
 from .core.camera_models import CameraRecord
 from .core.geometry import fundamental_from_world2cam
 
+# 64-bit word offsets of the pointer fields inside an ldp_ref_desc (patched per call without numpy field lookups)
+_CERT_WORD = N.REF_DESC_DTYPE.fields["cert"][1] // 8
+_WARP_WORD = N.REF_DESC_DTYPE.fields["warp"][1] // 8
+_IMAGE_WORD = N.REF_DESC_DTYPE.fields["image"][1] // 8
+assert N.REF_DESC_DTYPE.itemsize % 8 == 0
+
 SAMPLE_CAP_DEFAULT = 0.9     # matcher.sample_thresh, reference core/matcher.py:92
 BORDER_DEFAULT = 2           # reference core/pipeline.py:646
 TILES_DEFAULT = 24           # reference core/pipeline.py:647
@@ -86,7 +92,8 @@ class RefBatch:
                  pair_cache: Optional[PairConstantCache] = None) -> None:
         self.H, self.W, self.w_match, self.h_match = int(H), int(W), int(w_match), int(h_match)
         self.device = torch.device(device)
-        self._rows: List[np.void] = []
+        self._arr = np.zeros((16,), dtype=N.REF_DESC_DTYPE)       # descriptor rows, grown by doubling
+        self._n = 0
         self._keep_alive: List[object] = []
         self.nbr_uids: List[List[int]] = []
         self.ref_uids: List[int] = []
@@ -95,7 +102,23 @@ class RefBatch:
         self.pairs = pair_cache or PairConstantCache()
 
     def __len__(self) -> int:
-        return len(self._rows)
+        return self._n
+
+    def _new_row(self, template: Optional[np.ndarray] = None):
+        """Next descriptor row (a view into the batch's array), initialised from ``template`` or zeroed; also returns the
+        row as uint64 words for pointer patching without numpy field lookups."""
+        if self._n == self._arr.shape[0]:
+            grown = np.zeros((2 * self._n,), dtype=N.REF_DESC_DTYPE)
+            grown[:self._n] = self._arr
+            self._arr = grown
+        i = self._n
+        self._n += 1
+        if template is not None:
+            self._arr[i] = template
+        else:
+            self._arr[i] = np.zeros((), dtype=N.REF_DESC_DTYPE)
+        words = self._arr.view(np.uint64).reshape(self._arr.shape[0], -1)[i]
+        return self._arr[i:i + 1], words
 
     def _check_plane(self, t: torch.Tensor, shape, what: str, allow_pinned_host: bool = False) -> torch.Tensor:
         if not isinstance(t, torch.Tensor):
@@ -150,8 +173,7 @@ class RefBatch:
             return t
 
         key = (id(ref_cam), tuple(id(c) for c in nbr_cams), self.w_match, self.h_match, iw, ih)
-        row = self.pairs.row_template(key, (ref_cam, tuple(nbr_cams)), make_template).copy()
-        cert_ptrs, warp_ptrs = row["cert"], row["warp"]
+        row1, words = self._new_row(self.pairs.row_template(key, (ref_cam, tuple(nbr_cams)), make_template))
         for k in range(nn):
             c = self._check_plane(cert_planes[k], (self.H, self.W), "certainty plane", allow_pinned_host=True)
             w = self._check_plane(warp_planes[k], (self.H, self.W, 4), "warp plane", allow_pinned_host=True)
@@ -160,15 +182,15 @@ class RefBatch:
                 self.force_scalar_loads = True
             if wp % 16 != 0:
                 raise ValueError("warp planes must be 16-byte aligned")
-            cert_ptrs[k] = cp
-            warp_ptrs[k] = wp
+            words[_CERT_WORD + k] = cp
+            words[_WARP_WORD + k] = wp
             self._keep_alive += [c, w]
         self._keep_alive.append(image)
-        row["image"] = image.data_ptr()
-        row["rng_stream"] = np.uint32(int(rng_stream) & 0xFFFFFFFF)
-        row["weight_sum_override"] = np.float32(weight_sum_override)
-        self._add_masks(row, nn, mask_a, masks_b)
-        self._rows.append(row)
+        words[_IMAGE_WORD] = image.data_ptr()
+        row1["rng_stream"] = np.uint32(int(rng_stream) & 0xFFFFFFFF)
+        if weight_sum_override:
+            row1["weight_sum_override"] = np.float32(weight_sum_override)
+        self._add_masks(row1, nn, mask_a, masks_b)
         self.nbr_uids.append(uids)
         self.ref_uids.append(int(ref_cam.uid))
 
@@ -191,16 +213,16 @@ class RefBatch:
                 raise ValueError("all masks of a reference view must share one resolution")
             self._keep_alive.append(m)
             if j == 0:
-                row["mask_a"] = m.data_ptr()
+                row["mask_a"][0] = m.data_ptr()
             else:
-                row["mask_b"][j - 1] = m.data_ptr()
+                row["mask_b"][0, j - 1] = m.data_ptr()
                 self.has_warped_masks = True
         if shape is not None:
             mh, mw = shape
-            row["mask_w"], row["mask_h"] = mw, mh
+            row["mask_w"][0], row["mask_h"][0] = mw, mh
             # F.interpolate(mode="nearest") scale: f32(in) / f32(out) (reference core/pipeline.py:373-378)
-            row["mask_sx"] = np.float32(mw) / np.float32(self.W)
-            row["mask_sy"] = np.float32(mh) / np.float32(self.H)
+            row["mask_sx"][0] = np.float32(mw) / np.float32(self.W)
+            row["mask_sy"][0] = np.float32(mh) / np.float32(self.H)
 
     def add_cert_only(self, cert_planes: Sequence[torch.Tensor], rng_stream: int = 0,
                       weight_sum_override: float = 0.0) -> None:
@@ -208,24 +230,21 @@ class RefBatch:
         nn = len(cert_planes)
         if nn > N.LDP_MAX_NN:
             raise ValueError(f"at most {N.LDP_MAX_NN} neighbours per reference view")
-        row = np.zeros((), dtype=N.REF_DESC_DTYPE)
+        row1, words = self._new_row()
         for k in range(nn):
             c = self._check_plane(cert_planes[k], (self.H, self.W), "certainty plane", allow_pinned_host=True)
             if c.data_ptr() % 16 != 0:
                 self.force_scalar_loads = True
-            row["cert"][k] = c.data_ptr()
+            words[_CERT_WORD + k] = c.data_ptr()
             self._keep_alive.append(c)
-        row["nn"] = nn
-        row["rng_stream"] = np.uint32(int(rng_stream) & 0xFFFFFFFF)
-        row["weight_sum_override"] = np.float32(weight_sum_override)
-        self._rows.append(row)
+        row1["nn"] = nn
+        row1["rng_stream"] = np.uint32(int(rng_stream) & 0xFFFFFFFF)
+        row1["weight_sum_override"] = np.float32(weight_sum_override)
         self.nbr_uids.append(list(range(nn)))
-        self.ref_uids.append(len(self._rows) - 1)
+        self.ref_uids.append(self._n - 1)
 
     def desc_array(self) -> np.ndarray:
-        if not self._rows:
-            return np.zeros((0,), dtype=N.REF_DESC_DTYPE)
-        return np.stack(self._rows).astype(N.REF_DESC_DTYPE, copy=False)
+        return self._arr[:self._n]
 
 
 @dataclass
