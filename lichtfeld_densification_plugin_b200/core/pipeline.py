@@ -230,11 +230,11 @@ def _split_reference(out: DensifyOutputs, host: dict, r: int, nbr_uids: List[int
                 break
             cnt = int(host["group_count"][r][g])
             if cnt > 0:
-                dbg_m[nbr_uids[g]] = host["dbg_matches"][pos:pos + cnt].copy()
-                dbg_c[nbr_uids[g]] = host["dbg_cert"][pos:pos + cnt].copy()
+                dbg_m[nbr_uids[g]] = host["dbg_matches"][pos:pos + cnt]
+                dbg_c[nbr_uids[g]] = host["dbg_cert"][pos:pos + cnt]
             pos += cnt
-    rec = host["ply"][15 * a:15 * b].copy() if "ply" in host else None
-    return _TriangulatedReference(xyz=host["xyz"][a:b].copy(), rgb=host["rgb"][a:b].copy(), err=host["err"][a:b].copy(),
+    rec = host["ply"][15 * a:15 * b] if "ply" in host else None
+    return _TriangulatedReference(xyz=host["xyz"][a:b], rgb=host["rgb"][a:b], err=host["err"][a:b],
                                   debug_matches_by_nbr=dbg_m, debug_cert_by_nbr=dbg_c, ply_records=rec)
 
 
@@ -344,6 +344,11 @@ def collect_refs(pending: _PendingLaunch, errors: Optional[list] = None, ring=No
         ring.wait(out)                                 # the current stream (which does the read-back) follows the ring stream
     host = _download(out, pending.collect_debug, pending.ply_records)
     triangulate_refs.last_uniforms_used = host["uniforms_used"].copy()
+    # the arrays handed to the caller are its own: ONE copy per output array out of the (reused) page-locked buffer, the
+    # per-view results are slices of those copies
+    for name in ("xyz", "rgb", "err", "dbg_matches", "dbg_cert"):
+        if name in host:
+            host[name] = host[name].copy()
     results: List[Optional[_TriangulatedReference]] = []
     for r in range(pending.n):
         try:
