@@ -578,63 +578,117 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
     }
 }
 
-// K2c fix-up: one CTA per view.  The view's entries of the worklist (null-vector iteration not converged: grossly
-// inconsistent matches) are re-evaluated with the Jacobi solver, one thread each.  Usually the list is empty and the
-// kernel ends at once.
+// K2c fix-up + plan: one CTA per view.  (1) The view's entries of the worklist (null-vector iteration not converged: grossly
+// inconsistent matches) are re-evaluated with the Jacobi solver, one thread each - usually there are none.  (2) The view's
+// output plan, once for all of its pack CTAs: kept points per neighbour group, groups in order of first appearance
+// (reference core/pipeline.py:685-695), and for every 128-sample tile and group the row (relative to the view's first row)
+// at which that tile's kept samples of that group start.
 __global__ void __launch_bounds__(K2_THREADS)
 ldp_fix_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
                const GeomArgs ga)
 {
     __shared__ RefConst rc;
     __shared__ PairConst pc[LDP_MAX_NN];
+    __shared__ int s_tot[LDP_MAX_NN], s_first[LDP_MAX_NN], s_base[LDP_MAX_NN];
+    constexpr int TB = 128;                                 // tiles staged per block step
+    __shared__ int s_c[TB * LDP_MAX_NN], s_f[TB * LDP_MAX_NN];
     grid_dependency_sync();
     const int r = blockIdx.x + ga.ref0, tid = threadIdx.x;
     const int n = ws.fix_count[ga.sub];
-    if (n <= 0) return;
-    const int2* fix_list = ws.fix_list + (size_t)ga.ref0 * ws.sel_cap;
-    stage_constants(refs + r, rc, pc, tid, K2_THREADS);
-    __syncthreads();
-    for (int e = tid; e < n; e += K2_THREADS) {
-        const int2 it = fix_list[e];
-        if (it.x != r) continue;
-        const int i = it.y;
-        const size_t o = (size_t)r * ws.sel_cap + i;
-        SampleRec rec;
-        float craw;
-        load_record(ws, P, o, rec, craw);
-        SampleResult s;
-        eval_sample<true>(P, rc, pc, ga, rec, craw, s);
-        store_sample(P, ws, out, o, s);
-        if (s.keep) {
-            atomicAdd(&ws.kept[r], 1);
-            atomicAdd(&ws.blk_cnt[((size_t)r * ga.nb2 + i / K2_THREADS) * LDP_MAX_NN + s.grp], 1);
+    if (n > 0) {
+        const int2* fix_list = ws.fix_list + (size_t)ga.ref0 * ws.sel_cap;
+        stage_constants(refs + r, rc, pc, tid, K2_THREADS);
+        __syncthreads();
+        for (int e = tid; e < n; e += K2_THREADS) {
+            const int2 it = fix_list[e];
+            if (it.x != r) continue;
+            const int i = it.y;
+            const size_t o = (size_t)r * ws.sel_cap + i;
+            SampleRec rec;
+            float craw;
+            load_record(ws, P, o, rec, craw);
+            SampleResult s;
+            eval_sample<true>(P, rc, pc, ga, rec, craw, s);
+            store_sample(P, ws, out, o, s);
+            if (s.keep) {
+                atomicAdd(&ws.kept[r], 1);
+                atomicAdd(&ws.blk_cnt[((size_t)r * ga.nb2 + i / K2_THREADS) * LDP_MAX_NN + s.grp], 1);
+            }
         }
+        __syncthreads();
+    }
+    // ---- plan: thread g < LDP_MAX_NN owns group g and walks the view's tiles (loads independent of the running sum)
+    const int S = __ldcg(out.n_samples + r);
+    const int nb = (S + K2_THREADS - 1) / K2_THREADS;
+    int32_t* cnt = ws.blk_cnt + (size_t)r * ga.nb2 * LDP_MAX_NN;
+    int32_t* fst = ws.blk_first + (size_t)r * ga.nb2 * LDP_MAX_NN;
+    // the tile statistics are staged in shared memory by all threads (coalesced, every load in flight at once); thread g then
+    // walks its group's column there
+    int tot = 0, first = 0x7fffffff;
+    for (int t0 = 0; t0 < nb; t0 += TB) {
+        const int nt = min(TB, nb - t0) * LDP_MAX_NN;
+        for (int e = tid; e < nt; e += K2_THREADS) {
+            s_c[e] = __ldcg(cnt + t0 * LDP_MAX_NN + e);
+            s_f[e] = __ldcg(fst + t0 * LDP_MAX_NN + e);
+        }
+        __syncthreads();
+        if (tid < LDP_MAX_NN)
+            for (int e = tid; e < nt; e += LDP_MAX_NN) { tot += s_c[e]; first = min(first, s_f[e]); }
+        __syncthreads();
+    }
+    if (tid < LDP_MAX_NN) { s_tot[tid] = tot; s_first[tid] = first; }
+    __syncthreads();
+    if (tid == 0) {
+        int order[LDP_MAX_NN];
+        int m = 0;
+        for (int g = 0; g < LDP_MAX_NN; ++g) { s_base[g] = 0; if (s_first[g] != 0x7fffffff) order[m++] = g; }
+        for (int a = 1; a < m; ++a) {                       // insertion sort by first appearance
+            const int g = order[a];
+            int q = a - 1;
+            while (q >= 0 && s_first[order[q]] > s_first[g]) { order[q + 1] = order[q]; --q; }
+            order[q + 1] = g;
+        }
+        int acc = 0;
+        for (int a = 0; a < m; ++a) { const int g = order[a]; s_base[g] = acc; acc += s_tot[g]; }
+        for (int a = 0; a < LDP_MAX_NN; ++a) {
+            out.group_order[(size_t)r * LDP_MAX_NN + a] = (a < m) ? order[a] : -1;
+            out.group_count[(size_t)r * LDP_MAX_NN + a] = s_tot[a];
+        }
+    }
+    __syncthreads();
+    // tile t, group g: rows of the group in earlier tiles (+ the group's base) -> blk_first
+    int run = (tid < LDP_MAX_NN) ? s_base[tid] : 0;
+    for (int t0 = 0; t0 < nb; t0 += TB) {
+        const int nt = min(TB, nb - t0) * LDP_MAX_NN;
+        for (int e = tid; e < nt; e += K2_THREADS) s_c[e] = __ldcg(cnt + t0 * LDP_MAX_NN + e);
+        __syncthreads();
+        if (tid < LDP_MAX_NN)
+            for (int e = tid; e < nt; e += LDP_MAX_NN) { const int c = s_c[e]; s_c[e] = run; run += c; }
+        __syncthreads();
+        for (int e = tid; e < nt; e += K2_THREADS) fst[t0 * LDP_MAX_NN + e] = s_c[e];
+        __syncthreads();
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3 plan + scatter: grid (tiles, views).  Output order of the reference (core/pipeline.py:685-695,753-780): neighbour
-// groups in order of first appearance over the sample order, sample order inside a group, kept samples only.
-// Every CTA derives the view's plan from the per-tile group statistics of the geometry kernel (a few KB, L2): group
-// totals, first appearances, kept samples of each group in earlier tiles; then
-// dst = view base (kept counts of earlier views) + group base + earlier tiles of the group + rank inside the tile.
+// K3 scatter: grid (tiles, views).  Output order of the reference (core/pipeline.py:685-695,753-780): neighbour groups in
+// order of first appearance over the sample order, sample order inside a group, kept samples only.
+// dst = view base (kept counts of earlier views) + [plan of ldp_fix_kernel: group base + earlier tiles of the group]
+//       + rank inside the tile.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(K3_THREADS)
 ldp_pack_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const ldp_outputs out,
                 const GeomArgs ga)
 {
     static_assert(K3_THREADS == K2_THREADS && K3_THREADS % LDP_MAX_NN == 0, "one pack CTA per geometry tile");
-    constexpr int NPART = K3_THREADS / LDP_MAX_NN;
-    __shared__ int s_part[3][NPART][LDP_MAX_NN];
-    __shared__ int s_tot[LDP_MAX_NN], s_first[LDP_MAX_NN], s_start[LDP_MAX_NN];
+    __shared__ int s_start[LDP_MAX_NN];
     __shared__ int s_wcnt[K3_THREADS / 32][LDP_MAX_NN];
     __shared__ long long s_red[K3_THREADS / 32];
     __shared__ long long s_off;
     grid_dependency_sync();
     const int r = blockIdx.y, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // ---- everything the CTA needs is requested in ONE batch, before the sample count that decides what is used:
-    //      the kernel is a chain of dependent L2 round trips otherwise.  Rows are sel_cap long and the tile tables nb2
-    //      long, so every address is valid; what lies beyond the view's samples is ignored below.
+    // ---- everything the CTA needs is requested in ONE batch, before the sample count that decides what is used.  Rows are
+    //      sel_cap long and the tile tables nb2 long, so every address is valid; what lies beyond the view's samples is ignored.
     const int i = b * K2_THREADS + tid;
     const bool in_row = i < (int)ws.sel_cap;
     const size_t o = (size_t)r * ws.sel_cap + i;
@@ -643,73 +697,18 @@ ldp_pack_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pc4 = pa, pd = pa;
     if (in_row) { pa = __ldcg(ws.pt0 + o); pc4 = __ldcg(ws.pt1 + o); }
     if (in_row && P.collect_debug && out.dbg_matches) pd = __ldcg(ws.dbgm + o);
-    constexpr int TMAX = 10;                              // table rows a thread owns in registers (80 tiles = 10240 samples); more: loop below
-    const int g_own = tid % LDP_MAX_NN, part = tid / LDP_MAX_NN;
-    const int32_t* cnt = ws.blk_cnt + (size_t)r * ga.nb2 * LDP_MAX_NN;
-    const int32_t* fst = ws.blk_first + (size_t)r * ga.nb2 * LDP_MAX_NN;
-    int cv[TMAX], fv[TMAX];
-#pragma unroll
-    for (int q = 0; q < TMAX; ++q) {
-        const int t = part + q * NPART;
-        cv[q] = (t < ga.nb2) ? __ldcg(cnt + t * LDP_MAX_NN + g_own) : 0;
-        fv[q] = (t < ga.nb2) ? __ldcg(fst + t * LDP_MAX_NN + g_own) : 0x7fffffff;
-    }
+    int start_g = 0;
+    if (tid < LDP_MAX_NN) start_g = __ldcg(ws.blk_first + ((size_t)r * ga.nb2 + b) * LDP_MAX_NN + tid);
+    long long partk = 0;
+    for (int q = tid; q < r; q += K3_THREADS) partk += (long long)__ldcg(ws.kept + q);
+    const int kept_r = __ldcg(ws.kept + r);
     const int nb = (S + K2_THREADS - 1) / K2_THREADS;
     if (b >= nb && b != 0) return;
-    const int f = (i < S) ? f_raw : 0;
-    {
-        int tot = 0, bef = 0, first = 0x7fffffff;
 #pragma unroll
-        for (int q = 0; q < TMAX; ++q) {
-            const int t = part + q * NPART;
-            if (t < nb) { tot += cv[q]; bef += (t < b) ? cv[q] : 0; first = min(first, fv[q]); }
-        }
-        for (int t = part + TMAX * NPART; t < nb; t += NPART) {          // very large M only
-            const int c = __ldcg(cnt + t * LDP_MAX_NN + g_own);
-            tot += c;
-            bef += (t < b) ? c : 0;
-            first = min(first, __ldcg(fst + t * LDP_MAX_NN + g_own));
-        }
-        s_part[0][part][g_own] = tot; s_part[1][part][g_own] = bef; s_part[2][part][g_own] = first;
-    }
-    long long partk = 0;
-    for (int q = tid; q < r; q += K3_THREADS) partk += (long long)ws.kept[q];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) partk += __shfl_xor_sync(0xffffffffu, partk, o);
+    for (int oo = 16; oo > 0; oo >>= 1) partk += __shfl_xor_sync(0xffffffffu, partk, oo);
     if (lane == 0) s_red[warp] = partk;
-    __syncthreads();
-    if (tid < LDP_MAX_NN) {
-        int tot = 0, bef = 0, first = 0x7fffffff;
-#pragma unroll
-        for (int q = 0; q < NPART; ++q) { tot += s_part[0][q][tid]; bef += s_part[1][q][tid]; first = min(first, s_part[2][q][tid]); }
-        s_tot[tid] = tot; s_start[tid] = bef; s_first[tid] = first;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        long long v = 0;
-        for (int q = 0; q < K3_THREADS / 32; ++q) v += s_red[q];
-        s_off = v;
-        int order[LDP_MAX_NN];
-        int m = 0;
-        for (int g = 0; g < LDP_MAX_NN; ++g) if (s_first[g] != 0x7fffffff) order[m++] = g;
-        for (int a = 1; a < m; ++a) {                       // insertion sort by first appearance
-            const int g = order[a];
-            int q = a - 1;
-            while (q >= 0 && s_first[order[q]] > s_first[g]) { order[q + 1] = order[q]; --q; }
-            order[q + 1] = g;
-        }
-        int acc = 0;
-        for (int a = 0; a < m; ++a) { const int g = order[a]; s_start[g] += acc; acc += s_tot[g]; }
-        if (b == 0) {
-            out.ref_offset[r] = v;
-            if (r == (int)gridDim.y - 1) out.ref_offset[r + 1] = v + ws.kept[r];
-            for (int a = 0; a < LDP_MAX_NN; ++a) {
-                out.group_order[(size_t)r * LDP_MAX_NN + a] = (a < m) ? order[a] : -1;
-                out.group_count[(size_t)r * LDP_MAX_NN + a] = s_tot[a];
-            }
-        }
-    }
-    if (b >= nb) return;
+    if (tid < LDP_MAX_NN) s_start[tid] = start_g;
+    const int f = (i < S) ? f_raw : 0;
     const int keep = f & 1, g = (f >> 2) & 0x1f;
     const unsigned same = __match_any_sync(0xffffffffu, keep ? g : -1);
     const int rank_in_warp = __popc(same & ((1u << lane) - 1u));
@@ -717,6 +716,17 @@ ldp_pack_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     __syncwarp();
     if (keep && rank_in_warp == 0) s_wcnt[warp][g] = __popc(same);
     __syncthreads();
+    if (tid == 0) {
+        long long v = 0;
+        for (int q = 0; q < K3_THREADS / 32; ++q) v += s_red[q];
+        s_off = v;
+        if (b == 0) {
+            out.ref_offset[r] = v;
+            if (r == (int)gridDim.y - 1) out.ref_offset[r + 1] = v + kept_r;
+        }
+    }
+    __syncthreads();
+    if (b >= nb) return;
     if (keep) {
         int before = s_start[g];
         for (int ww = 0; ww < warp; ++ww) before += s_wcnt[ww][g];
