@@ -266,7 +266,7 @@ def config5_block(args, dev, rank: int, world: int, ring) -> dict:
     depth = ring.depth
 
     class Shard:
-        def __init__(self, lo, hi, cap_refs):
+        def __init__(self, lo, hi, cap_refs, cloud=None):
             self.lo, self.hi = lo, hi
             self.inputs = SceneInputs(scene, list(range(lo, hi)), dev, seed=500)
             self.chunks = [(a, min(a + per, hi - lo)) for a in range(0, hi - lo, per)]
@@ -277,7 +277,8 @@ def config5_block(args, dev, rank: int, world: int, ring) -> dict:
                 batch = self.inputs.batch(ring.engines[j], scene, a, b, stream_base=0)
                 descs = ring.engines[j].upload_descs(batch)
                 self.prepared.append((j, ring.engines[j].prepare(batch, cfg, descs_dev=descs, outputs=self.outs[c])))
-            self.cloud = PackedCloud(cap_refs * sel_cap, dev)            # the SAME capacity on every rank: one padded collective
+            # the rank's cloud (the SAME capacity on every rank); N > 1: it lives in symmetric memory, where the peers read it
+            self.cloud = cloud if cloud is not None else PackedCloud(cap_refs * sel_cap, dev)
             self.plan = ConcatPlan([o.xyz for o in self.outs], [o.rgb for o in self.outs], [o.err for o in self.outs],
                                    [o.ref_offset[o.n_refs:o.n_refs + 1] for o in self.outs], per * sel_cap)
 
@@ -295,7 +296,20 @@ def config5_block(args, dev, rank: int, world: int, ring) -> dict:
 
     cap_refs = max(D.shard_bounds(R_all, q, world)[1] - D.shard_bounds(R_all, q, world)[0] for q in range(world))
     lo, hi = D.shard_bounds(R_all, rank, world)
-    shard = Shard(lo, hi, cap_refs)
+    # N > 1: the final all-gather is our own kernel reading the peers' clouds over NVLink (distributed.PeerClouds); the NCCL
+    # collective + compaction (distributed.all_gather_cloud) is timed beside it, and is what runs if the node offers no
+    # symmetric memory
+    peer, peer_err = None, None
+    if world > 1 and not int(os.environ.get("BENCH_NO_PEER", "0")):
+        try:
+            peer = D.PeerClouds(cap_refs * sel_cap, dev)
+        except Exception as exc:      # no peer access on this node: the library collective remains
+            peer_err = f"{type(exc).__name__}: {exc}"
+        ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            peer = None
+    shard = Shard(lo, hi, cap_refs, cloud=peer.cloud if peer is not None else None)
     gathered = PackedCloud(world * shard.cloud.capacity, dev) if world > 1 else None
     scratch = torch.empty((world, shard.cloud.packed.numel()), dtype=torch.uint8, device=dev) if world > 1 else None
     torch.cuda.synchronize(dev)
@@ -305,32 +319,42 @@ def config5_block(args, dev, rank: int, world: int, ring) -> dict:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def one_pass():
+    def one_pass(use_peer: bool):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
         shard.launch_all()
         e[1].record()
-        total, offsets = D.all_gather_cloud(shard.cloud, out=gathered, scratch=scratch)
+        if use_peer:
+            total, offsets = peer.gather(out=gathered)
+        else:
+            total, offsets = D.all_gather_cloud(shard.cloud, out=gathered, scratch=scratch)
         e[2].record()
         return e, total, offsets
 
     passes = max(3, min(10, args.steps))
-    for _ in range(2):
-        one_pass()
-    barrier()
-    ms_all, ms_compute, ms_gather = [], [], []
-    total = offsets = None
-    for _ in range(passes):
+
+    def timed_passes(use_peer: bool):
+        for _ in range(2):
+            one_pass(use_peer)
         barrier()
-        e, total, offsets = one_pass()
-        torch.cuda.synchronize(dev)
-        ms_all.append(e[0].elapsed_time(e[2]))
-        ms_compute.append(e[0].elapsed_time(e[1]))
-        ms_gather.append(e[1].elapsed_time(e[2]))
-    t = torch.tensor([float(np.median(ms_all)), float(np.median(ms_compute)), float(np.median(ms_gather))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_c, ms_g = (float(x) for x in t.tolist())
+        ms_all, ms_compute, ms_gather = [], [], []
+        total = offsets = None
+        for _ in range(passes):
+            barrier()
+            e, total, offsets = one_pass(use_peer)
+            torch.cuda.synchronize(dev)
+            ms_all.append(e[0].elapsed_time(e[2]))
+            ms_compute.append(e[0].elapsed_time(e[1]))
+            ms_gather.append(e[1].elapsed_time(e[2]))
+        t = torch.tensor([float(np.median(ms_all)), float(np.median(ms_compute)), float(np.median(ms_gather))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()], total, offsets
+
+    nccl_ms = None
+    if world > 1 and peer is not None:
+        nccl_ms, _, _ = timed_passes(False)            # the library collective, for comparison
+    (ms, ms_c, ms_g), total, offsets = timed_passes(peer is not None)
     n_total = int(offsets[-1].item())
     # ---- bit-exact check against the single-GPU result: rank 0 recomputes the whole scene alone (outside the timed region)
     same = None
@@ -368,10 +392,15 @@ def config5_block(args, dev, rank: int, world: int, ring) -> dict:
         "launches_per_rank": len(shard.chunks), "steps_in_flight": depth, "passes_timed": passes,
         "ms": ms, "ms_launches_and_local_concat": ms_c, "ms_all_gather_and_concat": ms_g,
         "points": n_total, "points_per_sec": n_total / (ms * 1e-3), "pairs_per_sec": R_all * scene.nn / (ms * 1e-3),
-        "all_gather": {"collective": "ncclAllGather (one call: count header + xyz | rgb | err, padded to capacity)" if world > 1 else "none (N = 1)",
-                       "bytes_sent_per_rank": pad_bytes if world > 1 else 0, "bytes_received_per_rank": pad_bytes * (world - 1),
+        "all_gather": {"collective": ("none (N = 1)" if world == 1 else
+                                      "own kernel: ldp_concat_points reads every peer's cloud (count header, then exactly that many rows) over "
+                                      "NVLink from symmetric memory, two device-side barriers; no padding moved" if peer is not None else
+                                      "ncclAllGather (one call: count header + xyz | rgb | err, padded to capacity) + ldp_concat_points"),
+                       "bytes_received_per_rank": (int(28 * n_total * (world - 1) / world) if peer is not None else pad_bytes * (world - 1)) if world > 1 else 0,
                        "payload_bytes_total": 28 * n_total, "ms": ms_g,
-                       "bus_gb_per_s": (pad_bytes * (world - 1) / (ms_g * 1e-3) / 1e9) if world > 1 and ms_g > 0 else None},
+                       "gb_per_s_received_per_rank": ((28 * n_total * (world - 1) / world if peer is not None else pad_bytes * (world - 1)) / (ms_g * 1e-3) / 1e9) if world > 1 and ms_g > 0 else None,
+                       "nccl_all_gather_plus_concat_ms": nccl_ms[2] if nccl_ms else None, "nccl_total_ms": nccl_ms[0] if nccl_ms else None,
+                       "peer_memory_error": peer_err},
         "limiter": ("all-gather" if ms_g > ms_c else "launches") if world > 1 else "launches",
         "equals_single_gpu_result": same if world > 1 else None,
         "equals_other_cut_into_launches": same if world == 1 else None,

@@ -790,7 +790,9 @@ int ldp_concat_points(const float* const* xyz_src, const float* const* rgb_src, 
     if (!xyz_src || !rgb_src || !err_src || !count_src || !xyz_out || !rgb_out || !err_out) return fail(LDP_ERR_INVALID, "null pointer");
     if (n_seg > 65535) return fail(LDP_ERR_INVALID, "too many segments");
     const long long blocks = (seg_cap * 3 + ldp::KO_THREADS * 4 - 1) / (ldp::KO_THREADS * 4);
-    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>(blocks, 64));
+    // enough CTAs to keep a few MB of (possibly remote) reads in flight: about four waves of CTAs over all segments
+    const long long per_seg = std::max<long long>(64, (long long)sm_count() * 8 * 4 / std::max(1, n_seg));
+    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>(blocks, per_seg));
     (void)launch_k(ldp::ldp_concat_points_kernel, dim3(gx, (unsigned)n_seg), dim3(ldp::KO_THREADS), 0, reinterpret_cast<cudaStream_t>(stream),
                    xyz_src, rgb_src, err_src, reinterpret_cast<const long long* const*>(count_src), (int)n_seg, (long long)seg_cap,
                    xyz_out, rgb_out, err_out, (long long)out_capacity, reinterpret_cast<long long*>(seg_offset_out),

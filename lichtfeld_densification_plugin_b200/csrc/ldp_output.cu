@@ -158,13 +158,43 @@ ldp_concat_points_kernel(const float* const* __restrict__ xyz_src, const float* 
     const float* __restrict__ rs = rgb_src[q];
     const float* __restrict__ es = err_src[q];
     const long long n3 = cnt * 3;
-    // flat copies: a row block covers KO_THREADS * 4 rows = 3072 floats of xyz / rgb per block step
-    for (long long e = ((long long)blockIdx.x * KO_THREADS + tid); e < n3; e += (long long)gridDim.x * KO_THREADS) {
-        xyz_out[base * 3 + e] = xs[e];
-        rgb_out[base * 3 + e] = rs[e];
+    // flat copies.  The sources may be a peer GPU's memory (distributed.PeerClouds: the all-gather IS this kernel), so they are
+    // read 16 bytes per request when aligned, several requests in flight per thread; the destination offset (base rows) is
+    // arbitrary, hence scalar stores.
+    const bool vec = ((reinterpret_cast<uintptr_t>(xs) | reinterpret_cast<uintptr_t>(rs) | reinterpret_cast<uintptr_t>(es)) & 15u) == 0;
+    const long long stride = (long long)gridDim.x * KO_THREADS, t0 = (long long)blockIdx.x * KO_THREADS + tid;
+    if (vec) {
+        const long long n3v = n3 >> 2, nev = cnt >> 2;
+        constexpr int UN = 4;                              // requests in flight per thread and array (a peer read costs microseconds)
+        for (long long e0 = t0; e0 < n3v; e0 += UN * stride) {
+            float4 a[UN], c[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const long long e = e0 + u * stride;
+                if (e < n3v) { a[u] = __ldcs(reinterpret_cast<const float4*>(xs) + e); c[u] = __ldcs(reinterpret_cast<const float4*>(rs) + e); }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const long long e = e0 + u * stride;
+                if (e < n3v) {
+                    float* xo = xyz_out + base * 3 + 4 * e;
+                    float* ro = rgb_out + base * 3 + 4 * e;
+                    xo[0] = a[u].x; xo[1] = a[u].y; xo[2] = a[u].z; xo[3] = a[u].w;
+                    ro[0] = c[u].x; ro[1] = c[u].y; ro[2] = c[u].z; ro[3] = c[u].w;
+                }
+            }
+        }
+        for (long long e = (n3v << 2) + t0; e < n3; e += stride) { xyz_out[base * 3 + e] = xs[e]; rgb_out[base * 3 + e] = rs[e]; }
+        for (long long e = t0; e < nev; e += stride) {
+            const float4 a = __ldcs(reinterpret_cast<const float4*>(es) + e);
+            float* eo = err_out + base + 4 * e;
+            eo[0] = a.x; eo[1] = a.y; eo[2] = a.z; eo[3] = a.w;
+        }
+        for (long long e = (nev << 2) + t0; e < cnt; e += stride) err_out[base + e] = es[e];
+    } else {
+        for (long long e = t0; e < n3; e += stride) { xyz_out[base * 3 + e] = xs[e]; rgb_out[base * 3 + e] = rs[e]; }
+        for (long long e = t0; e < cnt; e += stride) err_out[base + e] = es[e];
     }
-    for (long long e = ((long long)blockIdx.x * KO_THREADS + tid); e < cnt; e += (long long)gridDim.x * KO_THREADS)
-        err_out[base + e] = es[e];
 }
 
 }  // namespace ldp

@@ -128,6 +128,47 @@ def all_gather_cloud(cloud, group=None, out=None, scratch: Optional[torch.Tensor
     return out, plan.seg_offsets
 
 
+class PeerClouds:
+    """The final point all-gather as ONE kernel of ours over NVLink peer memory, instead of a library collective followed by a
+    compaction: every rank keeps its ``output.PackedCloud`` in symmetric memory (``torch.distributed._symmetric_memory``:
+    the same allocation mapped into every rank's address space of the node), and ``gather`` runs ``ldp_concat_points`` with
+    one segment per rank whose source pointers are the PEERS' clouds - the kernel reads each peer's point count from the
+    peer's header and then exactly that many rows, over NVLink / NVSwitch, straight into their place in the rank-ordered
+    cloud.  Nothing is padded, staged or copied twice, and the host learns no count.  Two device-side barriers of the
+    symmetric-memory handle (signal pads, stream-ordered) bracket the reads: every rank's cloud is complete before anybody
+    reads it, and nobody rewrites its cloud before every peer has read it.
+    Replaces reference core/pipeline.py:914-928 (single-process np.concatenate)."""
+
+    def __init__(self, capacity: int, device, group=None) -> None:
+        import torch.distributed._symmetric_memory as symm_mem
+        from .output import ConcatPlan, PackedCloud
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        nbytes = PackedCloud.nbytes(capacity)
+        self.storage = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.storage.zero_()
+        self.handle = symm_mem.rendezvous(self.storage, self.group)
+        self.cloud = PackedCloud(capacity, device, storage=self.storage)           # this rank's cloud: launches concatenate into it
+        self.peers = [self.cloud if p == self.rank else
+                      PackedCloud(capacity, device, storage=self.handle.get_buffer(p, (nbytes,), torch.uint8, 0))
+                      for p in range(self.world)]
+        self.plan = ConcatPlan([c.xyz for c in self.peers], [c.rgb for c in self.peers], [c.err for c in self.peers],
+                               [c.count for c in self.peers], self.cloud.capacity)
+        self.capacity = self.cloud.capacity
+
+    def gather(self, out=None):
+        """Every rank's points in rank order (= the single-GPU order) in ``out`` on THIS rank; returns (out, int64 device
+        tensor [world + 1] of the ranks' global row offsets).  Stream-ordered on the current stream; no host synchronisation."""
+        from .output import PackedCloud
+        if out is None:
+            out = PackedCloud(self.world * self.capacity, self.cloud.packed.device)
+        self.handle.barrier(channel=0)
+        self.plan.run(out)
+        self.handle.barrier(channel=1)
+        return out, self.plan.seg_offsets
+
+
 def all_gather_points(xyz: torch.Tensor, rgb: torch.Tensor, err: torch.Tensor, n_valid: Optional[int] = None,
                       group=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Order-preserving all-gather of per-rank packed points, exact-size results.
