@@ -44,9 +44,20 @@ struct KernelTimer {
     ~KernelTimer() { if (slot >= 0) cudaEventRecord(g_prof_ev[2 * slot + 1], st); }
 };
 
+constexpr int MAX_DEVICES = 64;
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = 0; }
+    return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
+}
+
+// per device (a process may drive several, possibly different, GPUs) and per calling thread: no shared mutable state
 int max_active_clusters(int csize, size_t smem) {
-    static int cache[9] = {0};
-    static size_t cache_smem = 0;
+    thread_local int cache_all[MAX_DEVICES][9] = {};
+    thread_local size_t cache_smem_all[MAX_DEVICES] = {};
+    const int dev = current_device();
+    int* cache = cache_all[dev];
+    size_t& cache_smem = cache_smem_all[dev];
     if (cache_smem != smem) { for (int i = 0; i < 9; ++i) cache[i] = 0; cache_smem = smem; }
     if (cache[csize]) return cache[csize];
     cudaLaunchConfig_t cfg = {};
@@ -81,15 +92,15 @@ int g_force_cluster = 0;      // test hook (ldp_debug_set_cluster)
 int g_sm_reserve = 0;         // ldp_set_sm_reserve
 int g_last_cluster = 0;
 
-int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
-        else cached = 148;
+int sm_count() {          // of the CURRENT device
+    thread_local int cached[MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached[dev] = n;
+        else { (void)cudaGetLastError(); cached[dev] = 148; }
     }
-    return cached;
+    return cached[dev];
 }
 
 constexpr size_t K1_SMEM_BUDGET = 200 * 1024;
@@ -311,7 +322,8 @@ static int vec_ok_for(const ldp_params* p) { return (p->W % 4 == 0 && p->scalar_
 
 // the fused first stage (ldp_front.cu): persistent CTAs, TMA ring, stream + normalise
 cudaError_t launch_front(const ldp_params* p, const ldp_ref_desc* refs, const ldp_outputs* out, Plan& plan, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured_dev[MAX_DEVICES] = {};
+        bool& configured = configured_dev[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(ldp::ldp_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -352,7 +364,8 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
                   Plan& plan, int vec_ok, cudaStream_t st, int ref0, int nsubrefs) {
     plan.geom.vec = vec_ok;
     plan.geom.ref0 = ref0;
-    static bool configured = false;
+    static bool configured_dev[MAX_DEVICES] = {};
+        bool& configured = configured_dev[current_device()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(ldp::ldp_draw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ldp::ldp_draw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
@@ -393,7 +406,8 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
           size_t n2 = 1;
           const size_t Mn = (size_t)std::min((long long)p->matches_per_ref, (long long)plan.geom.N);
           while (n2 < Mn) n2 <<= 1;
-          static bool topm_configured = false;
+          static bool topm_configured_dev[MAX_DEVICES] = {};
+        bool& topm_configured = topm_configured_dev[current_device()];
           if (!topm_configured) {
               (void)cudaFuncSetAttribute(ldp::ldp_topm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
               topm_configured = true;
@@ -542,7 +556,7 @@ float parallax_cos_threshold(float min_deg) {
 }
 
 ldp::GeomArgs make_geom_args(const ldp_params* p, const Plan& plan, int have_bestk, int ref0, int sub) {
-    static float cached_deg = -1.f, cached_cos = 1.f;
+    thread_local float cached_deg = -1.f, cached_cos = 1.f;
     if (p->min_parallax_deg != cached_deg) { cached_cos = parallax_cos_threshold(p->min_parallax_deg); cached_deg = p->min_parallax_deg; }
     ldp::GeomArgs ga;
     ga.par_cos_max = cached_cos;
@@ -812,7 +826,8 @@ int ldp_select_kcenters(const float* flat_poses, int32_t n, int32_t k, float* sc
     if (!flat_poses || !scratch || !centers_sorted || !centers_order) return fail(LDP_ERR_INVALID, "null pointer");
     const size_t smem = (size_t)n * ldp::KC_PAD * sizeof(float);
     if (smem <= K1_SMEM_BUDGET) {                        // the poses fit in shared memory (n <= 3011)
-        static bool configured = false;
+        static bool configured_dev[MAX_DEVICES] = {};
+        bool& configured = configured_dev[current_device()];
         if (!configured) {
             (void)cudaFuncSetAttribute(ldp::ldp_kcenters_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_BUDGET);
             configured = true;

@@ -295,3 +295,61 @@ def test_run_dense_pipeline_debug_state_and_latest_only_live_update(tmp_path):
     ds2 = DebugState(False)
     P.run_dense_pipeline(cams, refs[:3], nn_table, cfg, debug_state=ds2, match_source=match_source, w_match=scene.w_match, h_match=scene.h_match)
     assert not ds2.previews and ds2.released
+
+
+def test_concat_points_equals_concatenation_without_host_round_trip(out_mod):
+    """ldp_concat_points (reference core/pipeline.py:914-928, np.concatenate of the per-view arrays): segments with their own
+    padded arrays and device-side counts land back to back, in segment order; offsets and total stay on the device."""
+    rs = np.random.RandomState(3)
+    dev = torch.device("cuda", 0)
+    caps = [1000, 4096, 7, 2048, 1]
+    counts = [1000, 37, 0, 2047, 1]
+    xyz = [torch.from_numpy(rs.standard_normal((c, 3)).astype(np.float32)).to(dev) for c in caps]
+    rgb = [torch.from_numpy(rs.random_sample((c, 3)).astype(np.float32)).to(dev) for c in caps]
+    err = [torch.from_numpy(rs.random_sample((c,)).astype(np.float32)).to(dev) for c in caps]
+    cnt = [torch.tensor([c], dtype=torch.int64, device=dev) for c in counts]
+    plan = out_mod.ConcatPlan(xyz, rgb, err, cnt, max(caps))
+    dst = out_mod.PackedCloud(sum(caps), dev)
+    plan.run(dst)
+    torch.cuda.synchronize()
+    n = dst.total_points()
+    assert n == sum(counts)
+    assert plan.seg_offsets.cpu().tolist() == np.concatenate([[0], np.cumsum(counts)]).tolist()
+    assert torch.equal(dst.xyz[:n], torch.cat([a[:c] for a, c in zip(xyz, counts)]))
+    assert torch.equal(dst.rgb[:n], torch.cat([a[:c] for a, c in zip(rgb, counts)]))
+    assert torch.equal(dst.err[:n], torch.cat([a[:c] for a, c in zip(err, counts)]))
+    # a destination that is too small is filled to its capacity and never overrun
+    small = out_mod.PackedCloud(1024, dev)
+    guard = small.packed.clone()
+    plan.run(small)
+    torch.cuda.synchronize()
+    assert small.total_points() == small.capacity
+    assert torch.equal(small.xyz[:1000], xyz[0][:1000])
+
+
+def test_concat_launches_equals_one_launch(out_mod):
+    """Two launches over halves of a batch, concatenated on the device, give the cloud of the single launch (Philox streams
+    are keyed by the view): what run over a cut into launches - or over ranks - reassembles."""
+    from lichtfeld_densification_plugin_b200 import synth
+    from lichtfeld_densification_plugin_b200.engine import DensifyEngine, PathConfig
+    eng = DensifyEngine()
+    scene = synth.make_scene(16, "turbo", ref_fraction=0.4, nn=3)
+    cfg = PathConfig(matches_per_ref=3000, seed=11)
+    inputs = [synth.synth_ref_inputs(scene, rp, device=eng.device, cert_family="R", seed=8) for rp in range(scene.n_refs)]
+
+    def run(lo, hi):
+        b = eng.new_batch(scene.H, scene.W, scene.w_match, scene.h_match)
+        for rp in range(lo, hi):
+            inp = inputs[rp]
+            nn = len(inp["nbr_indices"])
+            b.add([inp["cert"][k] for k in range(nn)], [inp["warp"][k] for k in range(nn)], inp["image"],
+                  scene.cameras[inp["ref_index"]], [scene.cameras[j] for j in inp["nbr_indices"]], rng_stream=rp)
+        return eng.densify(b, cfg, outputs=eng.alloc_outputs(hi - lo, eng.sel_capacity(cfg.matches_per_ref)))
+    R = scene.n_refs
+    whole = run(0, R)
+    parts = [run(0, R // 2), run(R // 2, R)]
+    cloud = out_mod.concat_launches(parts)
+    torch.cuda.synchronize()
+    n = whole.total_points()
+    assert cloud.total_points() == n > 1000
+    assert torch.equal(cloud.xyz[:n], whole.xyz[:n]) and torch.equal(cloud.rgb[:n], whole.rgb[:n]) and torch.equal(cloud.err[:n], whole.err[:n])

@@ -56,3 +56,21 @@ def test_estimate_total_pairs_matches_reference():
     refs = [0, 3, 7, 19]
     for k in (1, 3, 5):
         assert _estimate_total_pairs(refs, nn, ids, k) == ref.pipeline._estimate_total_pairs(refs, nn, ids, k)
+
+
+def test_packed_cloud_layout_is_one_allocation():
+    """output.PackedCloud: header (int64 count) | xyz | rgb | err alias ONE buffer, every block 16-byte aligned, so that a
+    rank's cloud goes into a single collective / is read by a peer as one mapping (distributed.PeerClouds)."""
+    import torch
+    from lichtfeld_densification_plugin_b200.output import PackedCloud
+    c = PackedCloud(10, "cpu")
+    assert c.capacity == 12 and c.packed.numel() == PackedCloud.nbytes(10) == 16 + 28 * 12
+    c.xyz.fill_(1.0); c.rgb.fill_(2.0); c.err.fill_(3.0); c.count.fill_(7)
+    raw = c.packed.numpy()
+    assert int(raw[:8].view("<i8")[0]) == 7
+    f = raw[16:].view("<f4")
+    assert (f[:36] == 1.0).all() and (f[36:72] == 2.0).all() and (f[72:84] == 3.0).all()
+    again = PackedCloud(10, "cpu", storage=c.packed)
+    assert again.total_points() == 7 and torch.equal(again.err, c.err)
+    for cap in (1, 2, 3, 5, 4097):
+        assert PackedCloud.nbytes(cap) % 16 == 0
