@@ -617,39 +617,56 @@ ldp_fix_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const 
         }
         __syncthreads();
     }
-    // ---- plan: thread g < LDP_MAX_NN owns group g and walks the view's tiles (loads independent of the running sum)
-    const int S = __ldcg(out.n_samples + r);
-    const int nb = (S + K2_THREADS - 1) / K2_THREADS;
+    // ---- plan.  Thread (part, g) owns group g over one eighth of the view's tiles; the tile statistics are staged in shared
+    //      memory by all threads (coalesced, every load in flight at once, requested together with the sample count that says
+    //      how many of them mean something: the tables are nb2 tiles long, always readable).
+    constexpr int NPART = K2_THREADS / LDP_MAX_NN;
+    __shared__ int s_ptot[NPART][LDP_MAX_NN], s_pfirst[NPART][LDP_MAX_NN];
     int32_t* cnt = ws.blk_cnt + (size_t)r * ga.nb2 * LDP_MAX_NN;
     int32_t* fst = ws.blk_first + (size_t)r * ga.nb2 * LDP_MAX_NN;
-    // the tile statistics are staged in shared memory by all threads (coalesced, every load in flight at once); thread g then
-    // walks its group's column there
-    int tot = 0, first = 0x7fffffff;
+    const int g = tid % LDP_MAX_NN, part = tid / LDP_MAX_NN;
+    const int first_block = min(TB, ga.nb2) * LDP_MAX_NN;
+    for (int e = tid; e < first_block; e += K2_THREADS) {
+        s_c[e] = __ldcg(cnt + e);
+        s_f[e] = __ldcg(fst + e);
+    }
+    const int S = __ldcg(out.n_samples + r);
+    const int nb = (S + K2_THREADS - 1) / K2_THREADS;
+    int tot = 0, first = 0x7fffffff;                       // thread g < LDP_MAX_NN: the whole view
     for (int t0 = 0; t0 < nb; t0 += TB) {
-        const int nt = min(TB, nb - t0) * LDP_MAX_NN;
-        for (int e = tid; e < nt; e += K2_THREADS) {
-            s_c[e] = __ldcg(cnt + t0 * LDP_MAX_NN + e);
-            s_f[e] = __ldcg(fst + t0 * LDP_MAX_NN + e);
+        const int ntile = min(TB, nb - t0);
+        if (t0 > 0) {
+            __syncthreads();
+            for (int e = tid; e < ntile * LDP_MAX_NN; e += K2_THREADS) {
+                s_c[e] = __ldcg(cnt + t0 * LDP_MAX_NN + e);
+                s_f[e] = __ldcg(fst + t0 * LDP_MAX_NN + e);
+            }
         }
         __syncthreads();
-        if (tid < LDP_MAX_NN)
-            for (int e = tid; e < nt; e += LDP_MAX_NN) { tot += s_c[e]; first = min(first, s_f[e]); }
+        const int per = (ntile + NPART - 1) / NPART, ta = min(part * per, ntile), tb = min(ta + per, ntile);
+        int pt = 0, pf = 0x7fffffff;
+        for (int t = ta; t < tb; ++t) { pt += s_c[t * LDP_MAX_NN + g]; pf = min(pf, s_f[t * LDP_MAX_NN + g]); }
+        s_ptot[part][g] = pt;
+        s_pfirst[part][g] = pf;
         __syncthreads();
+        if (tid < LDP_MAX_NN)
+#pragma unroll
+            for (int q = 0; q < NPART; ++q) { tot += s_ptot[q][tid]; first = min(first, s_pfirst[q][tid]); }
     }
     if (tid < LDP_MAX_NN) { s_tot[tid] = tot; s_first[tid] = first; }
     __syncthreads();
     if (tid == 0) {
         int order[LDP_MAX_NN];
         int m = 0;
-        for (int g = 0; g < LDP_MAX_NN; ++g) { s_base[g] = 0; if (s_first[g] != 0x7fffffff) order[m++] = g; }
+        for (int q = 0; q < LDP_MAX_NN; ++q) { s_base[q] = 0; if (s_first[q] != 0x7fffffff) order[m++] = q; }
         for (int a = 1; a < m; ++a) {                       // insertion sort by first appearance
-            const int g = order[a];
+            const int gg = order[a];
             int q = a - 1;
-            while (q >= 0 && s_first[order[q]] > s_first[g]) { order[q + 1] = order[q]; --q; }
-            order[q + 1] = g;
+            while (q >= 0 && s_first[order[q]] > s_first[gg]) { order[q + 1] = order[q]; --q; }
+            order[q + 1] = gg;
         }
         int acc = 0;
-        for (int a = 0; a < m; ++a) { const int g = order[a]; s_base[g] = acc; acc += s_tot[g]; }
+        for (int a = 0; a < m; ++a) { const int gg = order[a]; s_base[gg] = acc; acc += s_tot[gg]; }
         for (int a = 0; a < LDP_MAX_NN; ++a) {
             out.group_order[(size_t)r * LDP_MAX_NN + a] = (a < m) ? order[a] : -1;
             out.group_count[(size_t)r * LDP_MAX_NN + a] = s_tot[a];
@@ -657,16 +674,25 @@ ldp_fix_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const 
     }
     __syncthreads();
     // tile t, group g: rows of the group in earlier tiles (+ the group's base) -> blk_first
-    int run = (tid < LDP_MAX_NN) ? s_base[tid] : 0;
+    int carried = s_base[g];                                // rows of group g before the block of tiles at hand
     for (int t0 = 0; t0 < nb; t0 += TB) {
-        const int nt = min(TB, nb - t0) * LDP_MAX_NN;
-        for (int e = tid; e < nt; e += K2_THREADS) s_c[e] = __ldcg(cnt + t0 * LDP_MAX_NN + e);
-        __syncthreads();
-        if (tid < LDP_MAX_NN)
-            for (int e = tid; e < nt; e += LDP_MAX_NN) { const int c = s_c[e]; s_c[e] = run; run += c; }
-        __syncthreads();
-        for (int e = tid; e < nt; e += K2_THREADS) fst[t0 * LDP_MAX_NN + e] = s_c[e];
-        __syncthreads();
+        const int ntile = min(TB, nb - t0);
+        if (nb > TB) {                                      // (a single block of tiles is still in shared memory from the first pass)
+            __syncthreads();
+            for (int e = tid; e < ntile * LDP_MAX_NN; e += K2_THREADS) s_c[e] = __ldcg(cnt + t0 * LDP_MAX_NN + e);
+            __syncthreads();
+            const int per0 = (ntile + NPART - 1) / NPART, a0 = min(part * per0, ntile), b0 = min(a0 + per0, ntile);
+            int pt = 0;
+            for (int t = a0; t < b0; ++t) pt += s_c[t * LDP_MAX_NN + g];
+            s_ptot[part][g] = pt;
+            __syncthreads();
+        }
+        const int per = (ntile + NPART - 1) / NPART, ta = min(part * per, ntile), tb = min(ta + per, ntile);
+        int run = carried, block_tot = 0;
+#pragma unroll
+        for (int q = 0; q < NPART; ++q) { const int v = s_ptot[q][g]; run += (q < part) ? v : 0; block_tot += v; }
+        for (int t = ta; t < tb; ++t) { const int c = s_c[t * LDP_MAX_NN + g]; fst[(t0 + t) * LDP_MAX_NN + g] = run; run += c; }
+        carried += block_tot;
     }
 }
 
