@@ -78,10 +78,21 @@ __device__ __forceinline__ uint32_t div_magic(uint32_t n, unsigned long long mag
 }
 
 __device__ __forceinline__ void quad_border_weights(float wv[4], int px, int x, int y, int W, int H, int border, int N) {
+    if (x + 3 < W && px + 3 < N) {
+        // the quad lies in one image row (always on the vector path): pixels j in [lo, hi] are inside, if the row is
+        const bool row_ok = y >= border && y <= H - 1 - border;
+        const int lo = border - x, hi = W - 1 - border - x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float m = (row_ok && j >= lo && j <= hi) ? 1.f : 0.f;
+            wv[j] = wv[j] * m;                                 // cert * inside.float(): inf * 0 = NaN like torch
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float m = (x >= border && x <= W - 1 - border && y >= border && y <= H - 1 - border) ? 1.f : 0.f;
-        float v = wv[j] * m;                                   // cert * inside.float(): inf * 0 = NaN like torch
+        float v = wv[j] * m;
         if (px + j >= N) v = 0.f;
         wv[j] = v;
         if (++x == W) { x = 0; ++y; }
@@ -139,7 +150,9 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
             const bool interior = y >= border && y <= H - 1 - border && x >= border && x + 3 <= W - 1 - border && px + 3 < N;
             if (!interior) quad_border_weights(wv, px, x, y, W, H, border, N);
             lmin = fminf(lmin, fminf(fminf(wv[0], wv[1]), fminf(wv[2], wv[3])));
-            lsum += (widen_f32(wv[0]) + widen_f32(wv[1])) + (widen_f32(wv[2]) + widen_f32(wv[3]));
+            // hardware conversions here: 4 per quad on the conversion pipe cost this kernel ~2.6 us of that pipe, the integer
+            // widening (widen_f32, right for the conversion-bound prep / draw kernels) a fifth of its issue slots
+            lsum += ((double)wv[0] + (double)wv[1]) + ((double)wv[2] + (double)wv[3]);
             *reinterpret_cast<float4*>(w + px) = make_float4(wv[0], wv[1], wv[2], wv[3]);
             *reinterpret_cast<uint32_t*>(bk + px) = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
         };
