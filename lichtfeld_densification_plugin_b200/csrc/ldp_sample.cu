@@ -143,10 +143,9 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
         const float* c2 = (NNMAX >= 3) ? s_cert[min(2, nn - 1)] : nullptr;
         const float* c3 = (NNMAX >= 4) ? s_cert[min(3, nn - 1)] : nullptr;
         // finishes one quad: cap, border mask, flags, f64 sum, stores
-        auto finish_quad = [&](int px, float wv[4], const int bi[4]) {
+        auto finish_quad_xy = [&](int px, int x, int y, float wv[4], const int bi[4]) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) wv[j] = (wv[j] > cap) ? cap : wv[j];          // torch.clamp(max=cap): NaN stays NaN
-            const int y = (int)div_magic((uint32_t)px, G.w_magic), x = px - y * W;
             const bool interior = y >= border && y <= H - 1 - border && x >= border && x + 3 <= W - 1 - border && px + 3 < N;
             if (!interior) quad_border_weights(wv, px, x, y, W, H, border, N);
             lmin = fminf(lmin, fminf(fminf(wv[0], wv[1]), fminf(wv[2], wv[3])));
@@ -155,6 +154,10 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
             lsum += ((double)wv[0] + (double)wv[1]) + ((double)wv[2] + (double)wv[3]);
             *reinterpret_cast<float4*>(w + px) = make_float4(wv[0], wv[1], wv[2], wv[3]);
             *reinterpret_cast<uint32_t*>(bk + px) = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+        };
+        auto finish_quad = [&](int px, float wv[4], const int bi[4]) {
+            const int y = (int)div_magic((uint32_t)px, G.w_magic);
+            finish_quad_xy(px, px - y * W, y, wv, bi);
         };
         auto take = [&](const float4& c, int k, float wv[4], int bi[4]) {              // NaN-propagating max, first index wins
             if (c.x > wv[0] || c.x != c.x) { wv[0] = c.x; bi[0] = k; }
@@ -213,6 +216,9 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
         } else if (G.vec && NNMAX > 0 && NNMAX <= 4) {
             // two quads per step: all 2*NNMAX 128-bit loads are issued before any of them is consumed
             constexpr int STEP = KS_THREADS * 4;
+            // (x, y) of the thread's quad, advanced by the pass stride instead of divided out of the pixel index every time
+            int qy = (int)div_magic((uint32_t)(base + tid * 4), G.w_magic), qx = base + tid * 4 - qy * W;
+            auto advance = [&](int& x, int& y) { x += G.step_dx; y += G.step_dy; if (x >= W) { x -= W; ++y; } };
             for (int it = 0; it < KS_SPAN / STEP; it += 2) {
                 const int pxa = base + it * STEP + tid * 4, pxb = pxa + STEP;
                 const bool va = pxa < N, vb = pxb < N;
@@ -236,8 +242,10 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
                 if (NNMAX >= 2) { take(a1, 1, wa, ia); take(b1, 1, wb, ib); }
                 if (NNMAX >= 3) { take(a2, 2, wa, ia); take(b2, 2, wb, ib); }
                 if (NNMAX >= 4) { take(a3, 3, wa, ia); take(b3, 3, wb, ib); }
-                finish_quad(pxa, wa, ia);
-                if (vb) finish_quad(pxb, wb, ib);
+                finish_quad_xy(pxa, qx, qy, wa, ia);
+                advance(qx, qy);
+                if (vb) finish_quad_xy(pxb, qx, qy, wb, ib);
+                advance(qx, qy);
             }
         } else {
             for (int it = 0; it < KS_SPAN / (KS_THREADS * 4); ++it) {
