@@ -215,6 +215,16 @@ def recorded_traffic():
         return None
 
 
+def recorded_instructions():
+    """warp instructions one step executes, from the committed ncu captures (profiles/dominant_kernel_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
+            d = json.load(f).get("warp_instructions_per_step") or {}
+        return int(sum(v for v in d.values() if isinstance(v, (int, float)))), d.get("note")
+    except Exception:
+        return None, None
+
+
 def _dbg(msg: str) -> None:
     if os.environ.get("BENCH_DEBUG"):
         print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
@@ -324,8 +334,10 @@ def config5_block(args, dev, rank: int, world: int, ring) -> dict:
         e[0].record()
         shard.launch_all()
         e[1].record()
-        if use_peer:
-            total, offsets = peer.gather(out=gathered)
+        if use_peer == "pull":
+            total, offsets = peer.gather(out=gathered, mode="pull")
+        elif use_peer:
+            total, offsets = peer.gather()
         else:
             total, offsets = D.all_gather_cloud(shard.cloud, out=gathered, scratch=scratch)
         e[2].record()
@@ -351,9 +363,10 @@ def config5_block(args, dev, rank: int, world: int, ring) -> dict:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(x) for x in t.tolist()], total, offsets
 
-    nccl_ms = None
+    nccl_ms = pull_ms = None
     if world > 1 and peer is not None:
         nccl_ms, _, _ = timed_passes(False)            # the library collective, for comparison
+        pull_ms, _, _ = timed_passes("pull")           # our kernel reading the peers instead of writing to them
     (ms, ms_c, ms_g), total, offsets = timed_passes(peer is not None)
     n_total = int(offsets[-1].item())
     # ---- bit-exact check against the single-GPU result: rank 0 recomputes the whole scene alone (outside the timed region)
@@ -393,13 +406,15 @@ def config5_block(args, dev, rank: int, world: int, ring) -> dict:
         "ms": ms, "ms_launches_and_local_concat": ms_c, "ms_all_gather_and_concat": ms_g,
         "points": n_total, "points_per_sec": n_total / (ms * 1e-3), "pairs_per_sec": R_all * scene.nn / (ms * 1e-3),
         "all_gather": {"collective": ("none (N = 1)" if world == 1 else
-                                      "own kernel: ldp_concat_points reads every peer's cloud (count header, then exactly that many rows) over "
-                                      "NVLink from symmetric memory, two device-side barriers; no padding moved" if peer is not None else
+                                      "own kernel: ldp_scatter_points pushes this rank's rows (exactly its count; counts read from the peers' "
+                                      "headers) into every rank's rank-ordered cloud over NVLink (symmetric memory), two device-side "
+                                      "barriers; no padding moved" if peer is not None else
                                       "ncclAllGather (one call: count header + xyz | rgb | err, padded to capacity) + ldp_concat_points"),
                        "bytes_received_per_rank": (int(28 * n_total * (world - 1) / world) if peer is not None else pad_bytes * (world - 1)) if world > 1 else 0,
                        "payload_bytes_total": 28 * n_total, "ms": ms_g,
                        "gb_per_s_received_per_rank": ((28 * n_total * (world - 1) / world if peer is not None else pad_bytes * (world - 1)) / (ms_g * 1e-3) / 1e9) if world > 1 and ms_g > 0 else None,
                        "nccl_all_gather_plus_concat_ms": nccl_ms[2] if nccl_ms else None, "nccl_total_ms": nccl_ms[0] if nccl_ms else None,
+                       "pull_variant_ms": pull_ms[2] if pull_ms else None,
                        "peer_memory_error": peer_err},
         "limiter": ("all-gather" if ms_g > ms_c else "launches") if world > 1 else "launches",
         "equals_single_gpu_result": same if world > 1 else None,
@@ -739,6 +754,17 @@ def gpu_arm(args) -> None:
                    "sampled rows (16 B each) are gathered over PCIe; each group's packed result (offsets, xyz, rgb, err, padded to "
                    "capacity) is copied D2H on a third stream as soon as the group is done"}
 
+    # the second roofline of the path: it executes ~78 M warp instructions per step (f64 cdf arithmetic, exact comparisons,
+    # per-sample eigenvectors), which bounds it by instruction issue well before HBM: 148 SMs x 4 schedulers x SM clock
+    n_inst, inst_note = recorded_instructions()
+    issue_roofline = None
+    if n_inst:
+        sm_clock = (clocks.get("sm_max_mhz") or 1965.0) * 1e6
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        peak_issue = n_sm * 4 * sm_clock
+        issue_roofline = {"bound": "instruction issue", "warp_instructions_per_step": n_inst, "peak_warp_instructions_per_s": peak_issue,
+                          "floor_ms_per_step": 1e3 * n_inst / peak_issue, "frac": n_inst / (ms_step * 1e-3) / peak_issue,
+                          "frac_one_launch_at_a_time": n_inst / (ms_single_step * 1e-3) / peak_issue, "source": inst_note}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -763,7 +789,8 @@ def gpu_arm(args) -> None:
                          "path_achieved": path_gbs, "path_frac": path_gbs / peak,
                          "path_frac_one_launch_at_a_time": path_gbs_single / peak,
                          "path_algorithmic_bytes_per_step": path_bytes,
-                         "path_note": "per GPU: SURVEY 8d bytes of one step (nn*H*W*4 + S*28 + K*28 per view) / ms_per_step / peak"},
+                         "path_note": "per GPU: SURVEY 8d bytes of one step (nn*H*W*4 + S*28 + K*28 per view) / ms_per_step / peak",
+                         "issue": issue_roofline},
             "e2e": e2e, "clocks": clocks,
         }
         if c5 is not None:

@@ -214,6 +214,16 @@ int ldp_concat_points(const float* const* xyz_src, const float* const* rgb_src, 
                       const int64_t* const* count_src, int32_t n_seg, int64_t seg_cap, float* xyz_out, float* rgb_out,
                       float* err_out, int64_t out_capacity, int64_t* seg_offset_out, int64_t* total_out, void* stream);
 
+/* The all-gather of the ranks' clouds as a push over NVLink peer memory (no reference counterpart: the reference is one process;
+ * replaces its final np.concatenate, core/pipeline.py:914-928, across ranks).  This rank's first *count_src[rank] rows of
+ * xyz / rgb / err are written into EVERY destination p < world at row sum(count_src[0..rank)): xyz_dst[p], rgb_dst[p],
+ * err_dst[p] are device arrays of `world` pointers (peer-mapped memory for p != rank); count_src[q] points at rank q's
+ * count (peer-mapped).  seg_offset_out [world + 1] / total_out: optional LOCAL outputs (every rank's row offset, total).
+ * The caller brackets the call with cross-rank barriers (all counts and clouds complete before; all pushes landed after). */
+int ldp_scatter_points(const float* xyz, const float* rgb, const float* err, const int64_t* const* count_src, int32_t rank,
+                       int32_t world, int64_t seg_cap, float* const* xyz_dst, float* const* rgb_dst, float* const* err_dst,
+                       int64_t out_capacity, int64_t* seg_offset_out, int64_t* total_out, void* stream);
+
 /* ---- pair generation on the device ---------------------------------------------
  * flat_poses: [n,16] f32 device, the row-major 4x4 world-to-camera transforms (CameraRecord.flat_pose()).
  *   ldp_select_kcenters    core/selection.py:36-54 select_cameras_kcenters: normalise the columns (mean, std + 1e-8), start

@@ -385,9 +385,16 @@ def _triangulate_ref(matched_ref: _MatchedReference, tri_ctx: _TriangulationCont
                      collect_debug_matches: bool = False) -> Optional[_TriangulatedReference]:
     """Triangulate matches for a single reference view (reference core/pipeline.py:602-780).
 
-    ``config.rng_mode``: "numpy" consumes the process-global MT19937 stream exactly like the reference's
-    ``np.random.choice`` (same draws, same stream position afterwards); "philox" (default) uses the
-    counter-based generator keyed by (config.seed, packed.ref_id).
+    ``config.rng_mode``: "numpy" consumes the process-global MT19937 stream like the reference's ``np.random.choice``:
+    the same uniforms, in the same order, and the same stream position afterwards.  The sampled INDICES are the
+    reference's bit for bit only given the same float32 normaliser ``s``: the reference takes ``weights.sum()`` from a
+    torch-CPU float32 reduction whose last bit depends on the thread count, the kernels take the float64 sum
+    rounded once.  When the two differ by an ulp, ``p = w / s`` and with it a handful of inverse-CDF hits move to a
+    neighbouring pixel (tests/test_gpu_properties.py::test_drop_in_triangulate_ref_numpy_global_stream bounds it: kept
+    points within 3 of the reference's, stream position identical); the parity tests pin ``s`` (``weight_sums=``) and are
+    exact.  "philox" (default) uses the counter-based generator keyed by (config.seed, packed.ref_id): reproducible from
+    run to run and across sharding, pinned value for value against the oracle
+    (tests/test_gpu_parity.py::test_bench_batch_philox_mode_vs_oracle), but not the reference's ``np.random.seed`` stream.
     """
     cfg = tri_ctx.config
     mode = getattr(cfg, "rng_mode", RNG_PHILOX)

@@ -817,6 +817,25 @@ int ldp_concat_points(const float* const* xyz_src, const float* const* rgb_src, 
     return LDP_OK;
 }
 
+int ldp_scatter_points(const float* xyz, const float* rgb, const float* err, const int64_t* const* count_src, int32_t rank,
+                       int32_t world, int64_t seg_cap, float* const* xyz_dst, float* const* rgb_dst, float* const* err_dst,
+                       int64_t out_capacity, int64_t* seg_offset_out, int64_t* total_out, void* stream) {
+    if (world < 1 || world > 64 || rank < 0 || rank >= world || seg_cap < 0 || out_capacity < 0) return fail(LDP_ERR_INVALID, "bad rank / world / size");
+    g_launches = 0;
+    if (!xyz || !rgb || !err || !count_src || !xyz_dst || !rgb_dst || !err_dst) return fail(LDP_ERR_INVALID, "null pointer");
+    const long long blocks = (seg_cap * 3 + ldp::KO_THREADS * 4 - 1) / (ldp::KO_THREADS * 4);
+    const long long per_dst = std::max<long long>(32, (long long)sm_count() * 8 * 2 / world);
+    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>(blocks, per_dst));
+    (void)launch_k(ldp::ldp_scatter_points_kernel, dim3(gx, (unsigned)world), dim3(ldp::KO_THREADS), 0, reinterpret_cast<cudaStream_t>(stream),
+                   xyz, rgb, err, reinterpret_cast<const long long* const*>(count_src), (int)rank, (int)world, (long long)seg_cap,
+                   xyz_dst, rgb_dst, err_dst, (long long)out_capacity, reinterpret_cast<long long*>(seg_offset_out),
+                   reinterpret_cast<long long*>(total_out));
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ldp_scatter_points_kernel");
+    return LDP_OK;
+}
+
 // ---- pair generation on the device (ldp_select.cu)
 int ldp_select_kcenters(const float* flat_poses, int32_t n, int32_t k, float* scratch, int32_t* centers_sorted,
                         int32_t* centers_order, void* stream) {

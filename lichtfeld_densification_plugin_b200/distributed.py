@@ -130,43 +130,75 @@ def all_gather_cloud(cloud, group=None, out=None, scratch: Optional[torch.Tensor
 
 class PeerClouds:
     """The final point all-gather as ONE kernel of ours over NVLink peer memory, instead of a library collective followed by a
-    compaction: every rank keeps its ``output.PackedCloud`` in symmetric memory (``torch.distributed._symmetric_memory``:
-    the same allocation mapped into every rank's address space of the node), and ``gather`` runs ``ldp_concat_points`` with
-    one segment per rank whose source pointers are the PEERS' clouds - the kernel reads each peer's point count from the
-    peer's header and then exactly that many rows, over NVLink / NVSwitch, straight into their place in the rank-ordered
-    cloud.  Nothing is padded, staged or copied twice, and the host learns no count.  Two device-side barriers of the
-    symmetric-memory handle (signal pads, stream-ordered) bracket the reads: every rank's cloud is complete before anybody
-    reads it, and nobody rewrites its cloud before every peer has read it.
+    compaction.  Every rank keeps its ``output.PackedCloud`` AND the rank-ordered result cloud in symmetric memory
+    (``torch.distributed._symmetric_memory``: the same allocations mapped into every rank's address space of the node).
+    ``gather`` (push, the default) runs ``ldp_scatter_points``: the rank reads every peer's point count from the peer's
+    header and writes its own rows - exactly that many, nothing padded or staged - into EVERY rank's result at the row the
+    lower ranks' counts give, with posted 16-byte stores over NVLink / NVSwitch.  ``mode="pull"`` is the mirror image
+    (``ldp_concat_points`` with the peers' clouds as sources: remote loads, each a round trip - slower, kept for comparison).
+    Two device-side barriers of the symmetric-memory handle (signal pads, stream-ordered) bracket the kernel: every rank's
+    cloud and count are complete before anybody looks at them, and every push has landed before anybody reads its result
+    (or rewrites its cloud).  The host learns no count.
     Replaces reference core/pipeline.py:914-928 (single-process np.concatenate)."""
 
     def __init__(self, capacity: int, device, group=None) -> None:
+        import numpy as np
         import torch.distributed._symmetric_memory as symm_mem
         from .output import ConcatPlan, PackedCloud
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
+        dev = torch.device(device)
         nbytes = PackedCloud.nbytes(capacity)
-        self.storage = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.storage = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
         self.storage.zero_()
         self.handle = symm_mem.rendezvous(self.storage, self.group)
-        self.cloud = PackedCloud(capacity, device, storage=self.storage)           # this rank's cloud: launches concatenate into it
+        self.cloud = PackedCloud(capacity, dev, storage=self.storage)              # this rank's cloud: launches concatenate into it
+        self.capacity = self.cloud.capacity
         self.peers = [self.cloud if p == self.rank else
-                      PackedCloud(capacity, device, storage=self.handle.get_buffer(p, (nbytes,), torch.uint8, 0))
+                      PackedCloud(capacity, dev, storage=self.handle.get_buffer(p, (nbytes,), torch.uint8, 0))
                       for p in range(self.world)]
         self.plan = ConcatPlan([c.xyz for c in self.peers], [c.rgb for c in self.peers], [c.err for c in self.peers],
-                               [c.count for c in self.peers], self.cloud.capacity)
-        self.capacity = self.cloud.capacity
+                               [c.count for c in self.peers], self.capacity)
+        # the result, also symmetric: every rank writes its slice into every rank's copy
+        out_bytes = PackedCloud.nbytes(self.world * self.capacity)
+        self.out_storage = symm_mem.empty(out_bytes, dtype=torch.uint8, device=dev)
+        self.out_storage.zero_()
+        self.out_handle = symm_mem.rendezvous(self.out_storage, self.group)
+        self.out = PackedCloud(self.world * self.capacity, dev, storage=self.out_storage)
+        self.out_peers = [self.out if p == self.rank else
+                          PackedCloud(self.world * self.capacity, dev, storage=self.out_handle.get_buffer(p, (out_bytes,), torch.uint8, 0))
+                          for p in range(self.world)]
+        tab = np.array([[c.count.data_ptr() for c in self.peers], [o.xyz.data_ptr() for o in self.out_peers],
+                        [o.rgb.data_ptr() for o in self.out_peers], [o.err.data_ptr() for o in self.out_peers]], dtype=np.int64)
+        self.tables = torch.from_numpy(tab).to(dev)
+        self.seg_offsets = torch.zeros((self.world + 1,), dtype=torch.int64, device=dev)
 
-    def gather(self, out=None):
-        """Every rank's points in rank order (= the single-GPU order) in ``out`` on THIS rank; returns (out, int64 device
-        tensor [world + 1] of the ranks' global row offsets).  Stream-ordered on the current stream; no host synchronisation."""
+    def gather(self, out=None, mode: str = "push"):
+        """Every rank's points in rank order (= the single-GPU order) on THIS rank; returns (PackedCloud, int64 device tensor
+        [world + 1] of the ranks' global row offsets).  Stream-ordered on the current stream; no host synchronisation.
+        ``mode="push"`` fills the symmetric ``self.out`` (``out`` is ignored); ``mode="pull"`` fills ``out``."""
+        import ctypes as C
+        from . import _native as N
         from .output import PackedCloud
-        if out is None:
-            out = PackedCloud(self.world * self.capacity, self.cloud.packed.device)
+        if mode == "pull":
+            if out is None:
+                out = PackedCloud(self.world * self.capacity, self.cloud.packed.device)
+            self.handle.barrier(channel=0)
+            self.plan.run(out)
+            self.handle.barrier(channel=1)
+            return out, self.plan.seg_offsets
+        lib = N.load()
+        stream = torch.cuda.current_stream(self.cloud.packed.device).cuda_stream
+        t = self.tables
         self.handle.barrier(channel=0)
-        self.plan.run(out)
+        N.check(lib.ldp_scatter_points(C.c_void_p(self.cloud.xyz.data_ptr()), C.c_void_p(self.cloud.rgb.data_ptr()),
+                                       C.c_void_p(self.cloud.err.data_ptr()), C.c_void_p(t[0].data_ptr()), self.rank, self.world,
+                                       self.capacity, C.c_void_p(t[1].data_ptr()), C.c_void_p(t[2].data_ptr()),
+                                       C.c_void_p(t[3].data_ptr()), self.out.capacity, C.c_void_p(self.seg_offsets.data_ptr()),
+                                       C.c_void_p(self.out.count.data_ptr()), C.c_void_p(stream)), "ldp_scatter_points")
         self.handle.barrier(channel=1)
-        return out, self.plan.seg_offsets
+        return self.out, self.seg_offsets
 
 
 def all_gather_points(xyz: torch.Tensor, rgb: torch.Tensor, err: torch.Tensor, n_valid: Optional[int] = None,
