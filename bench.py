@@ -565,12 +565,18 @@ def gpu_arm(args) -> None:
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    if DEPTH > 1:
-        eng.lib.ldp_set_sm_reserve(0)                    # one launch sequence at a time: the first draw kernel takes every SM
+    ring_reserve = [e.sm_reserve for e in ring.engines]
+
+    def set_reserve(values):
+        """(the reserve travels in ldp_params: prepared launches are rebuilt when it changes)"""
+        for e, v in zip(ring.engines, values):
+            e.sm_reserve = v
+        prepared.clear()
+    set_reserve([0] * DEPTH)                             # one launch sequence at a time: the first draw kernel takes every SM
     ms_single, o = timed(1, steps)
     ms_total = ms_single
     if DEPTH > 1:
-        eng.lib.ldp_set_sm_reserve(16)                   # DensifyRing's setting: SMs for the other steps in flight
+        set_reserve(ring_reserve)                        # DensifyRing's setting (16): SMs for the other steps in flight
         ms_total, o = timed(DEPTH, steps)                # the headline: DEPTH steps in flight
     _dbg("timed loop done")
     # keep the GPU under the same load a little longer so the clock sampler sees the loaded state
@@ -605,7 +611,7 @@ def gpu_arm(args) -> None:
 
     # ---- per-kernel timing (after the timed region; CUDA events around each kernel on the launch stream)
     import ctypes as C
-    eng.lib.ldp_set_sm_reserve(0)
+    set_reserve([0] * DEPTH)
     eng.lib.ldp_profile_enable(1)
     n_prof = 20
     buf = (C.c_float * 64)()

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LDP_ABI_VERSION 11
+#define LDP_ABI_VERSION 12
 #define LDP_MAX_NN 16          /* neighbours per reference view (the panel clamps to 10) */
 #define LDP_MAX_BINS 4096      /* coverage tiles per map: ceil(W/tile)*ceil(H/tile), tile = max(1, W/24) */
 
@@ -84,6 +84,10 @@ typedef struct ldp_params {
                                   take raw planes too; 0: unknown -- the two-kernel path that reads the warp planes is used */
     uint64_t seed;             /* Philox key */
     int64_t uniforms_per_ref;  /* explicit mode: doubles available per reference view */
+    int32_t sm_reserve;        /* SMs the one-CTA-per-SM first draw kernel leaves to kernels of OTHER launches in flight on other
+                                  streams (engine.DensifyRing passes 16) or to a collective; 0 = take every SM; -1 = the
+                                  process-wide default of ldp_set_sm_reserve.  Per call: no shared state between engines */
+    int32_t reserved3;
 } ldp_params;
 
 /* Per reference view: where its matcher outputs live and its camera constants.  Array of n_refs in
@@ -254,8 +258,8 @@ int ldp_voxel_workspace_bytes(int64_t n, size_t* bytes_out);
 int ldp_voxel_downsample(const float* xyz, const float* rgb, int64_t n, double voxel_size, float* xyz_out, float* rgb_out,
                          int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
 
-/* SMs the one-CTA-per-SM first draw kernel leaves free (process-wide; default 0; the environment variable
- * LDP_SM_RESERVE, when set, wins).  With several launches in flight on different streams (engine.DensifyRing) or a
+/* SMs the one-CTA-per-SM first draw kernel leaves free when ldp_params.sm_reserve is -1 (process-wide default, initially 0; the
+ * environment variable LDP_SM_RESERVE, when set, wins over both).  With several launches in flight on different streams (engine.DensifyRing) or a
  * collective running beside the path, the free SMs let the other kernels make progress: measured 0.1445 -> 0.1420 ms per
  * step at 3 launches in flight with 16. */
 int ldp_set_sm_reserve(int n_sms);

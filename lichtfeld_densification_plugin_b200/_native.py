@@ -13,7 +13,7 @@ import numpy as np
 
 from . import build as _build
 
-LDP_ABI_VERSION = 11
+LDP_ABI_VERSION = 12
 LDP_MAX_NN = 16
 LDP_MAX_BINS = 4096
 
@@ -58,6 +58,7 @@ class LdpParams(C.Structure):
         ("nn_max", C.c_int32), ("prologue", C.c_int32),
         ("certainty_floor", C.c_float), ("no_warped_masks", C.c_int32),
         ("seed", C.c_uint64), ("uniforms_per_ref", C.c_int64),
+        ("sm_reserve", C.c_int32), ("reserved3", C.c_int32),
     ]
 
 

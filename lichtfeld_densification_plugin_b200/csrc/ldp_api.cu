@@ -483,7 +483,7 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     }
     // ---- round 1: independent CTAs, as many per view as the device has SMs for (one CTA per SM: the table fills it)
     static const int env_reserve = [] { const char* e = getenv("LDP_SM_RESERVE"); return e ? atoi(e) : -1; }();   // SMs left to concurrent
-    const int sm_reserve = env_reserve >= 0 ? env_reserve : g_sm_reserve;                                             // kernels (other launches in
+    const int sm_reserve = env_reserve >= 0 ? env_reserve : (p->sm_reserve >= 0 ? p->sm_reserve : g_sm_reserve);                                             // kernels (other launches in
     int c_first = (sm_count() - sm_reserve) / nsubrefs;                                                            // flight, communication)
     if (c_first < 1) c_first = 1;
     if (c_first > (int)plan.ws.draw_cmax) c_first = (int)plan.ws.draw_cmax;

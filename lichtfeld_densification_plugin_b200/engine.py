@@ -288,6 +288,7 @@ class DensifyEngine:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self._workspace: Optional[torch.Tensor] = None
         self._pinned: Optional[torch.Tensor] = None
+        self.sm_reserve = -1         # SMs the first draw kernel leaves to other launches in flight (-1: process default, 0: none)
         self.pairs = PairConstantCache()
 
     def new_batch(self, H: int, W: int, w_match: int, h_match: int) -> RefBatch:
@@ -312,6 +313,7 @@ class DensifyEngine:
         p.prologue = 0 if cfg.certainty_floor is None else 1
         p.certainty_floor = float(np.float32(cfg.certainty_floor if cfg.certainty_floor is not None else 0.0))
         p.no_warped_masks = 0 if batch.has_warped_masks else 1
+        p.sm_reserve = int(self.sm_reserve)
         p.seed = int(cfg.seed) & 0xFFFFFFFFFFFFFFFF
         p.uniforms_per_ref = int(uniforms_per_ref)
         return p
@@ -510,8 +512,8 @@ class DensifyRing:
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.engines = [DensifyEngine(device) for _ in range(depth)]
-        if depth > 1:      # process-wide: the first draw kernel leaves SMs to the other launches in flight
-            N.check(self.engines[0].lib.ldp_set_sm_reserve(int(sm_reserve)), "ldp_set_sm_reserve")
+        for e in self.engines:       # per engine (passed with every call): the first draw kernel leaves SMs to the other launches in flight
+            e.sm_reserve = int(sm_reserve) if depth > 1 else 0
         self.device = self.engines[0].device
         self.streams = [torch.cuda.Stream(self.device) for _ in range(depth)]
         self.depth = depth
