@@ -568,6 +568,8 @@ ldp::GeomArgs make_geom_args(const ldp_params* p, const Plan& plan, int have_bes
     ga.discard = have_bestk ? discard_mode : 0;
     static const int fuse_mode = [] { const char* e = getenv("LDP_FUSE_GATHER"); return e ? atoi(e) : 1; }();
     ga.fused = fuse_mode;
+    static const int prefetch_mode = [] { const char* e = getenv("LDP_GEOM_PREFETCH"); return e ? atoi(e) : 1; }();
+    ga.l2_prefetch = prefetch_mode;
     return ga;
 }
 

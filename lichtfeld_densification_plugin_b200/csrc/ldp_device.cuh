@@ -242,6 +242,19 @@ __device__ __forceinline__ void philox_uniform2(uint64_t seed, uint32_t stream, 
     u[1] = ((double)(r[2] >> 5) * 67108864.0 + (double)(r[3] >> 6)) * (1.0 / 9007199254740992.0);
 }
 
+// Slice i of n of [base, base + bytes) -> L2, as one bulk prefetch (whole 16-byte units inside the array only).  The sampled pixels
+// of a view touch most sectors of its reference image and of its winner row in random order; read that way they are DRAM row
+// misses, read once front to back they are a few hundred KB of streaming that the view's CTAs then hit in L2.
+__device__ __forceinline__ void l2_prefetch_slice(const void* base, size_t bytes, int i, int n) {
+    const size_t chunk = ((bytes + n - 1) / n + 15) & ~(size_t)15;
+    const uintptr_t b0 = reinterpret_cast<uintptr_t>(base);
+    const uintptr_t lo = (b0 + (size_t)i * chunk + 15) & ~(uintptr_t)15;
+    uintptr_t hi = b0 + (size_t)(i + 1) * chunk;
+    if (hi > b0 + bytes) hi = b0 + bytes;
+    hi &= ~(uintptr_t)15;
+    if (hi > lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(lo), "r"((uint32_t)(hi - lo)) : "memory");
+}
+
 __device__ __forceinline__ float4 ld_stream4(const float* p) {   // read-once data: evict-first
     return __ldcs(reinterpret_cast<const float4*>(p));
 }

@@ -29,15 +29,18 @@ constexpr int KFIX_BLOCKS = 148;
 // np.degrees on float32 multiplies by f32(180) / f32(pi) evaluated in f32 (measured)
 #define RAD2DEG_F32 57.295776367187500f
 
-struct PairConst {          // one neighbour, staged in shared memory
-    float P2[12];
-    float C2[3];
+struct alignas(16) PairConst {   // one neighbour, staged in shared memory.  144 bytes: the lanes of a warp read the same field of
+    float P2[12];                // DIFFERENT neighbours; at a stride of 128 bytes those words share a bank (4-way conflicts on
+    float C2[3];                 // every constant), at 36 words neighbour k sits 4k banks further (128-bit reads stay aligned)
     float F[9];
     float sxB, syB;
     int group;
+    int pad0;
     const float* warp;
     const float* cert;
+    int pad1[4];
 };
+static_assert(sizeof(PairConst) == 144, "PairConst stride");
 struct RefConst {
     float P1[12];
     float C1[3];
@@ -52,6 +55,7 @@ struct GeomArgs {           // launch-constant extras computed on the host
     int ref0;               // first view of this sub-launch
     int sub;                // sub-batch index (selects the fix-up counter)
     int discard;            // 1: drop the dead weight rows from L2 (LDP_DISCARD=0 turns it off)
+    int l2_prefetch;        // 1: bulk L2 prefetch of the view's reference image and winner row (LDP_GEOM_PREFETCH=0 turns it off)
     int fused;              // 1: the geometry kernel gathers its own inputs (no gather kernel, no record round trip)
 };
 
@@ -62,22 +66,61 @@ __device__ __forceinline__ void l2_discard_line(const void* p) {
     asm volatile("discard.global.L2 [%0], 128;" :: "l"(p) : "memory");
 }
 
-__device__ __forceinline__ void stage_constants(const ldp_ref_desc* rd, RefConst& rc, PairConst* pc, int t, int nt) {
-    if (t < 12) rc.P1[t] = rd->P1[t];
-    if (t < 3) rc.C1[t] = rd->C1[t];
-    if (t == 0) {
-        rc.sxA = rd->sxA; rc.syA = rd->syA; rc.sx_img = rd->sx_img; rc.sy_img = rd->sy_img;
-        rc.img_w = rd->img_w; rc.img_h = rd->img_h; rc.nn = rd->nn; rc.image = rd->image;
-    }
-    const int nn = rd->nn;
-    for (int e = t; e < nn * 12; e += nt) pc[e / 12].P2[e % 12] = rd->P2[e / 12][e % 12];
-    for (int e = t; e < nn * 9; e += nt) pc[e / 9].F[e % 9] = rd->F[e / 9][e % 9];
-    for (int e = t; e < nn * 3; e += nt) pc[e / 3].C2[e % 3] = rd->C2[e / 3][e % 3];
-    for (int e = t; e < nn; e += nt) {
-        pc[e].sxB = rd->sxB[e]; pc[e].syB = rd->syB[e]; pc[e].group = rd->group[e];
-        pc[e].warp = rd->warp[e]; pc[e].cert = rd->cert[e];
+// The view's camera constants, descriptor -> shared memory, in ONE global round trip: the 451 words from sxA to group[] are
+// contiguous in ldp_ref_desc, every thread loads its words (and pointers) before it stores any of them, and nothing depends
+// on a loaded value (the rows beyond nn are copied too: never read).  A CTA's warps sit through this before they can do
+// anything else, 3634 times per step: the per-field loops it replaces cost eight dependent round trips (4.7k cycles of 23k).
+constexpr int DESC_WORDS = 4 + 12 + 3 + LDP_MAX_NN * (12 + 3 + 9 + 3);
+static_assert(offsetof(ldp_ref_desc, group) + sizeof(int32_t) * LDP_MAX_NN - offsetof(ldp_ref_desc, sxA) == DESC_WORDS * 4, "descriptor layout");
+static_assert(offsetof(RefConst, sy_img) - offsetof(RefConst, sxA) == 12, "RefConst layout");
+__device__ __forceinline__ uint32_t* desc_word_slot(int e, RefConst& rc, PairConst* pc) {
+    if (e < 4) return reinterpret_cast<uint32_t*>(&rc.sxA) + e;
+    if (e < 16) return reinterpret_cast<uint32_t*>(rc.P1) + (e - 4);
+    if (e < 19) return reinterpret_cast<uint32_t*>(rc.C1) + (e - 16);
+    e -= 19;
+    if (e < LDP_MAX_NN * 12) return reinterpret_cast<uint32_t*>(pc[e / 12].P2) + e % 12;
+    e -= LDP_MAX_NN * 12;
+    if (e < LDP_MAX_NN * 3) return reinterpret_cast<uint32_t*>(pc[e / 3].C2) + e % 3;
+    e -= LDP_MAX_NN * 3;
+    if (e < LDP_MAX_NN * 9) return reinterpret_cast<uint32_t*>(pc[e / 9].F) + e % 9;
+    e -= LDP_MAX_NN * 9;
+    if (e < LDP_MAX_NN) return reinterpret_cast<uint32_t*>(&pc[e].sxB);
+    e -= LDP_MAX_NN;
+    if (e < LDP_MAX_NN) return reinterpret_cast<uint32_t*>(&pc[e].syB);
+    return reinterpret_cast<uint32_t*>(&pc[e - LDP_MAX_NN].group);
+}
+// stage_load puts the loads in flight (registers), stage_store waits for them: a kernel issues its other independent loads in
+// between.  slices > 0: the CTA also asks L2 for its share (slice of slices) of the view's reference image.
+constexpr int DESC_PER = 4;                                   // words per thread: one pass for CTAs of >= 113 threads
+struct StagedDesc {
+    uint32_t v[DESC_PER];
+    const float* p_warp; const float* p_cert; const uint8_t* p_img;
+    int img_w, img_h, nn;
+};
+__device__ __forceinline__ void stage_load(const ldp_ref_desc* rd, int t, int nt, StagedDesc& sd) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&rd->sxA);
+    sd.p_warp = nullptr; sd.p_cert = nullptr; sd.p_img = nullptr; sd.img_w = sd.img_h = sd.nn = 0;
+    if (t < LDP_MAX_NN) { sd.p_warp = rd->warp[t]; sd.p_cert = rd->cert[t]; }
+    if (t == LDP_MAX_NN) { sd.p_img = rd->image; sd.img_w = rd->img_w; sd.img_h = rd->img_h; sd.nn = rd->nn; }
+#pragma unroll
+    for (int q = 0; q < DESC_PER; ++q) sd.v[q] = (t + q * nt < DESC_WORDS) ? __ldg(src + t + q * nt) : 0u;
+}
+__device__ __forceinline__ void stage_store(const StagedDesc& sd, RefConst& rc, PairConst* pc, int t, int nt,
+                                            int slice = 0, int slices = 0) {
+#pragma unroll
+    for (int q = 0; q < DESC_PER; ++q) if (t + q * nt < DESC_WORDS) *desc_word_slot(t + q * nt, rc, pc) = sd.v[q];
+    if (t < LDP_MAX_NN) { pc[t].warp = sd.p_warp; pc[t].cert = sd.p_cert; }
+    if (t == LDP_MAX_NN) {
+        rc.image = sd.p_img; rc.img_w = sd.img_w; rc.img_h = sd.img_h; rc.nn = sd.nn;
+        if (slices > 0) l2_prefetch_slice(sd.p_img, (size_t)sd.img_w * sd.img_h * 3, slice, slices);
     }
 }
+__device__ __forceinline__ void stage_constants(const ldp_ref_desc* rd, RefConst& rc, PairConst* pc, int t, int nt) {
+    StagedDesc sd;
+    stage_load(rd, t, nt, sd);
+    stage_store(sd, rc, pc, t, nt);
+}
+static_assert(DESC_PER * 113 >= DESC_WORDS, "stage_load covers the descriptor in one pass");
 
 // Cyclic Jacobi eigen-decomposition of the symmetric 4x4 M (f64): eigenvector of the smallest eigenvalue.
 __device__ void jacobi_smallest_eigvec4(const double* __restrict__ Min, double* __restrict__ vout) {
@@ -238,6 +281,25 @@ struct SampleResult {
     bool converged;
 };
 
+#ifdef LDP_GEOM_CLOCKS   // dev (scratch/geom_clocks.py): cycles per phase of warp 0 of three CTAs of every view, in ws.dbgclk
+#define GCLK_DECL long long gck[12] = {0,0,0,0,0,0,0,0,0,0,0,0}; long long gck_last = clock64();
+#define GCLK_ARGS , long long* gck, long long& gck_last
+#define GCLK_PASS , gck, gck_last
+#define GCLK(slot) do { const long long t_ = clock64(); gck[slot] += t_ - gck_last; gck_last = t_; } while (0)
+__device__ __forceinline__ void gclk_use(float x) { asm volatile("" :: "f"(x)); }
+__device__ __forceinline__ void gclk_use(int x) { asm volatile("" :: "r"(x)); }
+__device__ __forceinline__ void gclk_use(uint32_t x) { asm volatile("" :: "r"(x)); }
+#define GCLK_USE(x) gclk_use(x)
+#define GCLK_FLUSH do { if (threadIdx.x == 0 && (blockIdx.x == 5 || blockIdx.x == 40 || blockIdx.x == 70)) for (int q_ = 0; q_ < 12; ++q_) ws.dbgclk[(size_t)r * 32 + (blockIdx.x == 5 ? 0 : blockIdx.x == 40 ? 1 : 2) * 12 + q_] = gck[q_]; } while (0)   /* three CTAs per view, plain stores */
+#else
+#define GCLK_DECL
+#define GCLK_ARGS
+#define GCLK_PASS
+#define GCLK(slot) do { } while (0)
+#define GCLK_USE(x) do { } while (0)
+#define GCLK_FLUSH do { } while (0)
+#endif
+
 // Compact per-sample record written by the gather kernel and consumed (coalesced) by the compute kernel.
 struct SampleRec {
     float4 wv;              // winning neighbour's warp row: xA, yA, xB, yB in [-1, 1]
@@ -257,11 +319,11 @@ __device__ __forceinline__ float cert_at(const ldp_params& P, const PairConst* p
 }
 
 __device__ __forceinline__ void gather_sample(const ldp_params& P, const RefConst& rc, const PairConst* pc, const ProView& pv,
-                                              const GeomArgs& ga, const uint8_t* __restrict__ bestk_row, int idx,
+                                              const GeomArgs& ga, int k_pre, int idx,
                                               SampleRec& rec, float& craw) {
     int k = 0;                                                                    // core/pipeline.py:634-635,652
     if (ga.have_bestk) {
-        k = bestk_row[idx];
+        k = k_pre;                         // the stream kernel's winner byte at idx, fetched by the caller
     } else {                               // stage entry point: arg-max over neighbours at the sampled pixel only
         float best = cert_at(P, pc, pv, 0, idx);
         for (int q = 1; q < rc.nn; ++q) {
@@ -295,7 +357,7 @@ __device__ __forceinline__ void gather_sample(const ldp_params& P, const RefCons
 // ---- compute: everything else the reference computes for one sampled pixel (core/pipeline.py:653-769)
 template <bool ROBUST>
 __device__ __forceinline__ void eval_sample(const ldp_params& P, const RefConst& rc, const PairConst* pc, const GeomArgs& ga,
-                                            const SampleRec& rec, float craw, SampleResult& o) {
+                                            const SampleRec& rec, float craw, SampleResult& o GCLK_ARGS) {
     const int k = (int)(rec.k_cert & 0xffu);
     const PairConst& pk = pc[k];
     o.grp = pk.group;
@@ -363,6 +425,7 @@ __device__ __forceinline__ void eval_sample(const ldp_params& P, const RefConst&
         o.cr = col[0]; o.cg = col[1]; o.cb = col[2];
     }
 
+    GCLK_USE(o.cr); GCLK_USE(o.cg); GCLK_USE(o.cb); GCLK_USE(o.good); GCLK(3);
     o.X0 = o.X1 = o.X2 = 0.f;
     o.err = __int_as_float(0x7fc00000);
     o.keep = 0;
@@ -378,7 +441,9 @@ __device__ __forceinline__ void eval_sample(const ldp_params& P, const RefConst&
             A[12 + j] = (double)__fsub_rn(__fmul_rn(vB, pk.P2[8 + j]), pk.P2[4 + j]);
         }
         double v[4];
+        GCLK_USE(__double2hiint(A[0])); GCLK_USE(__double2hiint(A[15])); GCLK(4);
         o.converged = null_vector4<ROBUST>(A, v);
+        GCLK_USE(__double2hiint(v[0])); GCLK_USE(__double2hiint(v[3])); GCLK(5);
         // core/geometry.py:85-87: w = where(|Xh3| < 1e-12, 1e-12, Xh3); X = Xh / w
         float X0, X1, X2, X3;
         {
@@ -416,6 +481,7 @@ __device__ __forceinline__ void eval_sample(const ldp_params& P, const RefConst&
             }
         }
         o.X0 = X0; o.X1 = X1; o.X2 = X2; o.err = err; o.keep = keep;
+        GCLK_USE(o.X0); GCLK_USE(o.err); GCLK_USE(o.keep); GCLK(6);
     }
     o.dcert = 0.f;
     o.dbg = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -481,7 +547,7 @@ ldp_gather_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
 #pragma unroll
     for (int q = 0; q < KG_SPT; ++q) {
         const int i = i0 + q * KG_THREADS + threadIdx.x;
-        if (i < S) gather_sample(P, rc, pc, pv, ga, ws.bestk + (size_t)r * ws.n_pad, idx[q], rec[q], craw[q]);
+        if (i < S) gather_sample(P, rc, pc, pv, ga, ga.have_bestk ? (int)ws.bestk[(size_t)r * ws.n_pad + idx[q]] : 0, idx[q], rec[q], craw[q]);
     }
 #pragma unroll
     for (int q = 0; q < KG_SPT; ++q) {
@@ -514,25 +580,37 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
     __shared__ int s_cnt[LDP_MAX_NN], s_first[LDP_MAX_NN];
     __shared__ ProView pv;
     const int r = blockIdx.y + ga.ref0;
-    stage_constants(refs + r, rc, pc, threadIdx.x, K2_THREADS);          // host-written descriptors: no kernel produces them
+    GCLK_DECL
+    // host-written descriptors, no kernel produces them: their loads are put in flight first and collected after the sample
+    // indices are requested, one round trip for both; the prefetches are hints (the winner row was written three kernels ago)
+    StagedDesc sd;
+    stage_load(refs + r, threadIdx.x, K2_THREADS, sd);
+    if (ga.fused && ga.l2_prefetch && ga.have_bestk && threadIdx.x == LDP_MAX_NN + 32)
+        l2_prefetch_slice(ws.bestk + (size_t)r * ws.n_pad, (size_t)P.H * P.W, blockIdx.x, gridDim.x);
     if (ga.fused && P.prologue) stage_proview(refs + r, pv, threadIdx.x);
+    GCLK(0);
     grid_dependency_sync();
+    GCLK(10);
     const int i0 = blockIdx.x * K2_THREADS;
     int idx_f = 0;
     if (ga.fused) {
         const int32_t* sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
         const int i_ = i0 + threadIdx.x;
         idx_f = (i_ < (int)ws.sel_cap) ? __ldg(sel + i_) : 0;
-        if (ga.discard & 1) {
-            const char* row = reinterpret_cast<const char*>(ws.w + (size_t)r * ws.n_pad);
-            const int nlines = (int)(ws.n_pad * sizeof(float) / 128);
-            for (int l = i0 + threadIdx.x; l < nlines; l += gridDim.x * K2_THREADS) l2_discard_line(row + (size_t)l * 128);
-        }
     }
     const int S = out.n_samples[r];
+    stage_store(sd, rc, pc, threadIdx.x, K2_THREADS, blockIdx.x, (ga.fused && ga.l2_prefetch) ? (int)gridDim.x : 0);
+    if (ga.fused && (ga.discard & 1)) {
+        const char* row = reinterpret_cast<const char*>(ws.w + (size_t)r * ws.n_pad);
+        const int nlines = (int)(ws.n_pad * sizeof(float) / 128);
+        for (int l = i0 + threadIdx.x; l < nlines; l += gridDim.x * K2_THREADS) l2_discard_line(row + (size_t)l * 128);
+    }
     if (i0 >= S) return;
+    int k_pre = 0;                          // needs no staged constant: requested before the barrier
+    if (ga.fused && ga.have_bestk && i0 + (int)threadIdx.x < S) k_pre = ws.bestk[(size_t)r * ws.n_pad + idx_f];
     if (threadIdx.x < LDP_MAX_NN) { s_cnt[threadIdx.x] = 0; s_first[threadIdx.x] = 0x7fffffff; }
     __syncthreads();
+    GCLK_USE(idx_f); GCLK(1);
     const int i = i0 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int keep = 0, grp = -1;
@@ -540,10 +618,11 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
         const size_t o = (size_t)r * ws.sel_cap + i;
         SampleRec rec;
         float craw;
-        if (ga.fused) gather_sample(P, rc, pc, pv, ga, ws.bestk + (size_t)r * ws.n_pad, idx_f, rec, craw);
+        if (ga.fused) gather_sample(P, rc, pc, pv, ga, k_pre, idx_f, rec, craw);
         else load_record(ws, P, o, rec, craw);
+        GCLK_USE(rec.tex[0]); GCLK_USE(rec.tex[2]); GCLK_USE(rec.wv.x); GCLK(2);
         SampleResult s;
-        eval_sample<false>(P, rc, pc, ga, rec, craw, s);
+        eval_sample<false>(P, rc, pc, ga, rec, craw, s GCLK_PASS);
         if (!s.converged && ga.fused) {     // the fix-up reads the record
             ws.pt0[o] = rec.wv;
             ws.pt1[o] = make_float4(__uint_as_float(rec.tex[0]), __uint_as_float(rec.tex[1]), __uint_as_float(rec.tex[2]),
@@ -560,6 +639,7 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
         }
         keep = s.keep;
         grp = s.grp;
+        GCLK(7);
     }
     // per-tile group statistics for the pack kernels: kept count and first sample position per group
     const unsigned same = __match_any_sync(0xffffffffu, grp);
@@ -570,12 +650,15 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
         if (kept_same) atomicAdd(&s_cnt[grp], __popc(kept_same));
     }
     if (lane == 0 && kept_all) atomicAdd(&ws.kept[r], __popc(kept_all));
+    GCLK(8);
     __syncthreads();
+    GCLK(9);
     if (threadIdx.x < LDP_MAX_NN) {
         const size_t t = ((size_t)r * ga.nb2 + blockIdx.x) * LDP_MAX_NN + threadIdx.x;
         ws.blk_cnt[t] = s_cnt[threadIdx.x];
         ws.blk_first[t] = s_first[threadIdx.x];
     }
+    GCLK_FLUSH;
 }
 
 // K2c fix-up + plan: one CTA per view.  (1) The view's entries of the worklist (null-vector iteration not converged: grossly
@@ -608,7 +691,8 @@ ldp_fix_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const 
             float craw;
             load_record(ws, P, o, rec, craw);
             SampleResult s;
-            eval_sample<true>(P, rc, pc, ga, rec, craw, s);
+            GCLK_DECL
+            eval_sample<true>(P, rc, pc, ga, rec, craw, s GCLK_PASS);
             store_sample(P, ws, out, o, s);
             if (s.keep) {
                 atomicAdd(&ws.kept[r], 1);

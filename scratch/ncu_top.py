@@ -14,5 +14,5 @@ for r in rows:
         except Exception: pass
 tot = sum(d[3] for d in data); ts = sum(d[4] for d in data)
 print("total inst", tot, "samples", ts)
-for d in sorted(data, key=lambda d: -d[3])[:top]:
+for d in sorted(data, key=lambda d: -(d[4] if "--samp" in sys.argv else d[3]))[:top]:
     print(f"{d[0][:14]:>14}:{d[1]:<4} inst {d[3]/1e6:6.2f}M {100*d[3]/max(tot,1):5.1f}% samp {100*d[4]/max(ts,1):5.1f}%  {d[2].strip()[:100]}")
