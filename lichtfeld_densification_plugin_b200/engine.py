@@ -287,7 +287,6 @@ class DensifyEngine:
         self.lib = N.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self._workspace: Optional[torch.Tensor] = None
-        self._pinned: Optional[torch.Tensor] = None
         self.sm_reserve = -1         # SMs the first draw kernel leaves to other launches in flight (-1: process default, 0: none)
         self.pairs = PairConstantCache()
 
@@ -468,14 +467,6 @@ class DensifyEngine:
             out.sample_flags = torch.zeros((R, sel_cap), dtype=torch.uint8, device=dev)
             out.sample_xyzerr = torch.zeros((R, sel_cap, 4), dtype=torch.float32, device=dev)
         return out
-
-    def pinned_like(self, packed: torch.Tensor) -> torch.Tensor:
-        """A page-locked host buffer for device->host reads of ``packed`` (cached, grown on demand; its contents are valid
-        until the next read through it)."""
-        n = int(packed.numel())
-        if self._pinned is None or self._pinned.numel() < n:
-            self._pinned = torch.empty((max(n, 1 << 20),), dtype=torch.uint8).pin_memory()
-        return self._pinned[:n]
 
 
 class PreparedLaunch:
