@@ -236,12 +236,13 @@ int ldp_scatter_points(const float* xyz, const float* rgb, const float* err, con
  *                          centers_sorted [k] = sorted(centers) (what the reference returns); centers_order [k] = pick order.
  *                          1 <= k <= n <= 8192 (the reference clamps k the same way before the loop).
  *   ldp_nearest_neighbors  core/selection.py:57-70 nearest_neighbors: for every view the k nearest other views by Euclidean
- *                          distance of the poses, ascending.  idx_out [n,k] int64.  k <= min(n - 1, 16).  The distances are
- *                          torch.cdist's own float32 values (|x|^2 + |y|^2 - 2 x.y as ONE K = 18 dot product of float32
- *                          FMAs in index order, row norms as eight lanes added left to right; measured against torch), so
- *                          near-equal distances - the left / right neighbours of a ring camera - come out in the
- *                          reference's order.  EXACTLY equal float32 distances: lower index first (torch.topk leaves that
- *                          order to std::nth_element / std::partial_sort). */
+ *                          distance of the poses, ascending.  idx_out [n,k] int64.  k <= min(n - 1, 16).  The reference's
+ *                          table index for index: the distances are torch.cdist's own float32 values (|x|^2 + |y|^2 - 2 x.y
+ *                          as ONE K = 18 dot product of float32 FMAs in index order, row norms as eight lanes added left to
+ *                          right; measured against torch), so near-equal distances - the left / right neighbours of a ring
+ *                          camera - come out in the reference's order; and EXACTLY equal float32 distances are ordered by
+ *                          torch.topk's own CPU selection (std::partial_sort for k * 64 <= n, else std::nth_element +
+ *                          std::sort over (value, index) pairs, libstdc++'s moves restated one for one). */
 int ldp_select_kcenters(const float* flat_poses, int32_t n, int32_t k, float* scratch, int32_t* centers_sorted,
                         int32_t* centers_order, void* stream);
 int ldp_nearest_neighbors(const float* flat_poses, int32_t n, int32_t k, int64_t* idx_out, void* stream);

@@ -870,9 +870,8 @@ int ldp_nearest_neighbors(const float* flat_poses, int32_t n, int32_t k, int64_t
     if (n <= 1 || k == 0) return LDP_OK;
     if (k > n - 1 || k > ldp::KNN_MAX_K) return fail(LDP_ERR_INVALID, "nearest neighbours needs k <= min(n - 1, 16)");
     if (!flat_poses || !idx_out) return fail(LDP_ERR_INVALID, "null pointer");
-    const unsigned grid = (unsigned)((n + 7) / 8);
-    (void)launch_k(ldp::ldp_knn_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), flat_poses, (int)n, (int)k,
-                   reinterpret_cast<long long*>(idx_out));
+    (void)launch_k(ldp::ldp_knn_kernel, dim3((unsigned)n), dim3(ldp::KNN_THREADS), 0, reinterpret_cast<cudaStream_t>(stream), flat_poses,
+                   (int)n, (int)k, reinterpret_cast<long long*>(idx_out));
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ldp_knn_kernel");

@@ -151,15 +151,121 @@ ldp_kcenters_kernel(const float* __restrict__ X, int n, int k, float* __restrict
     }
 }
 
-// One warp per view: distances to every other view, the k smallest in ascending order (ties: lower index first).
-// The distances are torch.cdist's own float32 values (reference core/selection.py:66; ATen _euclidean_dist, used above 25 rows):
+// One CTA per view: distances to every view, then torch.topk's own selection of the k smallest.
+// The distances are torch.cdist's float32 values (reference core/selection.py:66; ATen _euclidean_dist, used above 25 rows):
 //   d(i, j) = sqrt(max(x1_[i] . x2_[j], 0)),  x1_ = [-2 x, |x|^2, 1],  x2_ = [x, 1, |x|^2]
 // with the K = 18 dot product accumulated as a chain of float32 FMAs in index order (what the sgemm does) and the row norms
 // summed as eight lanes (a[i] + a[i + 8]) added left to right -- both orders measured against torch 2.11 (oracle:
-// cdist_squared_f32).  The cancellation error of this formula (~1e-6 on poses of norm ~10) is what decides the order of the
-// left / right neighbours of a ring camera, so it is reproduced, not avoided.  Where two float32 distances are EXACTLY equal
-// the reference's order is whatever std::nth_element / std::partial_sort leave (torch.topk); here the lower index comes first.
+// cdist_squared_f32).  The cancellation error of this formula (~1e-6 on poses of norm ~10) decides the order of the left /
+// right neighbours of a ring camera, so it is reproduced, not avoided; the diagonal is +inf (dist.fill_diagonal_).
+// Where float32 distances are EXACTLY equal - a third of the rows of a ring scene - the reference's order is whatever
+// torch.topk's CPU kernel leaves: (value, index) pairs, a value-only comparator (NaN last) and, for k * 64 <= n,
+// std::partial_sort(begin, begin + k, end), else std::nth_element(begin, begin + k - 1, end) + std::sort(begin, begin + k - 1).
+// Those are deterministic sequences of moves; libstdc++'s are restated below one for one (oracle: topk_smallest_like_torch,
+// pinned against torch.topk and the reference's frozen tables), run by one thread per view on the row in shared memory.
 constexpr int KNN_MAX_K = 16;
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_CHUNK = 2048;                 // heap path: distances staged per chunk (any n)
+constexpr int KNN_SELECT_MAX = 64 * KNN_MAX_K;  // selection path: n < 64 k <= 1024 pairs in shared memory
+struct KnnPair { float v; int i; };
+__device__ __forceinline__ bool knn_lt(const KnnPair& a, const KnnPair& b) {
+    return ((a.v == a.v) && (b.v != b.v)) || a.v < b.v;
+}
+// bits/stl_heap.h: __push_heap, __adjust_heap, __make_heap, __pop_heap; bits/stl_algo.h: __heap_select
+__device__ void knn_adjust_heap(KnnPair* v, int hole, int len, KnnPair value) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (knn_lt(v[child], v[child - 1])) --child;
+        v[hole] = v[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        v[hole] = v[child - 1];
+        hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;
+    while (hole > top && knn_lt(v[parent], value)) {
+        v[hole] = v[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    v[hole] = value;
+}
+__device__ void knn_make_heap(KnnPair* v, int len) {
+    if (len < 2) return;
+    for (int parent = (len - 2) / 2; ; --parent) {
+        knn_adjust_heap(v, parent, len, v[parent]);
+        if (parent == 0) return;
+    }
+}
+__device__ void knn_sort_heap(KnnPair* v, int len) {
+    while (len > 1) {
+        --len;
+        const KnnPair value = v[len];
+        v[len] = v[0];
+        knn_adjust_heap(v, 0, len, value);
+    }
+}
+__device__ void knn_heap_select(KnnPair* v, int middle, int last) {      // [0, middle) heap over [0, last)
+    knn_make_heap(v, middle);
+    for (int i = middle; i < last; ++i) {
+        if (knn_lt(v[i], v[0])) {
+            const KnnPair value = v[i];
+            v[i] = v[0];
+            knn_adjust_heap(v, 0, middle, value);
+        }
+    }
+}
+// bits/stl_algo.h: __move_median_to_first + __unguarded_partition (pivot at first), __insertion_sort, __introselect
+__device__ int knn_partition_pivot(KnnPair* v, int first, int last) {
+    const int a = first + 1, b = first + (last - first) / 2, c = last - 1;
+    int m;
+    if (knn_lt(v[a], v[b])) m = knn_lt(v[b], v[c]) ? b : (knn_lt(v[a], v[c]) ? c : a);
+    else m = knn_lt(v[a], v[c]) ? a : (knn_lt(v[b], v[c]) ? c : b);
+    { const KnnPair t = v[first]; v[first] = v[m]; v[m] = t; }
+    int lo = first + 1, hi = last;
+    for (;;) {
+        while (knn_lt(v[lo], v[first])) ++lo;
+        --hi;
+        while (knn_lt(v[first], v[hi])) --hi;
+        if (!(lo < hi)) return lo;
+        const KnnPair t = v[lo]; v[lo] = v[hi]; v[hi] = t;
+        ++lo;
+    }
+}
+__device__ void knn_insertion_sort(KnnPair* v, int first, int last) {
+    for (int i = first + 1; i < last; ++i) {
+        const KnnPair val = v[i];
+        if (knn_lt(val, v[first])) {
+            for (int q = i; q > first; --q) v[q] = v[q - 1];          // std::move_backward
+            v[first] = val;
+        } else {                                                     // __unguarded_linear_insert
+            int q = i;
+            while (knn_lt(val, v[q - 1])) { v[q] = v[q - 1]; --q; }
+            v[q] = val;
+        }
+    }
+}
+__device__ void knn_nth_element(KnnPair* v, int nth, int n) {
+    int first = 0, last = n;
+    if (first == last || nth == last) return;
+    int depth = (31 - __clz(n)) * 2;
+    while (last - first > 3) {
+        if (depth == 0) {
+            knn_heap_select(v + first, nth + 1 - first, last - first);
+            const KnnPair t = v[first]; v[first] = v[nth]; v[nth] = t;
+            return;
+        }
+        --depth;
+        const int cut = knn_partition_pivot(v, first, last);
+        if (cut <= nth) first = cut; else last = cut;
+    }
+    knn_insertion_sort(v, first, last);
+}
+
 __device__ __forceinline__ float cdist_row_norm16(const float* __restrict__ x) {
     float l[8];
 #pragma unroll
@@ -169,58 +275,61 @@ __device__ __forceinline__ float cdist_row_norm16(const float* __restrict__ x) {
     for (int i = 1; i < 8; ++i) s = __fadd_rn(s, l[i]);
     return s;
 }
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ float cdist_value(const float* xi_m2, float ni, const float* __restrict__ X, int j) {
+    float xj[KC_DIM];
+#pragma unroll
+    for (int c = 0; c < KC_DIM; ++c) xj[c] = X[(size_t)j * KC_DIM + c];
+    const float nj = cdist_row_norm16(xj);
+    float acc = __fmul_rn(xi_m2[0], xj[0]);                        // fma(a, b, 0)
+#pragma unroll
+    for (int c = 1; c < KC_DIM; ++c) acc = __fmaf_rn(xi_m2[c], xj[c], acc);
+    acc = __fmaf_rn(ni, 1.0f, acc);
+    acc = __fmaf_rn(1.0f, nj, acc);
+    return __fsqrt_rn(fmaxf(acc, 0.0f));                           // clamp_min_(0).sqrt_()
+}
+__global__ void __launch_bounds__(KNN_THREADS)
 ldp_knn_kernel(const float* __restrict__ X, int n, int k, long long* __restrict__ out)
 {
+    __shared__ KnnPair s_pair[KNN_SELECT_MAX];                     // selection path: the whole row; heap path: the heap
+    __shared__ float s_val[KNN_CHUNK];
     grid_dependency_sync();
-    const int lane = threadIdx.x & 31, row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= n) return;
+    const int row = blockIdx.x, tid = threadIdx.x;
     float xi[KC_DIM];
 #pragma unroll
     for (int j = 0; j < KC_DIM; ++j) xi[j] = X[(size_t)row * KC_DIM + j];
     const float ni = cdist_row_norm16(xi);
 #pragma unroll
     for (int j = 0; j < KC_DIM; ++j) xi[j] = __fmul_rn(xi[j], -2.0f);      // x1.mul(-2): exact
-    float bv[KNN_MAX_K];
-    int bi[KNN_MAX_K];
-#pragma unroll
-    for (int t = 0; t < KNN_MAX_K; ++t) { bv[t] = INFINITY; bi[t] = 0x7fffffff; }
-    for (int j = lane; j < n; j += 32) {
-        if (j == row) continue;                                    // dist.fill_diagonal_(inf)
-        float xj[KC_DIM];
-#pragma unroll
-        for (int c = 0; c < KC_DIM; ++c) xj[c] = X[(size_t)j * KC_DIM + c];
-        const float nj = cdist_row_norm16(xj);
-        float acc = __fmul_rn(xi[0], xj[0]);                       // fma(a, b, 0)
-#pragma unroll
-        for (int c = 1; c < KC_DIM; ++c) acc = __fmaf_rn(xi[c], xj[c], acc);
-        acc = __fmaf_rn(ni, 1.0f, acc);
-        acc = __fmaf_rn(1.0f, nj, acc);
-        float v = __fsqrt_rn(fmaxf(acc, 0.0f));                    // clamp_min_(0).sqrt_()
-        int vi = j;
-        // insert into this lane's ascending list (indices ascend within a lane, so ties keep the earlier one first)
-#pragma unroll
-        for (int t = 0; t < KNN_MAX_K; ++t) {
-            if (t < k && v < bv[t]) { const float tv = bv[t]; const int ti = bi[t]; bv[t] = v; bi[t] = vi; v = tv; vi = ti; }
+    if ((long long)k * 64 <= (long long)n) {
+        // std::partial_sort: only an element smaller than the heap's top moves anything, so the row is streamed
+        for (int base = 0; base < n; base += KNN_CHUNK) {
+            const int cnt = min(KNN_CHUNK, n - base);
+            for (int q = tid; q < cnt; q += KNN_THREADS) s_val[q] = (base + q == row) ? INFINITY : cdist_value(xi, ni, X, base + q);
+            __syncthreads();
+            if (tid == 0) {
+                int q = 0;
+                if (base == 0) {
+                    for (; q < k; ++q) { s_pair[q].v = s_val[q]; s_pair[q].i = q; }        // k <= 16 < KNN_CHUNK
+                    knn_make_heap(s_pair, k);
+                }
+                for (; q < cnt; ++q) {
+                    KnnPair e; e.v = s_val[q]; e.i = base + q;
+                    if (knn_lt(e, s_pair[0])) knn_adjust_heap(s_pair, 0, k, e);            // __pop_heap(first, middle, i)
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) knn_sort_heap(s_pair, k);
+    } else {                                                       // n < 64 k: the pairs fit
+        for (int j = tid; j < n; j += KNN_THREADS) { s_pair[j].v = (j == row) ? INFINITY : cdist_value(xi, ni, X, j); s_pair[j].i = j; }
+        __syncthreads();
+        if (tid == 0) {
+            knn_nth_element(s_pair, k - 1, n);
+            knn_insertion_sort(s_pair, 0, k - 1);                  // std::sort of k - 1 <= 15 elements is its insertion sort
         }
     }
-    // merge the 32 sorted lists: k rounds of a warp arg-min over the lanes' heads
-    for (int t = 0; t < k; ++t) {
-        float v = bv[0];
-        int i = bi[0], who = lane;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, i, o), ow = __shfl_xor_sync(0xffffffffu, who, o);
-            if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; who = ow; }
-        }
-        if (lane == 0) out[(size_t)row * k + t] = (long long)i;
-        if (lane == who) {                                          // pop the head
-#pragma unroll
-            for (int s = 0; s + 1 < KNN_MAX_K; ++s) { bv[s] = bv[s + 1]; bi[s] = bi[s + 1]; }
-            bv[KNN_MAX_K - 1] = INFINITY; bi[KNN_MAX_K - 1] = 0x7fffffff;
-        }
-    }
+    __syncthreads();
+    if (tid < k) out[(size_t)row * k + tid] = (long long)s_pair[tid].i;
 }
 
 }  // namespace ldp

@@ -700,17 +700,183 @@ def cdist_squared_f32(flat_poses: np.ndarray) -> np.ndarray:
     return acc
 
 
+# ---- torch.topk(largest=False) on a CPU row, including the order it leaves among EXACTLY equal values -------------------
+# ATen's CPU kernel (aten/src/ATen/native/cpu/SortingKernel.cpp, topk_impl_loop; not in /root/reference: torch 2.11 is the
+# reference's dependency) copies the row into (value, index) pairs and runs, with a comparator that looks at the value only
+# (NaN last),   k * 64 <= n :  std::partial_sort(begin, begin + k, end)
+#               otherwise   :  std::nth_element(begin, begin + k - 1, end) ; std::sort(begin, begin + k - 1)
+# Both are deterministic algorithms; which of several equal values end up in the first k places, and in what order, is decided
+# by their moves.  libstdc++'s versions (bits/stl_algo.h, bits/stl_heap.h: heap select + sort_heap; introselect with the
+# median-of-three pivot moved to the front, unguarded Hoare partition, insertion sort below four elements; introsort with a
+# threshold of 16) are restated below move for move.  Pinned against torch.topk itself on tie-heavy random rows
+# (tests/test_oracle_selection.py) and through the frozen neighbour tables of the live reference.
+
+def _topk_lt(x, y) -> bool:
+    a, b = x[0], y[0]
+    return ((a == a) and (b != b)) or a < b
+
+
+def _stl_push_heap(v, first, hole, top, value):
+    parent = (hole - 1) // 2
+    while hole > top and _topk_lt(v[first + parent], value):
+        v[first + hole] = v[first + parent]
+        hole = parent
+        parent = (hole - 1) // 2
+    v[first + hole] = value
+
+
+def _stl_adjust_heap(v, first, hole, length, value):
+    top = hole
+    child = hole
+    while child < (length - 1) // 2:
+        child = 2 * (child + 1)
+        if _topk_lt(v[first + child], v[first + child - 1]):
+            child -= 1
+        v[first + hole] = v[first + child]
+        hole = child
+    if (length & 1) == 0 and child == (length - 2) // 2:
+        child = 2 * (child + 1)
+        v[first + hole] = v[first + child - 1]
+        hole = child - 1
+    _stl_push_heap(v, first, hole, top, value)
+
+
+def _stl_make_heap(v, first, last):
+    length = last - first
+    if length < 2:
+        return
+    parent = (length - 2) // 2
+    while True:
+        _stl_adjust_heap(v, first, parent, length, v[first + parent])
+        if parent == 0:
+            return
+        parent -= 1
+
+
+def _stl_pop_heap(v, first, last, result):
+    value = v[result]
+    v[result] = v[first]
+    _stl_adjust_heap(v, first, 0, last - first, value)
+
+
+def _stl_heap_select(v, first, middle, last):
+    _stl_make_heap(v, first, middle)
+    for i in range(middle, last):
+        if _topk_lt(v[i], v[first]):
+            _stl_pop_heap(v, first, middle, i)
+
+
+def _stl_partial_sort(v, first, middle, last):
+    _stl_heap_select(v, first, middle, last)
+    while middle - first > 1:                       # std::__sort_heap
+        middle -= 1
+        _stl_pop_heap(v, first, middle, middle)
+
+
+def _stl_unguarded_partition_pivot(v, first, last):
+    mid = first + (last - first) // 2
+    a, b, c = first + 1, mid, last - 1              # std::__move_median_to_first(first, first + 1, mid, last - 1)
+    if _topk_lt(v[a], v[b]):
+        m = b if _topk_lt(v[b], v[c]) else (c if _topk_lt(v[a], v[c]) else a)
+    else:
+        m = a if _topk_lt(v[a], v[c]) else (c if _topk_lt(v[b], v[c]) else b)
+    v[first], v[m] = v[m], v[first]
+    lo, hi = first + 1, last                        # std::__unguarded_partition(first + 1, last, pivot = first)
+    while True:
+        while _topk_lt(v[lo], v[first]):
+            lo += 1
+        hi -= 1
+        while _topk_lt(v[first], v[hi]):
+            hi -= 1
+        if not lo < hi:
+            return lo
+        v[lo], v[hi] = v[hi], v[lo]
+        lo += 1
+
+
+def _stl_unguarded_linear_insert(v, last):
+    val = v[last]
+    nxt = last - 1
+    while _topk_lt(val, v[nxt]):
+        v[last] = v[nxt]
+        last = nxt
+        nxt -= 1
+    v[last] = val
+
+
+def _stl_insertion_sort(v, first, last):
+    for i in range(first + 1, last):
+        if _topk_lt(v[i], v[first]):
+            val = v[i]
+            v[first + 1:i + 1] = v[first:i]         # std::move_backward
+            v[first] = val
+        else:
+            _stl_unguarded_linear_insert(v, i)
+
+
+def _stl_nth_element(v, first, nth, last):
+    if first == last or nth == last:
+        return
+    depth = ((last - first).bit_length() - 1) * 2
+    while last - first > 3:
+        if depth == 0:
+            _stl_heap_select(v, first, nth + 1, last)
+            v[first], v[nth] = v[nth], v[first]
+            return
+        depth -= 1
+        cut = _stl_unguarded_partition_pivot(v, first, last)
+        if cut <= nth:
+            first = cut
+        else:
+            last = cut
+    _stl_insertion_sort(v, first, last)
+
+
+def _stl_sort(v, first, last):
+    def loop(first, last, depth):
+        while last - first > 16:
+            if depth == 0:
+                _stl_partial_sort(v, first, last, last)
+                return
+            depth -= 1
+            cut = _stl_unguarded_partition_pivot(v, first, last)
+            loop(cut, last, depth)
+            last = cut
+    if first == last:
+        return
+    loop(first, last, ((last - first).bit_length() - 1) * 2)
+    if last - first > 16:
+        _stl_insertion_sort(v, first, first + 16)
+        for i in range(first + 16, last):
+            _stl_unguarded_linear_insert(v, i)
+    else:
+        _stl_insertion_sort(v, first, last)
+
+
+def topk_smallest_like_torch(row, k: int) -> list:
+    """Indices ``torch.topk(row, k, largest=False)`` returns for a CPU row (see the block comment above)."""
+    n = len(row)
+    v = [(float(row[j]), j) for j in range(n)]
+    if k * 64 <= n:
+        _stl_partial_sort(v, 0, k, n)
+    else:
+        _stl_nth_element(v, 0, k - 1, n)
+        _stl_sort(v, 0, k - 1)
+    return [v[j][1] for j in range(k)]
+
+
 def nearest_neighbors_cdist(flat_poses: np.ndarray, k: int) -> np.ndarray:
-    """core/selection.py:57-70 with torch.cdist's own float32 arithmetic (``cdist_squared_f32``): the k nearest other views,
-    ascending by (distance, index).  Ring cameras have left / right neighbours at mathematically equal distance; which one
-    comes first is decided by the rounding of THIS formula, so it has to be mirrored to get the reference's table."""
+    """core/selection.py:57-70 with torch.cdist's own float32 arithmetic (``cdist_squared_f32``) and torch.topk's own
+    selection (``topk_smallest_like_torch``): the reference's neighbour table, index for index.  Ring cameras have left /
+    right neighbours at mathematically equal distance; which one comes first is decided by the rounding of cdist's formula
+    and, where the float32 distances are exactly equal, by the moves of std::partial_sort / std::nth_element."""
     n = int(np.asarray(flat_poses).shape[0])
     if n <= 1:
         return np.empty((n, 0), dtype=np.int64)
     k = max(1, min(int(k), n - 1))
     D = np.sqrt(np.maximum(cdist_squared_f32(flat_poses), np.float32(0.0)))
     np.fill_diagonal(D, np.inf)
-    return np.argsort(D, axis=1, kind="stable")[:, :k].astype(np.int64)
+    return np.asarray([topk_smallest_like_torch(D[i], k) for i in range(n)], dtype=np.int64)
 
 
 def voxel_downsample(xyz: np.ndarray, rgb: np.ndarray, voxel_size: float):
