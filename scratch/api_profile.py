@@ -37,3 +37,12 @@ for _ in range(10):
     PL.triangulate_refs(mrs, ctx, rng_streams=streams)
 pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
+# the bench's own loop: per-call wall times (the result of the previous call is alive while the next one runs)
+import time as _t
+ts = []
+for _ in range(12):
+    torch.cuda.synchronize()
+    t0 = _t.perf_counter()
+    res = PL.triangulate_refs(mrs, ctx, rng_streams=streams)
+    ts.append(round(1e3 * (_t.perf_counter() - t0), 2))
+print("per-call ms:", ts)
