@@ -494,10 +494,16 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     ++g_launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "ldp_draw_kernel<1>");
     {
-        // ---- rounds 2.., coverage, compaction: one cluster per view; the largest size for which every view's cluster
-        // is resident at once (GPC boundaries make this smaller than sm_count / n_refs, so ask the occupancy API)
+        // ---- rounds 2.., coverage, compaction: one cluster per view.  The kernel is a chain of latency-bound phases (table
+        // rebuild, a few hundred draws per round, bitmap compaction): one CTA per 2^18 pixels is as fast as more of them
+        // (measured: 46 views at 512^2, 1 vs 2 vs 4 CTAs: 24.9 / 24.9 / 37 us) and leaves the other SMs to the launches in
+        // flight beside this one (3 in flight: 0.143 -> 0.136 ms per step; 640^2, 32 views: 4 -> 2 CTAs 1.33 -> 1.28 ms per
+        // 250 views).  Capped by what is resident at once (GPC boundaries make that smaller than sm_count / n_refs: ask the
+        // occupancy API).
+        int want = 1;
+        while (want < 8 && (long long)want * (1 << 18) < (long long)plan.geom.N) want <<= 1;
         int csize = 1;
-        for (int c = 8; c > 1; --c) {
+        for (int c = want; c > 1; c >>= 1) {
             if ((long long)nsubrefs * c > sm_count()) continue;
             if (max_active_clusters(c, plan.k1_smem) >= nsubrefs) { csize = c; break; }
         }
