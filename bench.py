@@ -562,12 +562,17 @@ def gpu_arm(args) -> None:
         if depth > 1:
             for st in ring.streams:
                 main.wait_stream(st)
+        e_own = torch.cuda.Event(enable_timing=True)
+        e_own.record()                                   # this rank's own steps are done (diagnostic: before the exchange)
         if world > 1:
             mine = torch.stack([o.ref_offset[R] for o in outs])
             dist.all_gather_into_tensor(counts_all.view(-1), mine)
         e1.record()
         barrier()
+        own_ms[depth] = e0.elapsed_time(e_own)
         return e0.elapsed_time(e1), last
+
+    own_ms = {}
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -601,8 +606,15 @@ def gpu_arm(args) -> None:
     launches_per_step = o.launches
     total_pts = o.total_points()
     S_total = int(o.n_samples.sum().item())
+    per_rank_ms = None
     if world > 1:
         t = torch.tensor([ms_total, ms_single], dtype=torch.float64, device=dev)
+        mine_t = torch.tensor([own_ms.get(DEPTH, ms_total), own_ms.get(1, ms_single)], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(mine_t) for _ in range(world)]
+        dist.all_gather(allt, mine_t)
+        per_rank_ms = {"note": "each rank's own steps, before the count exchange that ends the timed region",
+                       "ms_per_step": [round(float(x[0].item()) / steps, 5) for x in allt],
+                       "ms_per_step_one_launch_at_a_time": [round(float(x[1].item()) / steps, 5) for x in allt]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_single = float(t[0].item()), float(t[1].item())
         c = torch.tensor([total_pts, S_total], dtype=torch.int64, device=dev)
@@ -679,7 +691,7 @@ def gpu_arm(args) -> None:
     if args.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": ms_step, "ms_per_step_one_launch_at_a_time": ms_single_step,
-                              "kernels_ms": kdict, "front_kernel_alone_ms": dom_ms,
+                              "kernels_ms": kdict, "front_kernel_alone_ms": dom_ms, "per_rank": per_rank_ms,
                               "k1_frac": achieved / peak, "path_frac": path_gbs / peak, "path_frac_one_at_a_time": path_gbs_single / peak}))
         if world > 1:
             dist.barrier()
@@ -790,6 +802,7 @@ def gpu_arm(args) -> None:
                                       "the timed region" if world > 1 else "none")},
             "pairs_per_sec": pairs_per_s, "points_per_step": total_pts_all, "samples_per_step": S_all,
             "ms_per_step_one_launch_at_a_time": ms_single_step,
+            "per_rank": per_rank_ms,          # every rank's own device-timed figures (value uses the maximum)
             "gpu_launches": launches_per_step * steps,
             "kernels_ms": kdict,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
