@@ -341,22 +341,28 @@ cudaError_t launch_front(const ldp_params* p, const ldp_ref_desc* refs, const ld
 // the first kernel of the path (also launched alone by ldp_debug_launch_stream for the roofline measurement)
 void launch_stream(const ldp_params* p, const ldp_ref_desc* refs, Plan& plan, cudaStream_t st, int nsubrefs) {
     const dim3 grid((unsigned)plan.ws.nblk, (unsigned)nsubrefs);
-    if (p->prologue) switch (p->nn_max) {      // raw matcher planes: post-processing fused into the read
-          case 1: (void)launch_k(ldp::ldp_stream_kernel<1, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 2: (void)launch_k(ldp::ldp_stream_kernel<2, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 3: (void)launch_k(ldp::ldp_stream_kernel<3, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 4: (void)launch_k(ldp::ldp_stream_kernel<4, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          default: (void)launch_k(ldp::ldp_stream_kernel<0, true>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-      } else switch (p->nn_max) {   // max neighbours per view in this launch (0 = unknown)
-          case 1: (void)launch_k(ldp::ldp_stream_kernel<1, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 2: (void)launch_k(ldp::ldp_stream_kernel<2, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 3: (void)launch_k(ldp::ldp_stream_kernel<3, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 4: (void)launch_k(ldp::ldp_stream_kernel<4, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 5: (void)launch_k(ldp::ldp_stream_kernel<5, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 6: (void)launch_k(ldp::ldp_stream_kernel<6, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 7: (void)launch_k(ldp::ldp_stream_kernel<7, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          case 8: (void)launch_k(ldp::ldp_stream_kernel<8, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
-          default: (void)launch_k(ldp::ldp_stream_kernel<0, false>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+    if (p->prologue && !p->no_warped_masks) switch (p->nn_max) {      // raw matcher planes: post-processing fused into the read
+          case 1: (void)launch_k(ldp::ldp_stream_kernel<1, 2>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 2: (void)launch_k(ldp::ldp_stream_kernel<2, 2>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 3: (void)launch_k(ldp::ldp_stream_kernel<3, 2>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 4: (void)launch_k(ldp::ldp_stream_kernel<4, 2>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          default: (void)launch_k(ldp::ldp_stream_kernel<0, 2>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+    } else if (p->prologue) switch (p->nn_max) {                      // ... and no neighbour mask anywhere: no warp row is read
+          case 1: (void)launch_k(ldp::ldp_stream_kernel<1, 1>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 2: (void)launch_k(ldp::ldp_stream_kernel<2, 1>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 3: (void)launch_k(ldp::ldp_stream_kernel<3, 1>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 4: (void)launch_k(ldp::ldp_stream_kernel<4, 1>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          default: (void)launch_k(ldp::ldp_stream_kernel<0, 1>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+    } else switch (p->nn_max) {
+          case 1: (void)launch_k(ldp::ldp_stream_kernel<1, 0>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 2: (void)launch_k(ldp::ldp_stream_kernel<2, 0>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 3: (void)launch_k(ldp::ldp_stream_kernel<3, 0>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 4: (void)launch_k(ldp::ldp_stream_kernel<4, 0>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 5: (void)launch_k(ldp::ldp_stream_kernel<5, 0>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 6: (void)launch_k(ldp::ldp_stream_kernel<6, 0>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 7: (void)launch_k(ldp::ldp_stream_kernel<7, 0>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          case 8: (void)launch_k(ldp::ldp_stream_kernel<8, 0>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
+          default: (void)launch_k(ldp::ldp_stream_kernel<0, 0>, dim3(grid), dim3(ldp::KS_THREADS), 0, st, *p, refs, plan.ws, plan.geom); break;
       }
 }
 

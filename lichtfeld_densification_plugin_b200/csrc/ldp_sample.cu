@@ -106,8 +106,10 @@ __device__ __forceinline__ void quad_border_weights(float wv[4], int px, int x, 
 // in flight; 0: any nn (pointers in shared memory).
 // PRO: the planes are raw matcher outputs and the reference's post-processing (core/pipeline.py:405-430) is applied
 //      to every value as it is read (ldp_device.cuh:prologue_cert).
-template <int NNMAX, bool PRO>
-__global__ void __launch_bounds__(KS_THREADS, PRO ? 3 : (NNMAX > 4 ? 4 : KS_MIN_BLOCKS))      // PRO holds the warp rows too: more registers
+//      PRO = 1: no view of the launch has a neighbour mask (ldp_params.no_warped_masks): clamp and reference-view mask only - no warp
+//      row is read, registers and occupancy stay those of the plain kernel; PRO = 2: warped neighbour masks as well.
+template <int NNMAX, int PRO>
+__global__ void __launch_bounds__(KS_THREADS, PRO == 2 ? 3 : (NNMAX > 4 ? 4 : KS_MIN_BLOCKS))      // PRO 2 holds the warp rows too: more registers
 ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const Workspace ws, const SampleGeom G)
 {
     grid_dependency_sync();
@@ -191,7 +193,7 @@ ldp_stream_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
             c.x = (c.x < fl) ? fl : c.x; c.y = (c.y < fl) ? fl : c.y;               // torch.clamp(min=): NaN stays NaN
             c.z = (c.z < fl) ? fl : c.z; c.w = (c.w < fl) ? fl : c.w;
             if (has_a) { c.x = __fmul_rn(c.x, ma[0]); c.y = __fmul_rn(c.y, ma[1]); c.z = __fmul_rn(c.z, ma[2]); c.w = __fmul_rn(c.w, ma[3]); }
-            const uint8_t* mb = s_pv.mask_b[k];
+            const uint8_t* mb = (PRO == 2) ? s_pv.mask_b[k] : nullptr;
             if (mb) {                                                              // (xB, yB) of the 4 rows: read once, evict-first
                 const float2* g = reinterpret_cast<const float2*>(s_pv.warp[k] + (size_t)px * 4 + 2);
                 const float2 g0 = __ldcs(g), g1 = __ldcs(g + 2), g2 = __ldcs(g + 4), g3 = __ldcs(g + 6);
