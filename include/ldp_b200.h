@@ -80,8 +80,9 @@ typedef struct ldp_params {
                                   (nearest, zeros outside, align_corners = False).  0: planes are already processed */
     float certainty_floor;     /* f32(config.certainty_thresh), core/pipeline.py:407; read only if prologue */
     int32_t no_warped_masks;   /* prologue only.  1: the caller guarantees that every ldp_ref_desc.mask_b[k] of the launch is NULL
-                                  (no neighbour masks to sample through the warp), which lets the single fused front kernel
-                                  take raw planes too; 0: unknown -- the two-kernel path that reads the warp planes is used */
+                                  (no neighbour masks to sample through the warp): the first kernel's instantiation that reads
+                                  no warp row runs, with the plain kernel's registers and occupancy (and the experimental fused
+                                  front kernel may take raw planes); 0: unknown -- the instantiation that reads the warp planes */
     uint64_t seed;             /* Philox key */
     int64_t uniforms_per_ref;  /* explicit mode: doubles available per reference view */
     int32_t sm_reserve;        /* SMs the one-CTA-per-SM first draw kernel leaves to kernels of OTHER launches in flight on other
