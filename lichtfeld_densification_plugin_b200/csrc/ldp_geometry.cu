@@ -20,11 +20,14 @@
 
 namespace ldp {
 
-constexpr int K2_THREADS = 128;
+#ifndef K2_TILE
+#define K2_TILE 128
+#endif
+constexpr int K2_THREADS = K2_TILE;
 #ifndef K2_MIN_BLOCKS
 #define K2_MIN_BLOCKS 8
 #endif
-constexpr int K3_THREADS = 128;
+constexpr int K3_THREADS = K2_TILE;
 constexpr int KFIX_BLOCKS = 148;
 // np.degrees on float32 multiplies by f32(180) / f32(pi) evaluated in f32 (measured)
 #define RAD2DEG_F32 57.295776367187500f
