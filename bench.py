@@ -719,64 +719,87 @@ def gpu_arm(args) -> None:
     h_cert = cert.cpu().pin_memory()
     h_img = image.cpu().pin_memory()
     h_warp = warp.cpu().pin_memory()
-    d_cert = torch.empty_like(cert)
-    d_img = torch.empty_like(image)
+    # Two sets of device buffers: the upload of step i + 1 starts the moment step i's upload ends (the link never idles between
+    # steps), while step i's last kernels and its read-back are still running; every step's own H2D copies, kernels and D2H
+    # read are inside the timed region, its result is read one step later (and the last one before the clock stops).
+    SETS = 2
+    d_cert = [torch.empty_like(cert) for _ in range(SETS)]
+    d_img = [torch.empty_like(image) for _ in range(SETS)]
     bounds = [(R * g // E2E_CHUNKS, R * (g + 1) // E2E_CHUNKS) for g in range(E2E_CHUNKS)]
-    e2e_batches = [slots[0].batch(eng, scene, lo, hi, stream_base=rank * R, cert=d_cert, warp=h_warp, image=d_img) for lo, hi in bounds]
-    e2e_descs = [eng.upload_descs(b) for b in e2e_batches]
-    e2e_outs = [eng.alloc_outputs(hi - lo, sel_cap) for lo, hi in bounds]
+    e2e_batches = [[slots[0].batch(eng, scene, lo, hi, stream_base=rank * R, cert=d_cert[q], warp=h_warp, image=d_img[q])
+                    for lo, hi in bounds] for q in range(SETS)]
+    e2e_descs = [[eng.upload_descs(b) for b in e2e_batches[q]] for q in range(SETS)]
+    e2e_outs = [[eng.alloc_outputs(hi - lo, sel_cap) for lo, hi in bounds] for q in range(SETS)]
     copy_stream = torch.cuda.Stream(dev)
     back_stream = torch.cuda.Stream(dev)
-    copied = [torch.cuda.Event() for _ in bounds]
-    computed = [torch.cuda.Event() for _ in bounds]
+    copied = [[torch.cuda.Event() for _ in bounds] for _ in range(SETS)]
+    computed = [[torch.cuda.Event() for _ in bounds] for _ in range(SETS)]
+    read_back = [torch.cuda.Event() for _ in range(SETS)]
     # a group's whole packed result (offsets | xyz | rgb | err, padded to capacity) goes back in ONE device->host copy on
     # a third stream as soon as the group is done: no intermediate synchronisation to learn the counts first, and the
     # copy runs in the other PCIe direction while the next groups are still being uploaded
-    h_packed = [torch.empty_like(o.packed, device="cpu").pin_memory() for o in e2e_outs]
+    h_packed = [[torch.empty_like(o.packed, device="cpu").pin_memory() for o in e2e_outs[q]] for q in range(SETS)]
 
-    def e2e_step():
+    def e2e_submit(q):
+        """enqueue one step on buffer set q: uploads, launches, read-back; no host synchronisation"""
         main = torch.cuda.current_stream(dev)
-        copy_stream.wait_stream(main)
+        copy_stream.wait_event(computed[q][-1])          # the set's previous user has read its inputs (no-op the first time)
         with torch.cuda.stream(copy_stream):
             for g, (lo, hi) in enumerate(bounds):
-                d_cert[lo:hi].copy_(h_cert[lo:hi], non_blocking=True)
-                d_img[lo:hi].copy_(h_img[lo:hi], non_blocking=True)
-                copied[g].record(copy_stream)
+                d_cert[q][lo:hi].copy_(h_cert[lo:hi], non_blocking=True)
+                d_img[q][lo:hi].copy_(h_img[lo:hi], non_blocking=True)
+                copied[q][g].record(copy_stream)
+        back_stream.wait_event(read_back[q])             # ... and its results have left (host buffers of the set are reused)
         for g in range(E2E_CHUNKS):
-            main.wait_event(copied[g])
-            eng.densify(e2e_batches[g], cfg, descs_dev=e2e_descs[g], outputs=e2e_outs[g])
-            computed[g].record(main)
+            main.wait_event(copied[q][g])
+            eng.densify(e2e_batches[q][g], cfg, descs_dev=e2e_descs[q][g], outputs=e2e_outs[q][g])
+            computed[q][g].record(main)
             with torch.cuda.stream(back_stream):
-                back_stream.wait_event(computed[g])
-                h_packed[g].copy_(e2e_outs[g].packed, non_blocking=True)
-        back_stream.synchronize()
+                back_stream.wait_event(computed[q][g])
+                h_packed[q][g].copy_(e2e_outs[q][g].packed, non_blocking=True)
+        read_back[q].record(back_stream)
+
+    def e2e_finish(q):
+        """the result the caller reads: per-group offsets from the host copy of set q"""
+        read_back[q].synchronize()
         n = 0
-        for g, (lo, hi) in enumerate(bounds):          # the result the caller reads: per-group offsets from the host copy
-            n += int(h_packed[g][:8 * (hi - lo + 1)].view(torch.int64)[-1])
+        for g, (lo, hi) in enumerate(bounds):
+            n += int(h_packed[q][g][:8 * (hi - lo + 1)].view(torch.int64)[-1])
+        return n
+
+    def e2e_run(n_steps):
+        n = 0
+        e2e_submit(0)
+        for i in range(1, n_steps):
+            e2e_submit(i % SETS)
+            n = e2e_finish((i - 1) % SETS)
+        n = e2e_finish((n_steps - 1) % SETS)
         return n
 
     _dbg("e2e setup done")
     e2e_steps = max(3, min(steps, 20))
-    for _ in range(3):
-        n_e2e = e2e_step()
+    n_e2e = e2e_run(3)
+    torch.cuda.synchronize(dev)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        n_e2e = e2e_step()
+    n_e2e = e2e_run(e2e_steps)
     torch.cuda.synchronize(dev)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    S_e2e = int(sum(int(o.n_samples.sum().item()) for o in e2e_outs))
+    e2e_outs_flat = e2e_outs[0]
+    S_e2e = int(sum(int(o.n_samples.sum().item()) for o in e2e_outs_flat))
     e2e = {"value": world * n_e2e / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": int(h_cert.numel() * 4 + h_img.numel() + S_e2e * 16),
-           "d2h_bytes_per_step": int(sum(h.numel() for h in h_packed)), "ms_per_step": 1e3 * e2e_s,
+           "d2h_bytes_per_step": int(sum(h.numel() for h in h_packed[0])), "ms_per_step": 1e3 * e2e_s,
            "note": f"cert planes + ref images copied H2D from pinned memory in {E2E_CHUNKS} groups of views, the copy of a "
                    "group overlapping the kernels of the previous one; warp planes stay pinned on the host and only the "
                    "sampled rows (16 B each) are gathered over PCIe; each group's packed result (offsets, xyz, rgb, err, padded to "
-                   "capacity) is copied D2H on a third stream as soon as the group is done"}
+                   "capacity) is copied D2H on a third stream as soon as the group is done; two sets of device buffers: a step's "
+                   "upload starts when the previous step's upload ends, its result is read on the host one step later (every "
+                   "step's H2D, kernels, D2H and host read are inside the timed region)"}
 
     # the second roofline of the path: it executes ~78 M warp instructions per step (f64 cdf arithmetic, exact comparisons,
     # per-sample eigenvectors), which bounds it by instruction issue well before HBM: 148 SMs x 4 schedulers x SM clock
