@@ -269,7 +269,7 @@ def config5_block(args, dev, rank: int, world: int, ring) -> dict:
     from lichtfeld_densification_plugin_b200.output import ConcatPlan, PackedCloud
 
     scene = synth.make_scene(CONFIG5["n_views"], CONFIG5["setting"], CONFIG5["ref_fraction"], CONFIG5["nn"])
-    R_all, per = scene.n_refs, CONFIG5["refs_per_launch"]
+    R_all, per = scene.n_refs, int(os.environ.get("BENCH_C5_REFS_PER_LAUNCH", CONFIG5["refs_per_launch"]))
     cfg = PathConfig(matches_per_ref=CONFIG5["M"], seed=5)
     eng0 = ring.engines[0]
     sel_cap = eng0.sel_capacity(cfg.matches_per_ref)
@@ -395,6 +395,20 @@ def config5_block(args, dev, rank: int, world: int, ring) -> dict:
         k = ref_cloud.total_points()
         same = bool(k == n_total and torch.equal(ref_cloud.xyz[:k], total.xyz[:k]) and torch.equal(ref_cloud.rgb[:k], total.rgb[:k])
                     and torch.equal(ref_cloud.err[:k], total.err[:k]))
+        if not same and world == 1 and os.environ.get("BENCH_DEBUG"):
+            def per_view(os_, chunks_):
+                d = {}
+                for o_, (a_, b_) in zip(os_, chunks_):
+                    off_ = o_.ref_offset.cpu().numpy(); ns_ = o_.n_samples.cpu().numpy(); st_ = o_.status.cpu().numpy()
+                    ws_ = o_.weight_sum.cpu().numpy(); uu_ = o_.uniforms_used.cpu().numpy(); rr_ = o_.rounds.cpu().numpy()
+                    for r_ in range(b_ - a_):
+                        d[a_ + r_] = (int(ns_[r_]), int(st_[r_]), int(off_[r_ + 1] - off_[r_]), float(ws_[r_]), int(uu_[r_]), int(rr_[r_]))
+                return d
+            mine = per_view(shard.outs, shard.chunks)
+            alt = per_view(outs, [(a_, min(a_ + per_alt, R_all)) for a_ in range(0, R_all, per_alt)])
+            bad = [v for v in range(R_all) if mine[v] != alt[v]]
+            print("[bench] config5 cut check: views that differ (n_samples, status, kept):", [(v, mine[v], alt[v]) for v in bad[:10]],
+                  "totals", n_total, k, file=sys.stderr)
         h = hashlib.sha1()
         for a in (total.xyz[:n_total], total.rgb[:n_total], total.err[:n_total]):
             h.update(a.cpu().numpy().tobytes())

@@ -277,6 +277,7 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     w.flags = reinterpret_cast<uint8_t*>(carve(R * w.sel_cap));
     w.topk_keys = reinterpret_cast<unsigned long long*>(carve(R * w.topk_cap * sizeof(unsigned long long)));
     w.csum = reinterpret_cast<double*>(carve(R * w.nchunk_pad * sizeof(double)));
+    w.crem = reinterpret_cast<double*>(carve(R * w.nchunk_pad * sizeof(double)));
     w.dbgclk = reinterpret_cast<long long*>(carve(R * 32 * sizeof(long long)));
     plan->nb2 = (int)((w.sel_cap + ldp::K2_THREADS - 1) / ldp::K2_THREADS);
     w.blk_cnt = reinterpret_cast<int32_t*>(carve(R * plan->nb2 * LDP_MAX_NN * sizeof(int32_t)));

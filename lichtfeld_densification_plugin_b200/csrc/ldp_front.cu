@@ -416,6 +416,10 @@ ldp_front_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, cons
             const int wi = base / 32 + tid;
             if (wi < (int)ws.n_words) ws.bitmap[(size_t)r * ws.n_words + wi] = 0u;
         }
+        if (tid >= 64 && tid < 64 + (KF_TILE >> 5)) {      // ... and the round-1 mass table of its chunks (chunks hold >= 32 pixels)
+            const int ci = (base >> G.chunk_shift) + (tid - 64);
+            if (ci < ((base + KF_TILE + (1 << G.chunk_shift) - 1) >> G.chunk_shift) && ci < (int)ws.nchunk_pad) ws.crem[(size_t)r * ws.nchunk_pad + ci] = 0.0;
+        }
         uint32_t parity = 0u;
 #pragma unroll
         for (int q = 0; q < KF_STAGES; ++q) if (q == stg) { parity = uses[q] & 1u; ++uses[q]; }

@@ -316,9 +316,11 @@ ldp_prep_generic_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ ref
                         const SampleGeom G)
 {
     grid_dependency_sync();
-    {   // the draw kernels' selection bitmap: cleared here, one kernel ahead of its first use
+    {   // the draw kernels' selection bitmap and round-1 mass table: cleared here, one kernel ahead of their first use
         uint32_t* bm = ws.bitmap + (size_t)(blockIdx.y + G.ref0) * ws.n_words;
         for (int i = blockIdx.x * KS_THREADS + threadIdx.x; i < (int)ws.n_words; i += gridDim.x * KS_THREADS) bm[i] = 0u;
+        double* cr = ws.crem + (size_t)(blockIdx.y + G.ref0) * ws.nchunk_pad;
+        for (int i = blockIdx.x * KS_THREADS + threadIdx.x; i < (int)ws.nchunk_pad; i += gridDim.x * KS_THREADS) cr[i] = 0.0;
     }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int red_i[32];
@@ -482,9 +484,11 @@ ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 const SampleGeom G)
 {
     grid_dependency_sync();
-    {   // the draw kernels' selection bitmap: cleared here, one kernel ahead of its first use
+    {   // the draw kernels' selection bitmap and round-1 mass table: cleared here, one kernel ahead of their first use
         uint32_t* bm = ws.bitmap + (size_t)(blockIdx.y + G.ref0) * ws.n_words;
         for (int i = blockIdx.x * KS_THREADS + threadIdx.x; i < (int)ws.n_words; i += gridDim.x * KS_THREADS) bm[i] = 0u;
+        double* cr = ws.crem + (size_t)(blockIdx.y + G.ref0) * ws.nchunk_pad;
+        for (int i = blockIdx.x * KS_THREADS + threadIdx.x; i < (int)ws.nchunk_pad; i += gridDim.x * KS_THREADS) cr[i] = 0.0;
     }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int red_i[32];
@@ -735,6 +739,11 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     int32_t* __restrict__ fcnt = ws.fcnt + (size_t)r * ws.draw_cmax;
     int32_t* __restrict__ sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
     double* __restrict__ gcsum = ws.csum + (size_t)r * ws.nchunk_pad;
+    double* __restrict__ gcrem = ws.crem + (size_t)r * ws.nchunk_pad;
+    // where a found pixel's mass is accounted: round 1 (independent CTAs that may start at different times and all need the
+    // chunk sums as the prep kernel left them) in the side table, later rounds (one cluster, barriers between rounds) in place
+    double* __restrict__ gmass = (MODE == 1) ? gcrem : gcsum;
+    const double mass_sign = (MODE == 1) ? 1.0 : -1.0;
     const unsigned long long* __restrict__ gb = ws.gbins + (size_t)r * ws.bins_cap;
     const uint32_t* __restrict__ gone = (MODE == 2) ? ws.gone + (size_t)r * ws.n_words : nullptr;   // drawn in round 1
 
@@ -801,6 +810,20 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             for (int j = 0; j < 4; ++j) {
                 const int i = i0 + 2 * j * T;
                 d[j] = (i < nchunk) ? __ldcg(reinterpret_cast<const double2*>(gcsum + i)) : make_double2(0.0, 0.0);   // nchunk_pad is even
+            }
+            if (MODE == 2 && rounds == 1) {
+                // first table after round 1: its finds' mass (side table) leaves the chunk sums now.  Exact f64 arithmetic, so the
+                // difference is what subtracting find by find gives; every CTA of the cluster forms it for its own table, the
+                // first one also writes it back for the later rounds (whose own removals start after the barrier below)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + 2 * j * T;
+                    if (i < nchunk) {
+                        const double2 rm = __ldcg(reinterpret_cast<const double2*>(gcrem + i));
+                        d[j].x -= rm.x; d[j].y -= rm.y;
+                        if (crank == 0) *reinterpret_cast<double2*>(gcsum + i) = d[j];
+                    }
+                }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -1077,13 +1100,13 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 if (fresh0) {
                     flist[basepos + __popc(fm0 & below_mask)] = ii[0];
 #ifndef LDP_EXP_NORED
-                    red_add_f64(gcsum + (ii[0] >> cs), -widen_pos(hp[0]));      // the found mass leaves the chunk sum
+                    red_add_f64(gmass + (ii[0] >> cs), mass_sign * widen_pos(hp[0]));      // the found mass leaves the chunk sum
 #endif
                 }
                 if (fresh1) {
                     flist[basepos + n0 + __popc(fm1 & below_mask)] = ii[1];
 #ifndef LDP_EXP_NORED
-                    red_add_f64(gcsum + (ii[1] >> cs), -widen_pos(hp[1]));
+                    red_add_f64(gmass + (ii[1] >> cs), mass_sign * widen_pos(hp[1]));
 #endif
                 }
             }

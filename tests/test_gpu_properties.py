@@ -449,3 +449,56 @@ def test_ring_of_launches_gives_the_same_results(engine, fast_scene):
         xyz, rgb, off = want[idx % len(cuts)]
         k = int(off[-1])
         assert torch.equal(o.ref_offset, off) and torch.equal(o.xyz[:k], xyz) and torch.equal(o.rgb[:k], rgb), idx
+
+
+def test_launches_in_flight_with_late_starting_draw_ctas(engine):
+    """Regression: the first draw round of a view runs on several independent CTAs that build their search tables from the
+    view's chunk sums whenever they happen to start; with three launches in flight and more draw CTAs than SMs some start
+    after their siblings have found pixels.  The chunk sums must still read as the prep kernel left them (round-1 finds are
+    accounted in a side table).  BASELINE config-5 shapes (640^2, 42 views per launch: 126 one-CTA-per-SM draw CTAs per
+    launch), four passes of six launches back to back on the ring, against one engine running the launches one by one."""
+    from lichtfeld_densification_plugin_b200 import synth
+    from lichtfeld_densification_plugin_b200.engine import DensifyRing, PathConfig
+    dev = engine.device
+    scene = synth.make_scene(1000, "base", 0.25, 4)
+    R, per = scene.n_refs, 42
+    cfg = PathConfig(matches_per_ref=10000, seed=5)
+    inputs = [synth.synth_ref_inputs(scene, rp, device=dev, cert_family="R", seed=500) for rp in range(R)]
+
+    def batch_for(eng, lo, hi):
+        b = eng.new_batch(scene.H, scene.W, scene.w_match, scene.h_match)
+        for rp in range(lo, hi):
+            inp = inputs[rp]
+            k = len(inp["nbr_indices"])
+            b.add([inp["cert"][q] for q in range(k)], [inp["warp"][q] for q in range(k)], inp["image"],
+                  scene.cameras[inp["ref_index"]], [scene.cameras[j] for j in inp["nbr_indices"]], rng_stream=rp)
+        return b
+    chunks = [(a, min(a + per, R)) for a in range(0, R, per)]
+    sel_cap = engine.sel_capacity(cfg.matches_per_ref)
+    want = []
+    for lo, hi in chunks:
+        o = engine.densify(batch_for(engine, lo, hi), cfg)
+        torch.cuda.synchronize()
+        k = o.total_points()
+        want.append((o.n_samples.clone(), o.uniforms_used.clone(), o.ref_offset.clone(), o.xyz[:k].clone()))
+    ring = DensifyRing(dev, depth=3)
+    outs = [engine.alloc_outputs(hi - lo, sel_cap) for lo, hi in chunks]
+    prepared = []
+    for c, (lo, hi) in enumerate(chunks):
+        e = ring.engines[c % 3]
+        b = batch_for(e, lo, hi)
+        prepared.append((c % 3, e.prepare(b, cfg, descs_dev=e.upload_descs(b), outputs=outs[c])))
+    main = torch.cuda.current_stream(dev)
+    for _ in range(4):                                   # no host synchronisation between the passes
+        for st in ring.streams:
+            st.wait_stream(main)
+        for j, p in prepared:
+            with torch.cuda.stream(ring.streams[j]):
+                p.launch()
+        for st in ring.streams:
+            main.wait_stream(st)
+    torch.cuda.synchronize()
+    for c, o in enumerate(outs):
+        ns, uu, off, xyz = want[c]
+        assert torch.equal(o.n_samples, ns) and torch.equal(o.uniforms_used, uu), (c, (o.uniforms_used != uu).nonzero().flatten().tolist())
+        assert torch.equal(o.ref_offset, off) and torch.equal(o.xyz[:int(off[-1])], xyz), c
