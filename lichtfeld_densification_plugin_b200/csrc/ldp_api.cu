@@ -277,7 +277,7 @@ int make_plan(const ldp_params* p, void* base, Plan* plan) {
     w.flags = reinterpret_cast<uint8_t*>(carve(R * w.sel_cap));
     w.topk_keys = reinterpret_cast<unsigned long long*>(carve(R * w.topk_cap * sizeof(unsigned long long)));
     w.csum = reinterpret_cast<double*>(carve(R * w.nchunk_pad * sizeof(double)));
-    w.crem = reinterpret_cast<double*>(carve(R * w.nchunk_pad * sizeof(double)));
+    w.csum0 = reinterpret_cast<double*>(carve(R * w.nchunk_pad * sizeof(double)));
     w.dbgclk = reinterpret_cast<long long*>(carve(R * 32 * sizeof(long long)));
     plan->nb2 = (int)((w.sel_cap + ldp::K2_THREADS - 1) / ldp::K2_THREADS);
     w.blk_cnt = reinterpret_cast<int32_t*>(carve(R * plan->nb2 * LDP_MAX_NN * sizeof(int32_t)));
@@ -396,6 +396,7 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     if (plan.use_front) {
         if (plan.geom.chunk_shift > 7) {      // chunk sums are accumulated with atomics: start from zero
             e = cudaMemsetAsync(plan.ws.csum, 0, (size_t)nsubrefs * plan.ws.nchunk_pad * sizeof(double), st);
+            if (e == cudaSuccess) e = cudaMemsetAsync(plan.ws.csum0, 0, (size_t)nsubrefs * plan.ws.nchunk_pad * sizeof(double), st);
             if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(csum)");
         }
         { KernelTimer kt(st, "ldp_front_kernel");
@@ -466,6 +467,8 @@ int launch_sample(const ldp_params* p, const ldp_ref_desc* refs, const double* u
     if (!plan.use_front) {
     if (plan.geom.chunk_shift > 7) {      // chunk sums are accumulated with atomics: start from zero
         e = cudaMemsetAsync(plan.ws.csum + (size_t)ref0 * plan.ws.nchunk_pad, 0, (size_t)nsubrefs * plan.ws.nchunk_pad * sizeof(double), st);
+        if (e == cudaSuccess)
+            e = cudaMemsetAsync(plan.ws.csum0 + (size_t)ref0 * plan.ws.nchunk_pad, 0, (size_t)nsubrefs * plan.ws.nchunk_pad * sizeof(double), st);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(csum)");
     }
     { KernelTimer kt(st, "ldp_prep_kernel");

@@ -35,10 +35,9 @@ struct Workspace {
     int32_t* kept;       // [R]           kept points (atomic)
     unsigned long long* topk_keys;  // [R][topk_cap] no_filter candidate keys
     double* csum;        // [R][nchunk_pad] f64 sums of p per chunk
-    double* crem;        // [R][nchunk_pad] f64 mass of the pixels found in round 1, per chunk (zeroed by the prep kernel).  The
-                         //   independent CTAs of a view's first round build their tables from csum whenever they start: csum
-                         //   must stay as the prep kernel left it until all of them are done, so they account what they find here
-                         //   and the second draw kernel folds it into csum before round 2
+    double* csum0;       // [R][nchunk_pad] the same sums, written by the prep kernel and never modified: what the first draw round
+                         //   searches.  Its independent CTAs start whenever an SM is free - also after their siblings have removed
+                         //   their first finds from csum - and numpy's first round draws from the cdf of ALL weights
     double* partial;     // [R][nblk]    per-CTA f64 partial weight sums of the stream kernel
     int32_t* bflags;     // [R][nblk]    per-CTA NaN / negative flags
     RefStat* rstat;      // [R]

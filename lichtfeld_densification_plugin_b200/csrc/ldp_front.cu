@@ -247,6 +247,7 @@ ldp_front_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, cons
         const bool fast_div = (s >= 1.0f) && (s < 3.0e8f);
         float* __restrict__ w = ws.w + (size_t)r * ws.n_pad;
         double* __restrict__ csum = ws.csum + (size_t)r * ws.nchunk_pad;
+        double* __restrict__ csum0 = ws.csum0 + (size_t)r * ws.nchunk_pad;
         int lpos = 0;
         uint32_t lmin1 = 0xFFFFFFFFu;
         double a = 0.0;
@@ -306,11 +307,11 @@ ldp_front_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, cons
         if (cs <= 7) {
             const int gl = (1 << cs) >> 2;
             for (int o = 1; o < gl; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (px < N && (lane & (gl - 1)) == 0) csum[px >> cs] = a;
+            if (px < N && (lane & (gl - 1)) == 0) { csum[px >> cs] = a; csum0[px >> cs] = a; }
         } else {                                           // chunks wider than a warp row (zeroed by the host memset)
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (px < N && lane == 0) atomicAdd(&csum[px >> cs], a);
+            if (px < N && lane == 0) { atomicAdd(&csum[px >> cs], a); atomicAdd(&csum0[px >> cs], a); }
         }
         // positives / smallest positive exponent: one combined block reduction
         lpos = warp_sum(lpos);
@@ -415,10 +416,6 @@ ldp_front_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, cons
         if (tid < KF_TILE / 32) {                          // the draw kernels' selection bitmap of this tile's pixels
             const int wi = base / 32 + tid;
             if (wi < (int)ws.n_words) ws.bitmap[(size_t)r * ws.n_words + wi] = 0u;
-        }
-        if (tid >= 64 && tid < 64 + (KF_TILE >> 5)) {      // ... and the round-1 mass table of its chunks (chunks hold >= 32 pixels)
-            const int ci = (base >> G.chunk_shift) + (tid - 64);
-            if (ci < ((base + KF_TILE + (1 << G.chunk_shift) - 1) >> G.chunk_shift) && ci < (int)ws.nchunk_pad) ws.crem[(size_t)r * ws.nchunk_pad + ci] = 0.0;
         }
         uint32_t parity = 0u;
 #pragma unroll

@@ -316,11 +316,9 @@ ldp_prep_generic_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ ref
                         const SampleGeom G)
 {
     grid_dependency_sync();
-    {   // the draw kernels' selection bitmap and round-1 mass table: cleared here, one kernel ahead of their first use
+    {   // the draw kernels' selection bitmap: cleared here, one kernel ahead of its first use
         uint32_t* bm = ws.bitmap + (size_t)(blockIdx.y + G.ref0) * ws.n_words;
         for (int i = blockIdx.x * KS_THREADS + threadIdx.x; i < (int)ws.n_words; i += gridDim.x * KS_THREADS) bm[i] = 0u;
-        double* cr = ws.crem + (size_t)(blockIdx.y + G.ref0) * ws.nchunk_pad;
-        for (int i = blockIdx.x * KS_THREADS + threadIdx.x; i < (int)ws.nchunk_pad; i += gridDim.x * KS_THREADS) cr[i] = 0.0;
     }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int red_i[32];
@@ -368,6 +366,7 @@ ldp_prep_generic_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ ref
 
     float* __restrict__ w = ws.w + (size_t)r * ws.n_pad;
     double* __restrict__ csum = ws.csum + (size_t)r * ws.nchunk_pad;
+    double* __restrict__ csum0 = ws.csum0 + (size_t)r * ws.nchunk_pad;      // the copy the first draw round searches (see Workspace)
     const int cs = G.chunk_shift;
     const int gl = min(32, (1 << cs) >> 2);            // lanes that share one chunk
     int lpos = 0;
@@ -427,8 +426,8 @@ ldp_prep_generic_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ ref
         }
         for (int o = 1; o < gl; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if (px < N && (lane & (gl - 1)) == 0) {
-            if (cs <= 7) csum[px >> cs] = a;
-            else atomicAdd(&csum[px >> cs], a);          // chunks wider than a warp-row (zeroed by the host memset)
+            if (cs <= 7) { csum[px >> cs] = a; csum0[px >> cs] = a; }
+            else { atomicAdd(&csum[px >> cs], a); atomicAdd(&csum0[px >> cs], a); }      // chunks wider than a warp-row (zeroed by the host memset)
         }
     }
     const int npos = block_sum(lpos, red_i);
@@ -484,11 +483,9 @@ ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 const SampleGeom G)
 {
     grid_dependency_sync();
-    {   // the draw kernels' selection bitmap and round-1 mass table: cleared here, one kernel ahead of their first use
+    {   // the draw kernels' selection bitmap: cleared here, one kernel ahead of its first use
         uint32_t* bm = ws.bitmap + (size_t)(blockIdx.y + G.ref0) * ws.n_words;
         for (int i = blockIdx.x * KS_THREADS + threadIdx.x; i < (int)ws.n_words; i += gridDim.x * KS_THREADS) bm[i] = 0u;
-        double* cr = ws.crem + (size_t)(blockIdx.y + G.ref0) * ws.nchunk_pad;
-        for (int i = blockIdx.x * KS_THREADS + threadIdx.x; i < (int)ws.nchunk_pad; i += gridDim.x * KS_THREADS) cr[i] = 0.0;
     }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int red_i[32];
@@ -543,6 +540,7 @@ ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     LDP_PCLK(1);
 
     double* __restrict__ csum = ws.csum + (size_t)r * ws.nchunk_pad;
+    double* __restrict__ csum0 = ws.csum0 + (size_t)r * ws.nchunk_pad;      // the copy the first draw round searches (see Workspace)
     int lpos = 0;
     uint32_t lmin1 = 0xFFFFFFFFu;                      // (bit pattern - 1) of the smallest positive p; zeros wrap to the top
     int y = (int)div_magic((uint32_t)px, G.w_magic), x = px - y * W;
@@ -599,12 +597,12 @@ ldp_prep_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
             constexpr int GL = (CS >= 5 && CS <= 7) ? ((1 << CS) >> 2) : 1;
 #pragma unroll
             for (int o = 1; o < GL; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (px < N && (lane & (GL - 1)) == 0) csum[px >> CS] = a;
+            if (px < N && (lane & (GL - 1)) == 0) { csum[px >> CS] = a; csum0[px >> CS] = a; }
         } else {
             const int cs = G.chunk_shift;          // chunks wider than a warp row (zeroed by the host memset)
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (px < N && lane == 0) atomicAdd(&csum[px >> cs], a);
+            if (px < N && lane == 0) { atomicAdd(&csum[px >> cs], a); atomicAdd(&csum0[px >> cs], a); }
         }
         px += STEP;
         if (XCONST) {
@@ -739,11 +737,11 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
     int32_t* __restrict__ fcnt = ws.fcnt + (size_t)r * ws.draw_cmax;
     int32_t* __restrict__ sel = (out.sel_idx ? out.sel_idx : ws.sel) + (size_t)r * ws.sel_cap;
     double* __restrict__ gcsum = ws.csum + (size_t)r * ws.nchunk_pad;
-    double* __restrict__ gcrem = ws.crem + (size_t)r * ws.nchunk_pad;
-    // where a found pixel's mass is accounted: round 1 (independent CTAs that may start at different times and all need the
-    // chunk sums as the prep kernel left them) in the side table, later rounds (one cluster, barriers between rounds) in place
-    double* __restrict__ gmass = (MODE == 1) ? gcrem : gcsum;
-    const double mass_sign = (MODE == 1) ? 1.0 : -1.0;
+    // Round 1 runs on independent CTAs that may start at different times - after their siblings' first finds have left the chunk
+    // sums - and numpy's first round searches the cdf of ALL weights: they build their tables from the copy the prep kernel
+    // made (csum0, never modified); every find is removed from csum, which the later rounds (one cluster, barriers between
+    // rounds) search.
+    const double* __restrict__ gtable = (MODE == 1) ? ws.csum0 + (size_t)r * ws.nchunk_pad : gcsum;
     const unsigned long long* __restrict__ gb = ws.gbins + (size_t)r * ws.bins_cap;
     const uint32_t* __restrict__ gone = (MODE == 2) ? ws.gone + (size_t)r * ws.n_words : nullptr;   // drawn in round 1
 
@@ -809,21 +807,7 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int i = i0 + 2 * j * T;
-                d[j] = (i < nchunk) ? __ldcg(reinterpret_cast<const double2*>(gcsum + i)) : make_double2(0.0, 0.0);   // nchunk_pad is even
-            }
-            if (MODE == 2 && rounds == 1) {
-                // first table after round 1: its finds' mass (side table) leaves the chunk sums now.  Exact f64 arithmetic, so the
-                // difference is what subtracting find by find gives; every CTA of the cluster forms it for its own table, the
-                // first one also writes it back for the later rounds (whose own removals start after the barrier below)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = i0 + 2 * j * T;
-                    if (i < nchunk) {
-                        const double2 rm = __ldcg(reinterpret_cast<const double2*>(gcrem + i));
-                        d[j].x -= rm.x; d[j].y -= rm.y;
-                        if (crank == 0) *reinterpret_cast<double2*>(gcsum + i) = d[j];
-                    }
-                }
+                d[j] = (i < nchunk) ? __ldcg(reinterpret_cast<const double2*>(gtable + i)) : make_double2(0.0, 0.0);   // nchunk_pad is even
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -1100,13 +1084,13 @@ ldp_draw_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const
                 if (fresh0) {
                     flist[basepos + __popc(fm0 & below_mask)] = ii[0];
 #ifndef LDP_EXP_NORED
-                    red_add_f64(gmass + (ii[0] >> cs), mass_sign * widen_pos(hp[0]));      // the found mass leaves the chunk sum
+                    red_add_f64(gcsum + (ii[0] >> cs), -widen_pos(hp[0]));      // the found mass leaves the chunk sum
 #endif
                 }
                 if (fresh1) {
                     flist[basepos + n0 + __popc(fm1 & below_mask)] = ii[1];
 #ifndef LDP_EXP_NORED
-                    red_add_f64(gmass + (ii[1] >> cs), mass_sign * widen_pos(hp[1]));
+                    red_add_f64(gcsum + (ii[1] >> cs), -widen_pos(hp[1]));
 #endif
                 }
             }
