@@ -48,7 +48,7 @@ import numpy as np  # noqa: E402
 WORKLOAD = dict(name="garden-shaped 185 views, RoMa fast 512x512, ref_fraction 0.25 (46 refs), 4 nn/ref (184 pairs), "
                      "M=10000, all filters on", n_views=185, setting="fast", ref_fraction=0.25, nn=4, M=10000)
 CONFIG5 = dict(name="1000 views, RoMa base 640x640, ref_fraction 0.25 (250 refs), 4 nn/ref (1000 pairs), M=10000, all filters on",
-               n_views=1000, setting="base", ref_fraction=0.25, nn=4, M=10000, refs_per_launch=32)
+               n_views=1000, setting="base", ref_fraction=0.25, nn=4, M=10000, refs_per_launch=84)
 METRIC = "filtered_points_per_sec"
 UNIT = "points/s"
 CPU_SAMPLE = dict(steps=8, warmup=3)          # cpu_baseline inside the GPU arm: same code and sample shape as --impl reference
@@ -269,7 +269,13 @@ def config5_block(args, dev, rank: int, world: int, ring) -> dict:
     from lichtfeld_densification_plugin_b200.output import ConcatPlan, PackedCloud
 
     scene = synth.make_scene(CONFIG5["n_views"], CONFIG5["setting"], CONFIG5["ref_fraction"], CONFIG5["nn"])
-    R_all, per = scene.n_refs, int(os.environ.get("BENCH_C5_REFS_PER_LAUNCH", CONFIG5["refs_per_launch"]))
+    # views per launch: at most CONFIG5["refs_per_launch"], the rank's views cut into launches of equal size (a launch of 84 views
+    # at 640^2 fills the device better than three of 32: 1.0 vs 1.3 ms for the 250 views of one GPU)
+    R_all, per_max = scene.n_refs, int(os.environ.get("BENCH_C5_REFS_PER_LAUNCH", CONFIG5["refs_per_launch"]))
+    r_lo, r_hi = D.shard_bounds(R_all, rank, world)
+    r_max = max(D.shard_bounds(R_all, q, world)[1] - D.shard_bounds(R_all, q, world)[0] for q in range(world))
+    n_launch = max(1, -(-r_max // per_max))
+    per = -(-r_max // n_launch)
     cfg = PathConfig(matches_per_ref=CONFIG5["M"], seed=5)
     eng0 = ring.engines[0]
     sel_cap = eng0.sel_capacity(cfg.matches_per_ref)
