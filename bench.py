@@ -534,9 +534,14 @@ def gpu_arm(args) -> None:
     ring = DensifyRing(dev, DEPTH)
     eng = ring.engines[0]
     cfg = PathConfig(matches_per_ref=WORKLOAD["M"], seed=0)
-    slots = [SceneInputs(scene, list(range(R)), dev, seed=100 + rank + 1000 * j) for j in range(DEPTH)]
+    # Weak scaling = the same work on every GPU: all ranks process the same synthetic batches (same seeds, same Philox streams).
+    # Seeded by rank instead (BENCH_DATA_PER_RANK=1), the batches themselves differ in cost by up to 6 % (measured on ONE GPU:
+    # 0.1366 ms per step with the seeds of ranks 0 / 6, 0.1447 / 0.1451 ms with those of ranks 3 / 7), and the slowest batch
+    # would be reported as a scaling loss.
+    data_rank = rank if int(os.environ.get("BENCH_DATA_PER_RANK", "0")) else int(os.environ.get("BENCH_DATA_RANK", "0"))
+    slots = [SceneInputs(scene, list(range(R)), dev, seed=100 + data_rank + 1000 * j) for j in range(DEPTH)]
     torch.cuda.synchronize(dev)
-    batches = [slots[j].batch(ring.engines[j], scene, 0, R, stream_base=rank * R) for j in range(DEPTH)]
+    batches = [slots[j].batch(ring.engines[j], scene, 0, R, stream_base=data_rank * R) for j in range(DEPTH)]
     descs = [ring.engines[j].upload_descs(batches[j]) for j in range(DEPTH)]
     sel_cap = eng.sel_capacity(cfg.matches_per_ref)
     NBUF = max(2, DEPTH)      # output buffers in rotation
@@ -577,8 +582,10 @@ def gpu_arm(args) -> None:
             for st in ring.streams:
                 st.wait_event(e0)
         last = None
+        t_host = time.perf_counter()
         for i in range(n_steps):
             last = step(i, depth)
+        issue_ms[depth] = 1e3 * (time.perf_counter() - t_host)      # host time to enqueue the steps (the device runs behind)
         if depth > 1:
             for st in ring.streams:
                 main.wait_stream(st)
@@ -593,6 +600,7 @@ def gpu_arm(args) -> None:
         return e0.elapsed_time(e1), last
 
     own_ms = {}
+    issue_ms = {}
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -629,12 +637,16 @@ def gpu_arm(args) -> None:
     per_rank_ms = None
     if world > 1:
         t = torch.tensor([ms_total, ms_single], dtype=torch.float64, device=dev)
-        mine_t = torch.tensor([own_ms.get(DEPTH, ms_total), own_ms.get(1, ms_single)], dtype=torch.float64, device=dev)
+        mine_t = torch.tensor([own_ms.get(DEPTH, ms_total), own_ms.get(1, ms_single), issue_ms.get(DEPTH, 0.0),
+                               float(clocks.get("sm_mhz") or 0.0), float(clocks.get("power_w_max") or 0.0)], dtype=torch.float64, device=dev)
         allt = [torch.zeros_like(mine_t) for _ in range(world)]
         dist.all_gather(allt, mine_t)
         per_rank_ms = {"note": "each rank's own steps, before the count exchange that ends the timed region",
                        "ms_per_step": [round(float(x[0].item()) / steps, 5) for x in allt],
-                       "ms_per_step_one_launch_at_a_time": [round(float(x[1].item()) / steps, 5) for x in allt]}
+                       "ms_per_step_one_launch_at_a_time": [round(float(x[1].item()) / steps, 5) for x in allt],
+                       "host_enqueue_ms_per_step": [round(float(x[2].item()) / steps, 5) for x in allt],
+                       "sm_mhz_median_under_load": [float(x[3].item()) for x in allt],
+                       "power_w_max": [round(float(x[4].item()), 1) for x in allt]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_single = float(t[0].item()), float(t[1].item())
         c = torch.tensor([total_pts, S_total], dtype=torch.int64, device=dev)
@@ -746,7 +758,7 @@ def gpu_arm(args) -> None:
     d_cert = [torch.empty_like(cert) for _ in range(SETS)]
     d_img = [torch.empty_like(image) for _ in range(SETS)]
     bounds = [(R * g // E2E_CHUNKS, R * (g + 1) // E2E_CHUNKS) for g in range(E2E_CHUNKS)]
-    e2e_batches = [[slots[0].batch(eng, scene, lo, hi, stream_base=rank * R, cert=d_cert[q], warp=h_warp, image=d_img[q])
+    e2e_batches = [[slots[0].batch(eng, scene, lo, hi, stream_base=data_rank * R, cert=d_cert[q], warp=h_warp, image=d_img[q])
                     for lo, hi in bounds] for q in range(SETS)]
     e2e_descs = [[eng.upload_descs(b) for b in e2e_batches[q]] for q in range(SETS)]
     e2e_outs = [[eng.alloc_outputs(hi - lo, sel_cap) for lo, hi in bounds] for q in range(SETS)]
@@ -840,6 +852,8 @@ def gpu_arm(args) -> None:
             "config": {"workload": WORKLOAD["name"], "refs_per_gpu": R, "pairs_per_gpu": scene.n_pairs,
                        "l2_policy": "inputs larger than L2 (0.97 GB per step vs 126 MB); every step in flight has its own input tensors",
                        "steps_in_flight": DEPTH,
+                       "per_gpu_work": ("every rank processes the same synthetic batches (same seeds): identical work per GPU"
+                                        if not int(os.environ.get("BENCH_DATA_PER_RANK", "0")) else "batches seeded by rank (their cost differs by up to 6 %)"),
                        "rng": "philox4x32-10", "multi_gpu": ("views sharded, points stay on their rank, no collective per step; the "
                                       "ranks' kept-point counts (global row offsets) are exchanged once after the last step, inside "
                                       "the timed region" if world > 1 else "none")},
