@@ -331,6 +331,7 @@ def submit_refs(matched_refs: Sequence[_MatchedReference], tri_ctx: _Triangulati
     u_dev = None
     if uniforms is not None:
         u_dev = torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float64)).to(dev)
+        batch._keep_alive.append(u_dev)      # read by kernels on a ring stream: alive until the launch is collected, like the planes
     if ring is None:
         out = eng.densify(batch, pcfg, uniforms=u_dev, collect_debug=collect_debug_matches)
     else:
