@@ -32,18 +32,30 @@ constexpr int KFIX_BLOCKS = 148;
 // np.degrees on float32 multiplies by f32(180) / f32(pi) evaluated in f32 (measured)
 #define RAD2DEG_F32 57.295776367187500f
 
-struct alignas(16) PairConst {   // one neighbour, staged in shared memory.  144 bytes: the lanes of a warp read the same field of
-    float P2[12];                // DIFFERENT neighbours; at a stride of 128 bytes those words share a bank (4-way conflicts on
-    float C2[3];                 // every constant), at 36 words neighbour k sits 4k banks further (128-bit reads stay aligned)
-    float F[9];
+// The neighbours' constants, staged in shared memory as one table per field, each in the descriptor's own order: staging is a
+// word copy with a few range checks (no divisions), rows of P2 stay 16-byte aligned (128-bit reads), and the lanes of a warp that
+// read the same field of DIFFERENT neighbours hit different banks (row strides of 12 / 9 / 3 / 1 words).
+struct PairTable {
+    alignas(16) float P2[LDP_MAX_NN][12];
+    float F[LDP_MAX_NN][9];
+    float C2[LDP_MAX_NN][3];
+    float sxB[LDP_MAX_NN], syB[LDP_MAX_NN];
+    int group[LDP_MAX_NN];
+    const float* warp[LDP_MAX_NN];
+    const float* cert[LDP_MAX_NN];
+};
+struct PairView {           // neighbour k of the table
+    const float* P2; const float* C2; const float* F;
     float sxB, syB;
     int group;
-    int pad0;
     const float* warp;
-    const float* cert;
-    int pad1[4];
 };
-static_assert(sizeof(PairConst) == 144, "PairConst stride");
+__device__ __forceinline__ PairView pair_view(const PairTable& pt, int k) {
+    PairView v;
+    v.P2 = pt.P2[k]; v.C2 = pt.C2[k]; v.F = pt.F[k];
+    v.sxB = pt.sxB[k]; v.syB = pt.syB[k]; v.group = pt.group[k]; v.warp = pt.warp[k];
+    return v;
+}
 struct RefConst {
     float P1[12];
     float C1[3];
@@ -76,21 +88,21 @@ __device__ __forceinline__ void l2_discard_line(const void* p) {
 constexpr int DESC_WORDS = 4 + 12 + 3 + LDP_MAX_NN * (12 + 3 + 9 + 3);
 static_assert(offsetof(ldp_ref_desc, group) + sizeof(int32_t) * LDP_MAX_NN - offsetof(ldp_ref_desc, sxA) == DESC_WORDS * 4, "descriptor layout");
 static_assert(offsetof(RefConst, sy_img) - offsetof(RefConst, sxA) == 12, "RefConst layout");
-__device__ __forceinline__ uint32_t* desc_word_slot(int e, RefConst& rc, PairConst* pc) {
+__device__ __forceinline__ uint32_t* desc_word_slot(int e, RefConst& rc, PairTable& pt) {
     if (e < 4) return reinterpret_cast<uint32_t*>(&rc.sxA) + e;
     if (e < 16) return reinterpret_cast<uint32_t*>(rc.P1) + (e - 4);
     if (e < 19) return reinterpret_cast<uint32_t*>(rc.C1) + (e - 16);
     e -= 19;
-    if (e < LDP_MAX_NN * 12) return reinterpret_cast<uint32_t*>(pc[e / 12].P2) + e % 12;
+    if (e < LDP_MAX_NN * 12) return reinterpret_cast<uint32_t*>(&pt.P2[0][0]) + e;
     e -= LDP_MAX_NN * 12;
-    if (e < LDP_MAX_NN * 3) return reinterpret_cast<uint32_t*>(pc[e / 3].C2) + e % 3;
+    if (e < LDP_MAX_NN * 3) return reinterpret_cast<uint32_t*>(&pt.C2[0][0]) + e;
     e -= LDP_MAX_NN * 3;
-    if (e < LDP_MAX_NN * 9) return reinterpret_cast<uint32_t*>(pc[e / 9].F) + e % 9;
+    if (e < LDP_MAX_NN * 9) return reinterpret_cast<uint32_t*>(&pt.F[0][0]) + e;
     e -= LDP_MAX_NN * 9;
-    if (e < LDP_MAX_NN) return reinterpret_cast<uint32_t*>(&pc[e].sxB);
+    if (e < LDP_MAX_NN) return reinterpret_cast<uint32_t*>(pt.sxB) + e;
     e -= LDP_MAX_NN;
-    if (e < LDP_MAX_NN) return reinterpret_cast<uint32_t*>(&pc[e].syB);
-    return reinterpret_cast<uint32_t*>(&pc[e - LDP_MAX_NN].group);
+    if (e < LDP_MAX_NN) return reinterpret_cast<uint32_t*>(pt.syB) + e;
+    return reinterpret_cast<uint32_t*>(pt.group) + (e - LDP_MAX_NN);
 }
 // stage_load puts the loads in flight (registers), stage_store waits for them: a kernel issues its other independent loads in
 // between.  slices > 0: the CTA also asks L2 for its share (slice of slices) of the view's reference image.
@@ -108,17 +120,17 @@ __device__ __forceinline__ void stage_load(const ldp_ref_desc* rd, int t, int nt
 #pragma unroll
     for (int q = 0; q < DESC_PER; ++q) sd.v[q] = (t + q * nt < DESC_WORDS) ? __ldg(src + t + q * nt) : 0u;
 }
-__device__ __forceinline__ void stage_store(const StagedDesc& sd, RefConst& rc, PairConst* pc, int t, int nt,
+__device__ __forceinline__ void stage_store(const StagedDesc& sd, RefConst& rc, PairTable& pc, int t, int nt,
                                             int slice = 0, int slices = 0) {
 #pragma unroll
     for (int q = 0; q < DESC_PER; ++q) if (t + q * nt < DESC_WORDS) *desc_word_slot(t + q * nt, rc, pc) = sd.v[q];
-    if (t < LDP_MAX_NN) { pc[t].warp = sd.p_warp; pc[t].cert = sd.p_cert; }
+    if (t < LDP_MAX_NN) { pc.warp[t] = sd.p_warp; pc.cert[t] = sd.p_cert; }
     if (t == LDP_MAX_NN) {
         rc.image = sd.p_img; rc.img_w = sd.img_w; rc.img_h = sd.img_h; rc.nn = sd.nn;
         if (slices > 0) l2_prefetch_slice(sd.p_img, (size_t)sd.img_w * sd.img_h * 3, slice, slices);
     }
 }
-__device__ __forceinline__ void stage_constants(const ldp_ref_desc* rd, RefConst& rc, PairConst* pc, int t, int nt) {
+__device__ __forceinline__ void stage_constants(const ldp_ref_desc* rd, RefConst& rc, PairTable& pc, int t, int nt) {
     StagedDesc sd;
     stage_load(rd, t, nt, sd);
     stage_store(sd, rc, pc, t, nt);
@@ -312,8 +324,8 @@ struct SampleRec {
 
 // ---- gather: everything that needs a scattered load (core/pipeline.py:636-640,652-653,661-675)
 // certainty of neighbour q at pixel idx as the path sees it: raw planes go through the reference's post-processing
-__device__ __forceinline__ float cert_at(const ldp_params& P, const PairConst* pc, const ProView& pv, int q, int idx) {
-    float c = __ldg(pc[q].cert + idx);
+__device__ __forceinline__ float cert_at(const ldp_params& P, const PairTable& pc, const ProView& pv, int q, int idx) {
+    float c = __ldg(pc.cert[q] + idx);
     if (P.prologue) {
         const int y = idx / P.W;
         c = prologue_cert(c, q, idx, idx - y * P.W, y, P, pv);
@@ -321,7 +333,7 @@ __device__ __forceinline__ float cert_at(const ldp_params& P, const PairConst* p
     return c;
 }
 
-__device__ __forceinline__ void gather_sample(const ldp_params& P, const RefConst& rc, const PairConst* pc, const ProView& pv,
+__device__ __forceinline__ void gather_sample(const ldp_params& P, const RefConst& rc, const PairTable& pc, const ProView& pv,
                                               const GeomArgs& ga, int k_pre, int idx,
                                               SampleRec& rec, float& craw) {
     int k = 0;                                                                    // core/pipeline.py:634-635,652
@@ -334,7 +346,7 @@ __device__ __forceinline__ void gather_sample(const ldp_params& P, const RefCons
             if (c > best) { best = c; k = q; }
         }
     }
-    const PairConst& pk = pc[k];
+    const PairView pk = pair_view(pc, k);
     const float4 wv = __ldg(reinterpret_cast<const float4*>(pk.warp) + idx);      // core/pipeline.py:636-640,653
     craw = 0.f;
     if (P.collect_debug) craw = cert_at(P, pc, pv, k, idx);
@@ -359,10 +371,10 @@ __device__ __forceinline__ void gather_sample(const ldp_params& P, const RefCons
 
 // ---- compute: everything else the reference computes for one sampled pixel (core/pipeline.py:653-769)
 template <bool ROBUST>
-__device__ __forceinline__ void eval_sample(const ldp_params& P, const RefConst& rc, const PairConst* pc, const GeomArgs& ga,
+__device__ __forceinline__ void eval_sample(const ldp_params& P, const RefConst& rc, const PairTable& pc, const GeomArgs& ga,
                                             const SampleRec& rec, float craw, SampleResult& o GCLK_ARGS) {
     const int k = (int)(rec.k_cert & 0xffu);
-    const PairConst& pk = pc[k];
+    const PairView pk = pair_view(pc, k);
     o.grp = pk.group;
     const float4 wv = rec.wv;
     const float wm1 = (float)(P.w_match - 1), hm1 = (float)(P.h_match - 1);
@@ -522,7 +534,7 @@ ldp_gather_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, con
                   const GeomArgs ga)
 {
     __shared__ RefConst rc;
-    __shared__ PairConst pc[LDP_MAX_NN];
+    __shared__ PairTable pc;
     __shared__ ProView pv;
     const int r = blockIdx.y + ga.ref0;
     const int i0 = blockIdx.x * (KG_THREADS * KG_SPT);
@@ -579,7 +591,7 @@ ldp_geometry_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, c
                     const GeomArgs ga)
 {
     __shared__ RefConst rc;
-    __shared__ PairConst pc[LDP_MAX_NN];
+    __shared__ PairTable pc;
     __shared__ int s_cnt[LDP_MAX_NN], s_first[LDP_MAX_NN];
     __shared__ ProView pv;
     const int r = blockIdx.y + ga.ref0;
@@ -674,7 +686,7 @@ ldp_fix_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ refs, const 
                const GeomArgs ga)
 {
     __shared__ RefConst rc;
-    __shared__ PairConst pc[LDP_MAX_NN];
+    __shared__ PairTable pc;
     __shared__ int s_tot[LDP_MAX_NN], s_first[LDP_MAX_NN], s_base[LDP_MAX_NN];
     constexpr int TB = 128;                                 // tiles staged per block step
     __shared__ int s_c[TB * LDP_MAX_NN], s_f[TB * LDP_MAX_NN];
