@@ -224,9 +224,29 @@ __device__ __forceinline__ bool null_vector4(const double A[16], double v[4]) {
     const double i2 = rsqrt(fmax(m22 + mu - l20 * l20 - l21 * l21, mu * 1e-3));
     const double l32 = (m32 - l30 * l20 - l31 * l21) * i2;
     const double i3 = rsqrt(fmax(m33 + mu - l30 * l30 - l31 * l31 - l32 * l32, mu * 1e-3));
-    double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 1.0;
+    // Steps 1 and 2 are taken without normalising or testing: from x = e4 the forward solve is y = (0, 0, 0, i3), and two
+    // steps grow the vector by at most 1 / mu^2 (far inside the f64 range for any tr that is not itself denormal-small;
+    // an overflow would end in the Jacobi fix-up like any other non-convergence).  The test needs two normalised iterates
+    // anyway, so nothing converges later than before.
+    double x0, x1, x2, x3;
+    {
+        const double z3 = i3 * i3;
+        const double z2 = (-l32 * z3) * i2;
+        const double z1 = (-l21 * z2 - l31 * z3) * i1;
+        const double z0 = (-l10 * z1 - l20 * z2 - l30 * z3) * i0;
+        const double y0 = z0 * i0;
+        const double y1 = (z1 - l10 * y0) * i1;
+        const double y2 = (z2 - l20 * y0 - l21 * y1) * i2;
+        const double y3 = (z3 - l30 * y0 - l31 * y1 - l32 * y2) * i3;
+        const double w3 = y3 * i3;
+        const double w2 = (y2 - l32 * w3) * i2;
+        const double w1 = (y1 - l21 * w2 - l31 * w3) * i1;
+        const double w0 = (y0 - l10 * w1 - l20 * w2 - l30 * w3) * i0;
+        const double inv = rsqrt(w0 * w0 + w1 * w1 + w2 * w2 + w3 * w3);
+        x0 = w0 * inv; x1 = w1 * inv; x2 = w2 * inv; x3 = w3 * inv;
+    }
     bool converged = false;
-    for (int it = 0; it < INVIT_MAX; ++it) {
+    for (int it = 2; it < INVIT_MAX; ++it) {
         const double y0 = x0 * i0;                                   // L y = x
         const double y1 = (x1 - l10 * y0) * i1;
         const double y2 = (x2 - l20 * y0 - l21 * y1) * i2;
