@@ -255,9 +255,9 @@ __device__ __forceinline__ bool null_vector4(const double A[16], double v[4]) {
         const double z2 = (y2 - l32 * z3) * i2;
         const double z1 = (y1 - l21 * z2 - l31 * z3) * i1;
         const double z0 = (y0 - l10 * z1 - l20 * z2 - l30 * z3) * i0;
+        // (no sign to fix: z . x = |L^-1 x|^2 >= 0, the factorised matrix is positive definite by construction)
         const double inv = rsqrt(z0 * z0 + z1 * z1 + z2 * z2 + z3 * z3);
-        const double sgn = (z0 * x0 + z1 * x1 + z2 * x2 + z3 * x3) < 0.0 ? -inv : inv;
-        const double n0 = z0 * sgn, n1 = z1 * sgn, n2 = z2 * sgn, n3 = z3 * sgn;
+        const double n0 = z0 * inv, n1 = z1 * inv, n2 = z2 * inv, n3 = z3 * inv;
         const double e0 = n0 - x0, e1 = n1 - x1, e2 = n2 - x2, e3 = n3 - x3;
         x0 = n0; x1 = n1; x2 = n2; x3 = n3;
         if (e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3 < 1e-26) { converged = true; break; }
