@@ -192,6 +192,25 @@ __device__ void jacobi_smallest_eigvec4(const double* __restrict__ Min, double* 
     for (int k = 0; k < 4; ++k) vout[k] = (j == 0) ? V[k][0] : (j == 1) ? V[k][1] : (j == 2) ? V[k][2] : V[k][3];
 }
 
+// 1/sqrt(s) and 1/v in f64 for s, v in the normal range, to within a few ulp: the hardware's 2^-22 estimate and two Newton steps,
+// without the library routines' special-case paths (zero, infinity, denormals come out as NaN here: the callers' pivots are
+// clamped positive, and a NaN eigenvector ends in the Jacobi fix-up like any other non-convergence).  Neither value needs to be
+// correctly rounded: one scales an iterate, the other is multiplied and rounded to f32.
+__device__ __forceinline__ double rsqrt_newton(double s) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { const double t = s * y; const double e = fma(-t, y, 1.0); y = fma(0.5 * y, e, y); }
+    return y;
+}
+__device__ __forceinline__ double rcp_newton(double v) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { const double e = fma(-v, y, 1.0); y = fma(y, e, y); }
+    return y;
+}
+
 // Smallest-eigenvalue eigenvector of M = A^T A (A 4x4 row-major, f32 values held in f64).
 // ROBUST = false: inverse iteration on the Cholesky factor of M + mu*I (same eigenvectors; converges at
 // (sigma_4/sigma_3)^2 per step: 3-5 steps on consistent matches); returns false if not converged in INVIT_MAX.
@@ -217,13 +236,13 @@ __device__ __forceinline__ bool null_vector4(const double A[16], double v[4]) {
     // M + mu*I has the same eigenvectors; the shift keeps the Cholesky pivots positive when A is
     // numerically rank-3 (noise-free correspondences).
     const double mu = tr * 1e-13;
-    const double i0 = rsqrt(m00 + mu);
+    const double i0 = rsqrt_newton(m00 + mu);
     const double l10 = m10 * i0, l20 = m20 * i0, l30 = m30 * i0;
-    const double i1 = rsqrt(fmax(m11 + mu - l10 * l10, mu * 1e-3));
+    const double i1 = rsqrt_newton(fmax(m11 + mu - l10 * l10, mu * 1e-3));
     const double l21 = (m21 - l20 * l10) * i1, l31 = (m31 - l30 * l10) * i1;
-    const double i2 = rsqrt(fmax(m22 + mu - l20 * l20 - l21 * l21, mu * 1e-3));
+    const double i2 = rsqrt_newton(fmax(m22 + mu - l20 * l20 - l21 * l21, mu * 1e-3));
     const double l32 = (m32 - l30 * l20 - l31 * l21) * i2;
-    const double i3 = rsqrt(fmax(m33 + mu - l30 * l30 - l31 * l31 - l32 * l32, mu * 1e-3));
+    const double i3 = rsqrt_newton(fmax(m33 + mu - l30 * l30 - l31 * l31 - l32 * l32, mu * 1e-3));
     // Steps 1 and 2 are taken without normalising or testing: from x = e4 the forward solve is y = (0, 0, 0, i3), and two
     // steps grow the vector by at most 1 / mu^2 (far inside the f64 range for any tr that is not itself denormal-small;
     // an overflow would end in the Jacobi fix-up like any other non-convergence).  The test needs two normalised iterates
@@ -242,7 +261,7 @@ __device__ __forceinline__ bool null_vector4(const double A[16], double v[4]) {
         const double w2 = (y2 - l32 * w3) * i2;
         const double w1 = (y1 - l21 * w2 - l31 * w3) * i1;
         const double w0 = (y0 - l10 * w1 - l20 * w2 - l30 * w3) * i0;
-        const double inv = rsqrt(w0 * w0 + w1 * w1 + w2 * w2 + w3 * w3);
+        const double inv = rsqrt_newton(w0 * w0 + w1 * w1 + w2 * w2 + w3 * w3);
         x0 = w0 * inv; x1 = w1 * inv; x2 = w2 * inv; x3 = w3 * inv;
     }
     bool converged = false;
@@ -256,7 +275,7 @@ __device__ __forceinline__ bool null_vector4(const double A[16], double v[4]) {
         const double z1 = (y1 - l21 * z2 - l31 * z3) * i1;
         const double z0 = (y0 - l10 * z1 - l20 * z2 - l30 * z3) * i0;
         // (no sign to fix: z . x = |L^-1 x|^2 >= 0, the factorised matrix is positive definite by construction)
-        const double inv = rsqrt(z0 * z0 + z1 * z1 + z2 * z2 + z3 * z3);
+        const double inv = rsqrt_newton(z0 * z0 + z1 * z1 + z2 * z2 + z3 * z3);
         const double n0 = z0 * inv, n1 = z1 * inv, n2 = z2 * inv, n3 = z3 * inv;
         const double e0 = n0 - x0, e1 = n1 - x1, e2 = n2 - x2, e3 = n3 - x3;
         x0 = n0; x1 = n1; x2 = n2; x3 = n3;
@@ -487,7 +506,7 @@ __device__ __forceinline__ void eval_sample(const ldp_params& P, const RefConst&
                 X0 = __fdiv_rn((float)v[0], 1e-12f); X1 = __fdiv_rn((float)v[1], 1e-12f);
                 X2 = __fdiv_rn((float)v[2], 1e-12f); X3 = __fdiv_rn(w32, 1e-12f);
             } else {
-                const double iwv = 1.0 / v[3];
+                const double iwv = rcp_newton(v[3]);
                 X0 = (float)(v[0] * iwv); X1 = (float)(v[1] * iwv); X2 = (float)(v[2] * iwv); X3 = 1.0f;
             }
         }
