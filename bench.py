@@ -520,6 +520,18 @@ def gpu_arm(args) -> None:
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries ONE JSON line: whatever libraries write to file descriptor 1 while the run lasts (NCCL prints its version
+    # there) goes to stderr; the descriptor is restored for the line itself
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj) -> None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -722,9 +734,9 @@ def gpu_arm(args) -> None:
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "ms_per_step": ms_step, "ms_per_step_one_launch_at_a_time": ms_single_step,
-                              "kernels_ms": kdict, "front_kernel_alone_ms": dom_ms, "per_rank": per_rank_ms,
-                              "k1_frac": achieved / peak, "path_frac": path_gbs / peak, "path_frac_one_at_a_time": path_gbs_single / peak}))
+            emit({"quick": True, "ms_per_step": ms_step, "ms_per_step_one_launch_at_a_time": ms_single_step,
+                  "kernels_ms": kdict, "front_kernel_alone_ms": dom_ms, "per_rank": per_rank_ms,
+                  "k1_frac": achieved / peak, "path_frac": path_gbs / peak, "path_frac_one_at_a_time": path_gbs_single / peak})
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -881,7 +893,7 @@ def gpu_arm(args) -> None:
             line["api"] = api
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
