@@ -81,3 +81,24 @@ def test_nearest_neighbours_equal_reference_up_to_cdist_noise():
         assert nn_equivalent(idx, ref, flat, 5e-3), name
         if name.startswith("random"):
             assert np.array_equal(idx, ref), name
+
+
+def test_topk_restatement_equals_torch_topk_on_whole_matrices():
+    """The reference calls torch.topk on the whole [n, n] distance matrix (rows run in parallel inside ATen): row by row the
+    result must still be the restated selection, for lattice poses whose rows are full of exact ties, on both selection paths."""
+    import torch
+    rs = np.random.RandomState(12)
+    for n, k in ((40, 8), (200, 4), (300, 4), (700, 10), (1200, 16)):
+        flat = rs.randint(-2, 3, size=(n, 16)).astype(np.float32)
+        flat[:, 12:] = [0, 0, 0, 1]
+        m = torch.from_numpy(flat)
+        dist = torch.cdist(m, m, p=2)
+        dist.fill_diagonal_(float("inf"))
+        want = torch.topk(dist, k, largest=False, dim=1)[1].numpy()
+        D = dist.numpy()
+        got = np.asarray([O.topk_smallest_like_torch(D[i], k) for i in range(n)])
+        assert np.array_equal(got, want), (n, k, int((got != want).any(axis=1).sum()))
+        # and the restated cdist arithmetic gives torch's distances bit for bit on these poses
+        mine = np.sqrt(np.maximum(O.cdist_squared_f32(flat), np.float32(0.0)))
+        np.fill_diagonal(mine, np.inf)
+        assert np.array_equal(mine, D), (n, k)
