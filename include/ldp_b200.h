@@ -238,7 +238,8 @@ int ldp_scatter_points(const float* xyz, const float* rgb, const float* err, con
  *                          1 <= k <= n <= 8192 (the reference clamps k the same way before the loop).
  *   ldp_nearest_neighbors  core/selection.py:57-70 nearest_neighbors: for every view the k nearest other views by Euclidean
  *                          distance of the poses, ascending.  idx_out [n,k] int64.  k <= min(n - 1, 16).  The reference's
- *                          table index for index: the distances are torch.cdist's own float32 values (|x|^2 + |y|^2 - 2 x.y
+ *                          table index for index: the distances are torch.cdist's own float32 values (n <= 25: the direct
+ *                          kernel's sequential sum of squared differences; above: |x|^2 + |y|^2 - 2 x.y
  *                          as ONE K = 18 dot product of float32 FMAs in index order, row norms as eight lanes added left to
  *                          right; measured against torch), so near-equal distances - the left / right neighbours of a ring
  *                          camera - come out in the reference's order; and EXACTLY equal float32 distances are ordered by

@@ -287,6 +287,19 @@ __device__ __forceinline__ float cdist_value(const float* xi_m2, float ni, const
     acc = __fmaf_rn(1.0f, nj, acc);
     return __fsqrt_rn(fmaxf(acc, 0.0f));                           // clamp_min_(0).sqrt_()
 }
+// Up to 25 views torch.cdist does not go through the matrix product: cdist_impl takes the mm formulation only for r1 > 25 || r2 > 25
+// and otherwise runs the direct kernel (ATen DistanceOpsKernel.cpp, tdist_calc): a sequential float32 sum over the columns of
+// (a - b) * (a - b), multiply then add, then sqrt (oracle: cdist_f32, measured against torch).
+constexpr int CDIST_MM_ABOVE = 25;
+__device__ __forceinline__ float cdist_value_direct(const float* xi, const float* __restrict__ X, int j) {
+    float agg = 0.f;
+#pragma unroll
+    for (int c = 0; c < KC_DIM; ++c) {
+        const float d = fabsf(__fsub_rn(xi[c], X[(size_t)j * KC_DIM + c]));
+        agg = __fadd_rn(agg, __fmul_rn(d, d));
+    }
+    return __fsqrt_rn(agg);
+}
 __global__ void __launch_bounds__(KNN_THREADS)
 ldp_knn_kernel(const float* __restrict__ X, int n, int k, long long* __restrict__ out)
 {
@@ -298,8 +311,11 @@ ldp_knn_kernel(const float* __restrict__ X, int n, int k, long long* __restrict_
 #pragma unroll
     for (int j = 0; j < KC_DIM; ++j) xi[j] = X[(size_t)row * KC_DIM + j];
     const float ni = cdist_row_norm16(xi);
+    const bool direct = n <= CDIST_MM_ABOVE;                               // (such a row never takes the heap path: k * 64 > n)
+    if (!direct) {
 #pragma unroll
-    for (int j = 0; j < KC_DIM; ++j) xi[j] = __fmul_rn(xi[j], -2.0f);      // x1.mul(-2): exact
+        for (int j = 0; j < KC_DIM; ++j) xi[j] = __fmul_rn(xi[j], -2.0f);  // x1.mul(-2): exact
+    }
     if ((long long)k * 64 <= (long long)n) {
         // std::partial_sort: only an element smaller than the heap's top moves anything, so the row is streamed
         for (int base = 0; base < n; base += KNN_CHUNK) {
@@ -321,7 +337,10 @@ ldp_knn_kernel(const float* __restrict__ X, int n, int k, long long* __restrict_
         }
         if (tid == 0) knn_sort_heap(s_pair, k);
     } else {                                                       // n < 64 k: the pairs fit
-        for (int j = tid; j < n; j += KNN_THREADS) { s_pair[j].v = (j == row) ? INFINITY : cdist_value(xi, ni, X, j); s_pair[j].i = j; }
+        for (int j = tid; j < n; j += KNN_THREADS) {
+            s_pair[j].v = (j == row) ? INFINITY : (direct ? cdist_value_direct(xi, X, j) : cdist_value(xi, ni, X, j));
+            s_pair[j].i = j;
+        }
         __syncthreads();
         if (tid == 0) {
             knn_nth_element(s_pair, k - 1, n);

@@ -81,3 +81,18 @@ def test_pairs_feed_the_path(S):
     assert S._estimate_total_pairs(refs, nn, list(range(40)), 3) == 30
     with pytest.raises(Exception):
         S.nearest_neighbors(flat, 17) if False else S.nearest_neighbors_device(np.zeros((40, 15), np.float32), 3)
+
+
+def test_nearest_neighbours_small_scenes_take_torchs_direct_cdist(S):
+    """Up to 25 views torch.cdist runs its direct kernel, not the matrix product: the table must follow (12-view ring: 4 rows
+    differ between the two formulations).  Rings and random poses on both sides of the switch."""
+    from lichtfeld_densification_plugin_b200 import synth
+    rs = np.random.RandomState(4)
+    for n in (2, 3, 5, 12, 20, 25, 26, 30):
+        sc = synth.make_scene(max(n, 3), "turbo", 0.5, 2)
+        ring = np.stack([c.flat_pose() for c in sc.cameras], 0).astype(np.float32)[:n]
+        rnd = rs.standard_normal((n, 16)).astype(np.float32)
+        rnd[:, 12:] = [0, 0, 0, 1]
+        for flat in (ring, rnd):
+            for k in (1, 4):
+                assert np.array_equal(S.nearest_neighbors(flat, k), O.nearest_neighbors_cdist(flat, k)), (n, k)

@@ -102,3 +102,25 @@ def test_topk_restatement_equals_torch_topk_on_whole_matrices():
         mine = np.sqrt(np.maximum(O.cdist_squared_f32(flat), np.float32(0.0)))
         np.fill_diagonal(mine, np.inf)
         assert np.array_equal(mine, D), (n, k)
+
+
+def test_nearest_neighbours_small_scenes_equal_live_torch():
+    """torch.cdist switches formulation at 25 rows (direct sum of squared differences below, matrix product above): the
+    restatement follows, distances bit for bit where the direct kernel runs and tables index for index on both sides."""
+    import torch
+    from lichtfeld_densification_plugin_b200 import synth
+    rs = np.random.RandomState(0)
+    for n in (2, 3, 5, 12, 20, 25, 26, 30):
+        sc = synth.make_scene(max(n, 3), "turbo", 0.5, 2)
+        ring = np.stack([c.flat_pose() for c in sc.cameras], 0).astype(np.float32)[:n]
+        rnd = rs.standard_normal((n, 16)).astype(np.float32)
+        rnd[:, 12:] = [0, 0, 0, 1]
+        for flat in (ring, rnd):
+            m = torch.from_numpy(flat)
+            d = torch.cdist(m, m, p=2)
+            if n <= 25:
+                assert np.array_equal(O.cdist_f32(flat), d.numpy()), n
+            d.fill_diagonal_(float("inf"))
+            k = max(1, min(4, n - 1))
+            want = torch.topk(d, k, largest=False, dim=1)[1].numpy()
+            assert np.array_equal(O.nearest_neighbors_cdist(flat, 4), want), n
