@@ -14,6 +14,16 @@ constexpr int KC_MAX_PER_THREAD = 8;      // views per thread: V <= 8192
 constexpr int KC_DIM = 16;
 
 // np.add.reduce over 16 contiguous float32: r[j] = a[j] + a[8 + j], then ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
+// np.einsum("nd,nd->n") over 16 float32 products, as numpy's x86-64 wheels compute it (einsum_sumprod.c.src,
+// sum_of_products_contig_contig_outstride0_two; the einsum loops are built for the baseline SIMD width, 4 lanes, multiply then
+// add): lane j accumulates p[12+j], p[8+j], p[4+j], p[j] in that order, then (l0 + l1) + (l2 + l3).  Measured against np.einsum
+// (20 000 random rows: identical).  It decides the first k-centres pick when row norms tie, as they do on symmetric rings.
+__device__ __forceinline__ float einsum_row16(const float (&p)[KC_DIM]) {
+    float l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) l[j] = __fadd_rn(__fadd_rn(__fadd_rn(p[12 + j], p[8 + j]), p[4 + j]), p[j]);
+    return __fadd_rn(__fadd_rn(l[0], l[1]), __fadd_rn(l[2], l[3]));
+}
 __device__ __forceinline__ float pairwise16(const float (&a)[KC_DIM]) {
     float r[8];
 #pragma unroll
@@ -83,7 +93,7 @@ ldp_kcenters_kernel(const float* __restrict__ X, int n, int k, float* __restrict
                 R[(size_t)i * rs + j] = v;                            // a thread rewrites only its own rows
                 a[j] = __fmul_rn(v, v);
             }
-            argmax_merge(bv, bi, pairwise16(a), i);
+            argmax_merge(bv, bi, einsum_row16(a), i);
         }
     }
     auto block_argmax = [&](float v, int i) -> int {

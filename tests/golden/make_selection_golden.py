@@ -27,7 +27,10 @@ from lichtfeld_densification_plugin_b200 import synth  # noqa: E402
 def selection_cases():
     """name -> (flat poses [n,16] float64 as CameraRecord.flat_pose() gives them, k for k-centres, k for neighbours)"""
     out = {}
-    for name, nv, kc, kn in (("ring1000", 1000, 250, 4), ("ring185", 185, 46, 4), ("ring40", 40, 32, 8)):
+    # small symmetric rings: rows of exactly equal norm (the first k-centres pick is np.einsum's rounding) and fewer than 26 views
+    # (torch.cdist's direct kernel instead of the matrix product)
+    for name, nv, kc, kn in (("ring1000", 1000, 250, 4), ("ring185", 185, 46, 4), ("ring40", 40, 32, 8),
+                             ("ring24", 24, 3, 4), ("ring12", 12, 6, 4), ("ring25", 25, 25, 8), ("ring26", 26, 1, 8)):
         scene = synth.make_scene(nv, "turbo", 0.25, 4)
         out[name] = (np.stack([c.flat_pose() for c in scene.cameras], 0), kc, kn)
     rs = np.random.RandomState(77)

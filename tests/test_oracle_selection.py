@@ -124,3 +124,14 @@ def test_nearest_neighbours_small_scenes_equal_live_torch():
             k = max(1, min(4, n - 1))
             want = torch.topk(d, k, largest=False, dim=1)[1].numpy()
             assert np.array_equal(O.nearest_neighbors_cdist(flat, 4), want), n
+
+
+def test_einsum_row_reduction_restated_bit_for_bit():
+    """The first k-centres pick is argmax(np.einsum("nd,nd->n", Xn, Xn)): on symmetric rings the row norms tie and the pick is
+    einsum's rounding.  The restated order (4 lanes, last vector first, multiply then add, (l0 + l1) + (l2 + l3)) against
+    np.einsum itself; a mismatch here means numpy changed its einsum loops (the goldens would show it too)."""
+    rs = np.random.RandomState(6)
+    X = rs.standard_normal((20000, 16)).astype(np.float32)
+    assert np.array_equal(O._einsum_row_sum16_f32(X * X), np.einsum("nd,nd->n", X, X))
+    Y = (rs.randint(-3, 4, size=(5000, 16)) / np.float32(7.0)).astype(np.float32)      # many near-equal rows
+    assert np.array_equal(O._einsum_row_sum16_f32(Y * Y), np.einsum("nd,nd->n", Y, Y))
