@@ -392,7 +392,7 @@ ldp_prep_generic_kernel(const ldp_params P, const ldp_ref_desc* __restrict__ ref
             // per-tile arg-max.  A quad lies in one image row (W % 4 == 0 on this path) and touches at most two tiles:
             // pixels [0, nsplit) belong to tile tx0, the rest to tx0 + 1.  Both halves are handled without divergence.
             const int y = (int)div_magic((uint32_t)px, G.w_magic), x = px - y * W;
-            if (G.vec) {
+            if (G.vec && G.tile > 1) {         // (tiles one pixel wide - maps narrower than 48 px - put four tiles under a quad: per pixel)
                 const int tx0 = (int)div_magic((uint32_t)x, G.t_magic);
                 const int nsplit = min(4, (tx0 + 1) * G.tile - x);
                 const int brow = ((int)div_magic((uint32_t)y, G.t_magic) - ty0) * G.nbx + tx0;
