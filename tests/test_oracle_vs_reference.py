@@ -73,3 +73,46 @@ def test_sampler_and_geometry_functions(ref):
     assert np.array_equal(ref.geometry.reprojection_errors(a.P, X1, uv1), O.reprojection_error(a.P, X2, uv1))
     assert np.array_equal(ref.geometry.cheirality_mask(b.P, X1), O.in_front(b.P, X2))
     assert np.array_equal(ref.geometry.parallax_mask(a.C, b.C, X1, 0.5), O.parallax_ok(a.C, b.C, X2, 0.5))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_configurations_bit_identical(ref, seed):
+    """Random map / match sizes (down to maps narrower than 48 px: one-pixel coverage tiles), 1-4 neighbours, draw sizes, both
+    certainty families, filters on / partly off / off: outputs - or the exception raised - identical to the live reference
+    (a slice of scratch/oracle_fuzz.py, which ran 360 such configurations)."""
+    from tests import gpu_harness as G
+    from tests.golden.make_golden import build_scene
+    P = ref.pipeline
+    rs = np.random.RandomState(500 + seed)
+    H, W = int(rs.randint(24, 110)), int(rs.randint(24, 110))
+    hm, wm = (H, W) if rs.rand() < 0.5 else (int(rs.randint(16, 100)), int(rs.randint(16, 100)))
+    nn, M = int(rs.randint(1, 5)), int(rs.randint(1, min(2500, H * W // 3)))
+    c = dict(H=H, W=W, hm=hm, wm=wm, nn=nn, M=M, fam="T" if rs.rand() < 0.5 else "R", no_filter=bool(rs.rand() < 0.2),
+             seed=int(rs.randint(1, 10000)), sampson=float(rs.choice([5.0, 0.0, 1.0])), parallax=float(rs.choice([0.5, 0.0, 2.0])))
+    scene = build_scene(c)
+    inp = synth.synth_ref_inputs(scene, 0, cert_family=c["fam"], seed=c["seed"])
+    cams = scene.cameras
+    ri, nb = inp["ref_index"], inp["nbr_indices"]
+    cfg = ref.config.DensePipelineConfig(output_path="/tmp/unused.ply", matches_per_ref=M, no_filter=c["no_filter"],
+                                         sampson_thresh=c["sampson"], min_parallax_deg=c["parallax"])
+    ctx = P._TriangulationContext(cameras=P._build_camera_lookup(cams), config=cfg, matcher_sample_cap=0.9, w_match=wm, h_match=hm)
+    packed = P._PackedReferenceBatch(ref_id=cams[ri].uid, ref_path="", imA_np=inp["image"].numpy(), maskA_np=None,
+                                     wA_cam=cams[ri].width, hA_cam=cams[ri].height, nn_ids=[cams[j].uid for j in nb],
+                                     nn_masks=[None] * len(nb), nn_arrays=[None] * len(nb))
+    mr = P._MatchedReference(packed=packed, warp_list_cpu=[inp["warp"][k] for k in range(len(nb))],
+                             cert_list_cpu=[inp["cert"][k] for k in range(len(nb))], pair_index_by_nbr={}, image_by_nbr={})
+
+    def run(f):
+        np.random.seed(c["seed"])
+        try:
+            return f(), None
+        except Exception as exc:
+            return None, f"{type(exc).__name__}: {exc}"
+    want, err_w = run(lambda: P._triangulate_ref(mr, ctx, collect_debug_matches=False))
+    got, err_g = run(lambda: G.run_oracle_ref(scene, inp, c))
+    assert err_w == err_g, c
+    if want is None or got is None:
+        assert want is None and (got is None or got.xyz.shape[0] == 0), c
+        return
+    assert np.array_equal(want.xyz, got.xyz) and np.array_equal(want.rgb, got.rgb), c
+    assert np.array_equal(want.err, got.err, equal_nan=True), c
